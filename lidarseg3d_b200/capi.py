@@ -1,0 +1,90 @@
+"""ctypes binding of the C-ABI shared library (include/ls3d.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  Importing this module without a
+built ``_ls3d.so`` raises, and every wrapper raises ``RuntimeError`` on a non-zero status.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ls3d.so")
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int32
+c_float = ctypes.c_float
+
+
+class GemmArgs(ctypes.Structure):
+    """Mirror of ``ls3d_gemm_args`` (include/ls3d.h)."""
+
+    _fields_ = [
+        ("in0", c_void_p), ("in1", c_void_p),
+        ("ld0", c_int), ("c0", c_int), ("ld1", c_int), ("c1", c_int),
+        ("nbr", c_void_p),
+        ("koff", c_int), ("m_out", c_int),
+        ("w", c_void_p),
+        ("cin_pad", c_int), ("n_pad", c_int), ("cout", c_int), ("epi", c_int),
+        ("scale", c_void_p), ("shift", c_void_p),
+        ("relu", c_int),
+        ("res", c_void_p), ("ld_res", c_int), ("res_mode", c_int),
+        ("red0", c_void_p), ("red1", c_void_p),
+        ("ld_red0", c_int), ("ld_red1", c_int), ("red_c", c_int),
+        ("n_ln", c_int),
+        ("ln_g0", c_void_p), ("ln_b0", c_void_p), ("ln_g1", c_void_p), ("ln_b1", c_void_p),
+        ("ln_eps", c_float),
+        ("attn_k", c_void_p), ("attn_v", c_void_p), ("frame_off", c_void_p),
+        ("n_frames", c_int), ("n_tok", c_int), ("n_head", c_int),
+        ("attn_scale", c_float),
+        ("out", c_void_p), ("ld_out", c_int),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; fail loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(lidarseg3d_b200 has no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    L.ls3d_gather_gemm.argtypes = [ctypes.POINTER(GemmArgs), c_void_p]
+    L.ls3d_gather_gemm.restype = ctypes.c_int
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+
+
+# name -> (argtypes, restype); filled by the op modules below so the table is declared once
+_SIGNATURES = {}
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError(f"{what} failed with status {status}")
+
+
+def gather_gemm(args: GemmArgs):
+    check(lib().ls3d_gather_gemm(ctypes.byref(args), stream_ptr()), "ls3d_gather_gemm")

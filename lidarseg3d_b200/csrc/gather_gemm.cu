@@ -1,0 +1,415 @@
+// Gather-GEMM with fused epilogues on tcgen05 tensor cores (sm_100a).
+//
+// One kernel family serves every dense contraction of the MSeg3D / SDSeg3D forward path:
+//   * sparse 3-D convolution (SubM / strided / inverse) in output-stationary form
+//       out[j,:] = epi( sum_k  in[nbr[k][j], :] . W[k] )          (replaces spconv's per-offset
+//       gather -> cuBLAS mm -> scatter-add triple, reference call sites
+//       det3d/models/backbones/scn_unet.py:15-20,39-46,89-160)
+//   * every Linear(+BN)(+ReLU)(+residual)(+LayerNorm) of the point heads / TransVFE / SF-Phase
+//       decoder (koff = 1, nbr = identity), reference det3d/models/point_heads/*.py
+//   * the SF-Phase class-token cross attention as an epilogue of the q projection
+//       (reference det3d/models/point_heads/context_module.py:320-376).
+//
+// Tile: 128 output rows x n_pad columns, fp32 accumulator in TMEM.  K loop over
+// (kernel offset, 32-float channel chunk) "steps"; a step whose 128 rows have no neighbour is
+// skipped.  Producer warps gather A rows (128-bit loads, cvt.rna.tf32) and the W[k] chunk into
+// 128B-swizzled K-major shared tiles; one elected thread issues tcgen05.mma.kind::tf32; the
+// producer warps then turn into the epilogue (tcgen05.ld -> affine/ReLU/residual/LayerNorm/
+// attention -> global).
+#include "common.cuh"
+#include "../../include/ls3d.h"
+
+namespace ls3d {
+
+constexpr int TILE_M = 128;
+constexpr int KCH = 32;         // floats per K chunk = one 128-byte swizzle row
+constexpr int N_PROD = 128;     // producer / epilogue threads (4 warps)
+constexpr int N_THREADS = 160;  // + 1 MMA warp
+constexpr int MAX_KOFF = 27;
+constexpr int MAX_TOK = 48;
+constexpr int DHEAD = 24;
+
+struct SmemLayout {
+  uint32_t a_off[4], b_off[4];
+  uint32_t nbr_off, flags_off, bar_off, tmem_slot_off, total;
+};
+
+__host__ __device__ inline uint32_t a_stage_bytes() { return TILE_M * 128; }
+__host__ __device__ inline uint32_t b_stage_bytes(int n_pad) { return (uint32_t)n_pad * 128; }
+
+__device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) {
+  return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_args p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [A stages][B stages][nbr koff*128 ints][active flags][barriers][tmem slot]
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = a_stage_bytes();
+  const uint32_t b_bytes = b_stage_bytes(p.n_pad);
+  uint8_t* a_s = smem;
+  uint8_t* b_s = smem + STAGES * a_bytes;
+  int* nbr_s = (int*)(b_s + STAGES * b_bytes);
+  uint32_t* act_s = (uint32_t*)(nbr_s + p.koff * TILE_M);  // [koff][4] warp ballots
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(act_s + p.koff * 4) + 7) & ~(uintptr_t)7);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int row0 = blockIdx.x * TILE_M;
+  const int cin = p.c0 + p.c1;
+  const int nchunk = (p.cin_pad + KCH - 1) / KCH;
+
+  const uint32_t full_bar0 = smem_u32(bars);
+  const uint32_t empty_bar0 = smem_u32(bars + STAGES);
+  const uint32_t accum_bar = smem_u32(bars + 2 * STAGES);
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.n_pad) tmem_cols <<= 1;
+
+  // ---- setup
+  if (tid < N_PROD) {
+    const int r = row0 + tid;
+    for (int k = 0; k < p.koff; ++k) {
+      int j = -1;
+      if (r < p.m_out) j = p.nbr ? __ldg(p.nbr + (size_t)k * p.m_out + r) : r;
+      nbr_s[k * TILE_M + tid] = j;
+      uint32_t b = __ballot_sync(0xffffffffu, j >= 0);
+      if (lane == 0) act_s[k * 4 + warp] = b;
+    }
+  } else {
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(full_bar0 + 8 * s, N_PROD);
+        mbar_init(empty_bar0 + 8 * s, 1);
+      }
+      mbar_init(accum_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  // total active steps (uniform across the CTA)
+  int nsteps = 0;
+  for (int k = 0; k < p.koff; ++k) {
+    uint32_t any = act_s[k * 4] | act_s[k * 4 + 1] | act_s[k * 4 + 2] | act_s[k * 4 + 3];
+    if (any) nsteps += nchunk;
+  }
+
+  if (tid < N_PROD) {
+    // =========================== producer ===========================
+    int step = 0;
+    for (int k = 0; k < p.koff; ++k) {
+      uint32_t any = act_s[k * 4] | act_s[k * 4 + 1] | act_s[k * 4 + 2] | act_s[k * 4 + 3];
+      if (!any) continue;
+      for (int c = 0; c < nchunk; ++c, ++step) {
+        const int s = step % STAGES;
+        const uint32_t ph = (uint32_t)(step / STAGES) & 1u;
+        mbar_wait(empty_bar0 + 8 * s, ph ^ 1u);
+        uint8_t* a_dst = a_s + s * a_bytes;
+        uint8_t* b_dst = b_s + s * b_bytes;
+        // ---- A: 128 rows x 8 chunks of 16 B; 8 lanes cover one row
+        float4 av[8];
+        const int ch = tid & 7;
+        const int col = c * KCH + ch * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 16 + (tid >> 3);
+          const int j = nbr_s[k * TILE_M + r];
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j >= 0 && col < cin) {
+            const float* src = (col < p.c0) ? (p.in0 + (size_t)j * p.ld0 + col)
+                                            : (p.in1 + (size_t)j * p.ld1 + (col - p.c0));
+            v = ldg_f4(src);
+          }
+          av[it] = v;
+        }
+        // ---- B: n_pad rows x 8 chunks
+        const float* wk = p.w + (size_t)k * p.n_pad * p.cin_pad;
+        const int nb_it = p.n_pad / 16;
+        float4 bv[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          if (it < nb_it) {
+            const int idx = it * N_PROD + tid;
+            const int n = idx >> 3;
+            const int bcol = c * KCH + (idx & 7) * 4;
+            bv[it] = (bcol < p.cin_pad) ? ldg_f4(wk + (size_t)n * p.cin_pad + bcol)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 16 + (tid >> 3);
+          float4 v = av[it];
+          v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+          *reinterpret_cast<float4*>(a_dst + sw128(r, ch)) = v;
+        }
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          if (it < nb_it) {
+            const int idx = it * N_PROD + tid;
+            *reinterpret_cast<float4*>(b_dst + sw128(idx >> 3, idx & 7)) = bv[it];
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(full_bar0 + 8 * s);
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = make_idesc_tf32((uint32_t)p.n_pad);
+    int step = 0;
+    for (int k = 0; k < p.koff; ++k) {
+      uint32_t any = act_s[k * 4] | act_s[k * 4 + 1] | act_s[k * 4 + 2] | act_s[k * 4 + 3];
+      if (!any) continue;
+      for (int c = 0; c < nchunk; ++c, ++step) {
+        const int s = step % STAGES;
+        const uint32_t ph = (uint32_t)(step / STAGES) & 1u;
+        mbar_wait(full_bar0 + 8 * s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = make_desc_k_sw128(smem_u32(a_s + s * a_bytes));
+          const uint64_t bdesc = make_desc_k_sw128(smem_u32(b_s + s * b_bytes));
+          const int kc = min(KCH, p.cin_pad - c * KCH);  // multiple of 8
+          for (int kk = 0; kk < kc / 8; ++kk) {
+            // advance 8 tf32 = 32 B inside the 128 B swizzle row: +2 in the >>4 address field
+            umma_tf32(tmem_acc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                      (step > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar0 + 8 * s);
+          if (step == nsteps - 1) umma_commit(accum_bar);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  // =========================== epilogue ===========================
+  if (tid < N_PROD) {
+    if (nsteps > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+    const int r = row0 + tid;
+    const bool live = r < p.m_out;
+    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const bool have_acc = nsteps > 0;
+
+    if (p.epi == LS3D_EPI_ATTN) {
+      // q = acc + bias ; per head softmax(q.K^T * scale) V over the frame's class tokens
+      int f = 0;
+      for (int i = 1; i < p.n_frames; ++i)
+        if (r >= p.frame_off[i]) f = i;
+      const int L = p.n_tok;
+      for (int h = 0; h < p.n_head; ++h) {
+        uint32_t raw[24];
+        tmem_ld8(trow + h * DHEAD, raw);
+        tmem_ld8(trow + h * DHEAD + 8, raw + 8);
+        tmem_ld8(trow + h * DHEAD + 16, raw + 16);
+        tmem_ld_wait();
+        float q[DHEAD];
+#pragma unroll
+        for (int d = 0; d < DHEAD; ++d) {
+          float x = have_acc ? __uint_as_float(raw[d]) : 0.f;
+          q[d] = x + (p.shift ? __ldg(p.shift + h * DHEAD + d) : 0.f);
+        }
+        const float* kh = p.attn_k + ((size_t)(f * p.n_head + h) * L) * DHEAD;
+        const float* vh = p.attn_v + ((size_t)(f * p.n_head + h) * L) * DHEAD;
+        float sc[MAX_TOK];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int l = 0; l < MAX_TOK; ++l) {
+          if (l < L) {
+            float a = 0.f;
+#pragma unroll
+            for (int d4 = 0; d4 < DHEAD / 4; ++d4) {
+              float4 kv = ldg_f4(kh + l * DHEAD + d4 * 4);
+              a = fmaf(q[d4 * 4 + 0], kv.x, a);
+              a = fmaf(q[d4 * 4 + 1], kv.y, a);
+              a = fmaf(q[d4 * 4 + 2], kv.z, a);
+              a = fmaf(q[d4 * 4 + 3], kv.w, a);
+            }
+            a *= p.attn_scale;
+            sc[l] = a;
+            mx = fmaxf(mx, a);
+          }
+        }
+        float den = 0.f;
+        float o[DHEAD];
+#pragma unroll
+        for (int d = 0; d < DHEAD; ++d) o[d] = 0.f;
+#pragma unroll
+        for (int l = 0; l < MAX_TOK; ++l) {
+          if (l < L) {
+            float e = __expf(sc[l] - mx);
+            den += e;
+#pragma unroll
+            for (int d4 = 0; d4 < DHEAD / 4; ++d4) {
+              float4 vv = ldg_f4(vh + l * DHEAD + d4 * 4);
+              o[d4 * 4 + 0] = fmaf(e, vv.x, o[d4 * 4 + 0]);
+              o[d4 * 4 + 1] = fmaf(e, vv.y, o[d4 * 4 + 1]);
+              o[d4 * 4 + 2] = fmaf(e, vv.z, o[d4 * 4 + 2]);
+              o[d4 * 4 + 3] = fmaf(e, vv.w, o[d4 * 4 + 3]);
+            }
+          }
+        }
+        const float inv = 1.f / den;
+        if (live) {
+          float* dst = p.out + (size_t)r * p.ld_out + h * DHEAD;
+#pragma unroll
+          for (int d4 = 0; d4 < DHEAD / 4; ++d4)
+            *reinterpret_cast<float4*>(dst + d4 * 4) =
+                make_float4(o[d4 * 4] * inv, o[d4 * 4 + 1] * inv, o[d4 * 4 + 2] * inv, o[d4 * 4 + 3] * inv);
+        }
+      }
+    } else {
+      // value of column `col` after affine / residual / relu / channel-reduction
+      auto finish = [&](float acc, int col) -> float {
+        float x = acc;
+        if (p.scale) x *= __ldg(p.scale + col);
+        if (p.shift) x += __ldg(p.shift + col);
+        if (p.res_mode == 1 && live) x += __ldg(p.res + (size_t)r * p.ld_res + col);
+        if (p.relu) x = fmaxf(x, 0.f);
+        if (p.res_mode == 2 && live) x += __ldg(p.res + (size_t)r * p.ld_res + col);
+        if (p.red0 && live) {
+          // cat = [red0 (red_c ch) | red1 (red_c ch)] ; out[col] += cat[2col] + cat[2col+1]
+          const int c2 = 2 * col;
+          const float* src = (c2 < p.red_c) ? (p.red0 + (size_t)r * p.ld_red0 + c2)
+                                            : (p.red1 + (size_t)r * p.ld_red1 + (c2 - p.red_c));
+          x += __ldg(src) + __ldg(src + 1);
+        }
+        return x;
+      };
+      const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.cout & 3) == 0);
+      float mean[2] = {0.f, 0.f}, rstd[2] = {1.f, 1.f};
+      // LayerNorm statistics (up to two chained LayerNorms), exact two-pass form per LN
+      for (int ln = 0; ln < p.n_ln; ++ln) {
+        float s1 = 0.f;
+        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+          uint32_t raw[16];
+          tmem_ld16(trow + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = c0 + j;
+            if (col < p.cout) {
+              float x = finish(have_acc ? __uint_as_float(raw[j]) : 0.f, col);
+              if (ln == 1) x = (x - mean[0]) * rstd[0] * __ldg(p.ln_g0 + col) + __ldg(p.ln_b0 + col);
+              s1 += x;
+            }
+          }
+        }
+        const float m = s1 / (float)p.cout;
+        float s2 = 0.f;
+        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+          uint32_t raw[16];
+          tmem_ld16(trow + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = c0 + j;
+            if (col < p.cout) {
+              float x = finish(have_acc ? __uint_as_float(raw[j]) : 0.f, col);
+              if (ln == 1) x = (x - mean[0]) * rstd[0] * __ldg(p.ln_g0 + col) + __ldg(p.ln_b0 + col);
+              const float d = x - m;
+              s2 = fmaf(d, d, s2);
+            }
+          }
+        }
+        mean[ln] = m;
+        rstd[ln] = rsqrtf(s2 / (float)p.cout + p.ln_eps);
+      }
+      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16(trow + c0, raw);
+        tmem_ld_wait();
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = c0 + j;
+          float x = 0.f;
+          if (col < p.cout) {
+            x = finish(have_acc ? __uint_as_float(raw[j]) : 0.f, col);
+            if (p.n_ln > 0) x = (x - mean[0]) * rstd[0] * __ldg(p.ln_g0 + col) + __ldg(p.ln_b0 + col);
+            if (p.n_ln > 1) x = (x - mean[1]) * rstd[1] * __ldg(p.ln_g1 + col) + __ldg(p.ln_b1 + col);
+          }
+          y[j] = x;
+        }
+        if (live) {
+          float* dst = p.out + (size_t)r * p.ld_out + c0;
+          if (vec_ok) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              if (c0 + j4 * 4 < p.cout)
+                *reinterpret_cast<float4*>(dst + j4 * 4) =
+                    make_float4(y[j4 * 4], y[j4 * 4 + 1], y[j4 * 4 + 2], y[j4 * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.cout) dst[j] = y[j];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_acc, tmem_cols);
+}
+
+static size_t smem_bytes_for(int stages, int n_pad, int koff) {
+  size_t b = 1024;  // alignment slack
+  b += (size_t)stages * (a_stage_bytes() + b_stage_bytes(n_pad));
+  b += (size_t)koff * TILE_M * 4 + (size_t)koff * 16;
+  b += 8 + (2 * stages + 1) * 8 + 16;
+  return b;
+}
+
+}  // namespace ls3d
+
+extern "C" int ls3d_gather_gemm(const ls3d_gemm_args* a, void* stream) {
+  using namespace ls3d;
+  if (!a || !a->in0 || !a->w || !a->out) return LS3D_ERR_ARG;
+  if (a->m_out <= 0) return LS3D_OK;
+  if (a->koff < 1 || a->koff > MAX_KOFF) return LS3D_ERR_ARG;
+  if (!a->nbr && a->koff != 1) return LS3D_ERR_ARG;
+  if (a->n_pad % 16 || a->n_pad < 16 || a->n_pad > 256 || a->cout > a->n_pad) return LS3D_ERR_ARG;
+  if (a->cin_pad % 8 || a->cin_pad < a->c0 + a->c1) return LS3D_ERR_ARG;
+  if ((a->c0 & 3) || (a->c1 & 3) || (a->ld0 & 3) || (a->c1 && (a->ld1 & 3))) return LS3D_ERR_ARG;
+  if (a->epi == LS3D_EPI_ATTN) {
+    if (!a->attn_k || !a->attn_v || !a->frame_off || a->n_tok > MAX_TOK ||
+        a->n_head * DHEAD != a->cout || (a->ld_out & 3))
+      return LS3D_ERR_ARG;
+  }
+  if (a->n_ln < 0 || a->n_ln > 2) return LS3D_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ls3d_div_up(a->m_out, TILE_M);
+  // deepest pipeline that still lets two CTAs share one SM (<= ~110 KB each)
+  int stages = 4;
+  while (stages > 2 && smem_bytes_for(stages, a->n_pad, a->koff) > 110 * 1024) --stages;
+  const size_t smem = smem_bytes_for(stages, a->n_pad, a->koff);
+  cudaError_t e;
+#define LS3D_GG_LAUNCH(S)                                                                          \
+  {                                                                                                \
+    e = cudaFuncSetAttribute(gather_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                             (int)smem);                                                           \
+    if (e != cudaSuccess) return (int)e;                                                           \
+    gather_gemm_kernel<S><<<grid, N_THREADS, smem, st>>>(*a);                                      \
+  }
+  if (stages == 4) LS3D_GG_LAUNCH(4)
+  else if (stages == 3) LS3D_GG_LAUNCH(3)
+  else LS3D_GG_LAUNCH(2)
+#undef LS3D_GG_LAUNCH
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}

@@ -1,0 +1,89 @@
+"""Host side of the tcgen05 gather-GEMM (csrc/gather_gemm.cu): weight packing + launch helper."""
+import torch
+
+from . import capi
+
+
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest (ties away) fp32 -> tf32, kept in an fp32 container (== cvt.rna.tf32.f32)."""
+    xi = x.contiguous().view(torch.int32)
+    r = (xi + 0x1000) & ~0x1FFF
+    out = r.view(torch.float32)
+    return torch.where(torch.isfinite(x), out, x)
+
+
+def pad_to(v, m):
+    return (v + m - 1) // m * m
+
+
+class PackedWeight:
+    """W[koff][cin][cout] (spconv layout, reference scn_unet.py weight [kz,ky,kx,Cin,Cout]) packed as
+    [koff][n_pad][cin_pad] K-major, tf32-rounded, zero padded."""
+
+    def __init__(self, w_kio: torch.Tensor):
+        assert w_kio.dim() == 3
+        koff, cin, cout = w_kio.shape
+        self.koff, self.cin, self.cout = koff, cin, cout
+        self.cin_pad = pad_to(cin, 8)
+        self.n_pad = pad_to(cout, 16)
+        buf = torch.zeros(koff, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
+        buf[:, :cout, :cin] = round_tf32(w_kio.float()).permute(0, 2, 1)
+        self.data = buf.contiguous()
+
+    @staticmethod
+    def from_linear(weight_oi: torch.Tensor):
+        """nn.Linear / Conv1d(k=1) weight [cout, cin] -> koff = 1."""
+        return PackedWeight(weight_oi.t().unsqueeze(0))
+
+
+def run(x0, pw: PackedWeight, *, x1=None, nbr=None, m_out=None, scale=None, shift=None, relu=False,
+        res=None, res_mode=0, red=None, ln=(), ln_eps=1e-5, attn=None, out=None):
+    """Launch ls3d_gather_gemm.  ``x0``/``x1`` are [rows, C] fp32 row-major (row stride may exceed C).
+
+    attn = dict(k=[F,H,L,24], v=[F,H,L,24], frame_off=int32[F], scale=float) selects the attention
+    epilogue.  ``red`` = (t0, t1) enables the channel-reduction add.  ``ln`` = up to two (gamma, beta).
+    """
+    a = capi.GemmArgs()
+    assert x0.dtype == torch.float32 and x0.stride(1) == 1
+    c0 = x0.shape[1]
+    c1 = 0
+    a.in0, a.ld0, a.c0 = capi.ptr(x0), x0.stride(0), c0
+    if x1 is not None:
+        assert x1.dtype == torch.float32 and x1.stride(1) == 1
+        c1 = x1.shape[1]
+        a.in1, a.ld1 = capi.ptr(x1), x1.stride(0)
+    a.c1 = c1
+    assert c0 + c1 == pw.cin or (c0 + c1 <= pw.cin_pad and c0 + c1 >= pw.cin), (c0, c1, pw.cin)
+    if nbr is not None:
+        assert nbr.dtype == torch.int32 and nbr.is_contiguous() and nbr.shape[0] == pw.koff
+        m = nbr.shape[1]
+        a.nbr = capi.ptr(nbr)
+    else:
+        m = x0.shape[0]
+    if m_out is not None:
+        m = m_out
+    a.koff, a.m_out = pw.koff, m
+    a.w, a.cin_pad, a.n_pad, a.cout = capi.ptr(pw.data), pw.cin_pad, pw.n_pad, pw.cout
+    a.scale, a.shift, a.relu = capi.ptr(scale), capi.ptr(shift), int(relu)
+    if res is not None:
+        a.res, a.ld_res, a.res_mode = capi.ptr(res), res.stride(0), res_mode
+    if red is not None:
+        a.red0, a.red1 = capi.ptr(red[0]), capi.ptr(red[1])
+        a.ld_red0, a.ld_red1, a.red_c = red[0].stride(0), red[1].stride(0), red[0].shape[1]
+    a.n_ln = len(ln)
+    if len(ln) > 0:
+        a.ln_g0, a.ln_b0 = capi.ptr(ln[0][0]), capi.ptr(ln[0][1])
+    if len(ln) > 1:
+        a.ln_g1, a.ln_b1 = capi.ptr(ln[1][0]), capi.ptr(ln[1][1])
+    a.ln_eps = ln_eps
+    if attn is not None:
+        a.epi = 1
+        a.attn_k, a.attn_v = capi.ptr(attn["k"]), capi.ptr(attn["v"])
+        a.frame_off = capi.ptr(attn["frame_off"])
+        a.n_frames, a.n_head, a.n_tok = attn["k"].shape[0], attn["k"].shape[1], attn["k"].shape[2]
+        a.attn_scale = attn["scale"]
+    if out is None:
+        out = torch.empty(m, pw.cout, dtype=torch.float32, device=x0.device)
+    a.out, a.ld_out = capi.ptr(out), out.stride(0)
+    capi.gather_gemm(a)
+    return out
