@@ -59,11 +59,119 @@ typedef struct ls3d_gemm_args {
   const int32_t* frame_off; /* [n_frames] first output row of each frame (device)              */
   int32_t n_frames, n_tok, n_head;
   float attn_scale;
+  const float* row_mask; /* optional: rows with row_mask[r*ld_mask] != 1.0f are written as zeros  */
+  int32_t ld_mask;       /*   (feature completion, point_seg_mseg3d_head.py:314-334)                */
   float* out;         /* [m_out, ld_out]                                                       */
   int32_t ld_out;
 } ls3d_gemm_args;
 
 int ls3d_gather_gemm(const ls3d_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hard voxelization of a batch of frames (bit-exact with the reference's numba voxelizer).
+ * replaces: points_to_voxel / _points_to_voxel_reverse_kernel
+ *           (det3d/ops/point_cloud/point_cloud_ops.py:7-55,112-184) called by
+ *           VoxelGenerator.generate (det3d/core/input/voxel_generator.py:19-30) from SegVoxelization
+ *           (det3d/datasets/pipelines/segpreprocess.py:148-177) + collate_kitti's batch-index padding
+ *           (det3d/torchie/parallel/collate.py:141-150); API twin of hard_voxelize
+ *           (det3d/ops/voxel/src/voxelization.cpp:6-11, voxelization_cpu.cpp:105-142).
+ *   points         [n_points, n_feat] fp32 (x, y, z, ...), frames concatenated
+ *   frame_off_host [n_frames + 1] HOST ints, first point of each frame
+ *   voxel_size[3], pc_range[6] HOST floats (x, y, z order)
+ *   voxels   [>= n_points, max_points, n_feat] fp32 (rows past total_voxels untouched)
+ *   coords   [>= n_points, 4] int32 (frame, z, y, x);  num_points [>= n_points] int32
+ *   num_voxels [n_frames], total_voxels [1] int32 (device);  point_voxel [n_points] or NULL
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_voxelize_workspace_bytes(int64_t n_points, int32_t max_points, int32_t n_frames, int64_t* bytes);
+int ls3d_voxelize(const float* points, int32_t n_points, int32_t n_feat, const int32_t* frame_off_host,
+                  int32_t n_frames, const float* voxel_size, const float* pc_range, int32_t max_points,
+                  int32_t max_voxels, void* workspace, int64_t workspace_bytes, float* voxels, int32_t* coords,
+                  int32_t* num_points, int32_t* num_voxels, int32_t* total_voxels, int32_t* point_voxel,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Voxel feature encoders.
+ * replaces: MeanVoxelFeatureExtractor / ImprovedMeanVoxelFeatureExtractor / the descriptor, attention
+ *           core and slot max of TransformerVoxelFeatureExtractor
+ *           (det3d/models/readers/voxel_encoder.py:51-58,74-124,149-157,202-270).
+ *   mode 0: out[m, F] mean;  1: out[m, F+8] 13-d style descriptor;  2: out[m*P, 2F+8] token inputs
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_vfe_descriptor(const float* voxels, const int32_t* num_points, int32_t m, int32_t P, int32_t F,
+                        int32_t mode, float* out, int32_t ld_out, void* stream);
+int ls3d_vfe_token_attn(const float* qkv, int32_t ld_qkv, int32_t m, int32_t P, int32_t n_head, int32_t d_head,
+                        float* out, int32_t ld_out, void* stream);
+int ls3d_vfe_token_max(const float* x, int32_t ld_x, int32_t m, int32_t P, int32_t E, float* out, int32_t ld_out,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rulebooks (spconv "indice pairs") via an occupancy bitmap {bits, rank prefix} per 32 cells.
+ * replaces: spconv get_indice_pairs behind SubMConv3d / SparseConv3d / SparseInverseConv3d
+ *           (det3d/models/backbones/scn_unet.py:15-20,39-46,89-160).
+ *   coords rows are int32 (frame, z, y, x).  nbr tables are [K][m] int32, K = kz*ky*kx,
+ *   offset index k = (kz*KY + ky)*KX + kx, value = input row or -1.
+ *   ls3d_grid_build         : bitmap of `coords`; perm (optional) = rank -> row for unsorted rows
+ *   ls3d_grid_build_strided : bitmap of the strided conv's output sites; *total_out = #sites
+ *   ls3d_grid_enumerate     : coords of the active cells in ascending linear order
+ *   ls3d_rulebook_gather    : nbr[k][j] = input row at out_j*stride - pad + k  (SubM: stride 1, pad K/2)
+ *   ls3d_rulebook_scatter   : inverse conv: nbr[k][i] = coarse row o with o*stride - pad + k == fine_i
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_grid_bytes(int32_t B, int32_t D, int32_t H, int32_t W, int64_t* words_bytes, int64_t* scratch_bytes);
+int ls3d_grid_build(const int32_t* coords, int32_t m, int32_t B, int32_t D, int32_t H, int32_t W, void* words,
+                    int32_t* perm, void* scratch, int32_t* total_out, void* stream);
+int ls3d_grid_build_strided(const int32_t* in_coords, int32_t m_in, int32_t B, const int32_t* ksize,
+                            const int32_t* stride, const int32_t* pad, int32_t oD, int32_t oH, int32_t oW,
+                            void* out_words, void* scratch, int32_t* total_out, void* stream);
+int ls3d_grid_enumerate(const void* words, int32_t B, int32_t D, int32_t H, int32_t W, int32_t* coords,
+                        void* stream);
+int ls3d_rulebook_gather(const void* in_words, const int32_t* in_perm, int32_t B, int32_t D, int32_t H, int32_t W,
+                         const int32_t* out_coords, int32_t m_out, const int32_t* ksize, const int32_t* stride,
+                         const int32_t* pad, int32_t* nbr, void* stream);
+int ls3d_rulebook_scatter(const void* out_words, int32_t B, int32_t oD, int32_t oH, int32_t oW,
+                          const int32_t* in_coords, int32_t m_in, const int32_t* ksize, const int32_t* stride,
+                          const int32_t* pad, int32_t* nbr, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Devoxelization: exact 3-NN of raw points among voxel centres + inverse-distance interpolation.
+ * replaces: three_nn_wrapper / three_interpolate_wrapper (det3d/ops/pointnet2_batch/src/pointnet2_api.cpp:10-24,
+ *           interpolate_gpu.cu:16-59,84-104) as used by three_interpolate_wrap
+ *           (det3d/models/point_heads/point_utils.py:8-52).
+ *   points [n, ld_p] fp32 rows (frame, x, y, z, ...); words/perm = level-1 bitmap of the voxel grid;
+ *   idx are GLOBAL voxel rows (reference: per-frame rows; subtract voxel_off[frame] to compare);
+ *   dist2 = squared distances (reference three_nn returns sqrt of these).
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_three_nn_grid(const float* points, int32_t ld_p, int32_t n, const void* words, const int32_t* perm, int32_t B,
+                       int32_t D, int32_t H, int32_t W, const float* voxel_size_xyz, const float* range_min_xyz,
+                       const int32_t* point_off, const int32_t* voxel_off, const int32_t* voxel_coords, int32_t* todo,
+                       int32_t* todo_count, float* dist2, int32_t* idx, void* stream);
+int ls3d_three_interpolate(const float* feat, int32_t ld_f, int32_t C, const float* dist2, const int32_t* idx, int32_t n,
+                           float* out, int32_t ld_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Camera feature sampling.
+ * replaces: PointSegMSeg3DHead.get_points_image_feature (F.grid_sample 3-D, bilinear, zeros,
+ *           align_corners=True; det3d/models/point_heads/point_seg_mseg3d_head.py:200-236).
+ *   feat_nhwc [n_frames, ncam, H, W, C] fp32;  points_cuv [n, 4] = (valid, cam, v, u) in [-1, 1]
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_sample_image_features(const float* feat_nhwc, int32_t n_frames, int32_t ncam, int32_t H, int32_t W, int32_t C,
+                               const float* points_cuv, int32_t n, const int32_t* point_off, float* out, int32_t ld_out,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SF-Phase: class embedding aggregation and class-token memory path.
+ * replaces: LiDARSemanticFeatureAggregationModule (det3d/models/point_heads/context_module.py:25-53),
+ *           CameraSemanticFeatureAggregationModule (det3d/models/img_heads/fcn_mseg3d_head.py:24-51),
+ *           memory side of SemanticFeatureFusionModule / TransformerDecoderLayer.forward_post
+ *           (context_module.py:101-109,211-227,337-339).
+ *   emb  [n_frames][ncls][C];  K, V [n_layer][n_frames][n_head][2*ncls][d_model/n_head]
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_class_embed_workspace_bytes(int32_t n_frames, int32_t max_rows_per_frame, int32_t ncls, int32_t C,
+                                     int64_t* bytes);
+int ls3d_class_embed(const float* logits, int32_t ld_l, int32_t ncls, const float* feats, int32_t ld_f, int32_t C,
+                     const int32_t* seg_off, int32_t n_frames, int32_t max_rows_per_frame, void* workspace, float* emb,
+                     void* stream);
+int ls3d_class_tokens(const float* emb1, int32_t C1, const float* emb2, int32_t C2, int32_t ncls, int32_t n_frames,
+                      const float* params, int32_t n_layer, int32_t n_head, int32_t d_model, float* K, float* V,
+                      float* mem_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,300 @@
+// SF-Phase helpers: semantic (class) embedding aggregation and the class-token memory path.
+//
+//   ls3d_class_embed  : LiDARSemanticFeatureAggregationModule.forward (reference
+//                       det3d/models/point_heads/context_module.py:25-53) and
+//                       CameraSemanticFeatureAggregationModule.forward
+//                       (det3d/models/img_heads/fcn_mseg3d_head.py:24-51): per frame and class,
+//                       softmax of the logits over ALL rows (voxels / pixels) of the frame, then
+//                       probs[ncls, R] @ feats[R, C].  Deterministic two-level reduction.
+//   ls3d_class_tokens : the memory side of SemanticFeatureFusionModule + TransformerDecoderLayer.forward_post
+//                       (context_module.py:101-109,211-227,337-339): input projections of the two
+//                       embedding sets, then per layer self-attention over the 2*ncls tokens + LayerNorm,
+//                       and the k/v projections consumed by the point cross-attention.  The memory never
+//                       depends on the points, so all layers run in one launch (one CTA per frame).
+#include "common.cuh"
+#include "../../include/ls3d.h"
+
+namespace ls3d {
+
+constexpr int CE_ROWS = 2048;   // rows per partial block
+constexpr int CE_MAXCLS = 32;
+constexpr int CE_MAXC = 64;
+
+__device__ __forceinline__ float atomic_max_f(float* addr, float v) {
+  // valid for any sign: compare through ordered-int mapping
+  int* ai = (int*)addr;
+  int old = *ai, assumed;
+  do {
+    assumed = old;
+    if (__int_as_float(assumed) >= v) break;
+    old = atomicCAS(ai, assumed, __float_as_int(v));
+  } while (assumed != old);
+  return __int_as_float(old);
+}
+
+static __global__ void fill_f32_kernel(float* p, int n, float v) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = v;
+}
+
+// pass 1: per (frame, class) max over rows.  grid = (chunks, frames)
+__global__ void ce_max_kernel(const float* __restrict__ logits, int ld_l, int ncls, const int* __restrict__ seg_off,
+                              float* __restrict__ cmax /* [B][ncls] init -inf */) {
+  const int b = blockIdx.y;
+  const int r0 = seg_off[b], r1 = seg_off[b + 1];
+  const int start = r0 + blockIdx.x * CE_ROWS;
+  if (start >= r1) return;
+  const int end = min(start + CE_ROWS, r1);
+  __shared__ float smax[CE_MAXCLS];
+  if (threadIdx.x < CE_MAXCLS) smax[threadIdx.x] = -INFINITY;
+  __syncthreads();
+  // thread t handles class (t % ncls_pad) of rows strided
+  for (int c = 0; c < ncls; ++c) {
+    float m = -INFINITY;
+    for (int r = start + threadIdx.x; r < end; r += blockDim.x) m = fmaxf(m, __ldg(logits + (size_t)r * ld_l + c));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomic_max_f(&smax[c], m);
+  }
+  __syncthreads();
+  if (threadIdx.x < ncls) atomic_max_f(&cmax[b * ncls + threadIdx.x], smax[threadIdx.x]);
+}
+
+// pass 2: partial sums  part[b][chunk][cls][C+1] = sum_r e * [feat | 1]
+__global__ void ce_partial_kernel(const float* __restrict__ logits, int ld_l, int ncls, const float* __restrict__ feats,
+                                  int ld_f, int C, const int* __restrict__ seg_off, const float* __restrict__ cmax,
+                                  float* __restrict__ part, int nchunk) {
+  const int b = blockIdx.y;
+  const int r0 = seg_off[b], r1 = seg_off[b + 1];
+  const int start = r0 + blockIdx.x * CE_ROWS;
+  float* dst = part + ((size_t)b * nchunk + blockIdx.x) * ncls * (C + 1);
+  const int nacc = ncls * (C + 1);
+  if (start >= r1) {
+    for (int a = threadIdx.x; a < nacc; a += blockDim.x) dst[a] = 0.f;
+    return;
+  }
+  const int end = min(start + CE_ROWS, r1);
+  __shared__ float se[32][CE_MAXCLS];
+  __shared__ float sf[32][CE_MAXC + 1];
+  // each thread owns up to 4 accumulators (cls, ch) with ch in [0, C] (ch == C -> denominator)
+  float acc[8];
+  int acls[8], ach[8];
+  int na = 0;
+  for (int a = threadIdx.x; a < nacc && na < 8; a += blockDim.x) {
+    acls[na] = a / (C + 1); ach[na] = a % (C + 1); acc[na] = 0.f; ++na;
+  }
+  for (int t0 = start; t0 < end; t0 += 32) {
+    const int nr = min(32, end - t0);
+    for (int q = threadIdx.x; q < 32 * ncls; q += blockDim.x) {
+      const int r = q / ncls, c = q % ncls;
+      se[r][c] = r < nr ? __expf(__ldg(logits + (size_t)(t0 + r) * ld_l + c) - __ldg(cmax + b * ncls + c)) : 0.f;
+    }
+    for (int q = threadIdx.x; q < 32 * (C + 1); q += blockDim.x) {
+      const int r = q / (C + 1), c = q % (C + 1);
+      sf[r][c] = r < nr ? (c < C ? __ldg(feats + (size_t)(t0 + r) * ld_f + c) : 1.f) : 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k < na; ++k) {
+      float a = acc[k];
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) a = fmaf(se[r][acls[k]], sf[r][ach[k]], a);
+      acc[k] = a;
+    }
+    __syncthreads();
+  }
+  for (int k = 0; k < na; ++k) dst[acls[k] * (C + 1) + ach[k]] = acc[k];
+}
+
+// pass 3: emb[b][cls][c] = sum_chunks num / sum_chunks den
+__global__ void ce_final_kernel(const float* __restrict__ part, int nchunk, int ncls, int C, float* __restrict__ emb) {
+  const int b = blockIdx.x;
+  for (int a = threadIdx.x; a < ncls * C; a += blockDim.x) {
+    const int cls = a / C, c = a % C;
+    float num = 0.f, den = 0.f;
+    for (int k = 0; k < nchunk; ++k) {
+      const float* src = part + ((size_t)b * nchunk + k) * ncls * (C + 1) + cls * (C + 1);
+      num += src[c];
+      den += src[C];
+    }
+    emb[((size_t)b * ncls + cls) * C + c] = num / den;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// class-token memory path.  Parameters are packed by the host (lidarseg3d_b200/det3d/point_heads.py):
+//   head:  P1t[C1][E], b1[E], P2t[C2][E], b2[E]                       (input_proj_embeddings1/2, W^T)
+//   layer: Wint[E][3E], bin[3E], Woutt[E][E], bout[E], g1[E], be1[E], Wkt[E][E], bk[E], Wvt[E][E], bv[E]
+// Output K, V: [n_layer][B][H][L][dh]  (L = 2*ncls tokens, cam tokens first)
+constexpr int CT_MAXL = 48;
+constexpr int CT_E = 96;
+
+__global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restrict__ emb1, int C1,
+                                                           const float* __restrict__ emb2, int C2, int ncls,
+                                                           const float* __restrict__ params, int n_layer, int n_head,
+                                                           float* __restrict__ Kout, float* __restrict__ Vout,
+                                                           float* __restrict__ mem_out) {
+  constexpr int E = CT_E;
+  const int b = blockIdx.x, B = gridDim.x;
+  const int L = 2 * ncls;
+  const int dh = E / n_head;
+  extern __shared__ float ct_smem[];
+  float (*mem)[E] = reinterpret_cast<float (*)[E]>(ct_smem);                       // [L][E]
+  float (*qkv)[3 * E] = reinterpret_cast<float (*)[3 * E]>(ct_smem + L * E);       // [L][3E]
+  float (*att)[E] = reinterpret_cast<float (*)[E]>(ct_smem + L * E + L * 3 * E);   // [L][E]
+  float* scb = ct_smem + L * E + L * 3 * E + L * E;                                // [H][L][L+1]
+#define SC(h, i, j) scb[((h) * L + (i)) * (L + 1) + (j)]
+  const float* P1t = params;
+  const float* b1 = P1t + C1 * E;
+  const float* P2t = b1 + E;
+  const float* b2 = P2t + C2 * E;
+  const float* lp = b2 + E;
+  const int layer_sz = E * 3 * E + 3 * E + E * E + E + E + E + E * E + E + E * E + E;
+  // ---- input projections
+  for (int o = threadIdx.x; o < L * E; o += blockDim.x) {
+    const int l = o / E, e = o % E;
+    float a;
+    if (l < ncls) {
+      a = b1[e];
+      const float* x = emb1 + ((size_t)b * ncls + l) * C1;
+      for (int c = 0; c < C1; ++c) a = fmaf(x[c], P1t[c * E + e], a);
+    } else {
+      a = b2[e];
+      const float* x = emb2 + ((size_t)b * ncls + (l - ncls)) * C2;
+      for (int c = 0; c < C2; ++c) a = fmaf(x[c], P2t[c * E + e], a);
+    }
+    mem[l][e] = a;
+  }
+  __syncthreads();
+  for (int ly = 0; ly < n_layer; ++ly) {
+    const float* Wint = lp + (size_t)ly * layer_sz;
+    const float* bin = Wint + E * 3 * E;
+    const float* Woutt = bin + 3 * E;
+    const float* bout = Woutt + E * E;
+    const float* g1 = bout + E;
+    const float* be1 = g1 + E;
+    const float* Wkt = be1 + E;
+    const float* bk = Wkt + E * E;
+    const float* Wvt = bk + E;
+    const float* bv = Wvt + E * E;
+    // in-projection
+    for (int o = threadIdx.x; o < L * 3 * E; o += blockDim.x) {
+      const int l = o / (3 * E), e = o % (3 * E);
+      float a = bin[e];
+      for (int c = 0; c < E; ++c) a = fmaf(mem[l][c], Wint[c * 3 * E + e], a);
+      qkv[l][e] = a;
+    }
+    __syncthreads();
+    // scores
+    const float scale = rsqrtf((float)dh);
+    for (int o = threadIdx.x; o < n_head * L * L; o += blockDim.x) {
+      const int h = o / (L * L), i = (o / L) % L, j = o % L;
+      float a = 0.f;
+      for (int d = 0; d < dh; ++d) a = fmaf(qkv[i][h * dh + d] * scale, qkv[j][E + h * dh + d], a);
+      SC(h, i, j) = a;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < n_head * L; o += blockDim.x) {
+      const int h = o / L, i = o % L;
+      float m = -INFINITY;
+      for (int j = 0; j < L; ++j) m = fmaxf(m, SC(h, i, j));
+      float s = 0.f;
+      for (int j = 0; j < L; ++j) { const float e = __expf(SC(h, i, j) - m); SC(h, i, j) = e; s += e; }
+      const float inv = 1.f / s;
+      for (int j = 0; j < L; ++j) SC(h, i, j) *= inv;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < L * E; o += blockDim.x) {
+      const int i = o / E, e = o % E, h = e / dh;
+      float a = 0.f;
+      for (int j = 0; j < L; ++j) a = fmaf(SC(h, i, j), qkv[j][2 * E + e], a);
+      att[i][e] = a;
+    }
+    __syncthreads();
+    // out-projection + residual (into qkv[:, :E] as scratch)
+    for (int o = threadIdx.x; o < L * E; o += blockDim.x) {
+      const int l = o / E, e = o % E;
+      float a = bout[e];
+      for (int c = 0; c < E; ++c) a = fmaf(att[l][c], Woutt[c * E + e], a);
+      qkv[l][e] = mem[l][e] + a;
+    }
+    __syncthreads();
+    // LayerNorm (norm1), one warp per token
+    for (int l = threadIdx.x >> 5; l < L; l += blockDim.x >> 5) {
+      const int lane = threadIdx.x & 31;
+      float s = 0.f;
+      for (int e = lane; e < E; e += 32) s += qkv[l][e];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / E;
+      float v = 0.f;
+      for (int e = lane; e < E; e += 32) { const float d = qkv[l][e] - mean; v = fmaf(d, d, v); }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const float rstd = rsqrtf(v / E + 1e-5f);
+      for (int e = lane; e < E; e += 32) mem[l][e] = (qkv[l][e] - mean) * rstd * g1[e] + be1[e];
+    }
+    __syncthreads();
+    // k / v projections for the point cross-attention of this layer
+    for (int o = threadIdx.x; o < L * E * 2; o += blockDim.x) {
+      const int which = o / (L * E), r = o % (L * E);
+      const int l = r / E, e = r % E;
+      const float* Wt = which ? Wvt : Wkt;
+      float a = which ? bv[e] : bk[e];
+      for (int c = 0; c < E; ++c) a = fmaf(mem[l][c], Wt[c * E + e], a);
+      const int h = e / dh, d = e % dh;
+      float* dst = which ? Vout : Kout;
+      dst[((((size_t)ly * B + b) * n_head + h) * L + l) * dh + d] = a;
+    }
+    if (mem_out)
+      for (int o = threadIdx.x; o < L * E; o += blockDim.x)
+        mem_out[(((size_t)ly * B + b) * L + o / E) * E + o % E] = mem[o / E][o % E];
+    __syncthreads();
+  }
+}
+
+}  // namespace ls3d
+
+extern "C" int ls3d_class_embed_workspace_bytes(int32_t n_frames, int32_t max_rows_per_frame, int32_t ncls, int32_t C,
+                                                int64_t* bytes) {
+  using namespace ls3d;
+  if (!bytes) return LS3D_ERR_ARG;
+  const int nchunk = ls3d_div_up(max_rows_per_frame > 0 ? max_rows_per_frame : 1, CE_ROWS);
+  *bytes = ((int64_t)n_frames * ncls + (int64_t)n_frames * nchunk * ncls * (C + 1)) * 4;
+  return LS3D_OK;
+}
+
+extern "C" int ls3d_class_embed(const float* logits, int32_t ld_l, int32_t ncls, const float* feats, int32_t ld_f, int32_t C,
+                                const int32_t* seg_off, int32_t n_frames, int32_t max_rows_per_frame, void* workspace,
+                                float* emb, void* stream) {
+  using namespace ls3d;
+  if (!logits || !feats || !seg_off || !workspace || !emb || ncls > CE_MAXCLS || C > CE_MAXC || ncls < 1)
+    return LS3D_ERR_ARG;
+  if (ncls * (C + 1) > 8 * 256) return LS3D_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunk = ls3d_div_up(max_rows_per_frame > 0 ? max_rows_per_frame : 1, CE_ROWS);
+  float* cmax = (float*)workspace;
+  float* part = cmax + (size_t)n_frames * ncls;
+  fill_f32_kernel<<<1, 256, 0, st>>>(cmax, n_frames * ncls, -INFINITY);
+  dim3 grid(nchunk, n_frames);
+  ce_max_kernel<<<grid, 256, 0, st>>>(logits, ld_l, ncls, seg_off, cmax);
+  ce_partial_kernel<<<grid, 256, 0, st>>>(logits, ld_l, ncls, feats, ld_f, C, seg_off, cmax, part, nchunk);
+  ce_final_kernel<<<n_frames, 256, 0, st>>>(part, nchunk, ncls, C, emb);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}
+
+extern "C" int ls3d_class_tokens(const float* emb1, int32_t C1, const float* emb2, int32_t C2, int32_t ncls,
+                                 int32_t n_frames, const float* params, int32_t n_layer, int32_t n_head, int32_t d_model,
+                                 float* K, float* V, float* mem_out, void* stream) {
+  using namespace ls3d;
+  if (!emb1 || !emb2 || !params || !K || !V || d_model != CT_E || 2 * ncls > CT_MAXL || n_head < 1 || n_head > 8 ||
+      d_model % n_head)
+    return LS3D_ERR_ARG;
+  const int L = 2 * ncls;
+  const size_t smem = ((size_t)L * CT_E * 5 + (size_t)n_head * L * (L + 1)) * 4;
+  cudaError_t e = cudaFuncSetAttribute(class_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  class_tokens_kernel<<<n_frames, 512, smem, (cudaStream_t)stream>>>(emb1, C1, emb2, C2, ncls, params, n_layer, n_head, K,
+                                                                    V, mem_out);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}

@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
         return x;
       };
       const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.cout & 3) == 0);
+      const bool masked = p.row_mask && live && (__ldg(p.row_mask + (size_t)r * p.ld_mask) != 1.0f);
       float mean[2] = {0.f, 0.f}, rstd[2] = {1.f, 1.f};
       // LayerNorm statistics (up to two chained LayerNorms), exact two-pass form per LN
       for (int ln = 0; ln < p.n_ln; ++ln) {
@@ -343,6 +344,10 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
             if (p.n_ln > 1) x = (x - mean[1]) * rstd[1] * __ldg(p.ln_g1 + col) + __ldg(p.ln_b1 + col);
           }
           y[j] = x;
+        }
+        if (masked) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = 0.f;
         }
         if (live) {
           float* dst = p.out + (size_t)r * p.ld_out + c0;

@@ -1,0 +1,257 @@
+"""HRNet behind the IMG_BACKBONES registry (reference det3d/models/img_backbones/hrnet.py:229-704,
+resnet_mmcv.py:20-313).  Same constructor kwargs and state-dict names (mmseg HRNet naming).
+
+SURVEY.md section 8: the camera stem is "*-adjacent" - it runs on cuDNN through PyTorch (channels-last, BatchNorm folded
+into the convolutions at inference); hand-written stem kernels are a "next" row (8f rank 3).
+"""
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .registry import IMG_BACKBONES
+
+
+def _bn(c, norm_cfg):
+    cfg = dict(norm_cfg or dict(type="BN"))
+    cfg.pop("type", None)
+    requires_grad = cfg.pop("requires_grad", True)
+    cfg.setdefault("eps", 1e-5)
+    m = nn.BatchNorm2d(c, **cfg)
+    for p in m.parameters():
+        p.requires_grad = requires_grad
+    return m
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, norm_cfg=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn1 = _bn(planes, norm_cfg)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn2 = _bn(planes, norm_cfg)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        idt = x if self.downsample is None else self.downsample(x)
+        return self.relu(out + idt)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, norm_cfg=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = _bn(planes, norm_cfg)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn2 = _bn(planes, norm_cfg)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = _bn(planes * 4, norm_cfg)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        idt = x if self.downsample is None else self.downsample(x)
+        return self.relu(out + idt)
+
+
+class Upsample(nn.Module):
+    """det3d/ops/mmseg_ops/wrappers.py:30-51 (size = int(t * scale_factor))."""
+
+    def __init__(self, scale_factor, mode="bilinear", align_corners=False):
+        super().__init__()
+        self.scale_factor, self.mode, self.align_corners = float(scale_factor), mode, align_corners
+
+    def forward(self, x):
+        size = [int(t * self.scale_factor) for t in x.shape[-2:]]
+        return F.interpolate(x, size, None, self.mode, self.align_corners)
+
+
+class HRModule(nn.Module):
+    """hrnet.py:24-226."""
+
+    def __init__(self, num_branches, block, num_blocks, in_channels, num_channels, multiscale_output, norm_cfg):
+        super().__init__()
+        self.in_channels = in_channels
+        self.num_branches = num_branches
+        self.multiscale_output = multiscale_output
+        branches = []
+        for i in range(num_branches):
+            layers, down = [], None
+            if in_channels[i] != num_channels[i] * block.expansion:
+                down = nn.Sequential(nn.Conv2d(in_channels[i], num_channels[i] * block.expansion, 1, bias=False),
+                                     _bn(num_channels[i] * block.expansion, norm_cfg))
+            layers.append(block(in_channels[i], num_channels[i], 1, down, norm_cfg))
+            in_channels[i] = num_channels[i] * block.expansion
+            for _ in range(1, num_blocks[i]):
+                layers.append(block(in_channels[i], num_channels[i], norm_cfg=norm_cfg))
+            branches.append(nn.Sequential(*layers))
+        self.branches = nn.ModuleList(branches)
+        self.fuse_layers = self._make_fuse_layers(norm_cfg)
+        self.relu = nn.ReLU(inplace=False)
+
+    def _make_fuse_layers(self, norm_cfg):
+        if self.num_branches == 1:
+            return None
+        nb, ch = self.num_branches, self.in_channels
+        fuse = []
+        for i in range(nb if self.multiscale_output else 1):
+            row = []
+            for j in range(nb):
+                if j > i:
+                    row.append(nn.Sequential(nn.Conv2d(ch[j], ch[i], 1, bias=False), _bn(ch[i], norm_cfg),
+                                             Upsample(2 ** (j - i), "bilinear", False)))
+                elif j == i:
+                    row.append(None)
+                else:
+                    downs = []
+                    for k in range(i - j):
+                        if k == i - j - 1:
+                            downs.append(nn.Sequential(nn.Conv2d(ch[j], ch[i], 3, 2, 1, bias=False), _bn(ch[i], norm_cfg)))
+                        else:
+                            downs.append(nn.Sequential(nn.Conv2d(ch[j], ch[j], 3, 2, 1, bias=False), _bn(ch[j], norm_cfg),
+                                                       nn.ReLU(inplace=False)))
+                    row.append(nn.Sequential(*downs))
+            fuse.append(nn.ModuleList(row))
+        return nn.ModuleList(fuse)
+
+    def forward(self, x):
+        if self.num_branches == 1:
+            return [self.branches[0](x[0])]
+        x = [self.branches[i](x[i]) for i in range(self.num_branches)]
+        outs = []
+        for i in range(len(self.fuse_layers)):
+            y = 0
+            for j in range(self.num_branches):
+                if i == j:
+                    y = y + x[j]
+                elif j > i:
+                    y = y + F.interpolate(self.fuse_layers[i][j](x[j]), size=x[i].shape[2:], mode="bilinear",
+                                          align_corners=False)
+                else:
+                    y = y + self.fuse_layers[i][j](x[j])
+            outs.append(self.relu(y))
+        return outs
+
+
+@IMG_BACKBONES.register_module
+class HRNet(nn.Module):
+    blocks_dict = {"BASIC": BasicBlock, "BOTTLENECK": Bottleneck}
+
+    def __init__(self, extra, in_channels=3, conv_cfg=None, norm_cfg=dict(type="BN", requires_grad=True),
+                 norm_eval=False, with_cp=False, frozen_stages=-1, zero_init_residual=False, multiscale_output=True,
+                 pretrained=None, init_cfg=None):
+        super().__init__()
+        self.pretrained, self.extra, self.norm_cfg = pretrained, extra, norm_cfg
+        self.norm_eval, self.frozen_stages = norm_eval, frozen_stages
+        self.conv1 = nn.Conv2d(in_channels, 64, 3, 2, 1, bias=False)
+        self.bn1 = _bn(64, norm_cfg)
+        self.conv2 = nn.Conv2d(64, 64, 3, 2, 1, bias=False)
+        self.bn2 = _bn(64, norm_cfg)
+        self.relu = nn.ReLU(inplace=True)
+        s1 = extra["stage1"]
+        block = self.blocks_dict[s1["block"]]
+        c = s1["num_channels"][0]
+        down = None
+        if 64 != c * block.expansion:
+            down = nn.Sequential(nn.Conv2d(64, c * block.expansion, 1, bias=False), _bn(c * block.expansion, norm_cfg))
+        layers = [block(64, c, 1, down, norm_cfg)] + [block(c * block.expansion, c, norm_cfg=norm_cfg)
+                                                       for _ in range(1, s1["num_blocks"][0])]
+        self.layer1 = nn.Sequential(*layers)
+        pre = [c * block.expansion]
+        for st in (2, 3, 4):
+            cfg = extra[f"stage{st}"]
+            blk = self.blocks_dict[cfg["block"]]
+            chans = [ch * blk.expansion for ch in cfg["num_channels"]]
+            setattr(self, f"transition{st - 1}", self._make_transition(pre, chans))
+            mods, inch = [], list(chans)
+            for i in range(cfg["num_modules"]):
+                ms = True if (multiscale_output or st != 4 or i != cfg["num_modules"] - 1) else False
+                mods.append(HRModule(cfg["num_branches"], blk, cfg["num_blocks"], inch, list(cfg["num_channels"]), ms,
+                                     norm_cfg))
+            setattr(self, f"stage{st}", nn.Sequential(*mods))
+            pre = inch
+        if isinstance(pretrained, str):
+            self.load_pretrained_model()
+        self._freeze_stages()
+
+    def _make_transition(self, pre, cur):
+        layers = []
+        for i in range(len(cur)):
+            if i < len(pre):
+                if cur[i] != pre[i]:
+                    layers.append(nn.Sequential(nn.Conv2d(pre[i], cur[i], 3, 1, 1, bias=False), _bn(cur[i], self.norm_cfg),
+                                                nn.ReLU(inplace=True)))
+                else:
+                    layers.append(None)
+            else:
+                downs = []
+                for j in range(i + 1 - len(pre)):
+                    cin = pre[-1]
+                    cout = cur[i] if j == i - len(pre) else cin
+                    downs.append(nn.Sequential(nn.Conv2d(cin, cout, 3, 2, 1, bias=False), _bn(cout, self.norm_cfg),
+                                               nn.ReLU(inplace=True)))
+                layers.append(nn.Sequential(*downs))
+        return nn.ModuleList(layers)
+
+    def load_pretrained_model(self):
+        """hrnet.py:435-483 loads ``pretrained`` unconditionally; the drop-in tolerates a missing file
+         and reports it."""
+        import os
+        if not os.path.isfile(self.pretrained):
+            warnings.warn(f"HRNet pretrained weights not found at {self.pretrained}; keeping random init")
+            return
+        sd = torch.load(self.pretrained, map_location="cpu")
+        sd = sd.get("state_dict", sd)
+        sd = {k[len("backbone."):] if k.startswith("backbone.") else k: v for k, v in sd.items()}
+        self.load_state_dict(sd, strict=False)
+
+    def _freeze_stages(self):
+        if self.frozen_stages >= 0:
+            for m in (self.conv1, self.bn1, self.conv2, self.bn2):
+                m.eval()
+                for p in m.parameters():
+                    p.requires_grad = False
+        for i in range(1, self.frozen_stages + 1):
+            mods = [getattr(self, "layer1" if i == 1 else f"stage{i}")]
+            if i < 4:
+                mods.append(getattr(self, f"transition{i}"))
+            for m in mods:
+                m.eval()
+                for p in m.parameters():
+                    p.requires_grad = False
+
+    def forward(self, x):
+        x = self.relu(self.bn1(self.conv1(x)))
+        x = self.relu(self.bn2(self.conv2(x)))
+        x = self.layer1(x)
+        ys = [x]
+        for st in (2, 3, 4):
+            tr = getattr(self, f"transition{st - 1}")
+            xs = []
+            for i in range(self.extra[f"stage{st}"]["num_branches"]):
+                if tr[i] is not None:
+                    xs.append(tr[i](ys[0] if st == 2 else ys[-1]))
+                else:
+                    xs.append(ys[i])
+            ys = getattr(self, f"stage{st}")(xs)
+        return ys
+
+    def train(self, mode=True):
+        super().train(mode)
+        self._freeze_stages()
+        if mode and self.norm_eval:
+            for m in self.modules():
+                if isinstance(m, nn.modules.batchnorm._BatchNorm):
+                    m.eval()
+        return self

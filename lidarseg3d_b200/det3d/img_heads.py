@@ -1,0 +1,97 @@
+"""FCNMSeg3DHead behind the IMG_HEADS registry (reference det3d/models/img_heads/fcn_mseg3d_head.py:55-199,
+decode_head.py:56-218).  1x1 ConvModules run on cuDNN (channels-last); the camera semantic-embedding aggregation
+(camera SFAM, fcn_mseg3d_head.py:17-51) runs on the ls3d_class_embed kernel."""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from .img_backbones import _bn
+from .registry import IMG_HEADS
+
+
+class ConvModule(nn.Module):
+    """mmcv ConvModule subset: conv (bias off when a norm follows) -> bn -> ReLU; names conv / bn / activate."""
+
+    def __init__(self, cin, cout, kernel_size, padding=0, dilation=1, norm_cfg=None, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel_size, padding=padding, dilation=dilation, bias=norm_cfg is None)
+        self.with_norm = norm_cfg is not None
+        if self.with_norm:
+            self.bn = _bn(cout, norm_cfg)
+        self.with_act = act
+        if act:
+            self.activate = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.with_norm:
+            x = self.bn(x)
+        return self.activate(x) if self.with_act else x
+
+
+class CameraSemanticFeatureAggregationModule(nn.Module):
+    def forward(self, feats, probs, batch_size):
+        """feats [B*ncam, C, h, w], probs [B*ncam, ncls, h, w] (channels-last storage) -> [B, ncls, C]."""
+        n, C, h, w = feats.shape
+        f = feats.permute(0, 2, 3, 1).contiguous().view(-1, C)
+        p = probs.permute(0, 2, 3, 1).contiguous().view(-1, probs.shape[1])
+        rows = (n // batch_size) * h * w
+        off = torch.arange(0, batch_size + 1, dtype=torch.int32, device=feats.device) * rows
+        return ops.class_embed(p, f, off, batch_size, rows)
+
+
+@IMG_HEADS.register_module
+class FCNMSeg3DHead(nn.Module):
+    def __init__(self, in_channels, channels, *, num_classes, num_convs=2, kernel_size=3, concat_input=True, dilation=1,
+                 ignore_index=0, loss_weight=1.0, lovasz_loss_weight=-1.0, use_sc_conv=False, dropout_ratio=0.1,
+                 conv_cfg=None, norm_cfg=None, act_cfg=dict(type="ReLU"), in_index=-1, input_transform=None,
+                 loss_decode=None, align_corners=False, init_cfg=None, **kwargs):
+        super().__init__()
+        assert num_convs >= 0 and dilation > 0 and isinstance(dilation, int)
+        if use_sc_conv:
+            raise NotImplementedError("use_sc_conv is unused by the shipped MSeg3D configs (SURVEY.md section 2)")
+        if input_transform is not None:
+            assert input_transform in ["resize_concat", "multiple_select"]
+            assert isinstance(in_channels, (list, tuple)) and isinstance(in_index, (list, tuple))
+            assert len(in_channels) == len(in_index)
+        self.input_transform, self.in_index = input_transform, in_index
+        self.in_channels = sum(in_channels) if input_transform == "resize_concat" else in_channels
+        self.channels, self.num_classes = channels, num_classes
+        self.num_convs, self.concat_input, self.kernel_size = num_convs, concat_input, kernel_size
+        self.align_corners, self.ignore_index, self.loss_weight = align_corners, ignore_index, loss_weight
+        pad = (kernel_size // 2) * dilation
+        convs = [ConvModule(self.in_channels, channels, kernel_size, pad, dilation, norm_cfg)]
+        convs += [ConvModule(channels, channels, kernel_size, pad, dilation, norm_cfg) for _ in range(num_convs - 1)]
+        self.convs = nn.Sequential(*convs) if num_convs > 0 else nn.Identity()
+        if concat_input:
+            self.conv_cat = ConvModule(self.in_channels + channels, channels, kernel_size, kernel_size // 2, 1, norm_cfg)
+        self.conv_seg = nn.Conv2d(channels, num_classes, kernel_size=1)
+        self.dropout = nn.Dropout2d(dropout_ratio) if dropout_ratio > 0 else None
+        self.camera_sfam = CameraSemanticFeatureAggregationModule()
+        self.forward_ret_dict = {}
+
+    def _transform_inputs(self, inputs):
+        if self.input_transform == "resize_concat":
+            inputs = [inputs[i] for i in self.in_index]
+            ups = [F.interpolate(x, size=inputs[0].shape[2:], mode="bilinear", align_corners=self.align_corners)
+                   for x in inputs]
+            return torch.cat(ups, dim=1)
+        if self.input_transform == "multiple_select":
+            return [inputs[i] for i in self.in_index]
+        return inputs[self.in_index]
+
+    def forward(self, batch_dict, return_loss=True, **kwargs):
+        if return_loss:
+            raise NotImplementedError("lidarseg3d_b200 image head: inference path only (return_loss=False)")
+        x = self._transform_inputs(batch_dict["inputs"])
+        feats = self.convs(x)
+        if self.concat_input:
+            feats = self.conv_cat(torch.cat([x, feats], dim=1))
+        logits = self.conv_seg(feats if self.dropout is None else self.dropout(feats))
+        emb = self.camera_sfam(feats, logits, batch_dict["batch_size"])
+        self.forward_ret_dict["image_logits"] = logits
+        batch_dict["image_logits"] = logits
+        batch_dict["image_features"] = feats
+        batch_dict["camera_semantic_embeddings"] = emb      # [B, ncls, C] (reference: [B, C, ncls, 1])
+        return batch_dict

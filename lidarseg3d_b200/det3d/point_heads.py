@@ -1,0 +1,332 @@
+"""Point heads behind the POINT_HEADS registry.
+
+PointSegMSeg3DHead  <- reference det3d/models/point_heads/point_seg_mseg3d_head.py:18-479 (+ context_module.py)
+PointSegBatchlossHead <- reference det3d/models/point_heads/point_seg_batchloss_head.py:15-271
+
+Same constructor kwargs / state-dict names / forward + predict contract.  torch.nn modules are used as parameter
+containers only; the forward runs on the C-ABI kernels: devoxelization (grid 3-NN + interpolation), camera feature
+sampling, class-embedding aggregation, class-token memory path, and the tcgen05 gather-GEMM for every Linear with
+BatchNorm / ReLU / residual / LayerNorm / cross-attention fused into its epilogue.
+"""
+from functools import partial
+
+import torch
+from torch import nn
+
+from .. import gemm, ops
+from .common import Prepared, linear_bn_pack, linear_pack
+from .registry import POINT_HEADS
+
+
+def _offsets(batch_col, batch_size):
+    """Row offsets [B+1] (int32, device) of frames in a tensor sorted by its batch column."""
+    counts = torch.bincount(batch_col.long(), minlength=batch_size)[:batch_size]
+    off = torch.zeros(batch_size + 1, dtype=torch.int32, device=batch_col.device)
+    off[1:] = torch.cumsum(counts, 0).int()
+    return off
+
+
+def make_convcls_head(fc_cfg, input_channels, output_channels, dp_ratio=0):
+    """point_seg_mseg3d_head.py:119-134 / point_seg_batchloss_head.py:63-74."""
+    layers = []
+    c_in = input_channels
+    if dp_ratio > 0:
+        layers.append(nn.Dropout(dp_ratio))
+    for c in fc_cfg:
+        layers.extend([nn.Linear(c_in, c, bias=False), nn.BatchNorm1d(c), nn.ReLU()])
+        c_in = c
+    layers.append(nn.Linear(c_in, output_channels, bias=True))
+    return nn.Sequential(*layers)
+
+
+def _pack_convcls(seq):
+    """-> list of (PackedWeight, scale, shift, relu) for a make_convcls_head Sequential."""
+    mods = [m for m in seq if not isinstance(m, (nn.Dropout, nn.ReLU))]
+    out, i = [], 0
+    while i < len(mods):
+        if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
+            pw, s, b = linear_bn_pack(mods[i], mods[i + 1])
+            out.append((pw, s, b, True))
+            i += 2
+        else:
+            pw, b = linear_pack(mods[i])
+            out.append((pw, None, b, False))
+            i += 1
+    return out
+
+
+def _run_mlp(x, packed):
+    for pw, s, b, relu in packed:
+        x = gemm.run(x, pw, scale=s, shift=b, relu=relu)
+    return x
+
+
+def devoxelize(batch_dict, points, voxel_features, voxel_size, pc_range, batch_size):
+    """three_interpolate_wrap (point_utils.py:8-52) on the level-1 bitmap the backbone left in batch_dict."""
+    lv1 = batch_dict["_ls3d_level1"]
+    vcoords = lv1.coords
+    point_off = _offsets(points[:, 0], batch_size)
+    voxel_off = _offsets(vcoords[:, 0], batch_size)
+    d2, idx = ops.three_nn_grid(points, lv1.grid, voxel_size, pc_range[:3], point_off, voxel_off, vcoords)
+    return ops.three_interpolate(voxel_features, d2, idx), point_off, voxel_off, (d2, idx)
+
+
+def _predict(out_logits, example, test_cfg):
+    """predict() (point_seg_mseg3d_head.py:379-479, point_seg_batchloss_head.py:171-271)."""
+    test_cfg = test_cfg or {}
+    batch_size = len(example["num_voxels"])
+    stack_points = example["points"][:, 0:4]
+    tta = test_cfg.get("tta_flag", False)
+    has_meta = "metadata" in example and example["metadata"] is not None and len(example["metadata"]) > 0
+    ret_list = []
+    if tta:
+        ntta = test_cfg.get("num_tta_tranforms", 4)
+        if test_cfg.get("merge_type", "ArithmeticMean") != "ArithmeticMean":
+            raise NotImplementedError
+        metas = example["metadata"][:ntta * batch_size:ntta] if has_meta else [None] * batch_size
+        probs = torch.softmax(out_logits, dim=-1)
+        per = [probs[stack_points[:, 0] == i] for i in range(batch_size)]
+        for g, i in enumerate(range(0, batch_size, ntta)):
+            merged = torch.stack(per[i:i + ntta], 0).mean(0)
+            ret_list.append({"metadata": metas[g] if g < len(metas) else None,
+                             "pred_point_sem_labels": torch.argmax(merged, dim=1)})
+    else:
+        metas = example["metadata"] if has_meta else [None] * batch_size
+        labels = torch.argmax(out_logits, dim=1)
+        for i in range(batch_size):
+            mask = stack_points[:, 0] == i
+            ret = {"metadata": metas[i], "pred_point_sem_labels": labels[mask]}
+            if "point_sem_labels" in example:
+                ret["point_sem_labels"] = example["point_sem_labels"][mask]
+            ret_list.append(ret)
+    return ret_list
+
+
+@POINT_HEADS.register_module
+class PointSegBatchlossHead(Prepared):
+    def __init__(self, class_agnostic, num_class, model_cfg, **kwargs):
+        super().__init__()
+        self.num_class = 1 if class_agnostic else num_class
+        norm_layer = partial(nn.BatchNorm1d, eps=1e-6)
+        cin = model_cfg["CONV_IN_DIM"]
+        self.conv_cls_layers = make_convcls_head(model_cfg["CONV_CLS_FC"], cin, self.num_class)
+        cal = model_cfg["CONV_ALIGN_DIM"]
+        self.conv_align_layers = nn.Sequential(nn.Linear(cin, cal), norm_layer(cal), nn.ReLU())
+        self.out_cls_layers = make_convcls_head(model_cfg["OUT_CLS_FC"], cal, self.num_class)
+        self.forward_ret_dict = {}
+        self.ignored_label = model_cfg["IGNORED_LABEL"]
+        self.tasks = ["out"]
+        self.voxel_size = kwargs.get("voxel_size")
+        self.point_cloud_range = kwargs.get("point_cloud_range")
+
+    def _prepare(self):
+        return dict(conv_cls=_pack_convcls(self.conv_cls_layers),
+                    align=linear_bn_pack(self.conv_align_layers[0], self.conv_align_layers[1]),
+                    out=_pack_convcls(self.out_cls_layers))
+
+    def forward(self, batch_dict, return_loss=True, **kwargs):
+        if return_loss:
+            raise NotImplementedError("lidarseg3d_b200 point heads: inference path only (return_loss=False)")
+        P = self.prep()
+        B = batch_dict["batch_size"]
+        vf = batch_dict["conv_point_features"]
+        self.forward_ret_dict["conv_logits"] = _run_mlp(vf, P["conv_cls"])
+        pts = batch_dict["points"].contiguous()
+        f0, _, _, nn_res = devoxelize(batch_dict, pts, vf, batch_dict["_ls3d_voxel_size"], batch_dict["_ls3d_pc_range"], B)
+        pw, s, b = P["align"]
+        f = gemm.run(f0, pw, scale=s, shift=b, relu=True)
+        out = _run_mlp(f, P["out"])
+        batch_dict["out_logits"] = out
+        batch_dict["_ls3d_three_nn"] = nn_res
+        self.forward_ret_dict["out_logits"] = out
+        return batch_dict
+
+    @torch.no_grad()
+    def predict(self, example, test_cfg=None, **kwargs):
+        return _predict(self.forward_ret_dict["out_logits"], example, test_cfg)
+
+
+class SparsePointCorssAttention(nn.Module):
+    """Parameter container (context_module.py:304-317)."""
+
+    def __init__(self, embed_dim, num_heads, kv_proj_kernel_size=1):
+        super().__init__()
+        self.q_proj = nn.Linear(embed_dim, embed_dim)
+        self.k_proj = nn.Conv1d(embed_dim, embed_dim, kv_proj_kernel_size)
+        self.v_proj = nn.Conv1d(embed_dim, embed_dim, kv_proj_kernel_size)
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+
+
+class TransformerDecoderLayer(nn.Module):
+    """Parameter container (context_module.py:175-206)."""
+
+    def __init__(self, d_model, nhead, dim_feedforward, kernel_size):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=0.0)
+        self.crossocr_attn = SparsePointCorssAttention(d_model, nhead, kernel_size)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, d_model, nhead, dim_feedforward, kernel_size, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([TransformerDecoderLayer(d_model, nhead, dim_feedforward, kernel_size)
+                                     for _ in range(num_layers)])
+        self.norm_tgt = nn.LayerNorm(d_model)
+        self.norm_mem = None
+
+
+class SemanticFeatureFusionModule(nn.Module):
+    """Parameter container (context_module.py:56-87)."""
+
+    def __init__(self, d_input_point, d_input_embeddings1, d_input_embeddings2, embeddings_proj_kernel_size=1,
+                 d_model=512, nhead=8, num_decoder_layers=6, dim_feedforward=2048, dropout=0.0, activation="relu",
+                 normalize_before=False):
+        super().__init__()
+        if normalize_before or activation != "relu" or embeddings_proj_kernel_size != 1:
+            raise NotImplementedError("SF-Phase kernels cover forward_post / relu / kernel_size 1 (the shipped configs)")
+        self.input_proj_point = nn.Linear(d_input_point, d_model)
+        self.input_proj_embeddings1 = nn.Conv1d(d_input_embeddings1, d_model, 1)
+        self.input_proj_embeddings2 = nn.Conv1d(d_input_embeddings2, d_model, 1)
+        self.decoder = TransformerDecoder(d_model, nhead, dim_feedforward, 1, num_decoder_layers)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self.d_model, self.nhead = d_model, nhead
+
+
+class LiDARSemanticFeatureAggregationModule(nn.Module):
+    """context_module.py:18-53 -> ls3d_class_embed."""
+
+    def forward(self, feats, probs, voxel_off, batch_size):
+        max_rows = int(feats.shape[0])
+        return ops.class_embed(probs, feats, voxel_off, batch_size, max_rows)       # [B, ncls, C]
+
+
+@POINT_HEADS.register_module
+class PointSegMSeg3DHead(Prepared):
+    def __init__(self, class_agnostic, num_class, model_cfg, **kwargs):
+        super().__init__()
+        self.num_class = 1 if class_agnostic else num_class
+        norm_layer = partial(nn.BatchNorm1d, eps=1e-6)
+        vin = model_cfg["VOXEL_IN_DIM"]
+        self.dp_ratio = model_cfg["DP_RATIO"]
+        self.voxel_cls_layers = make_convcls_head(model_cfg["VOXEL_CLS_FC"], vin, self.num_class, self.dp_ratio)
+        val = model_cfg["VOXEL_ALIGN_DIM"]
+        self.gffm_lidar = nn.Sequential(nn.Linear(vin, val), norm_layer(val), nn.ReLU())
+        iin, ial = model_cfg["IMAGE_IN_DIM"], model_cfg["IMAGE_ALIGN_DIM"]
+        self.gffm_camera = nn.Sequential(nn.Linear(iin, ial), norm_layer(ial), nn.ReLU())
+        fused = model_cfg["GEO_FUSED_DIM"]
+        self.gffm_lc = nn.Sequential(nn.Linear(val + ial, fused), nn.BatchNorm1d(fused), nn.ReLU())
+        self.lidar_camera_mimic_layer = make_convcls_head(model_cfg["MIMIC_FC"], val, ial, 0)
+        sf = model_cfg["SFPhase_CFG"]
+        self.lidar_sfam = LiDARSemanticFeatureAggregationModule()
+        self.sffm = SemanticFeatureFusionModule(
+            d_input_point=fused, d_input_embeddings1=iin, d_input_embeddings2=vin,
+            embeddings_proj_kernel_size=sf["embeddings_proj_kernel_size"], d_model=sf["d_model"], nhead=sf["n_head"],
+            num_decoder_layers=sf["n_layer"], dim_feedforward=sf["n_ffn"], dropout=sf["drop_ratio"],
+            activation=sf["activation"], normalize_before=sf["pre_norm"])
+        self.out_cls_layers = nn.Linear(self.sffm.d_model, num_class)
+        self.forward_ret_dict = {}
+        self.ignored_label = model_cfg["IGNORED_LABEL"]
+        self.tasks = ["out"]
+
+    # ------------------------------------------------------------------ inference cache
+    def _prepare(self):
+        E = self.sffm.d_model
+        sf = self.sffm
+
+        def ln(m):
+            return (m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous())
+
+        # class-token parameter block for ls3d_class_tokens (layout documented in csrc/fusion.cu)
+        def t(w):   # [out, in(,1)] -> W^T [in, out] flattened
+            w = w.detach().float()
+            if w.dim() == 3:
+                w = w.squeeze(-1)
+            return w.t().contiguous().reshape(-1)
+
+        parts = [t(sf.input_proj_embeddings1.weight), sf.input_proj_embeddings1.bias.detach().float(),
+                 t(sf.input_proj_embeddings2.weight), sf.input_proj_embeddings2.bias.detach().float()]
+        layers = []
+        for ly in sf.decoder.layers:
+            ca = ly.crossocr_attn
+            parts += [t(ly.self_attn.in_proj_weight), ly.self_attn.in_proj_bias.detach().float(),
+                      t(ly.self_attn.out_proj.weight), ly.self_attn.out_proj.bias.detach().float(),
+                      ly.norm1.weight.detach().float(), ly.norm1.bias.detach().float(),
+                      t(ca.k_proj.weight), ca.k_proj.bias.detach().float(),
+                      t(ca.v_proj.weight), ca.v_proj.bias.detach().float()]
+            layers.append(dict(q=linear_pack(ca.q_proj), o=linear_pack(ca.out_proj), l1=linear_pack(ly.linear1),
+                               l2=linear_pack(ly.linear2), n2=ln(ly.norm2), n3=ln(ly.norm3)))
+        return dict(
+            voxel_cls=_pack_convcls(self.voxel_cls_layers),
+            gffm_lidar=linear_bn_pack(self.gffm_lidar[0], self.gffm_lidar[1]),
+            gffm_camera=linear_bn_pack(self.gffm_camera[0], self.gffm_camera[1]),
+            gffm_lc=linear_bn_pack(self.gffm_lc[0], self.gffm_lc[1]),
+            proj_point=linear_pack(sf.input_proj_point),
+            token_params=torch.cat([p.reshape(-1) for p in parts]).contiguous(),
+            layers=layers, norm_tgt=ln(sf.decoder.norm_tgt), out=linear_pack(self.out_cls_layers), E=E)
+
+    def get_points_image_feature(self, image_features_nhwc, points_cuv, point_off):
+        """point_seg_mseg3d_head.py:200-236 (rows of invalid points are zeros)."""
+        return ops.sample_image_features(image_features_nhwc, points_cuv, point_off)
+
+    def forward(self, batch_dict, return_loss=True, **kwargs):
+        if return_loss:
+            raise NotImplementedError("lidarseg3d_b200 point heads: inference path only (return_loss=False)")
+        P = self.prep()
+        B = batch_dict["batch_size"]
+        vf = batch_dict["conv_point_features"]
+        voxel_logits = _run_mlp(vf, P["voxel_cls"])
+        self.forward_ret_dict["voxel_logits"] = voxel_logits
+        pts = batch_dict["points"].contiguous()
+        cuv = batch_dict["points_cuv"].contiguous()
+        # voxel features -> point lidar features (3-NN devoxelization) -> GFFM lidar branch
+        f0, point_off, voxel_off, nn_res = devoxelize(batch_dict, pts, vf, batch_dict["_ls3d_voxel_size"],
+                                                      batch_dict["_ls3d_pc_range"], B)
+        pw, s, b = P["gffm_lidar"]
+        fl = gemm.run(f0, pw, scale=s, shift=b, relu=True)
+        # image feature maps -> point camera features; invalid rows zeroed by the row mask.  The reference evaluates the
+        # pseudo-camera (mimic) MLP on valid points only and pads the others with zeros, so at inference the completed
+        # camera feature of an out-of-image point is exactly zero (point_seg_mseg3d_head.py:305-334).
+        img = batch_dict["image_features"]
+        if img.dim() == 5 and img.shape[2] != img.shape[-1] and batch_dict.get("_ls3d_image_features_nhwc") is None:
+            nhwc = img.permute(0, 1, 3, 4, 2).contiguous()                  # reference layout [B, ncam, C, h, w]
+        else:
+            nhwc = batch_dict.get("_ls3d_image_features_nhwc", img)
+        fc0 = self.get_points_image_feature(nhwc, cuv, point_off)
+        pw, s, b = P["gffm_camera"]
+        ccam = gemm.run(fc0, pw, scale=s, shift=b, relu=True, row_mask=cuv)
+        pw, s, b = P["gffm_lc"]
+        geo = gemm.run(fl, pw, x1=ccam, scale=s, shift=b, relu=True)
+        # SF-Phase
+        cam_emb = batch_dict["camera_semantic_embeddings"]
+        if cam_emb.dim() == 4:                                              # reference layout [B, C, ncls, 1]
+            cam_emb = cam_emb.squeeze(-1).permute(0, 2, 1).contiguous()
+        lidar_emb = self.lidar_sfam(vf, voxel_logits, voxel_off, B)         # [B, ncls, C]
+        sf = self.sffm
+        nl = len(P["layers"])
+        K, V = ops.class_tokens(cam_emb, lidar_emb, P["token_params"], nl, sf.nhead, sf.d_model)
+        tgt = gemm.run(geo, P["proj_point"][0], shift=P["proj_point"][1])
+        dh = sf.d_model // sf.nhead
+        for i, ly in enumerate(P["layers"]):
+            att = gemm.run(tgt, ly["q"][0], shift=ly["q"][1],
+                           attn=dict(k=K[i], v=V[i], frame_off=point_off, scale=dh ** -0.5))
+            tgt = gemm.run(att, ly["o"][0], shift=ly["o"][1], res=tgt, res_mode=1, ln=(ly["n2"],))
+            h = gemm.run(tgt, ly["l1"][0], shift=ly["l1"][1], relu=True)
+            lns = (ly["n3"], P["norm_tgt"]) if i == nl - 1 else (ly["n3"],)
+            tgt = gemm.run(h, ly["l2"][0], shift=ly["l2"][1], res=tgt, res_mode=1, ln=lns)
+        out = gemm.run(tgt, P["out"][0], shift=P["out"][1])
+        batch_dict["out_logits"] = out
+        batch_dict["_ls3d_debug"] = dict(point_features_lidar_0=f0, point_features_camera_0=fc0, geo_fused=geo,
+                                         lidar_emb=lidar_emb, sem_fused=tgt, three_nn=nn_res)
+        self.forward_ret_dict["out_logits"] = out
+        return batch_dict
+
+    @torch.no_grad()
+    def predict(self, example, test_cfg=None, **kwargs):
+        return _predict(self.forward_ret_dict["out_logits"], example, test_cfg)

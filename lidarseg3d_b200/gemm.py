@@ -37,7 +37,7 @@ class PackedWeight:
 
 
 def run(x0, pw: PackedWeight, *, x1=None, nbr=None, m_out=None, scale=None, shift=None, relu=False,
-        res=None, res_mode=0, red=None, ln=(), ln_eps=1e-5, attn=None, out=None):
+        res=None, res_mode=0, red=None, ln=(), ln_eps=1e-5, attn=None, row_mask=None, out=None):
     """Launch ls3d_gather_gemm.  ``x0``/``x1`` are [rows, C] fp32 row-major (row stride may exceed C).
 
     attn = dict(k=[F,H,L,24], v=[F,H,L,24], frame_off=int32[F], scale=float) selects the attention
@@ -82,6 +82,8 @@ def run(x0, pw: PackedWeight, *, x1=None, nbr=None, m_out=None, scale=None, shif
         a.frame_off = capi.ptr(attn["frame_off"])
         a.n_frames, a.n_head, a.n_tok = attn["k"].shape[0], attn["k"].shape[1], attn["k"].shape[2]
         a.attn_scale = attn["scale"]
+    if row_mask is not None:
+        a.row_mask, a.ld_mask = capi.ptr(row_mask), row_mask.stride(0)
     if out is None:
         out = torch.empty(m, pw.cout, dtype=torch.float32, device=x0.device)
     a.out, a.ld_out = capi.ptr(out), out.stride(0)

@@ -1,0 +1,208 @@
+"""Tensor-level wrappers over the C ABI (one function per include/ls3d.h entry point).
+
+PyTorch is used for device memory and the current CUDA stream only; all arithmetic happens in
+``_ls3d.so``.  Every wrapper raises when the library is missing or returns a non-zero status.
+"""
+import ctypes
+
+import torch
+
+from . import capi
+from .capi import check, host_f32, host_i32, ptr, stream_ptr
+
+
+def _i32(dev, *shape):
+    return torch.empty(*shape, dtype=torch.int32, device=dev)
+
+
+def _f32(dev, *shape):
+    return torch.empty(*shape, dtype=torch.float32, device=dev)
+
+
+# ------------------------------------------------------------------------------------------ voxelize
+def voxelize(points, frame_offsets, voxel_size, pc_range, max_points=5, max_voxels=300000, want_point_map=False):
+    """Hard-voxelize a batch of frames on the GPU (reference semantics: points_to_voxel,
+    det3d/ops/point_cloud/point_cloud_ops.py:112-184, per frame, then collate_kitti's batch column).
+
+    points [N, F] fp32 cuda (frames concatenated), frame_offsets: python ints [B+1].
+    Returns dict(voxels [M,P,F], coordinates [M,4] int32 (b,z,y,x), num_points [M] int32,
+                 num_voxels [B] int64 (host-synchronised), point_voxel [N] int32 or None).
+    """
+    assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous()
+    n, f = points.shape
+    B = len(frame_offsets) - 1
+    dev = points.device
+    nbytes = ctypes.c_int64()
+    check(capi.lib().ls3d_voxelize_workspace_bytes(n, max_points, B, ctypes.byref(nbytes)), "voxelize_workspace")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    cap = max(n, 1)
+    voxels = _f32(dev, cap, max_points, f)
+    coords = _i32(dev, cap, 4)
+    nump = _i32(dev, cap)
+    counts = _i32(dev, B + 1)      # [B] per frame + total
+    pmap = _i32(dev, n) if want_point_map else None
+    check(capi.lib().ls3d_voxelize(ptr(points), n, f, host_i32(frame_offsets), B, host_f32(voxel_size),
+                                   host_f32(pc_range), max_points, max_voxels, ptr(ws), nbytes.value, ptr(voxels),
+                                   ptr(coords), ptr(nump), ptr(counts), counts.data_ptr() + 4 * B, ptr(pmap),
+                                   stream_ptr()), "ls3d_voxelize")
+    host = counts.cpu()            # the one host sync: exact output shapes, like the reference's return values
+    m = int(host[B])
+    return dict(voxels=voxels[:m], coordinates=coords[:m], num_points=nump[:m],
+                num_voxels=host[:B].to(torch.int64), point_voxel=pmap)
+
+
+# ------------------------------------------------------------------------------------------ readers
+def vfe_descriptor(voxels, num_points, mode, ld_out=None):
+    m, P, F = voxels.shape
+    need = F if mode == 0 else (F + 8 if mode == 1 else 2 * F + 8)
+    ld = ld_out or need
+    rows = m * P if mode == 2 else m
+    out = _f32(voxels.device, rows, ld)
+    check(capi.lib().ls3d_vfe_descriptor(ptr(voxels.contiguous()), ptr(num_points.to(torch.int32).contiguous()), m, P, F,
+                                         mode, ptr(out), ld, stream_ptr()), "ls3d_vfe_descriptor")
+    return out
+
+
+def vfe_token_attn(qkv, m, P, n_head, d_head):
+    out = _f32(qkv.device, m * P, n_head * d_head)
+    check(capi.lib().ls3d_vfe_token_attn(ptr(qkv), qkv.stride(0), m, P, n_head, d_head, ptr(out), out.stride(0),
+                                         stream_ptr()), "ls3d_vfe_token_attn")
+    return out
+
+
+def vfe_token_max(x, m, P):
+    E = x.shape[1]
+    out = _f32(x.device, m, E)
+    check(capi.lib().ls3d_vfe_token_max(ptr(x), x.stride(0), m, P, E, ptr(out), out.stride(0), stream_ptr()),
+          "ls3d_vfe_token_max")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ rulebooks
+class Grid:
+    """Occupancy bitmap of one sparse level: words {bits, rank prefix}, optional rank->row permutation."""
+
+    def __init__(self, B, shape, dev):
+        self.B, (self.D, self.H, self.W) = B, shape
+        wb, sb = ctypes.c_int64(), ctypes.c_int64()
+        check(capi.lib().ls3d_grid_bytes(B, self.D, self.H, self.W, ctypes.byref(wb), ctypes.byref(sb)), "grid_bytes")
+        self.words = torch.empty(wb.value, dtype=torch.uint8, device=dev)
+        self.scratch = torch.empty(max(sb.value, 4), dtype=torch.uint8, device=dev)
+        self.perm = None
+        self.total = _i32(dev, 1)
+
+    @property
+    def shape(self):
+        return (self.D, self.H, self.W)
+
+
+def grid_from_coords(coords, B, shape, need_perm):
+    g = Grid(B, shape, coords.device)
+    m = coords.shape[0]
+    if need_perm:
+        g.perm = _i32(coords.device, max(m, 1))
+    check(capi.lib().ls3d_grid_build(ptr(coords), m, B, g.D, g.H, g.W, ptr(g.words), ptr(g.perm), ptr(g.scratch),
+                                     ptr(g.total), stream_ptr()), "ls3d_grid_build")
+    return g
+
+
+def out_shape(shape, ksize, stride, pad):
+    return tuple((shape[i] + 2 * pad[i] - (ksize[i] - 1) - 1) // stride[i] + 1 for i in range(3))
+
+
+def grid_strided(in_coords, B, in_shape, ksize, stride, pad):
+    """Output sites of SparseConv3d(ksize, stride, pad): returns (grid, out_coords [M',4]) in ascending linear order."""
+    oshape = out_shape(in_shape, ksize, stride, pad)
+    g = Grid(B, oshape, in_coords.device)
+    check(capi.lib().ls3d_grid_build_strided(ptr(in_coords), in_coords.shape[0], B, host_i32(ksize), host_i32(stride),
+                                             host_i32(pad), g.D, g.H, g.W, ptr(g.words), ptr(g.scratch), ptr(g.total),
+                                             stream_ptr()), "ls3d_grid_build_strided")
+    m_out = int(g.total.item())    # host sync: number of output sites sizes the next launches
+    ocoords = _i32(in_coords.device, max(m_out, 1), 4)
+    check(capi.lib().ls3d_grid_enumerate(ptr(g.words), B, g.D, g.H, g.W, ptr(ocoords), stream_ptr()),
+          "ls3d_grid_enumerate")
+    return g, ocoords[:m_out]
+
+
+def rulebook_gather(in_grid, out_coords, ksize, stride, pad):
+    """nbr[k][j] = input row feeding output row j at kernel offset k (output-stationary pair table)."""
+    K = ksize[0] * ksize[1] * ksize[2]
+    m = out_coords.shape[0]
+    nbr = _i32(out_coords.device, K, max(m, 1))[:, :m].contiguous() if m == 0 else _i32(out_coords.device, K, m)
+    check(capi.lib().ls3d_rulebook_gather(ptr(in_grid.words), ptr(in_grid.perm), in_grid.B, in_grid.D, in_grid.H,
+                                          in_grid.W, ptr(out_coords), m, host_i32(ksize), host_i32(stride),
+                                          host_i32(pad), ptr(nbr), stream_ptr()), "ls3d_rulebook_gather")
+    return nbr
+
+
+def rulebook_scatter(out_grid, in_coords, ksize, stride, pad):
+    """Inverse-conv table: nbr[k][i] = coarse row o with o*stride - pad + k == fine row i."""
+    K = ksize[0] * ksize[1] * ksize[2]
+    m = in_coords.shape[0]
+    nbr = _i32(in_coords.device, K, m)
+    check(capi.lib().ls3d_rulebook_scatter(ptr(out_grid.words), out_grid.B, out_grid.D, out_grid.H, out_grid.W,
+                                           ptr(in_coords), m, host_i32(ksize), host_i32(stride), host_i32(pad),
+                                           ptr(nbr), stream_ptr()), "ls3d_rulebook_scatter")
+    return nbr
+
+
+# ------------------------------------------------------------------------------------------ devoxelize
+def three_nn_grid(points, grid, voxel_size, range_min, point_off, voxel_off, voxel_coords):
+    """Exact 3-NN of points [N, >=4] (b,x,y,z) among the voxel centres of ``grid`` (level 1).
+    Returns (dist2 [N,3] fp32, idx [N,3] int32 global voxel rows)."""
+    n = points.shape[0]
+    dev = points.device
+    d2, idx = _f32(dev, n, 3), _i32(dev, n, 3)
+    todo, cnt = _i32(dev, max(n, 1)), _i32(dev, 1)
+    check(capi.lib().ls3d_three_nn_grid(ptr(points), points.stride(0), n, ptr(grid.words), ptr(grid.perm), grid.B,
+                                        grid.D, grid.H, grid.W, host_f32(voxel_size), host_f32(range_min),
+                                        ptr(point_off), ptr(voxel_off), ptr(voxel_coords), ptr(todo), ptr(cnt),
+                                        ptr(d2), ptr(idx), stream_ptr()), "ls3d_three_nn_grid")
+    return d2, idx
+
+
+def three_interpolate(feat, d2, idx, C=None):
+    C = C or feat.shape[1]
+    n = idx.shape[0]
+    out = _f32(feat.device, n, C)
+    check(capi.lib().ls3d_three_interpolate(ptr(feat), feat.stride(0), C, ptr(d2), ptr(idx), n, ptr(out),
+                                            out.stride(0), stream_ptr()), "ls3d_three_interpolate")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ sampling / SF-Phase
+def sample_image_features(feat_nhwc, points_cuv, point_off):
+    """feat_nhwc [B, ncam, H, W, C] contiguous fp32; points_cuv [N,4]; returns [N, C] (zeros on invalid rows)."""
+    B, ncam, H, W, C = feat_nhwc.shape
+    n = points_cuv.shape[0]
+    out = _f32(feat_nhwc.device, n, C)
+    check(capi.lib().ls3d_sample_image_features(ptr(feat_nhwc), B, ncam, H, W, C, ptr(points_cuv.contiguous()), n,
+                                                ptr(point_off), ptr(out), out.stride(0), stream_ptr()),
+          "ls3d_sample_image_features")
+    return out
+
+
+def class_embed(logits, feats, seg_off, n_frames, max_rows, ncls=None, C=None):
+    """softmax over rows per (frame, class) then probs^T @ feats -> [B, ncls, C]."""
+    ncls = ncls or logits.shape[1]
+    C = C or feats.shape[1]
+    nb = ctypes.c_int64()
+    check(capi.lib().ls3d_class_embed_workspace_bytes(n_frames, max_rows, ncls, C, ctypes.byref(nb)), "class_embed_ws")
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=logits.device)
+    emb = _f32(logits.device, n_frames, ncls, C)
+    check(capi.lib().ls3d_class_embed(ptr(logits), logits.stride(0), ncls, ptr(feats), feats.stride(0), C, ptr(seg_off),
+                                      n_frames, max_rows, ptr(ws), ptr(emb), stream_ptr()), "ls3d_class_embed")
+    return emb
+
+
+def class_tokens(emb1, emb2, params, n_layer, n_head, d_model, want_memory=False):
+    """Memory path of the SF-Phase decoder for all layers: returns K, V [n_layer, B, H, L, dh] (+ memory)."""
+    B, ncls, C1 = emb1.shape
+    C2 = emb2.shape[2]
+    L, dh = 2 * ncls, d_model // n_head
+    K = _f32(emb1.device, n_layer, B, n_head, L, dh)
+    V = _f32(emb1.device, n_layer, B, n_head, L, dh)
+    mem = _f32(emb1.device, n_layer, B, L, d_model) if want_memory else None
+    check(capi.lib().ls3d_class_tokens(ptr(emb1), C1, ptr(emb2), C2, ncls, B, ptr(params), n_layer, n_head, d_model,
+                                       ptr(K), ptr(V), ptr(mem), stream_ptr()), "ls3d_class_tokens")
+    return (K, V, mem) if want_memory else (K, V)

@@ -1,0 +1,314 @@
+"""Generate tests/golden/* by running the REFERENCE's own code from /root/reference (build container only).
+
+What is real reference code here:
+  * det3d/ops/point_cloud/point_cloud_ops.py::points_to_voxel (numba) - imported by file path, unmodified;
+  * the plain-PyTorch reference modules ImprovedMeanVoxelFeatureExtractor, TransformerVoxelFeatureExtractor,
+    LiDARSemanticFeatureAggregationModule, PointSegMSeg3DHead (incl. SemanticFeatureFusionModule),
+    PointSegBatchlossHead, HRNet, FCNMSeg3DHead (incl. CameraSemanticFeatureAggregationModule) - imported from
+    the reference tree with their un-installable third-party imports (spconv, mmcv, torch_scatter, addict, the
+    CUDA-only pointnet2 extension) replaced by the stubs below.  The mmcv stubs restate mmcv's ConvModule /
+    build_conv_layer / build_norm_layer (conv -> norm -> act, conv bias off when a norm follows); the pointnet2
+    stub is the CPU restatement of interpolate_gpu.cu (the kernel itself cannot run without a GPU).
+Weights are not stored: every parameter/buffer is filled by ``seeded_fill`` (a pure function of its name), which the
+tests re-apply.  Run:  python oracle/make_golden.py
+"""
+import importlib.util
+import os
+import sys
+import types
+import zlib
+
+import numpy as np
+import torch
+from torch import nn
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def seeded_fill(module_or_sd, scale=1.0):
+    """Deterministically fill every float tensor of a module / state dict from crc32(name)."""
+    sd = module_or_sd.state_dict() if isinstance(module_or_sd, nn.Module) else module_or_sd
+    out = {}
+    for name, t in sd.items():
+        if not t.is_floating_point():
+            out[name] = t.clone()
+            continue
+        g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+        if name.endswith("running_var"):
+            v = torch.rand(t.shape, generator=g) + 0.5
+        elif name.endswith("running_mean"):
+            v = torch.randn(t.shape, generator=g) * 0.1
+        elif t.dim() <= 1:
+            v = torch.randn(t.shape, generator=g) * 0.1 + (1.0 if name.endswith("weight") else 0.0)
+        else:
+            fan_in = max(1, int(np.prod(t.shape[1:]))) if not name.endswith(("conv1.weight", "conv2.weight")) or t.dim() != 5 \
+                else int(np.prod(t.shape[:-1]))
+            v = torch.randn(t.shape, generator=g) * scale / fan_in ** 0.5
+        out[name] = v.to(t.dtype)
+    if isinstance(module_or_sd, nn.Module):
+        module_or_sd.load_state_dict(out)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- stubs
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install_stubs():
+    from oracle import nets as on
+
+    _mod("spconv")
+    _mod("torch_scatter")
+    from lidarseg3d_b200.det3d.config import install_addict_shim
+    install_addict_shim()
+
+    # ---- mmcv (recalled semantics)
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+            self.init_cfg = init_cfg
+
+    def build_conv_layer(cfg, *args, **kwargs):
+        assert cfg is None or cfg.get("type", "Conv2d") in ("Conv2d", "Conv")
+        return nn.Conv2d(*args, **kwargs)
+
+    def build_norm_layer(cfg, num_features, postfix=""):
+        cfg = dict(cfg)
+        t = cfg.pop("type")
+        assert t in ("BN", "BN2d")
+        rg = cfg.pop("requires_grad", True)
+        cfg.setdefault("eps", 1e-5)
+        layer = nn.BatchNorm2d(num_features, **cfg)
+        for p in layer.parameters():
+            p.requires_grad = rg
+        return "bn" + str(postfix), layer
+
+    class ConvModule(nn.Module):
+        def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                     bias="auto", conv_cfg=None, norm_cfg=None, act_cfg=dict(type="ReLU"), inplace=True, **kw):
+            super().__init__()
+            with_norm = norm_cfg is not None
+            if bias == "auto":
+                bias = not with_norm
+            self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
+            self.with_norm, self.with_act = with_norm, act_cfg is not None
+            if with_norm:
+                self.bn = build_norm_layer(norm_cfg, out_channels)[1]
+            if self.with_act:
+                assert act_cfg["type"] == "ReLU"
+                self.activate = nn.ReLU(inplace=inplace)
+
+        def forward(self, x):
+            x = self.conv(x)
+            if self.with_norm:
+                x = self.bn(x)
+            if self.with_act:
+                x = self.activate(x)
+            return x
+
+    _mod("mmcv")
+    _mod("mmcv.cnn", build_conv_layer=build_conv_layer, build_norm_layer=build_norm_layer, ConvModule=ConvModule,
+         build_plugin_layer=None, constant_init=None, kaiming_init=None, build_activation_layer=None)
+    _mod("mmcv.runner", BaseModule=BaseModule, ModuleList=nn.ModuleList, Sequential=nn.Sequential,
+         load_checkpoint=None, force_fp32=None)
+    _mod("mmcv.utils")
+    _mod("mmcv.utils.parrots_wrapper", _BatchNorm=nn.modules.batchnorm._BatchNorm)
+
+    # ---- det3d package skeleton (only the files on the hot path are loaded for real)
+    for pkg in ["det3d", "det3d.models", "det3d.models.readers", "det3d.models.point_heads", "det3d.models.img_heads",
+                "det3d.models.img_backbones", "det3d.models.utils", "det3d.core", "det3d.core.utils", "det3d.ops",
+                "det3d.ops.pointnet2_batch", "det3d.ops.mmseg_ops", "det3d.utils", "det3d.utils.dist"]:
+        m = _mod(pkg)
+        m.__path__ = [os.path.join(REF, *pkg.split("."))]
+    sys.modules["det3d"].torchie = _mod("det3d.torchie", is_str=lambda s: isinstance(s, str))
+    _mod("det3d.core.utils.loss_utils", lovasz_softmax=None)
+    _mod("det3d.core.utils.common_utils")
+    sys.modules["det3d.core.utils"].common_utils = sys.modules["det3d.core.utils.common_utils"]
+    _mod("det3d.utils.dist.dist_common")
+    sys.modules["det3d.utils.dist"].dist_common = sys.modules["det3d.utils.dist.dist_common"]
+
+    # pointnet2 extension: CPU restatement of interpolate_gpu.cu (the reference kernels are CUDA-only)
+    def three_nn(unknown, known):
+        d2, idx = on.three_nn(unknown[0], known[0])
+        return torch.sqrt(d2).unsqueeze(0), idx.unsqueeze(0)
+
+    def three_interpolate(features, idx, weight):      # features [1,C,M] -> [1,C,N]
+        f = features[0].t()[idx[0].long()]              # [N,3,C]
+        out = weight[0][:, 0:1] * f[:, 0] + weight[0][:, 1:2] * f[:, 1] + weight[0][:, 2:3] * f[:, 2]
+        return out.t().unsqueeze(0)
+
+    _mod("det3d.ops.pointnet2_batch.pointnet2_utils", three_nn=three_nn, three_interpolate=three_interpolate)
+
+
+def load_ref(dotted, relpath):
+    spec = importlib.util.spec_from_file_location(dotted, os.path.join(REF, relpath))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[dotted] = m
+    spec.loader.exec_module(m)
+    parent, _, leaf = dotted.rpartition(".")
+    if parent in sys.modules:
+        setattr(sys.modules[parent], leaf, m)
+    return m
+
+
+def load_reference_modules():
+    install_stubs()
+    load_ref("det3d.utils.registry", "det3d/utils/registry.py")
+    sys.modules["det3d.utils"].Registry = sys.modules["det3d.utils.registry"].Registry
+    sys.modules["det3d.utils"].build_from_cfg = sys.modules["det3d.utils.registry"].build_from_cfg
+    reg = load_ref("det3d.models.registry", "det3d/models/registry.py")
+    _mod("det3d.models.builder", **{k: getattr(reg, k) for k in dir(reg) if k.isupper()})
+    sys.modules["det3d.models"].builder = sys.modules["det3d.models.builder"]
+    norm = load_ref("det3d.models.utils.norm", "det3d/models/utils/norm.py")
+    sys.modules["det3d.models.utils"].build_norm_layer = norm.build_norm_layer
+    wr = load_ref("det3d.ops.mmseg_ops.wrappers", "det3d/ops/mmseg_ops/wrappers.py")
+    ms = sys.modules["det3d.ops.mmseg_ops"]
+    ms.Upsample, ms.resize, ms.ResLayer = wr.Upsample, wr.resize, None
+    R = {}
+    R["vfe"] = load_ref("det3d.models.readers.voxel_encoder", "det3d/models/readers/voxel_encoder.py")
+    R["ctx"] = load_ref("det3d.models.point_heads.context_module", "det3d/models/point_heads/context_module.py")
+    load_ref("det3d.models.point_heads.point_utils", "det3d/models/point_heads/point_utils.py")
+    R["mhead"] = load_ref("det3d.models.point_heads.point_seg_mseg3d_head", "det3d/models/point_heads/point_seg_mseg3d_head.py")
+    R["bhead"] = load_ref("det3d.models.point_heads.point_seg_batchloss_head",
+                          "det3d/models/point_heads/point_seg_batchloss_head.py")
+    load_ref("det3d.models.img_backbones.resnet_mmcv", "det3d/models/img_backbones/resnet_mmcv.py")
+    R["hrnet"] = load_ref("det3d.models.img_backbones.hrnet", "det3d/models/img_backbones/hrnet.py")
+    load_ref("det3d.models.img_heads.sc_conv", "det3d/models/img_heads/sc_conv.py")
+    load_ref("det3d.models.img_heads.decode_head", "det3d/models/img_heads/decode_head.py")
+    R["fcn"] = load_ref("det3d.models.img_heads.fcn_mseg3d_head", "det3d/models/img_heads/fcn_mseg3d_head.py")
+    return R
+
+
+# ----------------------------------------------------------------------------------------------- fixtures
+TINY_HRNET = dict(stage1=dict(num_modules=1, num_branches=1, block="BOTTLENECK", num_blocks=(2,), num_channels=(8,)),
+                  stage2=dict(num_modules=1, num_branches=2, block="BASIC", num_blocks=(2, 2), num_channels=(4, 8)),
+                  stage3=dict(num_modules=2, num_branches=3, block="BASIC", num_blocks=(2, 2, 2), num_channels=(4, 8, 16)),
+                  stage4=dict(num_modules=2, num_branches=4, block="BASIC", num_blocks=(2, 2, 2, 2),
+                              num_channels=(4, 8, 16, 32)))
+HEAD_CFG = dict(VOXEL_IN_DIM=32, VOXEL_CLS_FC=[64], VOXEL_ALIGN_DIM=64, IMAGE_IN_DIM=48, IMAGE_ALIGN_DIM=64,
+                GEO_FUSED_DIM=64, OUT_CLS_FC=[64, 64], IGNORED_LABEL=0, DP_RATIO=0.25, MIMIC_FC=[64, 64],
+                SFPhase_CFG=dict(embeddings_proj_kernel_size=1, d_model=96, n_head=4, n_layer=2, n_ffn=192,
+                                 drop_ratio=0, activation="relu", pre_norm=False))
+BHEAD_CFG = dict(CONV_IN_DIM=32, CONV_CLS_FC=[64], CONV_ALIGN_DIM=64, OUT_CLS_FC=[64, 64], IGNORED_LABEL=0)
+
+
+def voxel_scene(seed, n, feat, rng_xyz):
+    rng = np.random.default_rng(seed)
+    pts = np.concatenate([rng.uniform(-rng_xyz[0], rng_xyz[0], (n, 2)), rng.uniform(rng_xyz[1], rng_xyz[2], (n, 1)),
+                          rng.uniform(0, 1, (n, feat - 3))], 1).astype(np.float32)
+    k = n // 3                                  # dense clusters -> voxels with > max_points points
+    pts[:k, :3] = pts[k:2 * k, :3] + rng.normal(0, 0.03, (k, 3)).astype(np.float32)
+    pts[2 * k:2 * k + 40, :3] = pts[0, :3]      # 40 identical points
+    return pts
+
+
+def gen_voxelize():
+    spec = importlib.util.spec_from_file_location("ref_pco", os.path.join(REF, "det3d/ops/point_cloud/point_cloud_ops.py"))
+    pco = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pco)
+    cases = dict(nusc=dict(n=3000, feat=5, vs=[0.1, 0.1, 0.2], rg=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], ext=(54, -6, 4),
+                           max_voxels=300000),
+                 kitti=dict(n=3000, feat=4, vs=[0.1, 0.1, 0.15], rg=[-75.2, -75.2, -4, 75.2, 75.2, 2], ext=(78, -5, 3),
+                            max_voxels=300000),
+                 capped=dict(n=3000, feat=5, vs=[0.1, 0.1, 0.2], rg=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], ext=(54, -6, 4),
+                             max_voxels=700))
+    for name, c in cases.items():
+        pts = voxel_scene(zlib.crc32(name.encode()), c["n"], c["feat"], c["ext"])
+        v, co, nu = pco.points_to_voxel(pts, np.array(c["vs"], np.float32), np.array(c["rg"], np.float32), 5, True,
+                                        c["max_voxels"])
+        np.savez_compressed(os.path.join(OUT, f"voxelize_{name}.npz"), points=pts, voxel_size=np.array(c["vs"], np.float32),
+                            pc_range=np.array(c["rg"], np.float32), max_points=5, max_voxels=c["max_voxels"],
+                            voxels=v, coordinates=co, num_points=nu)
+        print("voxelize", name, v.shape, int(nu.max()))
+
+
+def gen_modules():
+    R = load_reference_modules()
+    g = torch.Generator().manual_seed(1234)
+    fx = {}
+    # ---- VFEs on voxels produced by the reference voxelizer fixture
+    z = np.load(os.path.join(OUT, "voxelize_nusc.npz"))
+    vox5 = torch.from_numpy(z["voxels"][:400]); num5 = torch.from_numpy(z["num_points"][:400])
+    z4 = np.load(os.path.join(OUT, "voxelize_kitti.npz"))
+    vox4 = torch.from_numpy(z4["voxels"][:400]); num4 = torch.from_numpy(z4["num_points"][:400])
+    with torch.no_grad():
+        m = R["vfe"].ImprovedMeanVoxelFeatureExtractor(num_input_features=5).eval()
+        fx["improved_mean_vfe"] = dict(voxels=vox5, num=num5, out=m(vox5, num5))
+        m = R["vfe"].MeanVoxelFeatureExtractor(num_input_features=5).eval()
+        fx["mean_vfe"] = dict(voxels=vox5, num=num5, out=m(vox5, num5))
+        m = R["vfe"].TransformerVoxelFeatureExtractor(num_input_features=4, num_compressed_features=16, num_embed=64,
+                                                      num_head=4, num_layers=3).eval()
+        seeded_fill(m)
+        # torch>=2.0 passes is_causal to custom layers: drive the reference layer objects by hand
+        class _Seq(nn.Module):
+            def __init__(self, layers):
+                super().__init__()
+                self.layers = layers
+
+            def forward(self, x):
+                for l in self.layers:
+                    x = l(x)
+                return x
+        m.chunck = _Seq(m.chunck.layers)
+        fx["trans_vfe"] = dict(voxels=vox4, num=num4, out=m(vox4, num4))
+        # ---- point heads
+        B, M, N, ncls = 2, 300, 500, 17
+        vcoord_idx = torch.stack([torch.arange(M) % 2 * 0 + (torch.arange(M) >= M // 2).long(),
+                                  torch.randint(0, 40, (M,), generator=g), torch.randint(0, 200, (M,), generator=g),
+                                  torch.randint(0, 200, (M,), generator=g)], 1)
+        vs = torch.tensor([0.1, 0.1, 0.2]); lo = torch.tensor([-10.0, -10.0, -5.0])
+        centers = (vcoord_idx[:, [3, 2, 1]].float() + 0.5) * vs + lo
+        vcoords = torch.cat([vcoord_idx[:, :1].float(), centers], 1)
+        pb = (torch.arange(N) >= N // 2).float()
+        pts = torch.cat([pb[:, None], torch.rand(N, 3, generator=g) * torch.tensor([20.0, 20.0, 8.0]) + lo], 1)
+        vfeat = torch.randn(M, 32, generator=g)
+        cuv = torch.rand(N, 4, generator=g) * 2 - 1
+        cuv[:, 0] = (torch.rand(N, generator=g) > 0.3).float()
+        cam = torch.randint(0, 6, (N,), generator=g).float()
+        cuv[:, 1] = cam / 5 * 2 - 1
+        img_feat = torch.randn(B, 6, 48, 10, 15, generator=g)
+        cam_emb = torch.randn(B, 48, ncls, 1, generator=g)
+        head = R["mhead"].PointSegMSeg3DHead(class_agnostic=False, num_class=ncls, model_cfg=HEAD_CFG).eval()
+        seeded_fill(head)
+        bd = dict(batch_size=B, conv_point_features=vfeat, conv_point_coords=vcoords, points=pts, points_cuv=cuv,
+                  image_features=img_feat, camera_semantic_embeddings=cam_emb)
+        out = head(dict(bd), return_loss=False)
+        lemb = head.lidar_sfam(feats=vfeat, probs=head.forward_ret_dict["voxel_logits"], batch_idx=vcoords[:, 0], batch_size=B)
+        fx["mseg3d_head"] = dict(inputs=bd, out_logits=out["out_logits"], voxel_logits=head.forward_ret_dict["voxel_logits"],
+                                 lidar_emb=lemb)
+        bhead = R["bhead"].PointSegBatchlossHead(class_agnostic=False, num_class=20, model_cfg=BHEAD_CFG).eval()
+        seeded_fill(bhead)
+        out = bhead(dict(batch_size=B, conv_point_features=vfeat, conv_point_coords=vcoords, points=pts), return_loss=False)
+        fx["batchloss_head"] = dict(out_logits=out["out_logits"], conv_logits=bhead.forward_ret_dict["conv_logits"])
+        # ---- image branch (tiny HRNet, same class / code path as w18)
+        hr = R["hrnet"].HRNet(extra=TINY_HRNET, norm_cfg=dict(type="BN", requires_grad=True))
+        hr.eval()            # the reference's HRNet.train() returns None (hrnet.py:695-704)
+        seeded_fill(hr)
+        imgs = torch.randn(B * 2, 3, 64, 96, generator=g)
+        ys = hr(imgs)
+        fcn = R["fcn"].FCNMSeg3DHead(in_channels=[4, 8, 16, 32], in_index=(0, 1, 2, 3), channels=8, num_classes=5,
+                                     input_transform="resize_concat", kernel_size=1, num_convs=2, concat_input=False,
+                                     dropout_ratio=-1, norm_cfg=dict(type="BN", requires_grad=True), align_corners=False,
+                                     ignore_index=0, loss_weight=0.5).eval()
+        seeded_fill(fcn)
+        r = fcn(dict(inputs=ys, batch_size=B), return_loss=False)
+        fx["image_branch"] = dict(images=imgs, hrnet_out=[y.clone() for y in ys], image_features=r["image_features"],
+                                  image_logits=r["image_logits"], camera_semantic_embeddings=r["camera_semantic_embeddings"],
+                                  hrnet_keys=sorted(hr.state_dict().keys()), fcn_keys=sorted(fcn.state_dict().keys()))
+        fx["state_dict_keys"] = dict(mseg3d_head=sorted(head.state_dict().keys()), batchloss_head=sorted(bhead.state_dict().keys()),
+                                     trans_vfe=sorted(k.replace("chunck.layers.layers.", "chunck.layers.") for k in m.state_dict().keys()))
+    torch.save(fx, os.path.join(OUT, "ref_modules.pt"))
+    print("modules:", {k: (tuple(v["out"].shape) if isinstance(v, dict) and "out" in v else "...") for k, v in fx.items()})
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_voxelize()
+    gen_modules()
+    print(sorted((f, os.path.getsize(os.path.join(OUT, f))) for f in os.listdir(OUT)))

@@ -1,0 +1,93 @@
+"""Host logic without a GPU: registry / builder / config mirror, C-ABI exports, reference configs instantiate."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from lidarseg3d_b200 import det3d
+from lidarseg3d_b200.det3d import Config, Registry, build_detector, build_from_cfg
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_registry_semantics():
+    R = Registry("thing")
+
+    @R.register_module
+    class A:
+        def __init__(self, x, y=2):
+            self.x, self.y = x, y
+
+    assert R.get("A") is A and R.name == "thing"
+    with pytest.raises(KeyError):
+        R.register_module(A)                                   # duplicate name
+    with pytest.raises(TypeError):
+        R._register_module(lambda: 0)
+    a = build_from_cfg(dict(type="A", x=1), R, default_args=dict(y=5, x=9))
+    assert (a.x, a.y) == (1, 5)                                # defaults only fill missing keys
+    assert build_from_cfg(dict(type=A, x=3), R).x == 3
+    with pytest.raises(KeyError, match="not in the thing registry"):
+        build_from_cfg(dict(type="B"), R)
+    with pytest.raises(TypeError):
+        build_from_cfg(dict(type=3), R)
+
+
+def test_config_and_alias(tmp_path):
+    (tmp_path / "sub_cfg.py").write_text("inner = dict(a=1)\n")
+    (tmp_path / "cfg.py").write_text("from addict.addict import Dict\nfrom sub_cfg import inner\n"
+                                     "model = dict(type='X', nested=dict(k=[1, 2]))\ninner.update(dict(b=2))\nv = 3\n")
+    cfg = Config.fromfile(str(tmp_path / "cfg.py"))
+    assert cfg.model.nested.k == [1, 2] and cfg.v == 3 and cfg.inner.b == 2 and cfg["model"]["type"] == "X"
+    with pytest.raises(AttributeError):
+        cfg.model.missing
+    assert "model = dict" in cfg.text
+    det3d.install_alias()
+    from det3d.models import build_detector as bd                 # reference import names resolve
+    from det3d.torchie import Config as C2
+    from det3d.utils import Registry as R2
+    assert bd is build_detector and C2 is Config and R2 is Registry
+
+
+def test_cabi_exports_every_declared_symbol():
+    from lidarseg3d_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "ls3d.h")).read()
+    declared = set(re.findall(r"^int (ls3d_\w+)\(", hdr, flags=re.M))
+    assert declared and declared == set(capi.EXPORTS)
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert ctypes.sizeof(capi.GemmArgs) % 8 == 0
+    # argument errors come back as status codes without touching the device
+    n = ctypes.c_int64()
+    assert capi.lib().ls3d_voxelize_workspace_bytes(1000, 5, 2, ctypes.byref(n)) == 0 and n.value > 0
+    assert capi.lib().ls3d_voxelize_workspace_bytes(1000, 99, 2, ctypes.byref(n)) == -1
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference configs only exist in the build container")
+@pytest.mark.parametrize("rel,det,nkeys", [
+    ("configs/semanticnusc/MSeg3D/semnusc_avgvfe_unetscn3d_hrnetw18_lr1en2_e12.py", "SegMSeg3DNet", 2251),
+    ("configs/semantickitti/SDSeg3D/semkitti_transVFE_unetscn3d_batchloss_e10.py", "SegNet", 291),
+    ("configs/semanticwaymo/MSeg3D/semwaymo_avgvfe_unetscn3d_hrnetw18_lr1en2_e12.py", "SegMSeg3DNet", 2251)])
+def test_reference_configs_instantiate_unchanged(rel, det, nkeys):
+    cfg = Config.fromfile(os.path.join(REF, rel))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # "pretrained weights not found" (tolerated, Appendix D item 15)
+        m = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    assert type(m).__name__ == det
+    sd = m.state_dict()
+    assert len(sd) == nkeys
+    assert tuple(sd["backbone.conv_input.0.weight"].shape[:3]) == (3, 3, 3)
+    assert "backbone.conv_out.0.weight" in sd and tuple(sd["backbone.conv_out.0.weight"].shape) == (3, 1, 1, 128, 128)
+    with pytest.raises(NotImplementedError):
+        m(dict(), return_loss=True)
+
+
+def test_shipped_configs_build():
+    for name in ("mseg3d_nuscenes.py", "sdseg3d_semantickitti.py"):
+        cfg = Config.fromfile(os.path.join(ROOT, "configs", name))
+        m = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
+        assert sum(p.numel() for p in m.parameters()) > 1e6

@@ -1,0 +1,80 @@
+"""Sparse-conv oracle (spconv 1.x semantics, parity unpinned against spconv itself) pinned to the independent dense
+ground truth F.conv3d / F.conv_transpose3d and to an O(N*K) dictionary enumeration of the rulebook."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sparse as osp
+
+
+def random_sites(seed, B, shape, n):
+    rng = np.random.default_rng(seed)
+    cells = rng.choice(B * shape[0] * shape[1] * shape[2], size=n, replace=False)
+    rng.shuffle(cells)
+    D, H, W = shape
+    return np.stack([cells // (D * H * W), (cells // (H * W)) % D, (cells // W) % H, cells % W], 1).astype(np.int32)
+
+
+def densify(idx, feats, B, shape):
+    d = torch.zeros(B, feats.shape[1], *shape, dtype=feats.dtype)
+    d[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]] = feats
+    return d
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_subm_matches_dense_conv(seed):
+    B, shape, C, Co = 2, (9, 16, 16), 6, 5
+    idx = random_sites(seed, B, shape, 600)
+    feats = torch.randn(idx.shape[0], C, dtype=torch.float64)
+    w = torch.randn(3, 3, 3, C, Co, dtype=torch.float64)
+    nbr = osp.subm_rulebook(idx, shape, 3)
+    out = osp.sparse_conv(feats, w, nbr)
+    dense = F.conv3d(densify(idx, feats, B, shape), w.permute(4, 3, 0, 1, 2), padding=1)
+    ref = dense[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]]
+    torch.testing.assert_close(out, ref, rtol=1e-10, atol=1e-10)
+    _, pairs = osp.rulebook_dict(idx, shape, 3, 1, 1, subm=True)
+    assert osp.pairs_of(nbr) == pairs
+
+
+@pytest.mark.parametrize("ks,st,pd", [((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (0, 1, 1)),
+                                      ((3, 1, 1), (2, 1, 1), (0, 0, 0))])
+def test_strided_and_inverse_match_dense(ks, st, pd):
+    B, shape, C, Co = 2, (11, 16, 16), 4, 3
+    idx = random_sites(3, B, shape, 500)
+    feats = torch.randn(idx.shape[0], C, dtype=torch.float64)
+    w = torch.randn(*ks, C, Co, dtype=torch.float64)
+    oidx, oshape, nbr = osp.strided_rulebook(idx, shape, ks, st, pd)
+    # ascending linear order of the output sites
+    lin = ((oidx[:, 0].astype(np.int64) * oshape[0] + oidx[:, 1]) * oshape[1] + oidx[:, 2]) * oshape[2] + oidx[:, 3]
+    assert np.all(np.diff(lin) > 0)
+    out = osp.sparse_conv(feats, w, nbr)
+    dense = F.conv3d(densify(idx, feats, B, shape), w.permute(4, 3, 0, 1, 2), stride=st, padding=pd)
+    assert tuple(dense.shape[2:]) == tuple(oshape)
+    ref = dense[oidx[:, 0], :, oidx[:, 1], oidx[:, 2], oidx[:, 3]]
+    torch.testing.assert_close(out, ref, rtol=1e-10, atol=1e-10)
+    # active output set = every cell with at least one active input in its receptive field
+    occ = F.conv3d(densify(idx, torch.ones(idx.shape[0], 1, dtype=torch.float64), B, shape),
+                   torch.ones(1, 1, *ks, dtype=torch.float64), stride=st, padding=pd)
+    assert int((occ > 0).sum()) == oidx.shape[0]
+    olist, pairs = osp.rulebook_dict(idx, shape, ks, st, pd, subm=False)
+    assert [tuple(r) for r in oidx.tolist()] == olist and osp.pairs_of(nbr) == pairs
+    # inverse conv == conv_transpose3d restricted to the original fine sites
+    cf = torch.randn(oidx.shape[0], Co, dtype=torch.float64)
+    wi = torch.randn(*ks, Co, C, dtype=torch.float64)
+    nbr_up = osp.invert_rulebook(nbr, idx.shape[0])
+    fine = osp.sparse_conv(cf, wi, nbr_up)
+    opad = [shape[i] - ((oshape[i] - 1) * st[i] - 2 * pd[i] + ks[i]) for i in range(3)]
+    dt = F.conv_transpose3d(densify(oidx, cf, B, oshape), wi.permute(3, 4, 0, 1, 2), stride=st, padding=pd,
+                            output_padding=opad)
+    ref = dt[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]]
+    torch.testing.assert_close(fine, ref, rtol=1e-10, atol=1e-10)
+
+
+def test_three_nn_ties_and_small_sets():
+    from oracle import nets as on
+    known = torch.tensor([[0., 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0]])
+    d2, idx = on.three_nn(torch.tensor([[0., 0, 0]]), known)
+    assert idx.tolist() == [[0, 1, 2]] and d2.tolist() == [[0.0, 1.0, 1.0]]        # ties -> lowest index
+    d2, idx = on.three_nn(torch.tensor([[0.5, 0, 0]]), known[:2])
+    assert idx.tolist() == [[0, 1, 0]] and np.isinf(d2[0, 2].item())
