@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py - MSeg3D / SDSeg3D forward frames/s on B200 (+ sparse-conv roofline, + CPU baseline).
+
+    python bench.py --gpus N --steps K --warmup W              # our arm (CUDA kernels through the det3d API)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference algorithm on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic frames: GPU voxelization -> VFE -> sparse UNet ->
+devoxelization -> camera sampling -> GF/SF fusion -> per-point logits -> argmax.  ``value`` is timed with the raw inputs
+(points, images, points_cuv) already resident in HBM; ``e2e`` goes through the public API from pinned HOST buffers with
+the host->device copies and the device->host read of the labels inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "mseg3d_nuscenes": dict(cfg="mseg3d_nuscenes.py", spec="NUSC", frames_per_gpu=3, cam=True,
+                            desc="MSeg3D nuScenes LiDAR + 6-cam GF/SF fusion forward (BASELINE.json configs[2])"),
+    "sdseg3d_semantickitti": dict(cfg="sdseg3d_semantickitti.py", spec="KITTI", frames_per_gpu=4, cam=False,
+                                  desc="SDSeg3D SemanticKITTI LiDAR-only sparse-conv UNet forward (configs[1])"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mseg3d_nuscenes", choices=list(WORKLOADS))
+    ap.add_argument("--frames-per-gpu", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def make_batches(wl, spec, n_batches, frames_per_gpu, rank):
+    """Seeded synthetic batches as pinned HOST tensors: list of dict(frames=[...], images, cuv)."""
+    from lidarseg3d_b200 import synth
+    out = []
+    for b in range(n_batches):
+        seeds = [1000 * rank + b * frames_per_gpu + i for i in range(frames_per_gpu)]
+        frames = [synth.lidar_scan(spec, s) for s in seeds]
+        d = dict(frames=[torch.from_numpy(f).pin_memory() for f in frames])
+        if wl["cam"]:
+            d["cuv"] = torch.from_numpy(np.concatenate([synth.project_points(f[:, :3], spec) for f in frames])).pin_memory()
+            d["images"] = torch.from_numpy(np.stack([synth.camera_images(spec, s) for s in seeds])).pin_memory()
+        out.append(d)
+    return out
+
+
+def build_model(wl, seed=0):
+    from lidarseg3d_b200.det3d import Config, build_detector
+    cfg = Config.fromfile(os.path.join(ROOT, "configs", wl["cfg"]))
+    torch.manual_seed(seed)
+    m = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg).eval()
+    g = torch.Generator().manual_seed(seed)
+    for mod in m.modules():                      # non-trivial BN statistics so that folding is exercised
+        if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+            mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+    return cfg, m
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / CPU baseline
+def cpu_forward_once(wl, spec, cfg, sd, batch, nframes=1):
+    """The reference algorithm on the host: voxelize (numba-equivalent oracle) + oracle forward, ``nframes`` frames."""
+    from oracle import nets as on
+    from oracle import voxelize as ov
+    from lidarseg3d_b200 import synth
+    frames = [f.numpy() for f in batch["frames"][:nframes]]
+    vox = [ov.points_to_voxel(f, spec["voxel_size"], spec["pc_range"], 5, 300000) for f in frames]
+    v, c, n, nv, pts = ov.collate_frames([(a, b, cc, f) for (a, b, cc), f in zip(vox, frames)])
+    ex = dict(voxels=torch.from_numpy(v), coordinates=torch.from_numpy(c), num_points=torch.from_numpy(n),
+              num_voxels=torch.from_numpy(nv), shape=np.stack([synth.grid_shape(spec)] * nframes), points=torch.from_numpy(pts))
+    if wl["cam"]:
+        npts = sum(f.shape[0] for f in frames)
+        ex["points_cuv"] = batch["cuv"][:npts]
+        ex["images"] = batch["images"][:nframes]
+        ocfg = dict(voxel_size=spec["voxel_size"], pc_range=spec["pc_range"], hrnet_extra=cfg.model.img_backbone.extra,
+                    nhead=4, nlayer=6, num_convs=2)
+        out = on.mseg3d_forward(sd, ex, ocfg)
+    else:
+        out = on.segnet_forward(sd, ex, dict(voxel_size=spec["voxel_size"], pc_range=spec["pc_range"],
+                                             reader=dict(type="TransformerVoxelFeatureExtractor", num_head=4, num_layers=3)))
+    return out.argmax(1)
+
+
+def run_cpu(wl, spec, cfg, model, batches, steps, warmup, budget_s):
+    """Time the oracle port on all host cores, one frame per step, inside a wall-clock budget."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        cpu_forward_once(wl, spec, cfg, sd, batches[0])
+        first = time.perf_counter() - t0
+        w_done = 1
+        while w_done < warmup and (time.perf_counter() - t0) + first < budget_s * 0.3:
+            cpu_forward_once(wl, spec, cfg, sd, batches[w_done % len(batches)])
+            w_done += 1
+        times = []
+        for i in range(steps):
+            if times and (time.perf_counter() - t0) + np.mean(times) > budget_s:
+                break
+            t1 = time.perf_counter()
+            cpu_forward_once(wl, spec, cfg, sd, batches[i % len(batches)])
+            times.append(time.perf_counter() - t1)
+    sec = float(np.mean(times))
+    return dict(value=1.0 / sec, unit="frames/s", cores=cores, kind="port",
+                sample=f"1 frame per step ({len(times)} timed, {w_done} warm-up) of {wl['desc']}; oracle/ restatement "
+                       f"(numba-equivalent voxelizer + spconv-1.x-style gather/mm/scatter + PyTorch CPU heads/HRNet), "
+                       f"torch.set_num_threads({cores})"), sec, len(times), w_done
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    wl = WORKLOADS[args.workload]
+    from lidarseg3d_b200 import synth
+    spec = getattr(synth, wl["spec"])
+    fpg = args.frames_per_gpu or wl["frames_per_gpu"]
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    base = dict(metric="mseg3d_forward_frames_per_sec" if wl["cam"] else "sdseg3d_forward_frames_per_sec", unit="frames/s",
+                n_gpus=args.gpus, higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic",
+                dtype="tf32 tensor-core multiply / fp32 accumulate+storage (int32/int64 index work bit-exact)")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cfg, model = build_model(wl)
+        batches = make_batches(wl, spec, 2, 1, 0)
+        cb, sec, done, wdone = run_cpu(wl, spec, cfg, model, batches, args.steps, max(args.warmup, 1), args.cpu_budget_s * 1.6)
+        line = dict(base, impl="reference", value=cb["value"], steps=done, steps_requested=args.steps, warmup=wdone,
+                    ms_per_step=sec * 1e3, dtype="fp32 (CPU)", cpu_baseline=cb, gpu_launches=0,
+                    config=dict(workload=args.workload, description=wl["desc"], frames_per_step=1,
+                                points_per_frame=int(batches[0]["frames"][0].shape[0]),
+                                note="reference algorithm on the host cores; the reference itself cannot run (spconv/mmcv "
+                                     "not installable, docs say CPU mode unsupported) - oracle port, see DESIGN.md"),
+                    e2e=dict(value=cb["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU: the product path has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from lidarseg3d_b200 import capi, gemm, pipeline
+    torch.backends.cudnn.benchmark = True
+    cfg, model = build_model(wl)
+    model = model.to(dev)
+    NB = 4
+    batches = make_batches(wl, spec, NB, fpg, rank)
+    # device-resident copies of the raw inputs for the `value` measurement
+    dev_batches = []
+    for b in batches:
+        d = dict(frames=[f.to(dev) for f in b["frames"]])
+        if wl["cam"]:
+            d["cuv"], d["images"] = b["cuv"].to(dev), b["images"].to(dev)
+        dev_batches.append(d)
+    in_bytes = sum(f.numel() * 4 for f in batches[0]["frames"]) + (batches[0]["cuv"].numel() * 4 + batches[0]["images"].numel() * 4
+                                                                    if wl["cam"] else 0)
+    npts = sum(f.shape[0] for f in batches[0]["frames"])
+
+    def step(b, from_host):
+        ex = pipeline.build_example(b["frames"], spec["voxel_size"], spec["pc_range"], images=b.get("images"),
+                                    points_cuv=b.get("cuv"), device=dev)
+        preds = model(ex, return_loss=False)
+        labels = torch.cat([p["pred_point_sem_labels"] for p in preds])
+        if from_host:
+            return labels.to(torch.int16).cpu()
+        return labels
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(nsteps, from_host, src):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(nsteps):
+            step(src[i % NB], from_host)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist_on:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            step(dev_batches[i % NB], False)
+        # ---- value: inputs resident in HBM
+        capi.COUNTERS.clear()
+        gemm.PROFILE = []
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ms = timed(args.steps, False, dev_batches)
+        clocks = sampler.stop()
+        launches = capi.kernel_launches()
+        prof = gemm.PROFILE
+        gemm.PROFILE = None
+        # rulebook pair counts per launch (deterministic per batch) for the algorithmic-byte model, outside the timed region
+        pair_counts = []
+        for i in range(NB):
+            gemm.COUNT = []
+            step(dev_batches[i], False)
+            pair_counts.append(gemm.COUNT)
+        gemm.COUNT = None
+        # ---- e2e: pinned host buffers -> labels on the host
+        for i in range(2):
+            step(batches[i % NB], True)
+        ms_e2e = timed(args.steps, True, batches)
+    frames = args.steps * fpg * world
+    value = frames / (ms / 1e3)
+    e2e = frames / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant hand-written kernel family (gather-GEMM on the sparse convolutions)
+    roof = None
+    if prof and rank == 0:
+        torch.cuda.synchronize()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        per_step = len(prof) // args.steps
+        for i, p in enumerate(prof):
+            pairs = pair_counts[(i // per_step) % NB][i % per_step]
+            # N_in*Cin*4 + N_out*Cout*4 + K*Cin*Cout*4 + P*8 bytes ; 2*P*Cin*Cout flops
+            p["bytes"] = (p["rows_in"] * p["cin"] + p["m_out"] * p["cout"] + p["koff"] * p["cin"] * p["cout"]) * 4 + \
+                (pairs * 8 if p["sparse"] else 0)
+            p["flops"] = 2.0 * pairs * p["cin"] * p["cout"]
+        sp = [(p["bytes"], p["flops"], p["e0"].elapsed_time(p["e1"])) for p in prof if p["sparse"]]
+        al = [(p["bytes"], p["flops"], p["e0"].elapsed_time(p["e1"])) for p in prof]
+        tb, tf, tm = (sum(x[i] for x in sp) for i in range(3))
+        ab, af, am = (sum(x[i] for x in al) for i in range(3))
+        roof = dict(bound="hbm", kernel="gather_gemm_kernel (sparse SubM/strided/inverse conv launches)", achieved=tb / tm / 1e6,
+                    peak=peak, unit="GB/s", frac=tb / tm / 1e6 / peak, traffic=None,
+                    peak_source="MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
+                    launches_per_step=len(sp) // args.steps, avg_launch_us=tm / max(len(sp), 1) * 1e3,
+                    algorithmic_bytes_per_step=tb / args.steps, tflops=tf / tm / 1e9,
+                    share_of_step=tm / ms, all_gemm=dict(launches_per_step=len(al) // args.steps, gbs=ab / am / 1e6,
+                                                         tflops=af / am / 1e9, share_of_step=am / ms))
+
+    cb = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cb, _, _, _ = run_cpu(wl, spec, cfg, model, batches, 3, 1, args.cpu_budget_s)
+
+    if rank == 0:
+        line = dict(base, value=value, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
+                    config=dict(workload=args.workload, description=wl["desc"], frames_per_gpu=fpg, global_frames_per_step=fpg * world,
+                                points_per_step_per_gpu=npts, parallelism=f"frames sharded over {world} GPU(s), no data-path collective",
+                                l2="inputs larger than L2: 4 rotating pre-staged batches, %.0f MB of raw inputs each" % (in_bytes / 1e6),
+                                timed_region="GPU voxelize -> VFE -> sparse UNet -> devoxelize -> camera sampling -> GF/SF fusion "
+                                             "-> logits -> argmax (HRNet/FCN image branch on cuDNN inside)"),
+                    clocks=clocks, gpu_launches=launches,
+                    e2e=dict(value=e2e, unit="frames/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=in_bytes,
+                             d2h_bytes_per_step=npts * 2 + 4 * (fpg + 4)),
+                    roofline=roof, cpu_baseline=cb)
+        print(json.dumps(line))
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -111,9 +111,23 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+# C-ABI calls since the last COUNTERS.clear(), and the (lower-bound) number of kernels each call launches
+COUNTERS = {}
+KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_voxelize": 8, "ls3d_vfe_descriptor": 1, "ls3d_vfe_token_attn": 1,
+                    "ls3d_vfe_token_max": 1, "ls3d_grid_build": 4, "ls3d_grid_build_strided": 4, "ls3d_grid_enumerate": 1,
+                    "ls3d_rulebook_gather": 1, "ls3d_rulebook_scatter": 1, "ls3d_three_nn_grid": 2,
+                    "ls3d_three_interpolate": 1, "ls3d_sample_image_features": 1, "ls3d_class_embed": 4,
+                    "ls3d_class_tokens": 1}
+
+
+def kernel_launches():
+    return int(sum(KERNELS_PER_CALL.get(k, 0) * v for k, v in COUNTERS.items()))
+
+
 def check(status, what):
     if status != 0:
         raise RuntimeError(f"{what} failed with status {status}")
+    COUNTERS[what] = COUNTERS.get(what, 0) + 1
 
 
 def gather_gemm(args: GemmArgs):

@@ -16,6 +16,11 @@ def pad_to(v, m):
     return (v + m - 1) // m * m
 
 
+# bench.py instrumentation: PROFILE = list -> CUDA events + static sizes per launch; COUNT = list -> rulebook pair counts
+PROFILE = None
+COUNT = None
+
+
 class PackedWeight:
     """W[koff][cin][cout] (spconv layout, reference scn_unet.py weight [kz,ky,kx,Cin,Cout]) packed as
     [koff][n_pad][cin_pad] K-major, tf32-rounded, zero padded."""
@@ -87,5 +92,15 @@ def run(x0, pw: PackedWeight, *, x1=None, nbr=None, m_out=None, scale=None, shif
     if out is None:
         out = torch.empty(m, pw.cout, dtype=torch.float32, device=x0.device)
     a.out, a.ld_out = capi.ptr(out), out.stride(0)
-    capi.gather_gemm(a)
+    if COUNT is not None:
+        COUNT.append(int((nbr >= 0).sum()) if nbr is not None else m)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        capi.gather_gemm(a)
+        e1.record()
+        PROFILE.append(dict(e0=e0, e1=e1, sparse=nbr is not None, rows_in=x0.shape[0], m_out=m, cin=c0 + c1, cout=pw.cout,
+                            koff=pw.koff))
+    else:
+        capi.gather_gemm(a)
     return out

@@ -36,14 +36,13 @@ def lidar_scan(spec, seed):
     for d, a, w, hh in zip(wd, wa, ww, wh):
         n = np.array([np.cos(a), np.sin(a)])
         den = dx * n[0] + dy * n[1]
-        with np.errstate(divide="ignore", invalid="ignore"):
-            t = np.where(den > 1e-3, d / den, np.inf)
+        t = np.where(den > 1e-3, d / np.maximum(den, 1e-3), 1e9)
         px, py, pz = dx * t, dy * t, dz * t + h
         lateral = -px * n[1] + py * n[0]
         hit = (np.abs(lateral) < w / 2) & (pz > 0) & (pz < hh)
         r = np.where(hit & (t < r), t, r)
     ok = np.isfinite(r) & (r < 90.0) & (r > 1.0)
-    r = r + rng.normal(0, 0.02, r.shape)
+    r = np.where(ok, r, 1.0) + rng.normal(0, 0.02, r.shape)
     x, y, z = dx * r, dy * r, dz * r
     ring = np.repeat(np.arange(spec["beams"])[:, None], spec["azimuths"], 1)
     cols = [x, y, z]
