@@ -87,15 +87,31 @@ def make_batches(wl, spec, n_batches, frames_per_gpu, rank):
     """Seeded synthetic batches as pinned HOST tensors: list of dict(frames=[...], images, cuv)."""
     from lidarseg3d_b200 import synth
     out = []
+    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
     for b in range(n_batches):
         seeds = [1000 * rank + b * frames_per_gpu + i for i in range(frames_per_gpu)]
         frames = [synth.lidar_scan(spec, s) for s in seeds]
-        d = dict(frames=[torch.from_numpy(f).pin_memory() for f in frames])
+        d = dict(frames=[pin(torch.from_numpy(f)) for f in frames])
         if wl["cam"]:
-            d["cuv"] = torch.from_numpy(np.concatenate([synth.project_points(f[:, :3], spec) for f in frames])).pin_memory()
-            d["images"] = torch.from_numpy(np.stack([synth.camera_images(spec, s) for s in seeds])).pin_memory()
+            d["cuv"] = pin(torch.from_numpy(np.concatenate([synth.project_points(f[:, :3], spec) for f in frames])))
+            d["images"] = pin(torch.from_numpy(np.stack([synth.camera_images(spec, s) for s in seeds])))
         out.append(d)
     return out
+
+
+def global_frames(steps, frames_per_gpu, world):
+    """Whole-job unit count of the timed region (weak scaling: per-GPU work fixed)."""
+    return steps * frames_per_gpu * world
+
+
+def reduce_max_ms(ms, device):
+    """Max over ranks of the device-timed milliseconds (no-op for a single process)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(ms)
+    t = torch.tensor([ms], device=device if device is not None else "cpu", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def build_model(wl, seed=0):
@@ -239,12 +255,7 @@ def main():
             step(src[i % NB], from_host)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if dist_on:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return reduce_max_ms(e0.elapsed_time(e1), dev)
 
     with torch.no_grad():
         for i in range(max(args.warmup, 3)):
@@ -270,7 +281,7 @@ def main():
         for i in range(2):
             step(batches[i % NB], True)
         ms_e2e = timed(args.steps, True, batches)
-    frames = args.steps * fpg * world
+    frames = global_frames(args.steps, fpg, world)
     value = frames / (ms / 1e3)
     e2e = frames / (ms_e2e / 1e3)
 

@@ -35,7 +35,8 @@ typedef struct ls3d_gemm_args {
   const int32_t* nbr; /* [koff][m_out] input row per (offset, output row), -1 = none; NULL =   */
                       /* identity (dense Linear, requires koff == 1)                           */
   int32_t koff, m_out;
-  const float* w;     /* [koff][n_pad][cin_pad] (K-major), tf32-rounded, zero padded           */
+  const float* w;     /* precise=0: [koff][n_pad][cin_pad] (K-major) tf32-rounded, zero padded;  */
+                      /* precise=1: [koff][2][n_pad][cin_pad] = {trunc_tf32(W), W - trunc_tf32(W)} */
   int32_t cin_pad;    /* multiple of 8, >= c0 + c1                                             */
   int32_t n_pad;      /* multiple of 16 in [16, 256]                                           */
   int32_t cout;       /* valid output columns (<= n_pad)                                       */
@@ -63,6 +64,9 @@ typedef struct ls3d_gemm_args {
   int32_t ld_mask;       /*   (feature completion, point_seg_mseg3d_head.py:314-334)                */
   float* out;         /* [m_out, ld_out]                                                       */
   int32_t ld_out;
+  int32_t round_out;  /* 1: store outputs rounded to tf32 (cvt.rna); only useful with precise=0, where the  */
+                      /* operands of the next GEMM are truncated to tf32 by the tensor core               */
+  int32_t precise;    /* 1: error-compensated 3xTF32 (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi), fp32-level accuracy */
 } ls3d_gemm_args;
 
 int ls3d_gather_gemm(const ls3d_gemm_args* args, void* stream);
@@ -95,13 +99,14 @@ int ls3d_voxelize(const float* points, int32_t n_points, int32_t n_feat, const i
  *           core and slot max of TransformerVoxelFeatureExtractor
  *           (det3d/models/readers/voxel_encoder.py:51-58,74-124,149-157,202-270).
  *   mode 0: out[m, F] mean;  1: out[m, F+8] 13-d style descriptor;  2: out[m*P, 2F+8] token inputs
+ *   round_out (here and below): 1 = store tf32-rounded values (result feeds a gather-GEMM), 0 = exact fp32
  * ------------------------------------------------------------------------------------------------ */
 int ls3d_vfe_descriptor(const float* voxels, const int32_t* num_points, int32_t m, int32_t P, int32_t F,
-                        int32_t mode, float* out, int32_t ld_out, void* stream);
+                        int32_t mode, float* out, int32_t ld_out, int32_t round_out, void* stream);
 int ls3d_vfe_token_attn(const float* qkv, int32_t ld_qkv, int32_t m, int32_t P, int32_t n_head, int32_t d_head,
-                        float* out, int32_t ld_out, void* stream);
+                        float* out, int32_t ld_out, int32_t round_out, void* stream);
 int ls3d_vfe_token_max(const float* x, int32_t ld_x, int32_t m, int32_t P, int32_t E, float* out, int32_t ld_out,
-                       void* stream);
+                       int32_t round_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Rulebooks (spconv "indice pairs") via an occupancy bitmap {bits, rank prefix} per 32 cells.
@@ -144,7 +149,7 @@ int ls3d_three_nn_grid(const float* points, int32_t ld_p, int32_t n, const void*
                        const int32_t* point_off, const int32_t* voxel_off, const int32_t* voxel_coords, int32_t* todo,
                        int32_t* todo_count, float* dist2, int32_t* idx, void* stream);
 int ls3d_three_interpolate(const float* feat, int32_t ld_f, int32_t C, const float* dist2, const int32_t* idx, int32_t n,
-                           float* out, int32_t ld_out, void* stream);
+                           float* out, int32_t ld_out, int32_t round_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera feature sampling.
@@ -154,7 +159,7 @@ int ls3d_three_interpolate(const float* feat, int32_t ld_f, int32_t C, const flo
  * ------------------------------------------------------------------------------------------------ */
 int ls3d_sample_image_features(const float* feat_nhwc, int32_t n_frames, int32_t ncam, int32_t H, int32_t W, int32_t C,
                                const float* points_cuv, int32_t n, const int32_t* point_off, float* out, int32_t ld_out,
-                               void* stream);
+                               int32_t round_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SF-Phase: class embedding aggregation and class-token memory path.

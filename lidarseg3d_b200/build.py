@@ -33,8 +33,26 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed for {s}:\n{log}")
         if verbose:
             print(log)
-    subprocess.check_call([NVCC, "-shared", "-o", out] + objs + ["-lcudart"])
+    tmp = out + ".tmp"
+    subprocess.check_call([NVCC, "-shared", "-o", tmp] + objs + ["-lcudart"])
+    missing = _missing_symbols(tmp)
+    if missing:
+        os.remove(tmp)
+        if not force:
+            return build(force=True, verbose=verbose)
+        raise RuntimeError(f"_ls3d.so does not export {missing}")
+    os.replace(tmp, out)            # atomic: a concurrent snapshot never sees a half-written library
     return out
+
+
+def _missing_symbols(so_path):
+    """Every `int ls3d_*(` prototype of include/ls3d.h must be exported."""
+    import re
+    hdr = open(os.path.join(HERE, "..", "include", "ls3d.h")).read()
+    want = set(re.findall(r"^int (ls3d_\w+)\(", hdr, flags=re.M))
+    nm = subprocess.run(["nm", "-D", so_path], stdout=subprocess.PIPE, text=True).stdout
+    have = {ln.split()[-1] for ln in nm.splitlines() if " T " in ln}
+    return sorted(want - have)
 
 
 if __name__ == "__main__":

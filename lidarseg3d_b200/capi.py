@@ -38,7 +38,7 @@ class GemmArgs(ctypes.Structure):
         ("n_frames", c_int), ("n_tok", c_int), ("n_head", c_int),
         ("attn_scale", c_float),
         ("row_mask", c_void_p), ("ld_mask", c_int),
-        ("out", c_void_p), ("ld_out", c_int),
+        ("out", c_void_p), ("ld_out", c_int), ("round_out", c_int), ("precise", c_int),
     ]
 
 
@@ -73,9 +73,9 @@ PL = ctypes.POINTER(ctypes.c_int64)
 _SIGNATURES = {
     "ls3d_voxelize_workspace_bytes": ([L, I, I, PL], ctypes.c_int),
     "ls3d_voxelize": ([P, I, I, P, I, P, P, I, I, P, L, P, P, P, P, P, P, P], ctypes.c_int),
-    "ls3d_vfe_descriptor": ([P, P, I, I, I, I, P, I, P], ctypes.c_int),
-    "ls3d_vfe_token_attn": ([P, I, I, I, I, I, P, I, P], ctypes.c_int),
-    "ls3d_vfe_token_max": ([P, I, I, I, I, P, I, P], ctypes.c_int),
+    "ls3d_vfe_descriptor": ([P, P, I, I, I, I, P, I, I, P], ctypes.c_int),
+    "ls3d_vfe_token_attn": ([P, I, I, I, I, I, P, I, I, P], ctypes.c_int),
+    "ls3d_vfe_token_max": ([P, I, I, I, I, P, I, I, P], ctypes.c_int),
     "ls3d_grid_bytes": ([I, I, I, I, PL, PL], ctypes.c_int),
     "ls3d_grid_build": ([P, I, I, I, I, I, P, P, P, P, P], ctypes.c_int),
     "ls3d_grid_build_strided": ([P, I, I, P, P, P, I, I, I, P, P, P, P], ctypes.c_int),
@@ -83,8 +83,8 @@ _SIGNATURES = {
     "ls3d_rulebook_gather": ([P, P, I, I, I, I, P, I, P, P, P, P, P], ctypes.c_int),
     "ls3d_rulebook_scatter": ([P, I, I, I, I, P, I, P, P, P, P, P], ctypes.c_int),
     "ls3d_three_nn_grid": ([P, I, I, P, P, I, I, I, I, P, P, P, P, P, P, P, P, P, P], ctypes.c_int),
-    "ls3d_three_interpolate": ([P, I, I, P, P, I, P, I, P], ctypes.c_int),
-    "ls3d_sample_image_features": ([P, I, I, I, I, I, P, I, P, P, I, P], ctypes.c_int),
+    "ls3d_three_interpolate": ([P, I, I, P, P, I, P, I, I, P], ctypes.c_int),
+    "ls3d_sample_image_features": ([P, I, I, I, I, I, P, I, P, P, I, I, P], ctypes.c_int),
     "ls3d_class_embed_workspace_bytes": ([I, I, I, I, PL], ctypes.c_int),
     "ls3d_class_embed": ([P, I, I, P, I, I, P, I, I, P, P, P], ctypes.c_int),
     "ls3d_class_tokens": ([P, I, P, I, I, I, P, I, I, I, P, P, P, P], ctypes.c_int),

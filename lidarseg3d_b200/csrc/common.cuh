@@ -46,6 +46,17 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- cp.async (LDGSTS)
+// 16-byte global -> shared copy; src_bytes < 16 zero-fills the remainder (0 = pure zero fill)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -185,7 +185,7 @@ __global__ void three_nn_brute_kernel(const float* __restrict__ pts, int ld_p, N
 // out[n, :C] = sum_k w_k * feat[idx[n,k], :C],  w_k = (1/(sqrt(d2_k)+1e-8)) / sum_k(...)
 // (point_utils.py:29-32 + interpolate_gpu.cu:84-104), features row-major [M, ld_f]
 __global__ void three_interpolate_kernel(const float* __restrict__ feat, int ld_f, int C, const float* __restrict__ d2,
-                                         const int* __restrict__ idx, int n, float* __restrict__ out, int ld_out) {
+                                         const int* __restrict__ idx, int n, float* __restrict__ out, int ld_out, int rnd) {
   const int c4 = C / 4;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * c4) return;
@@ -210,6 +210,7 @@ __global__ void three_interpolate_kernel(const float* __restrict__ feat, int ld_
       acc.z = __fadd_rn(acc.z, __fmul_rn(wk, v.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(wk, v.w));
     }
   }
+  if (rnd) { acc.x = to_tf32(acc.x); acc.y = to_tf32(acc.y); acc.z = to_tf32(acc.z); acc.w = to_tf32(acc.w); }
   *reinterpret_cast<float4*>(out + (size_t)i * ld_out + c) = acc;
 }
 
@@ -237,12 +238,12 @@ extern "C" int ls3d_three_nn_grid(const float* points, int32_t ld_p, int32_t n, 
 }
 
 extern "C" int ls3d_three_interpolate(const float* feat, int32_t ld_f, int32_t C, const float* dist2, const int32_t* idx,
-                                      int32_t n, float* out, int32_t ld_out, void* stream) {
+                                      int32_t n, float* out, int32_t ld_out, int32_t round_out, void* stream) {
   using namespace ls3d;
   if (n <= 0) return LS3D_OK;
   if (!feat || !dist2 || !idx || !out || (C & 3) || (ld_f & 3) || (ld_out & 3)) return LS3D_ERR_ARG;
   three_interpolate_kernel<<<ls3d_div_up((long long)n * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      feat, ld_f, C, dist2, idx, n, out, ld_out);
+      feat, ld_f, C, dist2, idx, n, out, ld_out, round_out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }

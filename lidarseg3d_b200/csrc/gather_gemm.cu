@@ -41,13 +41,20 @@ __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
 }
 
-template <int STAGES>
+// SPLIT = true: error-compensated "3xTF32".  The tensor core truncates fp32 operands to tf32 (verified on B200), so with
+//   x = x_hi + x_lo (x_hi = trunc_tf32(x), x_lo = x - x_hi exactly) and W = W_hi + W_lo (split on the host),
+//   x.W ~= x_hi.W_hi + x_hi.W_lo + x_lo.W_hi   (dropped term x_lo.W_lo ~ 2^-22): fp32-level accuracy from three MMAs.
+// x_hi comes for free (the raw fp32 tile, truncated by the MMA); the producers derive the x_lo tile from the landed raw tile.
+template <int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][nbr koff*128 ints][active flags][barriers][tmem slot]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = a_stage_bytes();
-  const uint32_t b_bytes = b_stage_bytes(p.n_pad);
+  constexpr uint32_t NSPLIT = SPLIT ? 2u : 1u;
+  const uint32_t a_half = a_stage_bytes();            // one [128 x 32 float] tile
+  const uint32_t b_half = b_stage_bytes(p.n_pad);     // one [n_pad x 32 float] tile
+  const uint32_t a_bytes = NSPLIT * a_half;           // per stage: [A raw | A lo]
+  const uint32_t b_bytes = NSPLIT * b_half;           // per stage: [W hi | W lo]
   uint8_t* a_s = smem;
   uint8_t* b_s = smem + STAGES * a_bytes;
   int* nbr_s = (int*)(b_s + STAGES * b_bytes);
@@ -106,64 +113,74 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
 
   if (tid < N_PROD) {
     // =========================== producer ===========================
+    // cp.async (LDGSTS, zero-fill for missing rows) keeps up to STAGES-1 steps of gathers in flight per
+    // thread; a step is published (fence.proxy.async + mbarrier arrive) once its own copies have landed.
+    constexpr int DEPTH = STAGES - 1;
     int step = 0;
+    const int ch = tid & 7;
+    // make step j's tiles visible to the tensor core: (SPLIT) derive the x_lo tile from this thread's own landed
+    // chunks of the raw tile, then cross-proxy fence + mbarrier arrive
+    auto publish = [&](int j) {
+      const int sj = j % STAGES;
+      if (SPLIT) {
+        uint8_t* a_raw = a_s + sj * a_bytes;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const uint32_t off = sw128(it * 16 + (tid >> 3), ch);
+          float4 v = *reinterpret_cast<const float4*>(a_raw + off);
+          v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          *reinterpret_cast<float4*>(a_raw + a_half + off) = v;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(full_bar0 + 8 * sj);
+    };
     for (int k = 0; k < p.koff; ++k) {
       uint32_t any = act_s[k * 4] | act_s[k * 4 + 1] | act_s[k * 4 + 2] | act_s[k * 4 + 3];
       if (!any) continue;
+      const float* wk = p.w + (size_t)k * NSPLIT * p.n_pad * p.cin_pad;
       for (int c = 0; c < nchunk; ++c, ++step) {
         const int s = step % STAGES;
         const uint32_t ph = (uint32_t)(step / STAGES) & 1u;
         mbar_wait(empty_bar0 + 8 * s, ph ^ 1u);
-        uint8_t* a_dst = a_s + s * a_bytes;
-        uint8_t* b_dst = b_s + s * b_bytes;
-        // ---- A: 128 rows x 8 chunks of 16 B; 8 lanes cover one row
-        float4 av[8];
-        const int ch = tid & 7;
+        const uint32_t a_dst = smem_u32(a_s + s * a_bytes);
+        const uint32_t b_dst = smem_u32(b_s + s * b_bytes);
+        // ---- A: 128 rows x 8 chunks of 16 B; 8 lanes cover one row (4 full 128 B lines per warp request)
         const int col = c * KCH + ch * 4;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = it * 16 + (tid >> 3);
           const int j = nbr_s[k * TILE_M + r];
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j >= 0 && col < cin) {
-            const float* src = (col < p.c0) ? (p.in0 + (size_t)j * p.ld0 + col)
-                                            : (p.in1 + (size_t)j * p.ld1 + (col - p.c0));
-            v = ldg_f4(src);
-          }
-          av[it] = v;
+          const bool ok = (j >= 0) && (col < cin);
+          const float* src = p.in0;
+          if (ok) src = (col < p.c0) ? (p.in0 + (size_t)j * p.ld0 + col) : (p.in1 + (size_t)j * p.ld1 + (col - p.c0));
+          cp_async16(a_dst + sw128(r, ch), src, ok ? 16u : 0u);
         }
         // ---- B: n_pad rows x 8 chunks
-        const float* wk = p.w + (size_t)k * p.n_pad * p.cin_pad;
         const int nb_it = p.n_pad / 16;
-        float4 bv[16];
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          if (it < nb_it) {
-            const int idx = it * N_PROD + tid;
-            const int n = idx >> 3;
-            const int bcol = c * KCH + (idx & 7) * 4;
-            bv[it] = (bcol < p.cin_pad) ? ldg_f4(wk + (size_t)n * p.cin_pad + bcol)
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+        for (int it = 0; it < nb_it; ++it) {
+          const int idx = it * N_PROD + tid;
+          const int n = idx >> 3;
+          const int bcol = c * KCH + (idx & 7) * 4;
+          const bool ok = bcol < p.cin_pad;
+          cp_async16(b_dst + sw128(n, idx & 7), ok ? (wk + (size_t)n * p.cin_pad + bcol) : p.w, ok ? 16u : 0u);
+          if (SPLIT)
+            cp_async16(b_dst + b_half + sw128(n, idx & 7),
+                       ok ? (wk + (size_t)(p.n_pad + n) * p.cin_pad + bcol) : p.w, ok ? 16u : 0u);
         }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 16 + (tid >> 3);
-          float4 v = av[it];
-          v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-          *reinterpret_cast<float4*>(a_dst + sw128(r, ch)) = v;
+        cp_async_commit();
+        if (step >= DEPTH) {
+          cp_async_wait<DEPTH>();
+          publish(step - DEPTH);
         }
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          if (it < nb_it) {
-            const int idx = it * N_PROD + tid;
-            *reinterpret_cast<float4*>(b_dst + sw128(idx >> 3, idx & 7)) = bv[it];
-          }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(full_bar0 + 8 * s);
       }
     }
+    // drain: publish the last min(DEPTH, nsteps) steps
+    cp_async_wait<0>();
+    for (int j = (nsteps > DEPTH ? nsteps - DEPTH : 0); j < nsteps; ++j) publish(j);
   } else {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = make_idesc_tf32((uint32_t)p.n_pad);
@@ -179,11 +196,17 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
         if (lane == 0) {
           const uint64_t adesc = make_desc_k_sw128(smem_u32(a_s + s * a_bytes));
           const uint64_t bdesc = make_desc_k_sw128(smem_u32(b_s + s * b_bytes));
+          const uint64_t alo = make_desc_k_sw128(smem_u32(a_s + s * a_bytes + a_half));
+          const uint64_t blo = make_desc_k_sw128(smem_u32(b_s + s * b_bytes + b_half));
           const int kc = min(KCH, p.cin_pad - c * KCH);  // multiple of 8
           for (int kk = 0; kk < kc / 8; ++kk) {
             // advance 8 tf32 = 32 B inside the 128 B swizzle row: +2 in the >>4 address field
-            umma_tf32(tmem_acc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                      (step > 0 || kk > 0) ? 1u : 0u);
+            const uint64_t o = (uint64_t)(kk * 2);
+            umma_tf32(tmem_acc, adesc + o, bdesc + o, idesc, (step > 0 || kk > 0) ? 1u : 0u);
+            if (SPLIT) {
+              umma_tf32(tmem_acc, adesc + o, blo + o, idesc, 1u);
+              umma_tf32(tmem_acc, alo + o, bdesc + o, idesc, 1u);
+            }
           }
           umma_commit(empty_bar0 + 8 * s);
           if (step == nsteps - 1) umma_commit(accum_bar);
@@ -204,6 +227,7 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
     const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
     const bool have_acc = nsteps > 0;
 
+    auto rnd = [&](float x) -> float { return p.round_out ? to_tf32(x) : x; };
     if (p.epi == LS3D_EPI_ATTN) {
       // q = acc + bias ; per head softmax(q.K^T * scale) V over the frame's class tokens
       int f = 0;
@@ -268,7 +292,7 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
 #pragma unroll
           for (int d4 = 0; d4 < DHEAD / 4; ++d4)
             *reinterpret_cast<float4*>(dst + d4 * 4) =
-                make_float4(o[d4 * 4] * inv, o[d4 * 4 + 1] * inv, o[d4 * 4 + 2] * inv, o[d4 * 4 + 3] * inv);
+                make_float4(rnd(o[d4 * 4] * inv), rnd(o[d4 * 4 + 1] * inv), rnd(o[d4 * 4 + 2] * inv), rnd(o[d4 * 4 + 3] * inv));
         }
       }
     } else {
@@ -343,7 +367,7 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
             if (p.n_ln > 0) x = (x - mean[0]) * rstd[0] * __ldg(p.ln_g0 + col) + __ldg(p.ln_b0 + col);
             if (p.n_ln > 1) x = (x - mean[1]) * rstd[1] * __ldg(p.ln_g1 + col) + __ldg(p.ln_b1 + col);
           }
-          y[j] = x;
+          y[j] = rnd(x);
         }
         if (masked) {
 #pragma unroll
@@ -372,9 +396,9 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
   if (warp == 4) tmem_dealloc(tmem_acc, tmem_cols);
 }
 
-static size_t smem_bytes_for(int stages, int n_pad, int koff) {
+static size_t smem_bytes_for(int stages, int n_pad, int koff, int nsplit) {
   size_t b = 1024;  // alignment slack
-  b += (size_t)stages * (a_stage_bytes() + b_stage_bytes(n_pad));
+  b += (size_t)stages * nsplit * (a_stage_bytes() + b_stage_bytes(n_pad));
   b += (size_t)koff * TILE_M * 4 + (size_t)koff * 16;
   b += 8 + (2 * stages + 1) * 8 + 16;
   return b;
@@ -399,21 +423,34 @@ extern "C" int ls3d_gather_gemm(const ls3d_gemm_args* a, void* stream) {
   if (a->n_ln < 0 || a->n_ln > 2) return LS3D_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ls3d_div_up(a->m_out, TILE_M);
-  // deepest pipeline that still lets two CTAs share one SM (<= ~110 KB each)
+  // deepest pipeline that still lets two CTAs share one SM (<= ~110 KB each); tiles too big for that get one CTA per
+  // SM and as many stages as fit
+  const int nsplit = a->precise ? 2 : 1;
   int stages = 4;
-  while (stages > 2 && smem_bytes_for(stages, a->n_pad, a->koff) > 110 * 1024) --stages;
-  const size_t smem = smem_bytes_for(stages, a->n_pad, a->koff);
-  cudaError_t e;
-#define LS3D_GG_LAUNCH(S)                                                                          \
-  {                                                                                                \
-    e = cudaFuncSetAttribute(gather_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                             (int)smem);                                                           \
-    if (e != cudaSuccess) return (int)e;                                                           \
-    gather_gemm_kernel<S><<<grid, N_THREADS, smem, st>>>(*a);                                      \
+  while (stages > 2 && smem_bytes_for(stages, a->n_pad, a->koff, nsplit) > 110 * 1024) --stages;
+  if (smem_bytes_for(stages, a->n_pad, a->koff, nsplit) > 110 * 1024) {
+    stages = 4;
+    while (stages > 2 && smem_bytes_for(stages, a->n_pad, a->koff, nsplit) > 220 * 1024) --stages;
   }
-  if (stages == 4) LS3D_GG_LAUNCH(4)
-  else if (stages == 3) LS3D_GG_LAUNCH(3)
-  else LS3D_GG_LAUNCH(2)
+  const size_t smem = smem_bytes_for(stages, a->n_pad, a->koff, nsplit);
+  if (smem > 227 * 1024) return LS3D_ERR_ARG;
+  cudaError_t e;
+#define LS3D_GG_LAUNCH(S, P)                                                                         \
+  {                                                                                                  \
+    e = cudaFuncSetAttribute(gather_gemm_kernel<S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             (int)smem);                                                             \
+    if (e != cudaSuccess) return (int)e;                                                             \
+    gather_gemm_kernel<S, P><<<grid, N_THREADS, smem, st>>>(*a);                                     \
+  }
+  if (a->precise) {
+    if (stages == 4) LS3D_GG_LAUNCH(4, true)
+    else if (stages == 3) LS3D_GG_LAUNCH(3, true)
+    else LS3D_GG_LAUNCH(2, true)
+  } else {
+    if (stages == 4) LS3D_GG_LAUNCH(4, false)
+    else if (stages == 3) LS3D_GG_LAUNCH(3, false)
+    else LS3D_GG_LAUNCH(2, false)
+  }
 #undef LS3D_GG_LAUNCH
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;

@@ -22,7 +22,7 @@ __device__ __forceinline__ int frame_of_row(const int* off, int nf, int i) {
 
 __global__ void sample_image_kernel(const float* __restrict__ feat, int ncam, int H, int W, int C,
                                     const float* __restrict__ cuv, int n, const int* __restrict__ point_off, int n_frames,
-                                    float* __restrict__ out, int ld_out) {
+                                    float* __restrict__ out, int ld_out, int rnd) {
   const int lane16 = threadIdx.x & 15;
   const long long pt = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   if (pt >= n) return;
@@ -65,6 +65,7 @@ __global__ void sample_image_kernel(const float* __restrict__ feat, int ncam, in
         }
       }
     }
+    if (rnd) { acc.x = to_tf32(acc.x); acc.y = to_tf32(acc.y); acc.z = to_tf32(acc.z); acc.w = to_tf32(acc.w); }
     *reinterpret_cast<float4*>(dst + c * 4) = acc;
   }
 }
@@ -73,13 +74,13 @@ __global__ void sample_image_kernel(const float* __restrict__ feat, int ncam, in
 
 extern "C" int ls3d_sample_image_features(const float* feat_nhwc, int32_t n_frames, int32_t ncam, int32_t H, int32_t W,
                                           int32_t C, const float* points_cuv, int32_t n, const int32_t* point_off,
-                                          float* out, int32_t ld_out, void* stream) {
+                                          float* out, int32_t ld_out, int32_t round_out, void* stream) {
   using namespace ls3d;
   if (n <= 0) return LS3D_OK;
   if (!feat_nhwc || !points_cuv || !point_off || !out || (C & 3) || (ld_out & 3) || ncam < 1) return LS3D_ERR_ARG;
   const long long threads = (long long)n * 16;
   sample_image_kernel<<<ls3d_div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(feat_nhwc, ncam, H, W, C, points_cuv, n,
-                                                                                   point_off, n_frames, out, ld_out);
+                                                                                   point_off, n_frames, out, ld_out, round_out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }

@@ -17,7 +17,7 @@ constexpr int VFE_MAX_F = 8;
 // mode 1: out[M, F+8]    = [mean xyz, max xyz, min xyz, mean rest, density, std]  (ImprovedMeanVFE)
 // mode 2: out[M*P, 2F+8] = per slot [point features | descriptor]  (TransVFE token input)
 __global__ void vfe_descriptor_kernel(const float* __restrict__ voxels, const int* __restrict__ num_points,
-                                      int m, int P, int F, int mode, float* __restrict__ out, int ld_out) {
+                                      int m, int P, int F, int mode, float* __restrict__ out, int ld_out, int rnd) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= m) return;
   float pt[VFE_MAX_P][VFE_MAX_F];
@@ -32,7 +32,7 @@ __global__ void vfe_descriptor_kernel(const float* __restrict__ voxels, const in
     mean[c] = __fdiv_rn(a, nv);
   }
   if (mode == 0) {
-    for (int c = 0; c < F; ++c) out[(size_t)v * ld_out + c] = mean[c];
+    for (int c = 0; c < F; ++c) out[(size_t)v * ld_out + c] = rnd ? to_tf32(mean[c]) : mean[c];
     for (int c = F; c < ld_out; ++c) out[(size_t)v * ld_out + c] = 0.f;
     return;
   }
@@ -75,13 +75,13 @@ __global__ void vfe_descriptor_kernel(const float* __restrict__ voxels, const in
   desc[k++] = stdv;
   if (mode == 1) {
     float* dst = out + (size_t)v * ld_out;
-    for (int c = 0; c < k; ++c) dst[c] = desc[c];
+    for (int c = 0; c < k; ++c) dst[c] = rnd ? to_tf32(desc[c]) : desc[c];
     for (int c = k; c < ld_out; ++c) dst[c] = 0.f;
   } else {
     for (int s = 0; s < P; ++s) {
       float* dst = out + ((size_t)v * P + s) * ld_out;
-      for (int c = 0; c < F; ++c) dst[c] = pt[s][c];
-      for (int c = 0; c < k; ++c) dst[F + c] = desc[c];
+      for (int c = 0; c < F; ++c) dst[c] = rnd ? to_tf32(pt[s][c]) : pt[s][c];
+      for (int c = 0; c < k; ++c) dst[F + c] = rnd ? to_tf32(desc[c]) : desc[c];
       for (int c = F + k; c < ld_out; ++c) dst[c] = 0.f;
     }
   }
@@ -91,7 +91,7 @@ __global__ void vfe_descriptor_kernel(const float* __restrict__ voxels, const in
 // qkv rows: [q(E) | k(E) | v(E)], row index = voxel * P + slot.
 template <int DH>
 __global__ void vfe_token_attn_kernel(const float* __restrict__ qkv, int ld_qkv, int m, int P, int H,
-                                      float* __restrict__ out, int ld_out) {
+                                      float* __restrict__ out, int ld_out, int rnd) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)m * P * H;
   if (t >= total) return;
@@ -139,11 +139,13 @@ __global__ void vfe_token_attn_kernel(const float* __restrict__ qkv, int ld_qkv,
   float* dst = out + row * ld_out + h * DH;
 #pragma unroll
   for (int d = 0; d < DH; d += 4)
-    *reinterpret_cast<float4*>(dst + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+    *reinterpret_cast<float4*>(dst + d) =
+        rnd ? make_float4(to_tf32(o[d] * inv), to_tf32(o[d + 1] * inv), to_tf32(o[d + 2] * inv), to_tf32(o[d + 3] * inv))
+            : make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
 }
 
 __global__ void vfe_token_max_kernel(const float* __restrict__ x, int ld_x, int m, int P, int E,
-                                     float* __restrict__ out, int ld_out) {
+                                     float* __restrict__ out, int ld_out, int rnd) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int e4 = E / 4;
   if (t >= (long long)m * e4) return;
@@ -154,13 +156,14 @@ __global__ void vfe_token_max_kernel(const float* __restrict__ x, int ld_x, int 
     float4 q = ldg_f4(x + (v * P + s) * ld_x + c);
     r.x = fmaxf(r.x, q.x); r.y = fmaxf(r.y, q.y); r.z = fmaxf(r.z, q.z); r.w = fmaxf(r.w, q.w);
   }
+  if (rnd) { r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w); }
   *reinterpret_cast<float4*>(out + v * ld_out + c) = r;
 }
 
 }  // namespace ls3d
 
 extern "C" int ls3d_vfe_descriptor(const float* voxels, const int32_t* num_points, int32_t m, int32_t P,
-                                   int32_t F, int32_t mode, float* out, int32_t ld_out, void* stream) {
+                                   int32_t F, int32_t mode, float* out, int32_t ld_out, int32_t round_out, void* stream) {
   using namespace ls3d;
   if (m <= 0) return LS3D_OK;
   if (!voxels || !num_points || !out || P < 1 || P > VFE_MAX_P || F < 3 || F > VFE_MAX_F || mode < 0 ||
@@ -169,22 +172,22 @@ extern "C" int ls3d_vfe_descriptor(const float* voxels, const int32_t* num_point
   const int need = mode == 0 ? F : (mode == 1 ? F + 8 : 2 * F + 8);
   if (ld_out < need) return LS3D_ERR_ARG;
   vfe_descriptor_kernel<<<ls3d_div_up(m, 128), 128, 0, (cudaStream_t)stream>>>(voxels, num_points, m, P, F, mode,
-                                                                               out, ld_out);
+                                                                               out, ld_out, round_out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
 
 extern "C" int ls3d_vfe_token_attn(const float* qkv, int32_t ld_qkv, int32_t m, int32_t P, int32_t n_head,
-                                   int32_t d_head, float* out, int32_t ld_out, void* stream) {
+                                   int32_t d_head, float* out, int32_t ld_out, int32_t round_out, void* stream) {
   using namespace ls3d;
   if (m <= 0) return LS3D_OK;
   if (!qkv || !out || P < 1 || P > VFE_MAX_P || (ld_qkv & 3) || (ld_out & 3)) return LS3D_ERR_ARG;
   const long long total = (long long)m * P * n_head;
   const int grid = ls3d_div_up(total, 256);
   if (d_head == 16)
-    vfe_token_attn_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, ld_qkv, m, P, n_head, out, ld_out);
+    vfe_token_attn_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, ld_qkv, m, P, n_head, out, ld_out, round_out);
   else if (d_head == 32)
-    vfe_token_attn_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, ld_qkv, m, P, n_head, out, ld_out);
+    vfe_token_attn_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, ld_qkv, m, P, n_head, out, ld_out, round_out);
   else
     return LS3D_ERR_ARG;
   LS3D_LAUNCH_CHECK();
@@ -192,12 +195,12 @@ extern "C" int ls3d_vfe_token_attn(const float* qkv, int32_t ld_qkv, int32_t m, 
 }
 
 extern "C" int ls3d_vfe_token_max(const float* x, int32_t ld_x, int32_t m, int32_t P, int32_t E, float* out,
-                                  int32_t ld_out, void* stream) {
+                                  int32_t ld_out, int32_t round_out, void* stream) {
   using namespace ls3d;
   if (m <= 0) return LS3D_OK;
   if (!x || !out || (E & 3) || (ld_x & 3) || (ld_out & 3)) return LS3D_ERR_ARG;
   vfe_token_max_kernel<<<ls3d_div_up((long long)m * (E / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, ld_x, m, P, E,
-                                                                                                  out, ld_out);
+                                                                                                  out, ld_out, round_out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }

@@ -161,7 +161,10 @@ class UNetSCN3D(Prepared):
         shape1 = tuple(int(v) for v in (np.array(batch_dict["input_shape"][::-1]) + [1, 0, 0]))   # scn_unet.py:203
         coords1 = voxel_coords.int().contiguous()
         lv1 = SparseLevel(coords1, B, shape1, ops.grid_from_coords(coords1, B, shape1, need_perm=True))
-        x = self._conv(pad_cols(voxel_features.float()), P["conv_input"], lv1.subm_table())
+        vf = pad_cols(voxel_features.float())
+        if not gemm.PRECISE:
+            vf = gemm.round_tf32(vf)          # single-pass TF32 mode: operands must be tf32-representable
+        x = self._conv(vf, P["conv_input"], lv1.subm_table())
         for pk in P["conv1"]:
             x = self._block(x, pk, lv1.subm_table())
         feats = {1: x}

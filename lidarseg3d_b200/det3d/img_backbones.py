@@ -24,6 +24,41 @@ def _bn(c, norm_cfg):
     return m
 
 
+FUSED_CUDNN = True      # eval mode: BatchNorm folded into the conv, cuDNN fused conv+bias(+residual)+ReLU
+
+
+def _versions(*ts):
+    return tuple(t._version for t in ts if t is not None)
+
+
+def cbr(conv, bn, x, relu, z=None):
+    """conv -> BatchNorm -> (+z) -> (ReLU).  Training / CPU: plain modules.  Eval on CUDA: BN folded into the conv weights
+    (cached, refreshed when a parameter changes) and run as one cuDNN call."""
+    if bn.training or not x.is_cuda:
+        y = bn(conv(x))
+        if z is not None:
+            y = y + z
+        return torch.relu(y) if relu else y
+    key = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var) + (x.dtype,)
+    cache = getattr(conv, "_ls3d_fold", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            w = (conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+            b = (bn.bias - bn.running_mean * scale).contiguous()
+        cache = (key, w, b)
+        conv._ls3d_fold = cache
+    _, w, b = cache
+    if FUSED_CUDNN and relu and conv.groups == 1:
+        if z is None:
+            return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, 1)
+        return torch.cudnn_convolution_add_relu(x, w, z, 1.0, b, conv.stride, conv.padding, conv.dilation, 1)
+    y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if z is not None:
+        y = y + z
+    return torch.relu_(y) if relu else y
+
+
 class BasicBlock(nn.Module):
     expansion = 1
 
@@ -37,10 +72,9 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        idt = x if self.downsample is None else self.downsample(x)
-        return self.relu(out + idt)
+        idt = x if self.downsample is None else cbr(self.downsample[0], self.downsample[1], x, False)
+        out = cbr(self.conv1, self.bn1, x, True)
+        return cbr(self.conv2, self.bn2, out, True, z=idt)
 
 
 class Bottleneck(nn.Module):
@@ -58,11 +92,10 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
 
     def forward(self, x):
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        idt = x if self.downsample is None else self.downsample(x)
-        return self.relu(out + idt)
+        idt = x if self.downsample is None else cbr(self.downsample[0], self.downsample[1], x, False)
+        out = cbr(self.conv1, self.bn1, x, True)
+        out = cbr(self.conv2, self.bn2, out, True)
+        return cbr(self.conv3, self.bn3, out, True, z=idt)
 
 
 class Upsample(nn.Module):
@@ -136,10 +169,14 @@ class HRModule(nn.Module):
                 if i == j:
                     y = y + x[j]
                 elif j > i:
-                    y = y + F.interpolate(self.fuse_layers[i][j](x[j]), size=x[i].shape[2:], mode="bilinear",
-                                          align_corners=False)
+                    fl = self.fuse_layers[i][j]                     # conv1x1 + BN + Upsample, then resize (hrnet.py:216-220)
+                    t = fl[2](cbr(fl[0], fl[1], x[j], False))
+                    y = y + F.interpolate(t, size=x[i].shape[2:], mode="bilinear", align_corners=False)
                 else:
-                    y = y + self.fuse_layers[i][j](x[j])
+                    t = x[j]
+                    for seq in self.fuse_layers[i][j]:              # conv3x3 s2 + BN (+ReLU except the last)
+                        t = cbr(seq[0], seq[1], t, len(seq) == 3)
+                    y = y + t
             outs.append(self.relu(y))
         return outs
 
@@ -232,8 +269,8 @@ class HRNet(nn.Module):
                     p.requires_grad = False
 
     def forward(self, x):
-        x = self.relu(self.bn1(self.conv1(x)))
-        x = self.relu(self.bn2(self.conv2(x)))
+        x = cbr(self.conv1, self.bn1, x, True)
+        x = cbr(self.conv2, self.bn2, x, True)
         x = self.layer1(x)
         ys = [x]
         for st in (2, 3, 4):
@@ -241,7 +278,13 @@ class HRNet(nn.Module):
             xs = []
             for i in range(self.extra[f"stage{st}"]["num_branches"]):
                 if tr[i] is not None:
-                    xs.append(tr[i](ys[0] if st == 2 else ys[-1]))
+                    t = ys[0] if st == 2 else ys[-1]
+                    if isinstance(tr[i][0], nn.Conv2d):              # same resolution: conv3x3 + BN + ReLU
+                        t = cbr(tr[i][0], tr[i][1], t, True)
+                    else:                                            # new branch: chain of conv3x3 s2 + BN + ReLU
+                        for seq in tr[i]:
+                            t = cbr(seq[0], seq[1], t, True)
+                    xs.append(t)
                 else:
                     xs.append(ys[i])
             ys = getattr(self, f"stage{st}")(xs)

@@ -6,7 +6,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from .img_backbones import _bn
+from .img_backbones import _bn, cbr
 from .registry import IMG_HEADS
 
 
@@ -24,9 +24,9 @@ class ConvModule(nn.Module):
             self.activate = nn.ReLU(inplace=True)
 
     def forward(self, x):
-        x = self.conv(x)
         if self.with_norm:
-            x = self.bn(x)
+            return cbr(self.conv, self.bn, x, self.with_act)
+        x = self.conv(x)
         return self.activate(x) if self.with_act else x
 
 

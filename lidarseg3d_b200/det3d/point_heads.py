@@ -56,8 +56,9 @@ def _pack_convcls(seq):
 
 
 def _run_mlp(x, packed):
-    for pw, s, b, relu in packed:
-        x = gemm.run(x, pw, scale=s, shift=b, relu=relu)
+    """Hidden layers store tf32-rounded activations (they feed the next GEMM); the last layer's logits stay exact fp32."""
+    for i, (pw, s, b, relu) in enumerate(packed):
+        x = gemm.run(x, pw, scale=s, shift=b, relu=relu, round_out=i + 1 < len(packed))
     return x
 
 
@@ -68,7 +69,7 @@ def devoxelize(batch_dict, points, voxel_features, voxel_size, pc_range, batch_s
     point_off = _offsets(points[:, 0], batch_size)
     voxel_off = _offsets(vcoords[:, 0], batch_size)
     d2, idx = ops.three_nn_grid(points, lv1.grid, voxel_size, pc_range[:3], point_off, voxel_off, vcoords)
-    return ops.three_interpolate(voxel_features, d2, idx), point_off, voxel_off, (d2, idx)
+    return ops.three_interpolate(voxel_features, d2, idx, round_out=not gemm.PRECISE), point_off, voxel_off, (d2, idx)
 
 
 def _predict(out_logits, example, test_cfg):
@@ -273,7 +274,7 @@ class PointSegMSeg3DHead(Prepared):
 
     def get_points_image_feature(self, image_features_nhwc, points_cuv, point_off):
         """point_seg_mseg3d_head.py:200-236 (rows of invalid points are zeros)."""
-        return ops.sample_image_features(image_features_nhwc, points_cuv, point_off)
+        return ops.sample_image_features(image_features_nhwc, points_cuv, point_off, round_out=not gemm.PRECISE)
 
     def forward(self, batch_dict, return_loss=True, **kwargs):
         if return_loss:
@@ -320,7 +321,7 @@ class PointSegMSeg3DHead(Prepared):
             h = gemm.run(tgt, ly["l1"][0], shift=ly["l1"][1], relu=True)
             lns = (ly["n3"], P["norm_tgt"]) if i == nl - 1 else (ly["n3"],)
             tgt = gemm.run(h, ly["l2"][0], shift=ly["l2"][1], res=tgt, res_mode=1, ln=lns)
-        out = gemm.run(tgt, P["out"][0], shift=P["out"][1])
+        out = gemm.run(tgt, P["out"][0], shift=P["out"][1], round_out=False)
         batch_dict["out_logits"] = out
         batch_dict["_ls3d_debug"] = dict(point_features_lidar_0=f0, point_features_camera_0=fc0, geo_fused=geo,
                                          lidar_emb=lidar_emb, sem_fused=tgt, three_nn=nn_res)

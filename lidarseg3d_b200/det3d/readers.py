@@ -99,18 +99,18 @@ class TransformerVoxelFeatureExtractor(Prepared):
         M, Pn, F = features.shape
         E, H = self.num_embed, self.num_head
         Pk = self.prep()
-        tok = ops.vfe_descriptor(features, num_voxels, mode=2)                  # [M*P, 2F+8]
+        tok = ops.vfe_descriptor(features, num_voxels, mode=2, round_out=not gemm.PRECISE)                  # [M*P, 2F+8]
         L = Pk["layers"]
         # feature_conv (+bias) then LN1 of layer 0
         x = gemm.run(tok, Pk["conv"][0], shift=Pk["conv"][1], ln=(L[0]["n1"],))
         for i, ly in enumerate(L):
             qkv = gemm.run(x, ly["in_proj"][0], shift=ly["in_proj"][1])        # [M*P, 3E]
-            ctx = ops.vfe_token_attn(qkv, M, Pn, H, E // H)
+            ctx = ops.vfe_token_attn(qkv, M, Pn, H, E // H, round_out=not gemm.PRECISE)
             x = gemm.run(ctx, ly["out_proj"][0], shift=ly["out_proj"][1], res=x, res_mode=1, ln=(ly["n2"],))
             h = gemm.run(x, ly["lin1"][0], shift=ly["lin1"][1], relu=True)
             nxt = (L[i + 1]["n1"],) if i + 1 < len(L) else ()
             x = gemm.run(h, ly["lin2"][0], shift=ly["lin2"][1], res=x, res_mode=1, ln=nxt)
-        v = ops.vfe_token_max(x, M, Pn)
+        v = ops.vfe_token_max(x, M, Pn, round_out=not gemm.PRECISE)
         if self.compress_layer is not None:
-            v = gemm.run(v, Pk["compress"][0], shift=Pk["compress"][1], relu=True)
+            v = gemm.run(v, Pk["compress"][0], shift=Pk["compress"][1], relu=True, round_out=False)
         return v

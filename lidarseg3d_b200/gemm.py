@@ -21,6 +21,16 @@ PROFILE = None
 COUNT = None
 
 
+# True: error-compensated 3xTF32 everywhere (fp32-level accuracy; default).  False: single-pass TF32 with tf32-rounded
+# activations (faster, ~1e-3 relative error after the full network).
+PRECISE = True
+
+
+def trunc_tf32(x: torch.Tensor) -> torch.Tensor:
+    """What the tensor core does to an fp32 operand under kind::tf32: drop the 13 low mantissa bits."""
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
 class PackedWeight:
     """W[koff][cin][cout] (spconv layout, reference scn_unet.py weight [kz,ky,kx,Cin,Cout]) packed as
     [koff][n_pad][cin_pad] K-major, tf32-rounded, zero padded."""
@@ -31,8 +41,16 @@ class PackedWeight:
         self.koff, self.cin, self.cout = koff, cin, cout
         self.cin_pad = pad_to(cin, 8)
         self.n_pad = pad_to(cout, 16)
-        buf = torch.zeros(koff, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
-        buf[:, :cout, :cin] = round_tf32(w_kio.float()).permute(0, 2, 1)
+        self.precise = PRECISE
+        wt = w_kio.float().permute(0, 2, 1)
+        if self.precise:
+            buf = torch.zeros(koff, 2, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
+            hi = trunc_tf32(wt)
+            buf[:, 0, :cout, :cin] = hi
+            buf[:, 1, :cout, :cin] = wt - hi
+        else:
+            buf = torch.zeros(koff, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
+            buf[:, :cout, :cin] = round_tf32(wt)
         self.data = buf.contiguous()
 
     @staticmethod
@@ -42,7 +60,7 @@ class PackedWeight:
 
 
 def run(x0, pw: PackedWeight, *, x1=None, nbr=None, m_out=None, scale=None, shift=None, relu=False,
-        res=None, res_mode=0, red=None, ln=(), ln_eps=1e-5, attn=None, row_mask=None, out=None):
+        res=None, res_mode=0, red=None, ln=(), ln_eps=1e-5, attn=None, row_mask=None, out=None, round_out=True):
     """Launch ls3d_gather_gemm.  ``x0``/``x1`` are [rows, C] fp32 row-major (row stride may exceed C).
 
     attn = dict(k=[F,H,L,24], v=[F,H,L,24], frame_off=int32[F], scale=float) selects the attention
@@ -92,6 +110,8 @@ def run(x0, pw: PackedWeight, *, x1=None, nbr=None, m_out=None, scale=None, shif
     if out is None:
         out = torch.empty(m, pw.cout, dtype=torch.float32, device=x0.device)
     a.out, a.ld_out = capi.ptr(out), out.stride(0)
+    a.round_out = int(round_out and not pw.precise)
+    a.precise = int(pw.precise)
     if COUNT is not None:
         COUNT.append(int((nbr >= 0).sum()) if nbr is not None else m)
     if PROFILE is not None:

@@ -52,29 +52,29 @@ def voxelize(points, frame_offsets, voxel_size, pc_range, max_points=5, max_voxe
 
 
 # ------------------------------------------------------------------------------------------ readers
-def vfe_descriptor(voxels, num_points, mode, ld_out=None):
+def vfe_descriptor(voxels, num_points, mode, ld_out=None, round_out=False):
     m, P, F = voxels.shape
     need = F if mode == 0 else (F + 8 if mode == 1 else 2 * F + 8)
     ld = ld_out or need
     rows = m * P if mode == 2 else m
     out = _f32(voxels.device, rows, ld)
     check(capi.lib().ls3d_vfe_descriptor(ptr(voxels.contiguous()), ptr(num_points.to(torch.int32).contiguous()), m, P, F,
-                                         mode, ptr(out), ld, stream_ptr()), "ls3d_vfe_descriptor")
+                                         mode, ptr(out), ld, int(round_out), stream_ptr()), "ls3d_vfe_descriptor")
     return out
 
 
-def vfe_token_attn(qkv, m, P, n_head, d_head):
+def vfe_token_attn(qkv, m, P, n_head, d_head, round_out=False):
     out = _f32(qkv.device, m * P, n_head * d_head)
     check(capi.lib().ls3d_vfe_token_attn(ptr(qkv), qkv.stride(0), m, P, n_head, d_head, ptr(out), out.stride(0),
-                                         stream_ptr()), "ls3d_vfe_token_attn")
+                                         int(round_out), stream_ptr()), "ls3d_vfe_token_attn")
     return out
 
 
-def vfe_token_max(x, m, P):
+def vfe_token_max(x, m, P, round_out=False):
     E = x.shape[1]
     out = _f32(x.device, m, E)
-    check(capi.lib().ls3d_vfe_token_max(ptr(x), x.stride(0), m, P, E, ptr(out), out.stride(0), stream_ptr()),
-          "ls3d_vfe_token_max")
+    check(capi.lib().ls3d_vfe_token_max(ptr(x), x.stride(0), m, P, E, ptr(out), out.stride(0), int(round_out),
+                                        stream_ptr()), "ls3d_vfe_token_max")
     return out
 
 
@@ -161,24 +161,24 @@ def three_nn_grid(points, grid, voxel_size, range_min, point_off, voxel_off, vox
     return d2, idx
 
 
-def three_interpolate(feat, d2, idx, C=None):
+def three_interpolate(feat, d2, idx, C=None, round_out=False):
     C = C or feat.shape[1]
     n = idx.shape[0]
     out = _f32(feat.device, n, C)
     check(capi.lib().ls3d_three_interpolate(ptr(feat), feat.stride(0), C, ptr(d2), ptr(idx), n, ptr(out),
-                                            out.stride(0), stream_ptr()), "ls3d_three_interpolate")
+                                            out.stride(0), int(round_out), stream_ptr()), "ls3d_three_interpolate")
     return out
 
 
 # ------------------------------------------------------------------------------------------ sampling / SF-Phase
-def sample_image_features(feat_nhwc, points_cuv, point_off):
+def sample_image_features(feat_nhwc, points_cuv, point_off, round_out=False):
     """feat_nhwc [B, ncam, H, W, C] contiguous fp32; points_cuv [N,4]; returns [N, C] (zeros on invalid rows)."""
     B, ncam, H, W, C = feat_nhwc.shape
     n = points_cuv.shape[0]
     out = _f32(feat_nhwc.device, n, C)
     check(capi.lib().ls3d_sample_image_features(ptr(feat_nhwc), B, ncam, H, W, C, ptr(points_cuv.contiguous()), n,
-                                                ptr(point_off), ptr(out), out.stride(0), stream_ptr()),
-          "ls3d_sample_image_features")
+                                                ptr(point_off), ptr(out), out.stride(0), int(round_out),
+                                                stream_ptr()), "ls3d_sample_image_features")
     return out
 
 

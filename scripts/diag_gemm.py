@@ -8,9 +8,14 @@ torch.backends.cuda.matmul.allow_tf32 = False
 dev = "cuda"
 res = []
 
+def prep(x):
+    """single-pass mode expects tf32-representable activations (the tensor core truncates)"""
+    return x if gemm.PRECISE else gemm.round_tf32(x)
+
 def ref_gemm(x, w_kio, nbr):
-    # fp64 reference on tf32-rounded operands
-    xr = gemm.round_tf32(x).double(); wr = gemm.round_tf32(w_kio).double()
+    # fp64 reference: exact operands in precise (3xTF32) mode, tf32-rounded operands otherwise
+    xr = x.double() if gemm.PRECISE else gemm.round_tf32(x).double()
+    wr = w_kio.double() if gemm.PRECISE else gemm.round_tf32(w_kio).double()
     koff = w_kio.shape[0]
     m = nbr.shape[1] if nbr is not None else x.shape[0]
     out = torch.zeros(m, w_kio.shape[2], dtype=torch.float64, device=x.device)
@@ -33,7 +38,7 @@ def case(name, fn):
 def dense(m, cin, cout, seed=0):
     def f():
         g = torch.Generator(device=dev).manual_seed(seed)
-        x = torch.randn(m, cin, device=dev, generator=g)
+        x = prep(torch.randn(m, cin, device=dev, generator=g))
         w = torch.randn(1, cin, cout, device=dev, generator=g) / cin ** 0.5
         pw = gemm.PackedWeight(w)
         y = gemm.run(x, pw)
@@ -42,10 +47,10 @@ def dense(m, cin, cout, seed=0):
     return f
 
 def ident():
-    x = torch.randn(128, 32, device=dev)
+    x = prep(torch.randn(128, 32, device=dev))
     w = torch.eye(32, device=dev).unsqueeze(0)
     y = gemm.run(x, gemm.PackedWeight(w))
-    d = (y - gemm.round_tf32(x)).abs()
+    d = (y - x).abs()
     if d.max() > 0:
         bad = (d > 0).nonzero()[:8].tolist()
         print("ident mismatches at", bad, y[0, :8].tolist(), x[0, :8].tolist())
@@ -54,7 +59,7 @@ def ident():
 def sparse(m_in, m_out, cin, cout, koff=27, fill=0.3, seed=1):
     def f():
         g = torch.Generator(device=dev).manual_seed(seed)
-        x = torch.randn(m_in, cin, device=dev, generator=g)
+        x = prep(torch.randn(m_in, cin, device=dev, generator=g))
         w = torch.randn(koff, cin, cout, device=dev, generator=g) / (cin * koff * fill) ** 0.5
         nbr = torch.randint(0, m_in, (koff, m_out), device=dev, generator=g, dtype=torch.int32)
         drop = torch.rand(koff, m_out, device=dev, generator=g) > fill
@@ -68,7 +73,7 @@ def sparse(m_in, m_out, cin, cout, koff=27, fill=0.3, seed=1):
 def epilogue():
     g = torch.Generator(device=dev).manual_seed(5)
     m, cin, cout = 777, 64, 96
-    x = torch.randn(m, cin, device=dev, generator=g)
+    x = prep(torch.randn(m, cin, device=dev, generator=g))
     w = torch.randn(1, cin, cout, device=dev, generator=g) / 8
     sc = torch.rand(cout, device=dev, generator=g) + 0.5
     sh = torch.randn(cout, device=dev, generator=g)
@@ -86,7 +91,7 @@ def epilogue():
 def concat_red():
     g = torch.Generator(device=dev).manual_seed(6)
     m, c = 500, 64
-    a = torch.randn(m, c, device=dev, generator=g); b = torch.randn(m, c, device=dev, generator=g)
+    a = prep(torch.randn(m, c, device=dev, generator=g)); b = prep(torch.randn(m, c, device=dev, generator=g))
     w = torch.randn(1, 2 * c, c, device=dev, generator=g) / 11
     y = gemm.run(a, gemm.PackedWeight(w), x1=b, relu=True, red=(a, b))
     cat = torch.cat([a, b], 1)
@@ -96,7 +101,7 @@ def concat_red():
 def attn():
     g = torch.Generator(device=dev).manual_seed(7)
     m, e, H, L, F = 1000, 96, 4, 34, 3
-    x = torch.randn(m, e, device=dev, generator=g)
+    x = prep(torch.randn(m, e, device=dev, generator=g))
     w = torch.randn(1, e, e, device=dev, generator=g) / e ** 0.5
     bias = torch.randn(e, device=dev, generator=g)
     K = torch.randn(F, H, L, 24, device=dev, generator=g); V = torch.randn(F, H, L, 24, device=dev, generator=g)
@@ -109,23 +114,29 @@ def attn():
     o = torch.einsum("mhl,mhld->mhd", s.softmax(-1), Vf).reshape(m, e)
     return float((y.double() - o).abs().max())
 
-case("ident128x32", ident)
-case("dense_128_32_32", dense(128, 32, 32))
-case("dense_1000_64_64", dense(1000, 64, 64))
-case("dense_1000_16_32", dense(1000, 16, 32))
-case("dense_1000_48_64", dense(1000, 48, 64))
-case("dense_5000_128_128", dense(5000, 128, 128))
-case("dense_5000_256_128", dense(5000, 256, 128))
-case("dense_5000_96_192", dense(5000, 96, 192))
-case("dense_5000_192_96", dense(5000, 192, 96))
-case("dense_5000_96_17", dense(5000, 96, 17))
-case("dense_300_13p_32", dense(300, 16, 32))
-case("sparse_20000_32_32", sparse(20000, 20000, 32, 32))
-case("sparse_6000_128_128", sparse(6000, 5000, 128, 128))
-case("sparse_3000_256_128", sparse(3000, 3000, 256, 128, fill=0.5))
-case("epilogue_ln2", epilogue)
-case("concat_red", concat_red)
-case("attn", attn)
+def ladder(tag):
+  global res
+  print("=== mode", tag, flush=True)
+  _ladder()
+
+def _ladder():
+  case("ident128x32", ident)
+  case("dense_128_32_32", dense(128, 32, 32))
+  case("dense_1000_64_64", dense(1000, 64, 64))
+  case("dense_1000_16_32", dense(1000, 16, 32))
+  case("dense_1000_48_64", dense(1000, 48, 64))
+  case("dense_5000_128_128", dense(5000, 128, 128))
+  case("dense_5000_256_128", dense(5000, 256, 128))
+  case("dense_5000_96_192", dense(5000, 96, 192))
+  case("dense_5000_192_96", dense(5000, 192, 96))
+  case("dense_5000_96_17", dense(5000, 96, 17))
+  case("dense_300_13p_32", dense(300, 16, 32))
+  case("sparse_20000_32_32", sparse(20000, 20000, 32, 32))
+  case("sparse_6000_128_128", sparse(6000, 5000, 128, 128))
+  case("sparse_3000_256_128", sparse(3000, 3000, 256, 128, fill=0.5))
+  case("epilogue_ln2", epilogue)
+  case("concat_red", concat_red)
+  case("attn", attn)
 
 # quick timing of a realistic level-1 SubM conv: 57k sites, 32->32, ~5 nbrs/site
 def timing(m, cin, cout, fill, koff=27, iters=20):
@@ -147,10 +158,16 @@ def timing(m, cin, cout, fill, koff=27, iters=20):
     byts = m * cin * 4 + m * cout * 4 + koff * cin * cout * 4 + pairs * 8
     return dict(m=m, cin=cin, cout=cout, ms=ms, pairs=pairs, gbs=byts / ms / 1e6, gflops=2 * pairs * cin * cout / ms / 1e6)
 
-try:
+def timings():
+  try:
     for cfg in [(57000, 32, 32, 0.2), (90000, 64, 64, 0.45), (42000, 128, 128, 0.5), (17000, 128, 128, 0.5), (2000000, 32, 32, 0.2), (2000000, 64, 64, 0.3)]:
-        t = timing(*cfg); print("timing", t, flush=True); res.append(("timing", t))
-except Exception as e:
+        t = timing(*cfg); t["precise"] = gemm.PRECISE; print("timing", t, flush=True); res.append(("timing", t))
+  except Exception as e:
     traceback.print_exc()
+
+for mode in (True, False):
+    gemm.PRECISE = mode
+    ladder("precise(3xTF32)" if mode else "single-pass TF32")
+    timings()
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/diag_gemm.json", "w"), indent=1)
