@@ -24,7 +24,13 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+SWEEP_DEFAULT = [(0.005, 32), (0.005, 64), (0.01, 32), (0.01, 64), (0.01, 128), (0.02, 64)]      # (occupancy, channels)
+SWEEP_FULL = [(p, c) for p in (0.005, 0.01, 0.02, 0.05, 0.10) for c in (32, 64, 128, 256)]
+
 WORKLOADS = {
+    "spconv_sweep": dict(cfg=None, spec=None, frames_per_gpu=1, cam=False,
+                         desc="Sparse-conv sweep: 1000^3 grid, random occupancy, SubM 3^3 + SparseConv k3 s2 p1 "
+                              "(BASELINE.json configs[4])"),
     "mseg3d_nuscenes": dict(cfg="mseg3d_nuscenes.py", spec="NUSC", frames_per_gpu=3, cam=True,
                             desc="MSeg3D nuScenes LiDAR + 6-cam GF/SF fusion forward (BASELINE.json configs[2])"),
     "sdseg3d_semantickitti": dict(cfg="sdseg3d_semantickitti.py", spec="KITTI", frames_per_gpu=4, cam=False,
@@ -42,6 +48,7 @@ def parse():
     ap.add_argument("--frames-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--sweep-full", action="store_true", help="spconv_sweep: 0.5-10 %% x 32-256 ch (skips what does not fit)")
     return ap.parse_args()
 
 
@@ -178,9 +185,119 @@ def run_cpu(wl, spec, cfg, model, batches, steps, warmup, budget_s):
                        f"torch.set_num_threads({cores})"), sec, len(times), w_done
 
 
+# ------------------------------------------------------------------------------------------------ sparse-conv sweep
+def run_sweep(args):
+    """BASELINE.json configs[4]: independent 1000^3 grids per GPU (replicas), aggregate algorithmic GB/s."""
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from lidarseg3d_b200 import gemm, ops
+    G = 1000
+    shape = (G, G, G)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rows, skipped = [], []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for occ, C in (SWEEP_FULL if args.sweep_full else SWEEP_DEFAULT):
+        n = int(occ * G ** 3)
+        need = n * (2 * C * 4 + 27 * 4 * 2 + 64)
+        if need > 150e9:
+            skipped.append(dict(occupancy=occ, channels=C, reason="N*(Cin+Cout)*4 + rulebook > 150 GB"))
+            continue
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        cells = torch.unique(torch.randint(0, G ** 3, (int(n * 1.06),), device=dev, generator=g, dtype=torch.int64))
+        cells = cells[torch.randperm(cells.numel(), device=dev, generator=g)[:n]].sort().values
+        n = cells.numel()
+        coords = torch.stack([torch.zeros_like(cells), cells // (G * G), (cells // G) % G, cells % G], 1).int().contiguous()
+        del cells
+        feats = torch.randn(n, C, device=dev, generator=g)
+        w = torch.randn(27, C, C, device=dev, generator=g) / (27 * C) ** 0.5
+        pw = gemm.PackedWeight(w)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        torch.cuda.synchronize()
+        e[0].record()
+        grid = ops.grid_from_coords(coords, 1, shape, need_perm=False)
+        nbr = ops.rulebook_gather(grid, coords, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        e[1].record()
+        out = torch.empty(n, C, device=dev)
+        for _ in range(max(args.warmup, 3)):
+            gemm.run(feats, pw, nbr=nbr, out=out)
+        torch.cuda.synchronize()
+        e[2].record()
+        for _ in range(args.steps):
+            gemm.run(feats, pw, nbr=nbr, out=out)
+        e[3].record()
+        torch.cuda.synchronize()
+        pairs = int((nbr >= 0).sum())
+        ms = e[2].elapsed_time(e[3]) / args.steps
+        byts = (n * C + n * C + 27 * C * C) * 4 + pairs * 8
+        rows.append(dict(op="SubM3", occupancy=occ, channels=C, sites=n, pairs=pairs, ms=ms, gbs=byts / ms / 1e6,
+                         tflops=2.0 * pairs * C * C / ms / 1e9, frac=byts / ms / 1e6 / peak, rulebook_ms=e[0].elapsed_time(e[1])))
+        # strided conv k3 s2 p1 on the same sites
+        og, oc = ops.grid_strided(coords, 1, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+        nb2 = ops.rulebook_gather(grid, oc, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+        out2 = torch.empty(oc.shape[0], C, device=dev)
+        for _ in range(3):
+            gemm.run(feats, pw, nbr=nb2, out=out2)
+        torch.cuda.synchronize()
+        e[2].record()
+        for _ in range(args.steps):
+            gemm.run(feats, pw, nbr=nb2, out=out2)
+        e[3].record()
+        torch.cuda.synchronize()
+        pairs2 = int((nb2 >= 0).sum())
+        ms2 = e[2].elapsed_time(e[3]) / args.steps
+        b2 = (n * C + oc.shape[0] * C + 27 * C * C) * 4 + pairs2 * 8
+        rows.append(dict(op="SparseConv_k3s2p1", occupancy=occ, channels=C, sites=n, out_sites=int(oc.shape[0]), pairs=pairs2,
+                         ms=ms2, gbs=b2 / ms2 / 1e6, tflops=2.0 * pairs2 * C * C / ms2 / 1e9, frac=b2 / ms2 / 1e6 / peak))
+        del feats, w, pw, nbr, nb2, out, out2, grid, og, oc, coords
+        torch.cuda.empty_cache()
+    clocks = sampler.stop()
+    head = [r for r in rows if r["op"] == "SubM3"]
+    agg = float(np.mean([r["gbs"] for r in head])) if head else 0.0
+    if world > 1:
+        t = torch.tensor([agg], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        agg = float(t.item())
+    if rank == 0:
+        best = max(head, key=lambda r: r["gbs"]) if head else None
+        print(json.dumps(dict(metric="sparse_conv_subm_algorithmic_gbs", unit="GB/s", value=agg, n_gpus=args.gpus, steps=args.steps,
+                              warmup=max(args.warmup, 3), ms_per_step=float(np.mean([r["ms"] for r in head])) if head else None,
+                              higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic",
+                              dtype="3xTF32 (fp32-equivalent) multiply / fp32 accumulate" if gemm.PRECISE else "tf32",
+                              config=dict(workload="spconv_sweep", description=WORKLOADS["spconv_sweep"]["desc"],
+                                          l2="inputs larger than L2 (>= 640 MB of features per launch)",
+                                          value_is="mean SubM algorithmic GB/s over the sweep, summed over ranks (replicas)"),
+                              clocks=clocks, gpu_launches=len(rows) * (args.steps + 3),
+                              roofline=None if best is None else dict(bound="hbm", achieved=best["gbs"], peak=peak, unit="GB/s",
+                                                                     frac=best["frac"], traffic=None,
+                                                                     kernel=f"gather_gemm_kernel SubM3 occ={best['occupancy']} C={best['channels']}"),
+                              sweep=rows, skipped=skipped, cpu_baseline=None,
+                              e2e=dict(value=agg, unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0,
+                                       note="kernel sweep: operands are generated on the device; no host path exists for this config"))))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse()
+    if args.workload == "spconv_sweep":
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", 0)) == 0:
+                print(json.dumps(dict(impl="reference", unavailable="spconv_sweep has no CPU reference arm (use the default workload)")))
+            return
+        return run_sweep(args)
     wl = WORKLOADS[args.workload]
     from lidarseg3d_b200 import synth
     spec = getattr(synth, wl["spec"])

@@ -79,12 +79,20 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
   // ---- setup
   if (tid < N_PROD) {
     const int r = row0 + tid;
-    for (int k = 0; k < p.koff; ++k) {
-      int j = -1;
-      if (r < p.m_out) j = p.nbr ? __ldg(p.nbr + (size_t)k * p.m_out + r) : r;
-      nbr_s[k * TILE_M + tid] = j;
-      uint32_t b = __ballot_sync(0xffffffffu, j >= 0);
-      if (lane == 0) act_s[k * 4 + warp] = b;
+    // all koff rulebook entries of this row are fetched before any is consumed (independent loads in flight)
+    int jv[MAX_KOFF];
+#pragma unroll
+    for (int k = 0; k < MAX_KOFF; ++k) {
+      jv[k] = -1;
+      if (k < p.koff && r < p.m_out) jv[k] = p.nbr ? __ldg(p.nbr + (size_t)k * p.m_out + r) : r;
+    }
+#pragma unroll
+    for (int k = 0; k < MAX_KOFF; ++k) {
+      if (k < p.koff) {
+        nbr_s[k * TILE_M + tid] = jv[k];
+        uint32_t b = __ballot_sync(0xffffffffu, jv[k] >= 0);
+        if (lane == 0) act_s[k * 4 + warp] = b;
+      }
     }
   } else {
     if (lane == 0) {
