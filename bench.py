@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--frames-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--image-dtype", default="fp32", choices=["fp32", "fp16"],
+                    help="camera branch storage/operand type (fp32 = TF32 tensor-core convs; fp16 = fp16 operands, fp32 accumulate)")
     ap.add_argument("--sweep-full", action="store_true", help="spconv_sweep: 0.5-10 %% x 32-256 ch (skips what does not fit)")
     return ap.parse_args()
 
@@ -336,6 +338,8 @@ def main():
     torch.backends.cudnn.benchmark = True
     cfg, model = build_model(wl)
     model = model.to(dev)
+    if args.image_dtype == "fp16" and wl["cam"]:
+        model.image_dtype = torch.float16
     NB = 4
     batches = make_batches(wl, spec, NB, fpg, rank)
     # device-resident copies of the raw inputs for the `value` measurement
@@ -438,7 +442,8 @@ def main():
     if rank == 0:
         line = dict(base, value=value, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps,
                     config=dict(workload=args.workload, description=wl["desc"], frames_per_gpu=fpg, global_frames_per_step=fpg * world,
-                                points_per_step_per_gpu=npts, parallelism=f"frames sharded over {world} GPU(s), no data-path collective",
+                                points_per_step_per_gpu=npts, image_branch_dtype=args.image_dtype if wl["cam"] else None,
+                                parallelism=f"frames sharded over {world} GPU(s), no data-path collective",
                                 l2="inputs larger than L2: 4 rotating pre-staged batches, %.0f MB of raw inputs each" % (in_bytes / 1e6),
                                 timed_region="GPU voxelize -> VFE -> sparse UNet -> devoxelize -> camera sampling -> GF/SF fusion "
                                              "-> logits -> argmax (HRNet/FCN image branch on cuDNN inside)"),

@@ -66,6 +66,7 @@ typedef struct ls3d_gemm_args {
   int32_t ld_out;
   int32_t round_out;  /* 1: store outputs rounded to tf32 (cvt.rna); only useful with precise=0, where the  */
                       /* operands of the next GEMM are truncated to tf32 by the tensor core               */
+  int32_t debug_skip; /* development only, must be 0: bit0 no A gathers, bit1 no W loads, bit2 no MMA, bit3 no epilogue */
   int32_t precise;    /* 1: error-compensated 3xTF32 (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi), fp32-level accuracy */
 } ls3d_gemm_args;
 

@@ -38,7 +38,7 @@ class GemmArgs(ctypes.Structure):
         ("n_frames", c_int), ("n_tok", c_int), ("n_head", c_int),
         ("attn_scale", c_float),
         ("row_mask", c_void_p), ("ld_mask", c_int),
-        ("out", c_void_p), ("ld_out", c_int), ("round_out", c_int), ("precise", c_int),
+        ("out", c_void_p), ("ld_out", c_int), ("round_out", c_int), ("debug_skip", c_int), ("precise", c_int),
     ]
 
 

@@ -127,6 +127,30 @@ __global__ void ce_final_kernel(const float* __restrict__ part, int nchunk, int 
 constexpr int CT_MAXL = 48;
 constexpr int CT_E = 96;
 
+
+// out[l][e] = bias[e] + sum_c in[l][c] * Wt[c][e] for all l < L, e < NOUT.  One thread owns an output column and
+// keeps the L accumulators in registers, so every weight is read from global exactly once per CTA (coalesced over e)
+// and the activations come from shared memory as broadcasts.
+template <int MAXL, class StoreFn>
+__device__ __forceinline__ void tokens_matvec(const float* __restrict__ Wt, const float* __restrict__ bias, int nin,
+                                               int nout, const float* in_s, int ld_in, int L, StoreFn store) {
+  for (int e = threadIdx.x; e < nout; e += blockDim.x) {
+    float acc[MAXL];
+    const float b = bias[e];
+#pragma unroll
+    for (int l = 0; l < MAXL; ++l) acc[l] = b;
+    for (int c = 0; c < nin; ++c) {
+      const float w = __ldg(Wt + (size_t)c * nout + e);
+#pragma unroll
+      for (int l = 0; l < MAXL; ++l)
+        if (l < L) acc[l] = fmaf(in_s[l * ld_in + c], w, acc[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < MAXL; ++l)
+      if (l < L) store(l, e, acc[l]);
+  }
+}
+
 __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restrict__ emb1, int C1,
                                                            const float* __restrict__ emb2, int C2, int ncls,
                                                            const float* __restrict__ params, int n_layer, int n_head,
@@ -149,20 +173,14 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
   const float* lp = b2 + E;
   const int layer_sz = E * 3 * E + 3 * E + E * E + E + E + E + E * E + E + E * E + E;
   // ---- input projections
-  for (int o = threadIdx.x; o < L * E; o += blockDim.x) {
-    const int l = o / E, e = o % E;
-    float a;
-    if (l < ncls) {
-      a = b1[e];
-      const float* x = emb1 + ((size_t)b * ncls + l) * C1;
-      for (int c = 0; c < C1; ++c) a = fmaf(x[c], P1t[c * E + e], a);
-    } else {
-      a = b2[e];
-      const float* x = emb2 + ((size_t)b * ncls + (l - ncls)) * C2;
-      for (int c = 0; c < C2; ++c) a = fmaf(x[c], P2t[c * E + e], a);
-    }
-    mem[l][e] = a;
-  }
+  // stage the two embedding sets in shared memory (att is free here), then column-owner projections
+  float* e1s = &att[0][0];                       // [ncls][C1]
+  float* e2s = e1s + ncls * C1;                  // [ncls][C2]   (ncls*(C1+C2) <= L*E)
+  for (int o = threadIdx.x; o < ncls * C1; o += blockDim.x) e1s[o] = emb1[(size_t)b * ncls * C1 + o];
+  for (int o = threadIdx.x; o < ncls * C2; o += blockDim.x) e2s[o] = emb2[(size_t)b * ncls * C2 + o];
+  __syncthreads();
+  tokens_matvec<CT_MAXL / 2>(P1t, b1, C1, E, e1s, C1, ncls, [&](int l, int e, float v) { mem[l][e] = v; });
+  tokens_matvec<CT_MAXL / 2>(P2t, b2, C2, E, e2s, C2, ncls, [&](int l, int e, float v) { mem[ncls + l][e] = v; });
   __syncthreads();
   for (int ly = 0; ly < n_layer; ++ly) {
     const float* Wint = lp + (size_t)ly * layer_sz;
@@ -176,12 +194,7 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
     const float* Wvt = bk + E;
     const float* bv = Wvt + E * E;
     // in-projection
-    for (int o = threadIdx.x; o < L * 3 * E; o += blockDim.x) {
-      const int l = o / (3 * E), e = o % (3 * E);
-      float a = bin[e];
-      for (int c = 0; c < E; ++c) a = fmaf(mem[l][c], Wint[c * 3 * E + e], a);
-      qkv[l][e] = a;
-    }
+    tokens_matvec<CT_MAXL>(Wint, bin, E, 3 * E, &mem[0][0], E, L, [&](int l, int e, float v) { qkv[l][e] = v; });
     __syncthreads();
     // scores
     const float scale = rsqrtf((float)dh);
@@ -210,12 +223,7 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
     }
     __syncthreads();
     // out-projection + residual (into qkv[:, :E] as scratch)
-    for (int o = threadIdx.x; o < L * E; o += blockDim.x) {
-      const int l = o / E, e = o % E;
-      float a = bout[e];
-      for (int c = 0; c < E; ++c) a = fmaf(att[l][c], Woutt[c * E + e], a);
-      qkv[l][e] = mem[l][e] + a;
-    }
+    tokens_matvec<CT_MAXL>(Woutt, bout, E, E, &att[0][0], E, L, [&](int l, int e, float v) { qkv[l][e] = mem[l][e] + v; });
     __syncthreads();
     // LayerNorm (norm1), one warp per token
     for (int l = threadIdx.x >> 5; l < L; l += blockDim.x >> 5) {
@@ -234,15 +242,27 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
     }
     __syncthreads();
     // k / v projections for the point cross-attention of this layer
-    for (int o = threadIdx.x; o < L * E * 2; o += blockDim.x) {
-      const int which = o / (L * E), r = o % (L * E);
-      const int l = r / E, e = r % E;
-      const float* Wt = which ? Wvt : Wkt;
-      float a = which ? bv[e] : bk[e];
-      for (int c = 0; c < E; ++c) a = fmaf(mem[l][c], Wt[c * E + e], a);
-      const int h = e / dh, d = e % dh;
-      float* dst = which ? Vout : Kout;
-      dst[((((size_t)ly * B + b) * n_head + h) * L + l) * dh + d] = a;
+    {
+      // threads [0, E) own a K column, threads [E, 2E) a V column (one pass, weights read once)
+      for (int o = threadIdx.x; o < 2 * E; o += blockDim.x) {
+        const int which = o / E, e = o % E;
+        const float* Wt = which ? Wvt : Wkt;
+        float acc[CT_MAXL];
+        const float bb = which ? bv[e] : bk[e];
+#pragma unroll
+        for (int l = 0; l < CT_MAXL; ++l) acc[l] = bb;
+        for (int c = 0; c < E; ++c) {
+          const float w = __ldg(Wt + c * E + e);
+#pragma unroll
+          for (int l = 0; l < CT_MAXL; ++l)
+            if (l < L) acc[l] = fmaf(mem[l][c], w, acc[l]);
+        }
+        const int h = e / dh, d = e % dh;
+        float* dst = which ? Vout : Kout;
+#pragma unroll
+        for (int l = 0; l < CT_MAXL; ++l)
+          if (l < L) dst[((((size_t)ly * B + b) * n_head + h) * L + l) * dh + d] = acc[l];
+      }
     }
     if (mem_out)
       for (int o = threadIdx.x; o < L * E; o += blockDim.x)

@@ -10,29 +10,34 @@
 //   * the SF-Phase class-token cross attention as an epilogue of the q projection
 //       (reference det3d/models/point_heads/context_module.py:320-376).
 //
-// Tile: 128 output rows x n_pad columns, fp32 accumulator in TMEM.  K loop over
-// (kernel offset, 32-float channel chunk) "steps"; a step whose 128 rows have no neighbour is
-// skipped.  Producer warps gather A rows (128-bit loads, cvt.rna.tf32) and the W[k] chunk into
-// 128B-swizzled K-major shared tiles; one elected thread issues tcgen05.mma.kind::tf32; the
-// producer warps then turn into the epilogue (tcgen05.ld -> affine/ReLU/residual/LayerNorm/
-// attention -> global).
+// Persistent, warp-specialised CTA (one per SM), 128-row output tiles taken round-robin:
+//   warps 0-7   producers : per (kernel offset, 32-float channel chunk) "step" gather the tile's input rows and the W[k]
+//                           chunk with cp.async (zero fill for missing rows) into 128B-swizzled K-major smem stages and
+//                           hand completion to the "landed" mbarrier with cp.async.mbarrier.arrive.noinc - they never
+//                           wait for data, so all stages stay in flight and the ring runs ahead across tile boundaries;
+//                           steps whose 128 rows have no neighbour are skipped
+//   warps 8-11  splitters : wait "landed", (3xTF32) derive the x_lo tile from the raw tile, cross-proxy fence, publish "full"
+//   warp  12    MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=n_pad, K=8) into one of two TMEM
+//                           accumulator buffers; tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 13-16 epilogue  : tcgen05.ld -> folded BN / ReLU / residual / channel reduction / row mask / LayerNorm(s) /
+//                           class-token attention -> shared-memory panel -> coalesced global stores; overlaps the next
+//                           tile's main loop (double-buffered TMEM)
 #include "common.cuh"
 #include "../../include/ls3d.h"
 
 namespace ls3d {
 
 constexpr int TILE_M = 128;
-constexpr int KCH = 32;         // floats per K chunk = one 128-byte swizzle row
-constexpr int N_PROD = 128;     // producer / epilogue threads (4 warps)
-constexpr int N_THREADS = 160;  // + 1 MMA warp
+constexpr int KCH = 32;                 // floats per K chunk = one 128-byte swizzle row
+constexpr int N_PROD_WARPS = 8;
+constexpr int N_PROD = N_PROD_WARPS * 32;
+constexpr int SPLIT_WARP0 = N_PROD_WARPS;     // 4 splitter warps = one thread per tile row
+constexpr int MMA_WARP = N_PROD_WARPS + 4;
+constexpr int N_THREADS = (N_PROD_WARPS + 4 + 1 + 4) * 32;
 constexpr int MAX_KOFF = 27;
 constexpr int MAX_TOK = 48;
 constexpr int DHEAD = 24;
-
-struct SmemLayout {
-  uint32_t a_off[4], b_off[4];
-  uint32_t nbr_off, flags_off, bar_off, tmem_slot_off, total;
-};
+constexpr int MASK_RING = 8;            // > max stages: producers are never more than STAGES tiles ahead of the MMA warp
 
 __host__ __device__ inline uint32_t a_stage_bytes() { return TILE_M * 128; }
 __host__ __device__ inline uint32_t b_stage_bytes(int n_pad) { return (uint32_t)n_pad * 128; }
@@ -40,15 +45,260 @@ __host__ __device__ inline uint32_t b_stage_bytes(int n_pad) { return (uint32_t)
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t chunk) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
 }
+__device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1, %0;" ::"n"(N_PROD) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Epilogue of one 128-row tile (4 warps, thread `et` owns tile row `et`; its accumulator row starts at TMEM address trow).
+// Global traffic is coalesced: residual rows come in and results go out through a [128 x 16]-column shared-memory panel
+// (a warp request covers whole 64-byte row segments); per-column vectors (folded BN scale/shift, LayerNorm gamma/beta)
+// live in shared memory.  Finished pre-LayerNorm values are parked in TMEM over the accumulator columns.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PANEL = 16;
+constexpr int STG_LD = PANEL + 4;      // floats; 80-byte rows: 16-byte aligned, conflict-free for row-per-thread float4
+constexpr int COLV = 256;              // stride of the per-column vectors in smem: scale, shift, g0, b0, g1, b1
+
+__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+// cooperative [rows_valid x w] panel copy global -> stg (zero outside)
+__device__ __forceinline__ void panel_load(float* stg, const float* src, int ld, int row0, int rows_valid, int c0, int w,
+                                            int et) {
+  if (((ld | c0) & 3) == 0 && (w & 3) == 0) {
+#pragma unroll
+    for (int i = 0; i < PANEL / 4; ++i) {
+      const int idx = i * 128 + et, rr = idx / (PANEL / 4), cn = (idx % (PANEL / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rr < rows_valid && cn < w) v = ldg_f4(src + (size_t)(row0 + rr) * ld + c0 + cn);
+      *reinterpret_cast<float4*>(stg + rr * STG_LD + cn) = v;
+    }
+  } else {
+    for (int idx = et; idx < TILE_M * PANEL; idx += 128) {
+      const int rr = idx / PANEL, cn = idx % PANEL;
+      stg[rr * STG_LD + cn] = (rr < rows_valid && cn < w) ? __ldg(src + (size_t)(row0 + rr) * ld + c0 + cn) : 0.f;
+    }
+  }
+}
+// cooperative [rows_valid x w] panel copy stg -> global
+__device__ __forceinline__ void panel_store(const float* stg, float* dst, int ld, int row0, int rows_valid, int c0, int w,
+                                             int et) {
+  if (((ld | c0) & 3) == 0 && (w & 3) == 0) {
+#pragma unroll
+    for (int i = 0; i < PANEL / 4; ++i) {
+      const int idx = i * 128 + et, rr = idx / (PANEL / 4), cn = (idx % (PANEL / 4)) * 4;
+      if (rr < rows_valid && cn < w)
+        *reinterpret_cast<float4*>(dst + (size_t)(row0 + rr) * ld + c0 + cn) = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cn);
+    }
+  } else {
+    for (int idx = et; idx < TILE_M * PANEL; idx += 128) {
+      const int rr = idx / PANEL, cn = idx % PANEL;
+      if (rr < rows_valid && cn < w) dst[(size_t)(row0 + rr) * ld + c0 + cn] = stg[rr * STG_LD + cn];
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uint32_t trow, const int row0, const int et,
+                                              const float* colv, float* stg) {
+  const int r = row0 + et;
+  const bool live = r < p.m_out;
+  const int rows_valid = min(TILE_M, p.m_out - row0);
+  auto rnd = [&](float x) -> float { return p.round_out ? to_tf32(x) : x; };
+  float* my = stg + et * STG_LD;
+
+  if (p.epi == LS3D_EPI_ATTN) {
+    // q = acc + bias ; per head softmax(q.K^T * scale) V over the frame's class tokens
+    int f = 0;
+    for (int i = 1; i < p.n_frames; ++i)
+      if (r >= p.frame_off[i]) f = i;
+    const int L = p.n_tok;
+    for (int h = 0; h < p.n_head; ++h) {
+      uint32_t raw[24];
+      tmem_ld8(trow + h * DHEAD, raw);
+      tmem_ld8(trow + h * DHEAD + 8, raw + 8);
+      tmem_ld8(trow + h * DHEAD + 16, raw + 16);
+      tmem_ld_wait();
+      float q[DHEAD];
+#pragma unroll
+      for (int d = 0; d < DHEAD; ++d) q[d] = __uint_as_float(raw[d]) + colv[COLV + h * DHEAD + d];
+      const float* kh = p.attn_k + ((size_t)(f * p.n_head + h) * L) * DHEAD;
+      const float* vh = p.attn_v + ((size_t)(f * p.n_head + h) * L) * DHEAD;
+      float sc[MAX_TOK];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int l = 0; l < MAX_TOK; ++l) {
+        if (l < L) {
+          float a = 0.f;
+#pragma unroll
+          for (int d4 = 0; d4 < DHEAD / 4; ++d4) {
+            float4 kv = ldg_f4(kh + l * DHEAD + d4 * 4);
+            a = fmaf(q[d4 * 4 + 0], kv.x, a);
+            a = fmaf(q[d4 * 4 + 1], kv.y, a);
+            a = fmaf(q[d4 * 4 + 2], kv.z, a);
+            a = fmaf(q[d4 * 4 + 3], kv.w, a);
+          }
+          a *= p.attn_scale;
+          sc[l] = a;
+          mx = fmaxf(mx, a);
+        }
+      }
+      float den = 0.f;
+      float o[DHEAD];
+#pragma unroll
+      for (int d = 0; d < DHEAD; ++d) o[d] = 0.f;
+#pragma unroll
+      for (int l = 0; l < MAX_TOK; ++l) {
+        if (l < L) {
+          float e = __expf(sc[l] - mx);
+          den += e;
+#pragma unroll
+          for (int d4 = 0; d4 < DHEAD / 4; ++d4) {
+            float4 vv = ldg_f4(vh + l * DHEAD + d4 * 4);
+            o[d4 * 4 + 0] = fmaf(e, vv.x, o[d4 * 4 + 0]);
+            o[d4 * 4 + 1] = fmaf(e, vv.y, o[d4 * 4 + 1]);
+            o[d4 * 4 + 2] = fmaf(e, vv.z, o[d4 * 4 + 2]);
+            o[d4 * 4 + 3] = fmaf(e, vv.w, o[d4 * 4 + 3]);
+          }
+        }
+      }
+      const float inv = 1.f / den;
+      // the head's 24 outputs leave through two panels (16 + 8 columns)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int w = half ? DHEAD - PANEL : PANEL;
+#pragma unroll
+        for (int d4 = 0; d4 < PANEL / 4; ++d4) {
+          const int d = half * PANEL + d4 * 4;
+          if (d < DHEAD)
+            *reinterpret_cast<float4*>(my + d4 * 4) =
+                make_float4(rnd(o[d] * inv), rnd(o[d + 1] * inv), rnd(o[d + 2] * inv), rnd(o[d + 3] * inv));
+        }
+        bar_sync_epilogue();
+        panel_store(stg, p.out, p.ld_out, row0, rows_valid, h * DHEAD + half * PANEL, w, et);
+        bar_sync_epilogue();
+      }
+    }
+    return;
+  }
+
+  const bool masked = p.row_mask && live && (__ldg(p.row_mask + (size_t)r * p.ld_mask) != 1.0f);
+  // value of column `col` after affine / residual / relu / channel-reduction (resv = this row's residual at col)
+  auto finish = [&](float acc, int col, float resv) -> float {
+    float x = fmaf(acc, colv[col], colv[COLV + col]);
+    if (p.res_mode == 1) x += resv;
+    if (p.relu) x = fmaxf(x, 0.f);
+    if (p.res_mode == 2) x += resv;
+    if (p.red0 && live) {
+      // cat = [red0 (red_c ch) | red1 (red_c ch)] ; out[col] += cat[2col] + cat[2col+1]
+      const int c2 = 2 * col;
+      const float* src = (c2 < p.red_c) ? (p.red0 + (size_t)r * p.ld_red0 + c2) : (p.red1 + (size_t)r * p.ld_red1 + (c2 - p.red_c));
+      const float2 t = __ldg(reinterpret_cast<const float2*>(src));
+      x += t.x + t.y;
+    }
+    return x;
+  };
+  // one 16-column panel of finished values into v[] (columns >= cout -> 0)
+  auto finished_panel = [&](int c0, float* v) {
+    const int w = min(PANEL, p.cout - c0);
+    float rv[PANEL];
+    if (p.res_mode) {
+      panel_load(stg, p.res, p.ld_res, row0, rows_valid, c0, w, et);
+      bar_sync_epilogue();
+#pragma unroll
+      for (int j4 = 0; j4 < PANEL / 4; ++j4) {
+        const float4 t = *reinterpret_cast<const float4*>(my + j4 * 4);
+        rv[j4 * 4] = t.x; rv[j4 * 4 + 1] = t.y; rv[j4 * 4 + 2] = t.z; rv[j4 * 4 + 3] = t.w;
+      }
+      bar_sync_epilogue();
+    } else {
+#pragma unroll
+      for (int j = 0; j < PANEL; ++j) rv[j] = 0.f;
+    }
+    uint32_t raw[PANEL];
+    tmem_ld16(trow + c0, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < PANEL; ++j) v[j] = (j < w) ? finish(__uint_as_float(raw[j]), c0 + j, rv[j]) : 0.f;
+  };
+  auto emit_panel = [&](int c0, const float* v) {
+    const int w = min(PANEL, p.cout - c0);
+#pragma unroll
+    for (int j4 = 0; j4 < PANEL / 4; ++j4)
+      *reinterpret_cast<float4*>(my + j4 * 4) = masked ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                                       : make_float4(rnd(v[j4 * 4]), rnd(v[j4 * 4 + 1]), rnd(v[j4 * 4 + 2]), rnd(v[j4 * 4 + 3]));
+    bar_sync_epilogue();
+    panel_store(stg, p.out, p.ld_out, row0, rows_valid, c0, w, et);
+    bar_sync_epilogue();
+  };
+
+  if (p.n_ln == 0) {
+    for (int c0 = 0; c0 < p.cout; c0 += PANEL) {
+      float v[PANEL];
+      finished_panel(c0, v);
+      emit_panel(c0, v);
+    }
+    return;
+  }
+  // LayerNorm(s): exact two-pass statistics; finished values parked in TMEM over the accumulator columns
+  float mean[2] = {0.f, 0.f}, rstd[2] = {1.f, 1.f};
+  for (int ln = 0; ln < p.n_ln; ++ln) {
+    float s1 = 0.f;
+    for (int c0 = 0; c0 < p.cout; c0 += PANEL) {
+      float v[PANEL];
+      uint32_t raw[PANEL];
+      if (ln == 0) {
+        finished_panel(c0, v);
+      } else {
+        tmem_ld16(trow + c0, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < PANEL; ++j)
+          v[j] = (c0 + j < p.cout) ? (__uint_as_float(raw[j]) - mean[0]) * rstd[0] * colv[2 * COLV + c0 + j] + colv[3 * COLV + c0 + j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < PANEL; ++j) {
+        s1 += v[j];
+        raw[j] = __float_as_uint(v[j]);
+      }
+      tmem_st16(trow + c0, raw);
+    }
+    tmem_st_wait();
+    const float m = s1 / (float)p.cout;
+    float s2 = 0.f;
+    for (int c0 = 0; c0 < p.cout; c0 += 16) {
+      uint32_t raw[16];
+      tmem_ld16(trow + c0, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (c0 + j < p.cout) {
+          const float d = __uint_as_float(raw[j]) - m;
+          s2 = fmaf(d, d, s2);
+        }
+      }
+    }
+    mean[ln] = m;
+    rstd[ln] = rsqrtf(s2 / (float)p.cout + p.ln_eps);
+  }
+  const int last = p.n_ln - 1;
+  for (int c0 = 0; c0 < p.cout; c0 += PANEL) {
+    uint32_t raw[PANEL];
+    tmem_ld16(trow + c0, raw);
+    tmem_ld_wait();
+    float v[PANEL];
+#pragma unroll
+    for (int j = 0; j < PANEL; ++j)
+      v[j] = (c0 + j < p.cout) ? (__uint_as_float(raw[j]) - mean[last]) * rstd[last] * colv[(2 + 2 * last) * COLV + c0 + j] +
+                                     colv[(3 + 2 * last) * COLV + c0 + j]
+                               : 0.f;
+    emit_panel(c0, v);
+  }
+}
 
 // SPLIT = true: error-compensated "3xTF32".  The tensor core truncates fp32 operands to tf32 (verified on B200), so with
 //   x = x_hi + x_lo (x_hi = trunc_tf32(x), x_lo = x - x_hi exactly) and W = W_hi + W_lo (split on the host),
 //   x.W ~= x_hi.W_hi + x_hi.W_lo + x_lo.W_hi   (dropped term x_lo.W_lo ~ 2^-22): fp32-level accuracy from three MMAs.
 // x_hi comes for free (the raw fp32 tile, truncated by the MMA); the producers derive the x_lo tile from the landed raw tile.
 template <int STAGES, bool SPLIT>
-__global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_args p) {
+__global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_gemm_args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages][nbr koff*128 ints][active flags][barriers][tmem slot]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t NSPLIT = SPLIT ? 2u : 1u;
   const uint32_t a_half = a_stage_bytes();            // one [128 x 32 float] tile
@@ -57,51 +307,43 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
   const uint32_t b_bytes = NSPLIT * b_half;           // per stage: [W hi | W lo]
   uint8_t* a_s = smem;
   uint8_t* b_s = smem + STAGES * a_bytes;
-  int* nbr_s = (int*)(b_s + STAGES * b_bytes);
-  uint32_t* act_s = (uint32_t*)(nbr_s + p.koff * TILE_M);  // [koff][4] warp ballots
-  uint64_t* bars = (uint64_t*)(((uintptr_t)(act_s + p.koff * 4) + 7) & ~(uintptr_t)7);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+  int* nbr_s = (int*)(b_s + STAGES * b_bytes);                     // [2][koff][128]
+  uint32_t* act_s = (uint32_t*)(nbr_s + 2 * p.koff * TILE_M);      // [2][koff][4] warp ballots
+  uint32_t* mask_s = act_s + 2 * p.koff * 4;                       // [MASK_RING] active-offset masks
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(mask_s + MASK_RING) + 7) & ~(uintptr_t)7);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4 + MASK_RING);
+  float* colv = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);      // [6][COLV] per-column vectors
+  float* stg = colv + 6 * COLV;                                                      // [128][STG_LD] epilogue panel
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int row0 = blockIdx.x * TILE_M;
   const int cin = p.c0 + p.c1;
   const int nchunk = (p.cin_pad + KCH - 1) / KCH;
+  const int ntiles = (p.m_out + TILE_M - 1) / TILE_M;
 
   const uint32_t full_bar0 = smem_u32(bars);
   const uint32_t empty_bar0 = smem_u32(bars + STAGES);
-  const uint32_t accum_bar = smem_u32(bars + 2 * STAGES);
+  const uint32_t land_bar0 = smem_u32(bars + 2 * STAGES);       // cp.async data landed [STAGES]
+  const uint32_t accf_bar0 = smem_u32(bars + 3 * STAGES);       // accumulator full  [2]
+  const uint32_t acce_bar0 = smem_u32(bars + 3 * STAGES + 2);   // accumulator empty [2]
+  const uint32_t mask_bar0 = smem_u32(bars + 3 * STAGES + 4);   // mask published    [MASK_RING]
 
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.n_pad) tmem_cols <<= 1;
+  while (tmem_cols < 2u * (uint32_t)p.n_pad) tmem_cols <<= 1;
 
-  // ---- setup
-  if (tid < N_PROD) {
-    const int r = row0 + tid;
-    // all koff rulebook entries of this row are fetched before any is consumed (independent loads in flight)
-    int jv[MAX_KOFF];
-#pragma unroll
-    for (int k = 0; k < MAX_KOFF; ++k) {
-      jv[k] = -1;
-      if (k < p.koff && r < p.m_out) jv[k] = p.nbr ? __ldg(p.nbr + (size_t)k * p.m_out + r) : r;
-    }
-#pragma unroll
-    for (int k = 0; k < MAX_KOFF; ++k) {
-      if (k < p.koff) {
-        nbr_s[k * TILE_M + tid] = jv[k];
-        uint32_t b = __ballot_sync(0xffffffffu, jv[k] >= 0);
-        if (lane == 0) act_s[k * 4 + warp] = b;
-      }
-    }
-  } else {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
-#pragma unroll
       for (int s = 0; s < STAGES; ++s) {
-        mbar_init(full_bar0 + 8 * s, N_PROD);
+        mbar_init(full_bar0 + 8 * s, 128);
         mbar_init(empty_bar0 + 8 * s, 1);
+        mbar_init(land_bar0 + 8 * s, N_PROD);
       }
-      mbar_init(accum_bar, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(accf_bar0 + 8 * b, 1);
+        mbar_init(acce_bar0 + 8 * b, 128);
+      }
+      for (int m = 0; m < MASK_RING; ++m) mbar_init(mask_bar0 + 8 * m, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -110,305 +352,214 @@ __global__ void __launch_bounds__(N_THREADS) gather_gemm_kernel(const ls3d_gemm_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
-  // total active steps (uniform across the CTA)
-  int nsteps = 0;
-  for (int k = 0; k < p.koff; ++k) {
-    uint32_t any = act_s[k * 4] | act_s[k * 4 + 1] | act_s[k * 4 + 2] | act_s[k * 4 + 3];
-    if (any) nsteps += nchunk;
-  }
-
-  if (tid < N_PROD) {
-    // =========================== producer ===========================
-    // cp.async (LDGSTS, zero-fill for missing rows) keeps up to STAGES-1 steps of gathers in flight per
-    // thread; a step is published (fence.proxy.async + mbarrier arrive) once its own copies have landed.
-    constexpr int DEPTH = STAGES - 1;
-    int step = 0;
+  if (warp < N_PROD_WARPS) {
+    // =========================== producers ===========================
     const int ch = tid & 7;
-    // make step j's tiles visible to the tensor core: (SPLIT) derive the x_lo tile from this thread's own landed
-    // chunks of the raw tile, then cross-proxy fence + mbarrier arrive
-    auto publish = [&](int j) {
-      const int sj = j % STAGES;
-      if (SPLIT) {
-        uint8_t* a_raw = a_s + sj * a_bytes;
+    int g = 0;                                        // global step counter (ring position), continues across tiles
+    int ti = 0;
+    const int my_row = tid & (TILE_M - 1);            // thread t loads rulebook row (t & 127) for half of the offsets
+    const int khalf = (p.koff + 1) / 2;
+    const int k_lo = (tid < TILE_M) ? 0 : khalf;
+    const int k_hi = (tid < TILE_M) ? khalf : p.koff;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      const int r = tile * TILE_M + my_row;
+      // all rulebook entries are fetched before any is consumed (independent loads in flight)
+      int jv[(MAX_KOFF + 1) / 2];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const uint32_t off = sw128(it * 16 + (tid >> 3), ch);
-          float4 v = *reinterpret_cast<const float4*>(a_raw + off);
-          v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          *reinterpret_cast<float4*>(a_raw + a_half + off) = v;
+      for (int q = 0; q < (MAX_KOFF + 1) / 2; ++q) {
+        const int k = k_lo + q;
+        jv[q] = -1;
+        if (k < k_hi && r < p.m_out) jv[q] = p.nbr ? __ldg(p.nbr + (size_t)k * p.m_out + r) : r;
+      }
+      bar_sync_producers();                           // everyone finished issuing the tile that used nbr_s[buf] before
+      int* nb = nbr_s + buf * p.koff * TILE_M;
+      uint32_t* ac = act_s + buf * p.koff * 4;
+#pragma unroll
+      for (int q = 0; q < (MAX_KOFF + 1) / 2; ++q) {
+        const int k = k_lo + q;
+        if (k < k_hi) {
+          nb[k * TILE_M + my_row] = jv[q];
+          const uint32_t b = __ballot_sync(0xffffffffu, jv[q] >= 0);
+          if (lane == 0) ac[k * 4 + (warp & 3)] = b;
         }
       }
-      fence_proxy_async_smem();
-      mbar_arrive(full_bar0 + 8 * sj);
-    };
-    for (int k = 0; k < p.koff; ++k) {
-      uint32_t any = act_s[k * 4] | act_s[k * 4 + 1] | act_s[k * 4 + 2] | act_s[k * 4 + 3];
-      if (!any) continue;
-      const float* wk = p.w + (size_t)k * NSPLIT * p.n_pad * p.cin_pad;
-      for (int c = 0; c < nchunk; ++c, ++step) {
-        const int s = step % STAGES;
-        const uint32_t ph = (uint32_t)(step / STAGES) & 1u;
-        mbar_wait(empty_bar0 + 8 * s, ph ^ 1u);
-        const uint32_t a_dst = smem_u32(a_s + s * a_bytes);
-        const uint32_t b_dst = smem_u32(b_s + s * b_bytes);
-        // ---- A: 128 rows x 8 chunks of 16 B; 8 lanes cover one row (4 full 128 B lines per warp request)
-        const int col = c * KCH + ch * 4;
+      bar_sync_producers();
+      uint32_t mask = 0;
+      for (int k = 0; k < p.koff; ++k)
+        if (ac[k * 4] | ac[k * 4 + 1] | ac[k * 4 + 2] | ac[k * 4 + 3]) mask |= 1u << k;
+      if (mask == 0) mask = 1u;                       // keep >= 1 step per tile (an all-zero gather)
+      if (tid == 0) {
+        mask_s[ti % MASK_RING] = mask;
+        mbar_arrive(mask_bar0 + 8 * (ti % MASK_RING));
+      }
+      for (int k = 0; k < p.koff; ++k) {
+        if (!((mask >> k) & 1u)) continue;
+        const float* wk = p.w + (size_t)k * NSPLIT * p.n_pad * p.cin_pad;
+        for (int c = 0; c < nchunk; ++c, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+          mbar_wait(empty_bar0 + 8 * s, ph ^ 1u);
+          const uint32_t a_dst = smem_u32(a_s + s * a_bytes);
+          const uint32_t b_dst = smem_u32(b_s + s * b_bytes);
+          // ---- A: 128 rows x 8 chunks of 16 B; 8 lanes cover one row (4 full 128 B lines per warp request).
+          // Addresses of all copies are formed first so the copies issue back to back (the asm statements are ordering
+          // points for the compiler).
+          constexpr int A_IT = TILE_M * 8 / N_PROD;
+          const int col = c * KCH + ch * 4;
+          const float* asrc[A_IT];
+          uint32_t asz[A_IT];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 16 + (tid >> 3);
-          const int j = nbr_s[k * TILE_M + r];
-          const bool ok = (j >= 0) && (col < cin);
-          const float* src = p.in0;
-          if (ok) src = (col < p.c0) ? (p.in0 + (size_t)j * p.ld0 + col) : (p.in1 + (size_t)j * p.ld1 + (col - p.c0));
-          cp_async16(a_dst + sw128(r, ch), src, ok ? 16u : 0u);
-        }
-        // ---- B: n_pad rows x 8 chunks
-        const int nb_it = p.n_pad / 16;
-        for (int it = 0; it < nb_it; ++it) {
-          const int idx = it * N_PROD + tid;
-          const int n = idx >> 3;
-          const int bcol = c * KCH + (idx & 7) * 4;
-          const bool ok = bcol < p.cin_pad;
-          cp_async16(b_dst + sw128(n, idx & 7), ok ? (wk + (size_t)n * p.cin_pad + bcol) : p.w, ok ? 16u : 0u);
-          if (SPLIT)
-            cp_async16(b_dst + b_half + sw128(n, idx & 7),
-                       ok ? (wk + (size_t)(p.n_pad + n) * p.cin_pad + bcol) : p.w, ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        if (step >= DEPTH) {
-          cp_async_wait<DEPTH>();
-          publish(step - DEPTH);
+          for (int it = 0; it < A_IT; ++it) {
+            const int j = nb[k * TILE_M + it * (N_PROD / 8) + (tid >> 3)];
+            const bool ok = (j >= 0) && (col < cin) && !(p.debug_skip & 1);
+            asrc[it] = p.in0;
+            if (ok) asrc[it] = (col < p.c0) ? (p.in0 + (size_t)j * p.ld0 + col) : (p.in1 + (size_t)j * p.ld1 + (col - p.c0));
+            asz[it] = ok ? 16u : 0u;
+          }
+          // ---- B: n_pad rows x 8 chunks (x2 when split); n_pad * 8 / N_PROD <= 8 copies per thread
+          constexpr int B_IT = 256 * 8 / N_PROD;
+          const float* bsrc[B_IT];
+          uint32_t bsz[B_IT];
+#pragma unroll
+          for (int it = 0; it < B_IT; ++it) {
+            const int idx = it * N_PROD + tid;
+            const int n = idx >> 3;
+            const int bcol = c * KCH + (idx & 7) * 4;
+            const bool ok = (idx < p.n_pad * 8) && (bcol < p.cin_pad) && !(p.debug_skip & 2);
+            bsrc[it] = ok ? (wk + (size_t)n * p.cin_pad + bcol) : p.w;
+            bsz[it] = ok ? 16u : 0u;
+          }
+          if (!(p.debug_skip & 64)) {
+#pragma unroll
+            for (int it = 0; it < A_IT; ++it) cp_async16(a_dst + sw128(it * (N_PROD / 8) + (tid >> 3), ch), asrc[it], asz[it]);
+#pragma unroll
+            for (int it = 0; it < B_IT; ++it) {
+              const int idx = it * N_PROD + tid;
+              if (idx < p.n_pad * 8) {
+                cp_async16(b_dst + sw128(idx >> 3, idx & 7), bsrc[it], bsz[it]);
+                if (SPLIT)
+                  cp_async16(b_dst + b_half + sw128(idx >> 3, idx & 7),
+                             bsrc[it] + (bsz[it] ? (size_t)p.n_pad * p.cin_pad : 0), bsz[it]);
+              }
+            }
+          }
+          // the mbarrier is signalled by the hardware once this thread's copies above have landed
+          cp_async_mbar_arrive_noinc(land_bar0 + 8 * s);
         }
       }
     }
-    // drain: publish the last min(DEPTH, nsteps) steps
-    cp_async_wait<0>();
-    for (int j = (nsteps > DEPTH ? nsteps - DEPTH : 0); j < nsteps; ++j) publish(j);
-  } else {
+  } else if (warp < MMA_WARP) {
+    // =========================== splitters / publishers ===========================
+    const int row = tid - SPLIT_WARP0 * 32;           // tile row owned by this thread
+    int g = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      mbar_wait(mask_bar0 + 8 * (ti % MASK_RING), (uint32_t)(ti / MASK_RING) & 1u);
+      const uint32_t mask = *(volatile uint32_t*)&mask_s[ti % MASK_RING];
+      const int nst = __popc(mask) * nchunk;
+      for (int st = 0; st < nst; ++st, ++g) {
+        const int s = g % STAGES;
+        mbar_wait(land_bar0 + 8 * s, (uint32_t)(g / STAGES) & 1u);
+        if (SPLIT) {
+          uint8_t* a_raw = a_s + s * a_bytes;
+#pragma unroll
+          for (int cch = 0; cch < 8; ++cch) {
+            const uint32_t off = sw128(row, cch);
+            float4 v = *reinterpret_cast<const float4*>(a_raw + off);
+            v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(a_raw + a_half + off) = v;
+          }
+        }
+        fence_proxy_async_smem();                     // generic-proxy writes (cp.async / st.shared) -> async proxy (MMA)
+        mbar_arrive(full_bar0 + 8 * s);
+      }
+    }
+  } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = make_idesc_tf32((uint32_t)p.n_pad);
-    int step = 0;
-    for (int k = 0; k < p.koff; ++k) {
-      uint32_t any = act_s[k * 4] | act_s[k * 4 + 1] | act_s[k * 4 + 2] | act_s[k * 4 + 3];
-      if (!any) continue;
-      for (int c = 0; c < nchunk; ++c, ++step) {
-        const int s = step % STAGES;
-        const uint32_t ph = (uint32_t)(step / STAGES) & 1u;
-        mbar_wait(full_bar0 + 8 * s, ph);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint64_t adesc = make_desc_k_sw128(smem_u32(a_s + s * a_bytes));
-          const uint64_t bdesc = make_desc_k_sw128(smem_u32(b_s + s * b_bytes));
-          const uint64_t alo = make_desc_k_sw128(smem_u32(a_s + s * a_bytes + a_half));
-          const uint64_t blo = make_desc_k_sw128(smem_u32(b_s + s * b_bytes + b_half));
-          const int kc = min(KCH, p.cin_pad - c * KCH);  // multiple of 8
-          for (int kk = 0; kk < kc / 8; ++kk) {
-            // advance 8 tf32 = 32 B inside the 128 B swizzle row: +2 in the >>4 address field
-            const uint64_t o = (uint64_t)(kk * 2);
-            umma_tf32(tmem_acc, adesc + o, bdesc + o, idesc, (step > 0 || kk > 0) ? 1u : 0u);
-            if (SPLIT) {
-              umma_tf32(tmem_acc, adesc + o, blo + o, idesc, 1u);
-              umma_tf32(tmem_acc, alo + o, bdesc + o, idesc, 1u);
-            }
-          }
-          umma_commit(empty_bar0 + 8 * s);
-          if (step == nsteps - 1) umma_commit(accum_bar);
-        }
-        __syncwarp();
-      }
-    }
-  }
-
-  // =========================== epilogue ===========================
-  if (tid < N_PROD) {
-    if (nsteps > 0) {
-      mbar_wait(accum_bar, 0);
+    int g = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      mbar_wait(mask_bar0 + 8 * (ti % MASK_RING), (uint32_t)(ti / MASK_RING) & 1u);
+      const uint32_t mask = *(volatile uint32_t*)&mask_s[ti % MASK_RING];
+      mbar_wait(acce_bar0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
       tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * p.n_pad);
+      int nst = 0;
+      for (int k = 0; k < p.koff; ++k)
+        if ((mask >> k) & 1u) nst += nchunk;
+      int st = 0;
+      for (int k = 0; k < p.koff; ++k) {
+        if (!((mask >> k) & 1u)) continue;
+        for (int c = 0; c < nchunk; ++c, ++g, ++st) {
+          const int s = g % STAGES;
+          const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+          mbar_wait(full_bar0 + 8 * s, ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t adesc = make_desc_k_sw128(smem_u32(a_s + s * a_bytes));
+            const uint64_t bdesc = make_desc_k_sw128(smem_u32(b_s + s * b_bytes));
+            const uint64_t alo = make_desc_k_sw128(smem_u32(a_s + s * a_bytes + a_half));
+            const uint64_t blo = make_desc_k_sw128(smem_u32(b_s + s * b_bytes + b_half));
+            const int kc = min(KCH, p.cin_pad - c * KCH);  // multiple of 8
+            for (int kk = 0; kk < ((p.debug_skip & 4) ? 0 : kc / 8); ++kk) {
+              // advance 8 tf32 = 32 B inside the 128 B swizzle row: +2 in the >>4 address field
+              const uint64_t o = (uint64_t)(kk * 2);
+              umma_tf32(tacc, adesc + o, bdesc + o, idesc, (st > 0 || kk > 0) ? 1u : 0u);
+              if (SPLIT) {
+                umma_tf32(tacc, adesc + o, blo + o, idesc, 1u);
+                umma_tf32(tacc, alo + o, bdesc + o, idesc, 1u);
+              }
+            }
+            umma_commit(empty_bar0 + 8 * s);
+            if (st == nst - 1) umma_commit(accf_bar0 + 8 * buf);
+          }
+          __syncwarp();
+        }
+      }
     }
-    const int r = row0 + tid;
-    const bool live = r < p.m_out;
-    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
-    const bool have_acc = nsteps > 0;
-
-    auto rnd = [&](float x) -> float { return p.round_out ? to_tf32(x) : x; };
-    if (p.epi == LS3D_EPI_ATTN) {
-      // q = acc + bias ; per head softmax(q.K^T * scale) V over the frame's class tokens
-      int f = 0;
-      for (int i = 1; i < p.n_frames; ++i)
-        if (r >= p.frame_off[i]) f = i;
-      const int L = p.n_tok;
-      for (int h = 0; h < p.n_head; ++h) {
-        uint32_t raw[24];
-        tmem_ld8(trow + h * DHEAD, raw);
-        tmem_ld8(trow + h * DHEAD + 8, raw + 8);
-        tmem_ld8(trow + h * DHEAD + 16, raw + 16);
-        tmem_ld_wait();
-        float q[DHEAD];
-#pragma unroll
-        for (int d = 0; d < DHEAD; ++d) {
-          float x = have_acc ? __uint_as_float(raw[d]) : 0.f;
-          q[d] = x + (p.shift ? __ldg(p.shift + h * DHEAD + d) : 0.f);
-        }
-        const float* kh = p.attn_k + ((size_t)(f * p.n_head + h) * L) * DHEAD;
-        const float* vh = p.attn_v + ((size_t)(f * p.n_head + h) * L) * DHEAD;
-        float sc[MAX_TOK];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int l = 0; l < MAX_TOK; ++l) {
-          if (l < L) {
-            float a = 0.f;
-#pragma unroll
-            for (int d4 = 0; d4 < DHEAD / 4; ++d4) {
-              float4 kv = ldg_f4(kh + l * DHEAD + d4 * 4);
-              a = fmaf(q[d4 * 4 + 0], kv.x, a);
-              a = fmaf(q[d4 * 4 + 1], kv.y, a);
-              a = fmaf(q[d4 * 4 + 2], kv.z, a);
-              a = fmaf(q[d4 * 4 + 3], kv.w, a);
-            }
-            a *= p.attn_scale;
-            sc[l] = a;
-            mx = fmaxf(mx, a);
-          }
-        }
-        float den = 0.f;
-        float o[DHEAD];
-#pragma unroll
-        for (int d = 0; d < DHEAD; ++d) o[d] = 0.f;
-#pragma unroll
-        for (int l = 0; l < MAX_TOK; ++l) {
-          if (l < L) {
-            float e = __expf(sc[l] - mx);
-            den += e;
-#pragma unroll
-            for (int d4 = 0; d4 < DHEAD / 4; ++d4) {
-              float4 vv = ldg_f4(vh + l * DHEAD + d4 * 4);
-              o[d4 * 4 + 0] = fmaf(e, vv.x, o[d4 * 4 + 0]);
-              o[d4 * 4 + 1] = fmaf(e, vv.y, o[d4 * 4 + 1]);
-              o[d4 * 4 + 2] = fmaf(e, vv.z, o[d4 * 4 + 2]);
-              o[d4 * 4 + 3] = fmaf(e, vv.w, o[d4 * 4 + 3]);
-            }
-          }
-        }
-        const float inv = 1.f / den;
-        if (live) {
-          float* dst = p.out + (size_t)r * p.ld_out + h * DHEAD;
-#pragma unroll
-          for (int d4 = 0; d4 < DHEAD / 4; ++d4)
-            *reinterpret_cast<float4*>(dst + d4 * 4) =
-                make_float4(rnd(o[d4 * 4] * inv), rnd(o[d4 * 4 + 1] * inv), rnd(o[d4 * 4 + 2] * inv), rnd(o[d4 * 4 + 3] * inv));
-        }
-      }
-    } else {
-      // value of column `col` after affine / residual / relu / channel-reduction
-      auto finish = [&](float acc, int col) -> float {
-        float x = acc;
-        if (p.scale) x *= __ldg(p.scale + col);
-        if (p.shift) x += __ldg(p.shift + col);
-        if (p.res_mode == 1 && live) x += __ldg(p.res + (size_t)r * p.ld_res + col);
-        if (p.relu) x = fmaxf(x, 0.f);
-        if (p.res_mode == 2 && live) x += __ldg(p.res + (size_t)r * p.ld_res + col);
-        if (p.red0 && live) {
-          // cat = [red0 (red_c ch) | red1 (red_c ch)] ; out[col] += cat[2col] + cat[2col+1]
-          const int c2 = 2 * col;
-          const float* src = (c2 < p.red_c) ? (p.red0 + (size_t)r * p.ld_red0 + c2)
-                                            : (p.red1 + (size_t)r * p.ld_red1 + (c2 - p.red_c));
-          x += __ldg(src) + __ldg(src + 1);
-        }
-        return x;
-      };
-      const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.cout & 3) == 0);
-      const bool masked = p.row_mask && live && (__ldg(p.row_mask + (size_t)r * p.ld_mask) != 1.0f);
-      float mean[2] = {0.f, 0.f}, rstd[2] = {1.f, 1.f};
-      // LayerNorm statistics (up to two chained LayerNorms), exact two-pass form per LN
-      for (int ln = 0; ln < p.n_ln; ++ln) {
-        float s1 = 0.f;
-        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-          uint32_t raw[16];
-          tmem_ld16(trow + c0, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = c0 + j;
-            if (col < p.cout) {
-              float x = finish(have_acc ? __uint_as_float(raw[j]) : 0.f, col);
-              if (ln == 1) x = (x - mean[0]) * rstd[0] * __ldg(p.ln_g0 + col) + __ldg(p.ln_b0 + col);
-              s1 += x;
-            }
-          }
-        }
-        const float m = s1 / (float)p.cout;
-        float s2 = 0.f;
-        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-          uint32_t raw[16];
-          tmem_ld16(trow + c0, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = c0 + j;
-            if (col < p.cout) {
-              float x = finish(have_acc ? __uint_as_float(raw[j]) : 0.f, col);
-              if (ln == 1) x = (x - mean[0]) * rstd[0] * __ldg(p.ln_g0 + col) + __ldg(p.ln_b0 + col);
-              const float d = x - m;
-              s2 = fmaf(d, d, s2);
-            }
-          }
-        }
-        mean[ln] = m;
-        rstd[ln] = rsqrtf(s2 / (float)p.cout + p.ln_eps);
-      }
-      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-        uint32_t raw[16];
-        tmem_ld16(trow + c0, raw);
-        tmem_ld_wait();
-        float y[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c0 + j;
-          float x = 0.f;
-          if (col < p.cout) {
-            x = finish(have_acc ? __uint_as_float(raw[j]) : 0.f, col);
-            if (p.n_ln > 0) x = (x - mean[0]) * rstd[0] * __ldg(p.ln_g0 + col) + __ldg(p.ln_b0 + col);
-            if (p.n_ln > 1) x = (x - mean[1]) * rstd[1] * __ldg(p.ln_g1 + col) + __ldg(p.ln_b1 + col);
-          }
-          y[j] = rnd(x);
-        }
-        if (masked) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) y[j] = 0.f;
-        }
-        if (live) {
-          float* dst = p.out + (size_t)r * p.ld_out + c0;
-          if (vec_ok) {
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-              if (c0 + j4 * 4 < p.cout)
-                *reinterpret_cast<float4*>(dst + j4 * 4) =
-                    make_float4(y[j4 * 4], y[j4 * 4 + 1], y[j4 * 4 + 2], y[j4 * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.cout) dst[j] = y[j];
-          }
-        }
-      }
+  } else {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int et = q * 32 + lane;                      // tile row owned by this thread
+    for (int c = et; c < COLV; c += 128) {
+      const bool in = c < p.cout;
+      colv[c] = (in && p.scale) ? __ldg(p.scale + c) : 1.f;
+      colv[COLV + c] = (in && p.shift) ? __ldg(p.shift + c) : 0.f;
+      colv[2 * COLV + c] = (in && p.n_ln > 0) ? __ldg(p.ln_g0 + c) : 1.f;
+      colv[3 * COLV + c] = (in && p.n_ln > 0) ? __ldg(p.ln_b0 + c) : 0.f;
+      colv[4 * COLV + c] = (in && p.n_ln > 1) ? __ldg(p.ln_g1 + c) : 1.f;
+      colv[5 * COLV + c] = (in && p.n_ln > 1) ? __ldg(p.ln_b1 + c) : 0.f;
+    }
+    bar_sync_epilogue();
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      mbar_wait(accf_bar0 + 8 * buf, (uint32_t)(ti >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t)(buf * p.n_pad) + ((uint32_t)(q * 32) << 16);
+      if (!(p.debug_skip & 8)) epilogue_tile(p, trow, tile * TILE_M, et, colv, stg);
+      tc_fence_before();
+      mbar_arrive(acce_bar0 + 8 * buf);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_acc, tmem_cols);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 static size_t smem_bytes_for(int stages, int n_pad, int koff, int nsplit) {
   size_t b = 1024;  // alignment slack
   b += (size_t)stages * nsplit * (a_stage_bytes() + b_stage_bytes(n_pad));
-  b += (size_t)koff * TILE_M * 4 + (size_t)koff * 16;
-  b += 8 + (2 * stages + 1) * 8 + 16;
+  b += (size_t)2 * koff * TILE_M * 4 + (size_t)2 * koff * 16 + MASK_RING * 4;
+  b += 8 + (3 * stages + 4 + MASK_RING) * 8 + 16 + 32;
+  b += (size_t)(6 * COLV + TILE_M * STG_LD) * 4;
   return b;
 }
 
@@ -430,16 +581,18 @@ extern "C" int ls3d_gather_gemm(const ls3d_gemm_args* a, void* stream) {
   }
   if (a->n_ln < 0 || a->n_ln > 2) return LS3D_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = ls3d_div_up(a->m_out, TILE_M);
-  // deepest pipeline that still lets two CTAs share one SM (<= ~110 KB each); tiles too big for that get one CTA per
-  // SM and as many stages as fit
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int ntiles = ls3d_div_up(a->m_out, TILE_M);
+  const int grid = ntiles < num_sms ? ntiles : num_sms;          // persistent: one CTA per SM
   const int nsplit = a->precise ? 2 : 1;
   int stages = 4;
-  while (stages > 2 && smem_bytes_for(stages, a->n_pad, a->koff, nsplit) > 110 * 1024) --stages;
-  if (smem_bytes_for(stages, a->n_pad, a->koff, nsplit) > 110 * 1024) {
-    stages = 4;
-    while (stages > 2 && smem_bytes_for(stages, a->n_pad, a->koff, nsplit) > 220 * 1024) --stages;
-  }
+  while (stages > 2 && smem_bytes_for(stages, a->n_pad, a->koff, nsplit) > 227 * 1024) --stages;
   const size_t smem = smem_bytes_for(stages, a->n_pad, a->koff, nsplit);
   if (smem > 227 * 1024) return LS3D_ERR_ARG;
   cudaError_t e;

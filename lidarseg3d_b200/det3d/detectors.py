@@ -73,8 +73,14 @@ class SegMSeg3DNet(_SegBase):
     # once per input shape into a CUDA graph and replayed on a side stream, overlapping the (launch-latency-bound) sparse
     # LiDAR branch on the main stream.
     use_image_graph = True
+    # None = fp32 storage with TF32 tensor-core convolutions (cuDNN default).  torch.float16 = fp16 storage and operands with
+    # fp32 accumulation: the same 10-bit operand mantissa as TF32 at half the memory traffic (the high-resolution HRNet
+    # branches are bandwidth bound).
+    image_dtype = None
 
     def _image_branch(self, images, batch_size):
+        if self.image_dtype is not None:
+            images = images.to(self.image_dtype)
         img_data = dict(inputs=self.img_backbone(images), batch_size=batch_size)
         img_data = self.img_head(batch_dict=img_data, return_loss=False)
         return img_data["image_features"], img_data["image_logits"], img_data.get("camera_semantic_embeddings", None)

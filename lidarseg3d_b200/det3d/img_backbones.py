@@ -44,8 +44,8 @@ def cbr(conv, bn, x, relu, z=None):
     if cache is None or cache[0] != key:
         with torch.no_grad():
             scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-            w = (conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
-            b = (bn.bias - bn.running_mean * scale).contiguous()
+            w = (conv.weight * scale.view(-1, 1, 1, 1)).to(x.dtype).contiguous(memory_format=torch.channels_last)
+            b = (bn.bias - bn.running_mean * scale).to(x.dtype).contiguous()
         cache = (key, w, b)
         conv._ls3d_fold = cache
     _, w, b = cache

@@ -88,7 +88,11 @@ class FCNMSeg3DHead(nn.Module):
         feats = self.convs(x)
         if self.concat_input:
             feats = self.conv_cat(torch.cat([x, feats], dim=1))
-        logits = self.conv_seg(feats if self.dropout is None else self.dropout(feats))
+        cs = self.conv_seg
+        logits = F.conv2d(feats if self.dropout is None else self.dropout(feats), cs.weight.to(feats.dtype),
+                          cs.bias.to(feats.dtype))
+        if feats.dtype != torch.float32:               # fp16 image branch: hand fp32 maps to the fusion kernels
+            feats, logits = feats.float(), logits.float()
         emb = self.camera_sfam(feats, logits, batch_dict["batch_size"])
         self.forward_ret_dict["image_logits"] = logits
         batch_dict["image_logits"] = logits

@@ -94,11 +94,15 @@ def _predict(out_logits, example, test_cfg):
     else:
         metas = example["metadata"] if has_meta else [None] * batch_size
         labels = torch.argmax(out_logits, dim=1)
+        # frames are contiguous (collate order): per-frame masks of the reference == slices
+        counts = torch.bincount(stack_points[:, 0].long(), minlength=batch_size)[:batch_size].cpu().tolist()
+        lo = 0
         for i in range(batch_size):
-            mask = stack_points[:, 0] == i
-            ret = {"metadata": metas[i], "pred_point_sem_labels": labels[mask]}
+            sl = slice(lo, lo + counts[i])
+            lo += counts[i]
+            ret = {"metadata": metas[i], "pred_point_sem_labels": labels[sl]}
             if "point_sem_labels" in example:
-                ret["point_sem_labels"] = example["point_sem_labels"][mask]
+                ret["point_sem_labels"] = example["point_sem_labels"][sl]
             ret_list.append(ret)
     return ret_list
 

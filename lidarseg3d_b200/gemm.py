@@ -19,6 +19,7 @@ def pad_to(v, m):
 # bench.py instrumentation: PROFILE = list -> CUDA events + static sizes per launch; COUNT = list -> rulebook pair counts
 PROFILE = None
 COUNT = None
+DEBUG_SKIP = 0      # development only (see ls3d_gemm_args.debug_skip)
 
 
 # True: error-compensated 3xTF32 everywhere (fp32-level accuracy; default).  False: single-pass TF32 with tf32-rounded
@@ -112,6 +113,7 @@ def run(x0, pw: PackedWeight, *, x1=None, nbr=None, m_out=None, scale=None, shif
     a.out, a.ld_out = capi.ptr(out), out.stride(0)
     a.round_out = int(round_out and not pw.precise)
     a.precise = int(pw.precise)
+    a.debug_skip = DEBUG_SKIP
     if COUNT is not None:
         COUNT.append(int((nbr >= 0).sum()) if nbr is not None else m)
     if PROFILE is not None:

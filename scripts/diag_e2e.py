@@ -9,8 +9,9 @@ from lidarseg3d_b200 import pipeline, synth
 def rel(a, b):
     return float((a.cpu() - b).abs().max() / b.abs().max())
 
-def stage_errors(tag):
+def stage_errors(tag, image_dtype=None):
     cfg, m = _build("mseg3d_nuscenes.py")
+    m.image_dtype = image_dtype
     spec = dict(synth.NUSC); spec.update(beams=16, azimuths=400)
     hw = (128, 192)
     frames = [synth.lidar_scan(spec, s) for s in (0, 1)]
@@ -34,6 +35,7 @@ def stage_errors(tag):
     return r
 
 stage_errors("cudnn_tf32")
+stage_errors("cudnn_fp16", torch.float16)
 torch.backends.cudnn.allow_tf32 = False
 stage_errors("cudnn_fp32")
 torch.backends.cudnn.allow_tf32 = True
