@@ -179,24 +179,13 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
   }
 
   const bool masked = p.row_mask && live && (__ldg(p.row_mask + (size_t)r * p.ld_mask) != 1.0f);
-  // value of column `col` after affine / residual / relu / channel-reduction (resv = this row's residual at col)
-  auto finish = [&](float acc, int col, float resv) -> float {
-    float x = fmaf(acc, colv[col], colv[COLV + col]);
-    if (p.res_mode == 1) x += resv;
-    if (p.relu) x = fmaxf(x, 0.f);
-    if (p.res_mode == 2) x += resv;
-    if (p.red0 && live) {
-      // cat = [red0 (red_c ch) | red1 (red_c ch)] ; out[col] += cat[2col] + cat[2col+1]
-      const int c2 = 2 * col;
-      const float* src = (c2 < p.red_c) ? (p.red0 + (size_t)r * p.ld_red0 + c2) : (p.red1 + (size_t)r * p.ld_red1 + (c2 - p.red_c));
-      const float2 t = __ldg(reinterpret_cast<const float2*>(src));
-      x += t.x + t.y;
-    }
-    return x;
-  };
-  // one 16-column panel of finished values into v[] (columns >= cout -> 0)
+  const bool has_affine = p.scale || p.shift;
+  // one 16-column panel of finished values into v[]: acc * scale + shift, residual, ReLU, channel-reduction add.
+  // Every option is a warp-uniform branch around a short unrolled pass over the register panel.
   auto finished_panel = [&](int c0, float* v) {
     const int w = min(PANEL, p.cout - c0);
+    uint32_t raw[PANEL];
+    tmem_ld16(trow + c0, raw);
     float rv[PANEL];
     if (p.res_mode) {
       panel_load(stg, p.res, p.ld_res, row0, rows_valid, c0, w, et);
@@ -207,15 +196,47 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
         rv[j4 * 4] = t.x; rv[j4 * 4 + 1] = t.y; rv[j4 * 4 + 2] = t.z; rv[j4 * 4 + 3] = t.w;
       }
       bar_sync_epilogue();
-    } else {
-#pragma unroll
-      for (int j = 0; j < PANEL; ++j) rv[j] = 0.f;
     }
-    uint32_t raw[PANEL];
-    tmem_ld16(trow + c0, raw);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < PANEL; ++j) v[j] = (j < w) ? finish(__uint_as_float(raw[j]), c0 + j, rv[j]) : 0.f;
+    for (int j = 0; j < PANEL; ++j) v[j] = __uint_as_float(raw[j]);
+    if (has_affine) {
+#pragma unroll
+      for (int j4 = 0; j4 < PANEL / 4; ++j4) {
+        const float4 sc = *reinterpret_cast<const float4*>(colv + c0 + j4 * 4);
+        const float4 sh = *reinterpret_cast<const float4*>(colv + COLV + c0 + j4 * 4);
+        v[j4 * 4] = fmaf(v[j4 * 4], sc.x, sh.x); v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], sc.y, sh.y);
+        v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], sc.z, sh.z); v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], sc.w, sh.w);
+      }
+    }
+    if (p.res_mode == 1) {
+#pragma unroll
+      for (int j = 0; j < PANEL; ++j) v[j] += rv[j];
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < PANEL; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.res_mode == 2) {
+#pragma unroll
+      for (int j = 0; j < PANEL; ++j) v[j] += rv[j];
+    }
+    if (p.red0 && live) {
+      // cat = [red0 (red_c ch) | red1 (red_c ch)] ; out[col] += cat[2col] + cat[2col+1]: 32 consecutive source columns
+      const int c2 = 2 * c0;
+      const float* src = (c2 < p.red_c) ? (p.red0 + (size_t)r * p.ld_red0 + c2) : (p.red1 + (size_t)r * p.ld_red1 + (c2 - p.red_c));
+#pragma unroll
+      for (int j2 = 0; j2 < PANEL / 2; ++j2) {
+        const float4 t = ldg_f4(src + j2 * 4);
+        v[j2 * 2] += t.x + t.y;
+        v[j2 * 2 + 1] += t.z + t.w;
+      }
+    }
+    if (w < PANEL) {
+#pragma unroll
+      for (int j = 0; j < PANEL; ++j)
+        if (j >= w) v[j] = 0.f;
+    }
   };
   auto emit_panel = [&](int c0, const float* v) {
     const int w = min(PANEL, p.cout - c0);
@@ -223,8 +244,9 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
     for (int j4 = 0; j4 < PANEL / 4; ++j4)
       *reinterpret_cast<float4*>(my + j4 * 4) = masked ? make_float4(0.f, 0.f, 0.f, 0.f)
                                                        : make_float4(rnd(v[j4 * 4]), rnd(v[j4 * 4 + 1]), rnd(v[j4 * 4 + 2]), rnd(v[j4 * 4 + 3]));
+    if (p.debug_skip & 512) return;
     bar_sync_epilogue();
-    panel_store(stg, p.out, p.ld_out, row0, rows_valid, c0, w, et);
+    if (!(p.debug_skip & 256)) panel_store(stg, p.out, p.ld_out, row0, rows_valid, c0, w, et);
     bar_sync_epilogue();
   };
 
@@ -353,10 +375,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool poll = (p.debug_skip & 1024) != 0;
+  auto WAIT = [&](uint32_t bar, uint32_t parity) {
+    if (poll) mbar_wait_poll(bar, parity); else mbar_wait(bar, parity);
+  };
 
   if (warp < N_PROD_WARPS) {
     // =========================== producers ===========================
     const int ch = tid & 7;
+    const int rsub = tid >> 3;                         // row within a 32-row group (A) / 32-row group of W
+    constexpr int A_IT = TILE_M * 8 / N_PROD;
+    constexpr int B_IT = 256 * 8 / N_PROD;
+    uint32_t soff[B_IT];                               // swizzled smem offsets of (row it*32 + rsub, chunk ch)
+#pragma unroll
+    for (int it = 0; it < B_IT; ++it) soff[it] = sw128(it * (N_PROD / 8) + rsub, ch);
     int g = 0;                                        // global step counter (ring position), continues across tiles
     int ti = 0;
     const int my_row = tid & (TILE_M - 1);            // thread t loads rulebook row (t & 127) for half of the offsets
@@ -401,48 +433,39 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
         for (int c = 0; c < nchunk; ++c, ++g) {
           const int s = g % STAGES;
           const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
-          mbar_wait(empty_bar0 + 8 * s, ph ^ 1u);
+          WAIT(empty_bar0 + 8 * s, ph ^ 1u);
           const uint32_t a_dst = smem_u32(a_s + s * a_bytes);
           const uint32_t b_dst = smem_u32(b_s + s * b_bytes);
           // ---- A: 128 rows x 8 chunks of 16 B; 8 lanes cover one row (4 full 128 B lines per warp request).
-          // Addresses of all copies are formed first so the copies issue back to back (the asm statements are ordering
-          // points for the compiler).
-          constexpr int A_IT = TILE_M * 8 / N_PROD;
+          // Everything that does not depend on the row is hoisted: source tensor / column select per chunk, swizzled
+          // destination offsets per thread.  Sources are formed first so the copies issue back to back.
           const int col = c * KCH + ch * 4;
+          const bool col_ok = (col < cin) && !(p.debug_skip & 1);
+          const float* abase = (col < p.c0) ? (p.in0 + col) : (p.in1 + (col - p.c0));
+          const size_t ald = (col < p.c0) ? (size_t)p.ld0 : (size_t)p.ld1;
+          const int* nbk = nb + k * TILE_M + rsub;
           const float* asrc[A_IT];
           uint32_t asz[A_IT];
 #pragma unroll
           for (int it = 0; it < A_IT; ++it) {
-            const int j = nb[k * TILE_M + it * (N_PROD / 8) + (tid >> 3)];
-            const bool ok = (j >= 0) && (col < cin) && !(p.debug_skip & 1);
-            asrc[it] = p.in0;
-            if (ok) asrc[it] = (col < p.c0) ? (p.in0 + (size_t)j * p.ld0 + col) : (p.in1 + (size_t)j * p.ld1 + (col - p.c0));
+            const int j = nbk[it * (N_PROD / 8)];
+            const bool ok = (j >= 0) && col_ok;
+            asrc[it] = ok ? (abase + (size_t)j * ald) : p.in0;
             asz[it] = ok ? 16u : 0u;
-          }
-          // ---- B: n_pad rows x 8 chunks (x2 when split); n_pad * 8 / N_PROD <= 8 copies per thread
-          constexpr int B_IT = 256 * 8 / N_PROD;
-          const float* bsrc[B_IT];
-          uint32_t bsz[B_IT];
-#pragma unroll
-          for (int it = 0; it < B_IT; ++it) {
-            const int idx = it * N_PROD + tid;
-            const int n = idx >> 3;
-            const int bcol = c * KCH + (idx & 7) * 4;
-            const bool ok = (idx < p.n_pad * 8) && (bcol < p.cin_pad) && !(p.debug_skip & 2);
-            bsrc[it] = ok ? (wk + (size_t)n * p.cin_pad + bcol) : p.w;
-            bsz[it] = ok ? 16u : 0u;
           }
           if (!(p.debug_skip & 64)) {
 #pragma unroll
-            for (int it = 0; it < A_IT; ++it) cp_async16(a_dst + sw128(it * (N_PROD / 8) + (tid >> 3), ch), asrc[it], asz[it]);
+            for (int it = 0; it < A_IT; ++it) cp_async16(a_dst + soff[it], asrc[it], asz[it]);
+            // ---- B: n_pad rows x 8 chunks (x2 when split): row it*32 + rsub, chunk ch -> same swizzled offsets
+            const bool bok = (col < p.cin_pad) && !(p.debug_skip & 2);
+            const float* bsrc = wk + (size_t)rsub * p.cin_pad + col;
+            const uint32_t bsz = bok ? 16u : 0u;
 #pragma unroll
             for (int it = 0; it < B_IT; ++it) {
-              const int idx = it * N_PROD + tid;
-              if (idx < p.n_pad * 8) {
-                cp_async16(b_dst + sw128(idx >> 3, idx & 7), bsrc[it], bsz[it]);
-                if (SPLIT)
-                  cp_async16(b_dst + b_half + sw128(idx >> 3, idx & 7),
-                             bsrc[it] + (bsz[it] ? (size_t)p.n_pad * p.cin_pad : 0), bsz[it]);
+              if (it * (N_PROD / 8) < p.n_pad) {
+                const float* src = bok ? (bsrc + (size_t)it * (N_PROD / 8) * p.cin_pad) : p.w;
+                cp_async16(b_dst + soff[it], src, bsz);
+                if (SPLIT) cp_async16(b_dst + b_half + soff[it], bok ? (src + (size_t)p.n_pad * p.cin_pad) : p.w, bsz);
               }
             }
           }
@@ -456,12 +479,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
     const int row = tid - SPLIT_WARP0 * 32;           // tile row owned by this thread
     int g = 0, ti = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
-      mbar_wait(mask_bar0 + 8 * (ti % MASK_RING), (uint32_t)(ti / MASK_RING) & 1u);
+      WAIT(mask_bar0 + 8 * (ti % MASK_RING), (uint32_t)(ti / MASK_RING) & 1u);
       const uint32_t mask = *(volatile uint32_t*)&mask_s[ti % MASK_RING];
       const int nst = __popc(mask) * nchunk;
       for (int st = 0; st < nst; ++st, ++g) {
         const int s = g % STAGES;
-        mbar_wait(land_bar0 + 8 * s, (uint32_t)(g / STAGES) & 1u);
+        WAIT(land_bar0 + 8 * s, (uint32_t)(g / STAGES) & 1u);
         if (SPLIT) {
           uint8_t* a_raw = a_s + s * a_bytes;
 #pragma unroll
@@ -485,9 +508,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
     int g = 0, ti = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const int buf = ti & 1;
-      mbar_wait(mask_bar0 + 8 * (ti % MASK_RING), (uint32_t)(ti / MASK_RING) & 1u);
+      WAIT(mask_bar0 + 8 * (ti % MASK_RING), (uint32_t)(ti / MASK_RING) & 1u);
       const uint32_t mask = *(volatile uint32_t*)&mask_s[ti % MASK_RING];
-      mbar_wait(acce_bar0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
+      WAIT(acce_bar0 + 8 * buf, ((uint32_t)(ti >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(buf * p.n_pad);
       int nst = 0;
@@ -499,7 +522,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
         for (int c = 0; c < nchunk; ++c, ++g, ++st) {
           const int s = g % STAGES;
           const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
-          mbar_wait(full_bar0 + 8 * s, ph);
+          WAIT(full_bar0 + 8 * s, ph);
           tc_fence_after();
           if (lane == 0) {
             const uint64_t adesc = make_desc_k_sw128(smem_u32(a_s + s * a_bytes));
@@ -540,7 +563,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
     int ti = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const int buf = ti & 1;
-      mbar_wait(accf_bar0 + 8 * buf, (uint32_t)(ti >> 1) & 1u);
+      WAIT(accf_bar0 + 8 * buf, (uint32_t)(ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(buf * p.n_pad) + ((uint32_t)(q * 32) << 16);
       if (!(p.debug_skip & 8)) epilogue_tile(p, trow, tile * TILE_M, et, colv, stg);

@@ -31,8 +31,8 @@ for precise in (False, True):
                        ("dense_1.9M_64_192", (1900000, 64, 192, 1.0, 1, False))]:
         x, pw, nbr, out = setup(*args)
         row = {}
-        for skip in (0, 8, 15):
+        for skip in (0, 8, 15, 79):
             gemm.DEBUG_SKIP = skip
             row[skip] = round(t(x, pw, nbr, out), 1)
         gemm.DEBUG_SKIP = 0
-        print(f"precise={precise} {name} us by skip mask (1=noA 2=noW 4=noMMA 8=noEpi 16=noFence 32=plainArrive):", row, flush=True)
+        print(f"precise={precise} {name} us by skip mask (1=noA 2=noW 4=noMMA 8=noEpi 64=noCpAsyncIssue 256=noGlobalStore 512=noPanel 1024=pollWait):", row, flush=True)
