@@ -318,11 +318,8 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
 //   x = x_hi + x_lo (x_hi = trunc_tf32(x), x_lo = x - x_hi exactly) and W = W_hi + W_lo (split on the host),
 //   x.W ~= x_hi.W_hi + x_hi.W_lo + x_lo.W_hi   (dropped term x_lo.W_lo ~ 2^-22): fp32-level accuracy from three MMAs.
 // x_hi comes for free (the raw fp32 tile, truncated by the MMA); the producers derive the x_lo tile from the landed raw tile.
-// Steps are published in groups: G consecutive steps of a tile share one landed / full / empty barrier round
-// (NG groups in the ring, G * NG smem slots), which divides the number of barrier hand-offs per tile by G.
-template <bool SPLIT>
-__global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_gemm_args p, const int G, const int NG) {
-  const int STAGES = G * NG;                           // smem slots
+template <int STAGES, bool SPLIT>
+__global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_gemm_args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t NSPLIT = SPLIT ? 2u : 1u;
@@ -336,7 +333,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
   uint32_t* act_s = (uint32_t*)(nbr_s + 2 * p.koff * TILE_M);      // [2][koff][4] warp ballots
   uint32_t* mask_s = act_s + 2 * p.koff * 4;                       // [MASK_RING] active-offset masks
   uint64_t* bars = (uint64_t*)(((uintptr_t)(mask_s + MASK_RING) + 7) & ~(uintptr_t)7);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * NG + 4 + MASK_RING);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4 + MASK_RING);
   float* colv = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);      // [6][COLV] per-column vectors
   float* stg = colv + 6 * COLV;                                                      // [128][STG_LD] epilogue panel
 
@@ -347,19 +344,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
   const int nchunk = (p.cin_pad + KCH - 1) / KCH;
   const int ntiles = (p.m_out + TILE_M - 1) / TILE_M;
 
-  const uint32_t full_bar0 = smem_u32(bars);                    // group published to the MMA warp [NG]
-  const uint32_t empty_bar0 = smem_u32(bars + NG);              // group consumed                  [NG]
-  const uint32_t land_bar0 = smem_u32(bars + 2 * NG);           // group's cp.async data landed    [NG]
-  const uint32_t accf_bar0 = smem_u32(bars + 3 * NG);           // accumulator full  [2]
-  const uint32_t acce_bar0 = smem_u32(bars + 3 * NG + 2);       // accumulator empty [2]
-  const uint32_t mask_bar0 = smem_u32(bars + 3 * NG + 4);       // mask published    [MASK_RING]
+  const uint32_t full_bar0 = smem_u32(bars);
+  const uint32_t empty_bar0 = smem_u32(bars + STAGES);
+  const uint32_t land_bar0 = smem_u32(bars + 2 * STAGES);       // cp.async data landed [STAGES]
+  const uint32_t accf_bar0 = smem_u32(bars + 3 * STAGES);       // accumulator full  [2]
+  const uint32_t acce_bar0 = smem_u32(bars + 3 * STAGES + 2);   // accumulator empty [2]
+  const uint32_t mask_bar0 = smem_u32(bars + 3 * STAGES + 4);   // mask published    [MASK_RING]
 
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * (uint32_t)p.n_pad) tmem_cols <<= 1;
 
   if (warp == MMA_WARP) {
     if (lane == 0) {
-      for (int s = 0; s < NG; ++s) {
+      for (int s = 0; s < STAGES; ++s) {
         mbar_init(full_bar0 + 8 * s, 128);
         mbar_init(empty_bar0 + 8 * s, 1);
         mbar_init(land_bar0 + 8 * s, N_PROD);
@@ -430,18 +427,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
         mask_s[ti % MASK_RING] = mask;
         mbar_arrive(mask_bar0 + 8 * (ti % MASK_RING));
       }
-      const int nst = __popc(mask) * nchunk;
-      int st = 0, grp = 0;
       for (int k = 0; k < p.koff; ++k) {
         if (!((mask >> k) & 1u)) continue;
         const float* wk = p.w + (size_t)k * NSPLIT * p.n_pad * p.cin_pad;
-        for (int c = 0; c < nchunk; ++c) {
-          const int u = st % G;
-          if (u == 0) {
-            grp = g % NG;
-            WAIT(empty_bar0 + 8 * grp, ((uint32_t)(g / NG) & 1u) ^ 1u);
-          }
-          const int s = grp * G + u;
+        for (int c = 0; c < nchunk; ++c, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+          WAIT(empty_bar0 + 8 * s, ph ^ 1u);
           const uint32_t a_dst = smem_u32(a_s + s * a_bytes);
           const uint32_t b_dst = smem_u32(b_s + s * b_bytes);
           // ---- A: 128 rows x 8 chunks of 16 B; 8 lanes cover one row (4 full 128 B lines per warp request).
@@ -477,12 +469,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
               }
             }
           }
-          ++st;
-          if (u == G - 1 || st == nst) {
-            // the mbarrier is signalled by the hardware once this thread's copies of the whole group have landed
-            cp_async_mbar_arrive_noinc(land_bar0 + 8 * grp);
-            ++g;
-          }
+          // the mbarrier is signalled by the hardware once this thread's copies above have landed
+          cp_async_mbar_arrive_noinc(land_bar0 + 8 * s);
         }
       }
     }
@@ -494,27 +482,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
       WAIT(mask_bar0 + 8 * (ti % MASK_RING), (uint32_t)(ti / MASK_RING) & 1u);
       const uint32_t mask = *(volatile uint32_t*)&mask_s[ti % MASK_RING];
       const int nst = __popc(mask) * nchunk;
-      for (int st0 = 0; st0 < nst; st0 += G, ++g) {
-        const int grp = g % NG;
-        const int cnt = min(G, nst - st0);
-        WAIT(land_bar0 + 8 * grp, (uint32_t)(g / NG) & 1u);
+      for (int st = 0; st < nst; ++st, ++g) {
+        const int s = g % STAGES;
+        WAIT(land_bar0 + 8 * s, (uint32_t)(g / STAGES) & 1u);
         if (SPLIT) {
-          for (int u = 0; u < cnt; ++u) {
-            uint8_t* a_raw = a_s + (grp * G + u) * a_bytes;
+          uint8_t* a_raw = a_s + s * a_bytes;
 #pragma unroll
-            for (int cch = 0; cch < 8; ++cch) {
-              const uint32_t off = sw128(row, cch);
-              float4 v = *reinterpret_cast<const float4*>(a_raw + off);
-              v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-              v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-              v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-              v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-              *reinterpret_cast<float4*>(a_raw + a_half + off) = v;
-            }
+          for (int cch = 0; cch < 8; ++cch) {
+            const uint32_t off = sw128(row, cch);
+            float4 v = *reinterpret_cast<const float4*>(a_raw + off);
+            v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(a_raw + a_half + off) = v;
           }
         }
         fence_proxy_async_smem();                     // generic-proxy writes (cp.async / st.shared) -> async proxy (MMA)
-        mbar_arrive(full_bar0 + 8 * grp);
+        mbar_arrive(full_bar0 + 8 * s);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -531,18 +516,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
       int nst = 0;
       for (int k = 0; k < p.koff; ++k)
         if ((mask >> k) & 1u) nst += nchunk;
-      int st = 0, grp = 0;
+      int st = 0;
       for (int k = 0; k < p.koff; ++k) {
         if (!((mask >> k) & 1u)) continue;
-        for (int c = 0; c < nchunk; ++c) {
-          const int u = st % G;
-          if (u == 0) {
-            grp = g % NG;
-            WAIT(full_bar0 + 8 * grp, (uint32_t)(g / NG) & 1u);
-            tc_fence_after();
-          }
-          const int s = grp * G + u;
-          const bool last_of_group = (u == G - 1) || (st == nst - 1);
+        for (int c = 0; c < nchunk; ++c, ++g, ++st) {
+          const int s = g % STAGES;
+          const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+          WAIT(full_bar0 + 8 * s, ph);
+          tc_fence_after();
           if (lane == 0) {
             const uint64_t adesc = make_desc_k_sw128(smem_u32(a_s + s * a_bytes));
             const uint64_t bdesc = make_desc_k_sw128(smem_u32(b_s + s * b_bytes));
@@ -558,14 +539,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
                 umma_tf32(tacc, alo + o, bdesc + o, idesc, 1u);
               }
             }
-            if (last_of_group) {
-              umma_commit(empty_bar0 + 8 * grp);
-              if (st == nst - 1) umma_commit(accf_bar0 + 8 * buf);
-            }
+            umma_commit(empty_bar0 + 8 * s);
+            if (st == nst - 1) umma_commit(accf_bar0 + 8 * buf);
           }
           __syncwarp();
-          ++st;
-          if (last_of_group) ++g;
         }
       }
     }
@@ -600,12 +577,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-static size_t smem_bytes_for(int G, int NG, int n_pad, int koff, int nsplit) {
-  const int stages = G * NG;
+static size_t smem_bytes_for(int stages, int n_pad, int koff, int nsplit) {
   size_t b = 1024;  // alignment slack
   b += (size_t)stages * nsplit * (a_stage_bytes() + b_stage_bytes(n_pad));
   b += (size_t)2 * koff * TILE_M * 4 + (size_t)2 * koff * 16 + MASK_RING * 4;
-  b += 8 + (3 * NG + 4 + MASK_RING) * 8 + 16 + 32;
+  b += 8 + (3 * stages + 4 + MASK_RING) * 8 + 16 + 32;
   b += (size_t)(6 * COLV + TILE_M * STG_LD) * 4;
   return b;
 }
@@ -638,28 +614,28 @@ extern "C" int ls3d_gather_gemm(const ls3d_gemm_args* a, void* stream) {
   const int ntiles = ls3d_div_up(a->m_out, TILE_M);
   const int grid = ntiles < num_sms ? ntiles : num_sms;          // persistent: one CTA per SM
   const int nsplit = a->precise ? 2 : 1;
-  // group size: as many steps per barrier round as fit in ~88 KB; then as many groups as the 227 KB allow (>= 2)
-  const size_t sub = (size_t)nsplit * (a_stage_bytes() + b_stage_bytes(a->n_pad));
-  int G = (int)((88 * 1024) / sub);
-  if (G < 1) G = 1;
-  if (G > 4) G = 4;
-  const int nchunk = (a->cin_pad + KCH - 1) / KCH;
-  if (G > a->koff * nchunk) G = a->koff * nchunk;
-  int NG = 4;
-  while (NG > 2 && smem_bytes_for(G, NG, a->n_pad, a->koff, nsplit) > 227 * 1024) --NG;
-  while (G > 1 && smem_bytes_for(G, NG, a->n_pad, a->koff, nsplit) > 227 * 1024) --G;
-  const size_t smem = smem_bytes_for(G, NG, a->n_pad, a->koff, nsplit);
+  int stages = 4;
+  while (stages > 2 && smem_bytes_for(stages, a->n_pad, a->koff, nsplit) > 227 * 1024) --stages;
+  const size_t smem = smem_bytes_for(stages, a->n_pad, a->koff, nsplit);
   if (smem > 227 * 1024) return LS3D_ERR_ARG;
   cudaError_t e;
-  if (a->precise) {
-    e = cudaFuncSetAttribute(gather_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    gather_gemm_kernel<true><<<grid, N_THREADS, smem, st>>>(*a, G, NG);
-  } else {
-    e = cudaFuncSetAttribute(gather_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    gather_gemm_kernel<false><<<grid, N_THREADS, smem, st>>>(*a, G, NG);
+#define LS3D_GG_LAUNCH(S, P)                                                                         \
+  {                                                                                                  \
+    e = cudaFuncSetAttribute(gather_gemm_kernel<S, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             (int)smem);                                                             \
+    if (e != cudaSuccess) return (int)e;                                                             \
+    gather_gemm_kernel<S, P><<<grid, N_THREADS, smem, st>>>(*a);                                     \
   }
+  if (a->precise) {
+    if (stages == 4) LS3D_GG_LAUNCH(4, true)
+    else if (stages == 3) LS3D_GG_LAUNCH(3, true)
+    else LS3D_GG_LAUNCH(2, true)
+  } else {
+    if (stages == 4) LS3D_GG_LAUNCH(4, false)
+    else if (stages == 3) LS3D_GG_LAUNCH(3, false)
+    else LS3D_GG_LAUNCH(2, false)
+  }
+#undef LS3D_GG_LAUNCH
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
