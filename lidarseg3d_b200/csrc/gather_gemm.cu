@@ -59,49 +59,53 @@ constexpr int COLV = 256;              // stride of the per-column vectors in sm
 
 __device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
-// cooperative [rows_valid x w] panel copy global -> stg (zero outside)
-__device__ __forceinline__ void panel_load(float* stg, const float* src, int ld, int row0, int rows_valid, int c0, int w,
-                                            int et) {
+// Each epilogue warp stages only its own 32 rows, so a __syncwarp() is all the synchronisation a panel needs.
+// warp-cooperative [<=32 rows x w] panel copy global -> stgw (zero outside); rows0 = first global row of the warp
+__device__ __forceinline__ void panel_load(float* stgw, const float* src, int ld, int rows0, int rows_valid, int c0, int w,
+                                            int lane) {
   if (((ld | c0) & 3) == 0 && (w & 3) == 0) {
 #pragma unroll
     for (int i = 0; i < PANEL / 4; ++i) {
-      const int idx = i * 128 + et, rr = idx / (PANEL / 4), cn = (idx % (PANEL / 4)) * 4;
+      const int idx = i * 32 + lane, rr = idx / (PANEL / 4), cn = (idx % (PANEL / 4)) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rr < rows_valid && cn < w) v = ldg_f4(src + (size_t)(row0 + rr) * ld + c0 + cn);
-      *reinterpret_cast<float4*>(stg + rr * STG_LD + cn) = v;
+      if (rr < rows_valid && cn < w) v = ldg_f4(src + (size_t)(rows0 + rr) * ld + c0 + cn);
+      *reinterpret_cast<float4*>(stgw + rr * STG_LD + cn) = v;
     }
   } else {
-    for (int idx = et; idx < TILE_M * PANEL; idx += 128) {
+    for (int idx = lane; idx < 32 * PANEL; idx += 32) {
       const int rr = idx / PANEL, cn = idx % PANEL;
-      stg[rr * STG_LD + cn] = (rr < rows_valid && cn < w) ? __ldg(src + (size_t)(row0 + rr) * ld + c0 + cn) : 0.f;
+      stgw[rr * STG_LD + cn] = (rr < rows_valid && cn < w) ? __ldg(src + (size_t)(rows0 + rr) * ld + c0 + cn) : 0.f;
     }
   }
 }
-// cooperative [rows_valid x w] panel copy stg -> global
-__device__ __forceinline__ void panel_store(const float* stg, float* dst, int ld, int row0, int rows_valid, int c0, int w,
-                                             int et) {
+// warp-cooperative [<=32 rows x w] panel copy stgw -> global: 8 rows x 64 contiguous bytes per warp request
+__device__ __forceinline__ void panel_store(const float* stgw, float* dst, int ld, int rows0, int rows_valid, int c0, int w,
+                                             int lane) {
   if (((ld | c0) & 3) == 0 && (w & 3) == 0) {
 #pragma unroll
     for (int i = 0; i < PANEL / 4; ++i) {
-      const int idx = i * 128 + et, rr = idx / (PANEL / 4), cn = (idx % (PANEL / 4)) * 4;
+      const int idx = i * 32 + lane, rr = idx / (PANEL / 4), cn = (idx % (PANEL / 4)) * 4;
       if (rr < rows_valid && cn < w)
-        *reinterpret_cast<float4*>(dst + (size_t)(row0 + rr) * ld + c0 + cn) = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cn);
+        *reinterpret_cast<float4*>(dst + (size_t)(rows0 + rr) * ld + c0 + cn) = *reinterpret_cast<const float4*>(stgw + rr * STG_LD + cn);
     }
   } else {
-    for (int idx = et; idx < TILE_M * PANEL; idx += 128) {
+    for (int idx = lane; idx < 32 * PANEL; idx += 32) {
       const int rr = idx / PANEL, cn = idx % PANEL;
-      if (rr < rows_valid && cn < w) dst[(size_t)(row0 + rr) * ld + c0 + cn] = stg[rr * STG_LD + cn];
+      if (rr < rows_valid && cn < w) dst[(size_t)(rows0 + rr) * ld + c0 + cn] = stgw[rr * STG_LD + cn];
     }
   }
 }
 
-__device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uint32_t trow, const int row0, const int et,
-                                              const float* colv, float* stg) {
-  const int r = row0 + et;
+__device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uint32_t trow, const int tile_row0, const int et,
+                                              const float* colv, float* stg_all) {
+  const int lane = et & 31;
+  const int row0 = tile_row0 + (et & ~31);             // first global row of this warp's 32-row slice
+  const int r = tile_row0 + et;
   const bool live = r < p.m_out;
-  const int rows_valid = min(TILE_M, p.m_out - row0);
+  const int rows_valid = max(0, min(32, p.m_out - row0));
   auto rnd = [&](float x) -> float { return p.round_out ? to_tf32(x) : x; };
-  float* my = stg + et * STG_LD;
+  float* stg = stg_all + (et & ~31) * STG_LD;          // this warp's staging rows
+  float* my = stg + lane * STG_LD;
 
   if (p.epi == LS3D_EPI_ATTN) {
     // q = acc + bias ; per head softmax(q.K^T * scale) V over the frame's class tokens
@@ -170,9 +174,9 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
             *reinterpret_cast<float4*>(my + d4 * 4) =
                 make_float4(rnd(o[d] * inv), rnd(o[d + 1] * inv), rnd(o[d + 2] * inv), rnd(o[d + 3] * inv));
         }
-        bar_sync_epilogue();
-        panel_store(stg, p.out, p.ld_out, row0, rows_valid, h * DHEAD + half * PANEL, w, et);
-        bar_sync_epilogue();
+        __syncwarp();
+        panel_store(stg, p.out, p.ld_out, row0, rows_valid, h * DHEAD + half * PANEL, w, lane);
+        __syncwarp();
       }
     }
     return;
@@ -188,14 +192,14 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
     tmem_ld16(trow + c0, raw);
     float rv[PANEL];
     if (p.res_mode) {
-      panel_load(stg, p.res, p.ld_res, row0, rows_valid, c0, w, et);
-      bar_sync_epilogue();
+      panel_load(stg, p.res, p.ld_res, row0, rows_valid, c0, w, lane);
+      __syncwarp();
 #pragma unroll
       for (int j4 = 0; j4 < PANEL / 4; ++j4) {
         const float4 t = *reinterpret_cast<const float4*>(my + j4 * 4);
         rv[j4 * 4] = t.x; rv[j4 * 4 + 1] = t.y; rv[j4 * 4 + 2] = t.z; rv[j4 * 4 + 3] = t.w;
       }
-      bar_sync_epilogue();
+      __syncwarp();
     }
     tmem_ld_wait();
 #pragma unroll
@@ -244,10 +248,9 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
     for (int j4 = 0; j4 < PANEL / 4; ++j4)
       *reinterpret_cast<float4*>(my + j4 * 4) = masked ? make_float4(0.f, 0.f, 0.f, 0.f)
                                                        : make_float4(rnd(v[j4 * 4]), rnd(v[j4 * 4 + 1]), rnd(v[j4 * 4 + 2]), rnd(v[j4 * 4 + 3]));
-    if (p.debug_skip & 512) return;
-    bar_sync_epilogue();
-    if (!(p.debug_skip & 256)) panel_store(stg, p.out, p.ld_out, row0, rows_valid, c0, w, et);
-    bar_sync_epilogue();
+    __syncwarp();
+    panel_store(stg, p.out, p.ld_out, row0, rows_valid, c0, w, lane);
+    __syncwarp();
   };
 
   if (p.n_ln == 0) {
