@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
             const uint32_t bsz = bok ? 16u : 0u;
 #pragma unroll
             for (int it = 0; it < B_IT; ++it) {
-              if (it * (N_PROD / 8) < p.n_pad) {
+              if (it * (N_PROD / 8) + rsub < p.n_pad) {
                 const float* src = bok ? (bsrc + (size_t)it * (N_PROD / 8) * p.cin_pad) : p.w;
                 cp_async16(b_dst + soff[it], src, bsz);
                 if (SPLIT) cp_async16(b_dst + b_half + soff[it], bok ? (src + (size_t)p.n_pad * p.cin_pad) : p.w, bsz);

@@ -131,6 +131,9 @@ def _ladder():
   case("dense_5000_192_96", dense(5000, 192, 96))
   case("dense_5000_96_17", dense(5000, 96, 17))
   case("dense_300_13p_32", dense(300, 16, 32))
+  case("dense_3000_64_16", dense(3000, 64, 16))
+  case("dense_3000_32_48", dense(3000, 32, 48))
+  case("dense_3000_40_80", dense(3000, 40, 80))
   case("sparse_20000_32_32", sparse(20000, 20000, 32, 32))
   case("sparse_6000_128_128", sparse(6000, 5000, 128, 128))
   case("sparse_3000_256_128", sparse(3000, 3000, 256, 128, fill=0.5))

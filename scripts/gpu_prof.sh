@@ -1,14 +1,28 @@
 #!/bin/bash
+# ncu evidence for the dominant kernel: (1) launch list of one bench step, (2) full-set capture of three representative
+# gather-GEMM launches (isolated script), exported to text/CSV; the .ncu-rep is kept only if small.
 cd "$(dirname "$0")/.."
-O=gpurun_out; mkdir -p $O
-rm -f $O/*.ncu-rep
-P=${1:-1}
-LS3D_PRECISE=$P timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gather_gemm \
-    -o $O/prof_gemm_p$P -f python scripts/prof_gemm.py > $O/ncu_gemm_p$P.log 2>&1
-ncu -i $O/prof_gemm_p$P.ncu-rep --page raw --csv > $O/prof_gemm_p${P}_raw.csv 2>/dev/null
-ncu -i $O/prof_gemm_p$P.ncu-rep --page source --csv > $O/prof_gemm_p${P}_source.csv 2>/dev/null
-ncu -i $O/prof_gemm_p$P.ncu-rep --page details > $O/prof_gemm_p${P}_details.txt 2>/dev/null
-ls -la $O/*.ncu-rep
-SZ=$(stat -c %s $O/prof_gemm_p$P.ncu-rep); if [ "$SZ" -gt 40000000 ]; then rm -f $O/prof_gemm_p$P.ncu-rep; fi
-timeout 300 python scripts/diag_gemm.py > $O/diag_gemm.log 2>&1
-tail -n 3 $O/ncu_gemm_p$P.log; grep timing $O/diag_gemm.log | head -8
+O=gpurun_out; mkdir -p $O; rm -f $O/*.ncu-rep
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/launches_mseg3d.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_bench.log 2>&1
+LS3D_PRECISE=1 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gather_gemm \
+    -o $O/prof_gemm -f python scripts/prof_gemm.py > $O/ncu_gemm.log 2>&1
+ncu -i $O/prof_gemm.ncu-rep --page raw --csv > $O/prof_gemm_raw.csv 2>/dev/null
+ncu -i $O/prof_gemm.ncu-rep --page details > $O/prof_gemm_details.txt 2>/dev/null
+ncu -i $O/prof_gemm.ncu-rep --page source --csv > $O/prof_gemm_source.csv 2>/dev/null
+SZ=$(stat -c %s $O/prof_gemm.ncu-rep); if [ "$SZ" -gt 30000000 ]; then rm -f $O/prof_gemm.ncu-rep; fi
+python - <<'PY'
+import csv, collections
+rows = list(csv.reader(l for l in open('gpurun_out/launches_mseg3d.csv') if l.startswith('"')))
+hdr = rows[0]; ni = hdr.index('Kernel Name'); vi = hdr.index('Metric Value')
+agg = collections.defaultdict(lambda: [0, 0.0])
+for r in rows[1:]:
+    try:
+        agg[r[ni][:70]][0] += 1; agg[r[ni][:70]][1] += float(r[vi].replace(',', ''))
+    except Exception:
+        pass
+tot = sum(v[1] for v in agg.values())
+print('launches', sum(v[0] for v in agg.values()), 'total_ns', tot)
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+    print(f'{v[1]/tot*100:6.2f}%  {v[0]:5d}  {v[1]/1e3:10.1f} us  {k}')
+PY

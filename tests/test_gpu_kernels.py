@@ -155,6 +155,19 @@ def test_sparse_conv_vs_oracle_and_dense():
     assert float((out1.double() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("m,cin,cout", [(3000, 64, 16), (3000, 32, 48), (3000, 40, 80), (70000, 96, 17), (130, 16, 32)])
+def test_dense_gemm_shapes(m, cin, cout):
+    """Linear layers of every width used by the heads / TransVFE (n_pad = 16 ... 96), incl. partial tiles."""
+    _, gemm = _ops()
+    g = torch.Generator().manual_seed(m + cout)
+    x = torch.randn(m, cin, generator=g)
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    y = gemm.run(x.to(DEV), gemm.PackedWeight.from_linear(w.to(DEV)), shift=b.to(DEV), relu=True).cpu()
+    ref = torch.relu(x.double() @ w.double().t() + b.double())
+    assert float((y.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
 # ------------------------------------------------------------------------------------------ devoxelize (D1, D2)
 def test_three_nn_bit_exact_and_interpolate():
     ops, _ = _ops()
