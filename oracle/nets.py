@@ -189,17 +189,30 @@ def three_nn(unknown, known):
     if M == 0:
         return torch.from_numpy(d2o), torch.from_numpy(ido)
     CH = max(1, (1 << 24) // max(M, 1))
+    kk = min(3, M)
+    C = min(8, M)                                                                  # candidate pool per row
     for s in range(0, N, CH):
         uu = u[s:s + CH]
         dx = uu[:, None, 0] - k[None, :, 0]
         dy = uu[:, None, 1] - k[None, :, 1]
         dz = uu[:, None, 2] - k[None, :, 2]
         d = (dx * dx + dy * dy) + dz * dz                                           # fp32, left to right
-        kk = min(3, M)
-        # lexicographic (d, index) order == the sequential strict-'<' scan
-        part = np.argsort(d, axis=1, kind="stable")[:, :kk]
+        # lexicographic (d, index) order == the sequential strict-'<' scan.  Exact top-3 without a full sort: take the C
+        # smallest (unordered), order them by (d, index); rows whose 3rd distance ties with more than the pool holds fall
+        # back to the full stable sort.
+        cand = np.argpartition(d, C - 1, axis=1)[:, :C] if C < M else np.tile(np.arange(M), (d.shape[0], 1))
+        cd = np.take_along_axis(d, cand, 1)
+        order = np.lexsort((cand, cd), axis=1)[:, :kk]
+        part = np.take_along_axis(cand, order, 1)
+        pd = np.take_along_axis(cd, order, 1)
+        thr = pd[:, kk - 1]
+        bad = (d <= thr[:, None]).sum(1) > C - 1 if C < M else np.zeros(d.shape[0], bool)
+        if bad.any():
+            full = np.argsort(d[bad], axis=1, kind="stable")[:, :kk]
+            part[bad] = full
+            pd[bad] = np.take_along_axis(d[bad], full, 1)
         ido[s:s + CH, :kk] = part
-        d2o[s:s + CH, :kk] = np.take_along_axis(d, part, 1)
+        d2o[s:s + CH, :kk] = pd
     return torch.from_numpy(d2o), torch.from_numpy(ido)
 
 

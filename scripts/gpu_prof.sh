@@ -26,3 +26,5 @@ print('launches', sum(v[0] for v in agg.values()), 'total_ns', tot)
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
     print(f'{v[1]/tot*100:6.2f}%  {v[0]:5d}  {v[1]/1e3:10.1f} us  {k}')
 PY
+timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "dense_gemm or trans_vfe or sparse_conv" --timeout 120 2>&1 | tail -3
+timeout 300 python bench.py --workload sdseg3d_semantickitti --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_sdseg3d.log 2>&1; tail -c 700 $O/bench_sdseg3d.log
