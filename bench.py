@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     ap.add_argument("--image-dtype", default="fp32", choices=["fp32", "fp16"],
                     help="camera branch storage/operand type (fp32 = TF32 tensor-core convs; fp16 = fp16 operands, fp32 accumulate)")
+    ap.add_argument("--eager-images", action="store_true", help="run the camera branch eagerly (no CUDA graph), e.g. under ncu")
     ap.add_argument("--sweep-full", action="store_true", help="spconv_sweep: 0.5-10 %% x 32-256 ch (skips what does not fit)")
     return ap.parse_args()
 
@@ -340,6 +341,8 @@ def main():
     model = model.to(dev)
     if args.image_dtype == "fp16" and wl["cam"]:
         model.image_dtype = torch.float16
+    if args.eager_images and wl["cam"]:
+        model.use_image_graph = False
     NB = 4
     batches = make_batches(wl, spec, NB, fpg, rank)
     # device-resident copies of the raw inputs for the `value` measurement
@@ -386,7 +389,12 @@ def main():
         gemm.PROFILE = []
         sampler = ClockSampler(local_rank)
         sampler.start()
+        prof_range = os.environ.get("LS3D_PROFILE_RANGE") == "1"      # ncu --profile-from-start off: timed steps only
+        if prof_range:
+            torch.cuda.profiler.start()
         ms = timed(args.steps, False, dev_batches)
+        if prof_range:
+            torch.cuda.profiler.stop()
         clocks = sampler.stop()
         launches = capi.kernel_launches()
         prof = gemm.PROFILE

@@ -160,7 +160,28 @@ class UNetSCN3D(Prepared):
         B = batch_dict["batch_size"]
         shape1 = tuple(int(v) for v in (np.array(batch_dict["input_shape"][::-1]) + [1, 0, 0]))   # scn_unet.py:203
         coords1 = voxel_coords.int().contiguous()
+        # ---- phase 1: geometry of every level (bitmaps, output sites, rulebooks).  It depends on the coordinates only, so
+        # all of it - including the host reads of the site counts - is issued before any feature kernel; the GEMM chain
+        # below then runs without a single host synchronisation.
         lv1 = SparseLevel(coords1, B, shape1, ops.grid_from_coords(coords1, B, shape1, need_perm=True))
+        levels = {1: lv1}
+        down, up = {}, {}
+        for lv in (2, 3, 4):
+            ks, st, pd = self.down_geom[lv]
+            prev = levels[lv - 1]
+            grid, ocoords = ops.grid_strided(prev.coords, B, prev.shape, ks, st, pd)
+            levels[lv] = SparseLevel(ocoords, B, grid.shape, grid)
+            down[lv] = ops.rulebook_gather(prev.grid, ocoords, ks, st, pd)
+            up[lv] = ops.rulebook_scatter(grid, prev.coords, ks, st, pd)
+        enc = None
+        if self.conv_out is not None:
+            lp = self.last_pad if isinstance(self.last_pad, (tuple, list)) else (self.last_pad,) * 3
+            l4 = levels[4]
+            g5, c5 = ops.grid_strided(l4.coords, B, l4.shape, (3, 1, 1), (2, 1, 1), tuple(lp))
+            enc = (ops.rulebook_gather(l4.grid, c5, (3, 1, 1), (2, 1, 1), tuple(lp)), c5, g5.shape)
+        for lv in (1, 2, 3, 4):
+            levels[lv].subm_table()
+        # ---- phase 2: features
         vf = pad_cols(voxel_features.float())
         if not gemm.PRECISE:
             vf = gemm.round_tf32(vf)          # single-pass TF32 mode: operands must be tf32-representable
@@ -168,26 +189,14 @@ class UNetSCN3D(Prepared):
         for pk in P["conv1"]:
             x = self._block(x, pk, lv1.subm_table())
         feats = {1: x}
-        levels = {1: lv1}
-        down, up = {}, {}
         for lv in (2, 3, 4):
-            ks, st, pd = self.down_geom[lv]
-            prev = levels[lv - 1]
-            grid, ocoords = ops.grid_strided(prev.coords, B, prev.shape, ks, st, pd)
-            cur = SparseLevel(ocoords, B, grid.shape, grid)
-            down[lv] = ops.rulebook_gather(prev.grid, ocoords, ks, st, pd)
-            up[lv] = ops.rulebook_scatter(grid, prev.coords, ks, st, pd)
             cbr, blocks = P[f"conv{lv}"]
             y = self._conv(feats[lv - 1], cbr, down[lv])
             for pk in blocks:
-                y = self._block(y, pk, cur.subm_table())
-            feats[lv], levels[lv] = y, cur
-        if self.conv_out is not None:
-            lp = self.last_pad if isinstance(self.last_pad, (tuple, list)) else (self.last_pad,) * 3
-            l4 = levels[4]
-            g5, c5 = ops.grid_strided(l4.coords, B, l4.shape, (3, 1, 1), (2, 1, 1), tuple(lp))
-            nb5 = ops.rulebook_gather(l4.grid, c5, (3, 1, 1), (2, 1, 1), tuple(lp))
-            batch_dict["encoded_spconv_tensor"] = SparseTensorView(self._conv(feats[4], P["conv_out"], nb5), c5, g5.shape, B)
+                y = self._block(y, pk, levels[lv].subm_table())
+            feats[lv] = y
+        if enc is not None:
+            batch_dict["encoded_spconv_tensor"] = SparseTensorView(self._conv(feats[4], P["conv_out"], enc[0]), enc[1], enc[2], B)
             batch_dict["encoded_spconv_tensor_stride"] = 8
 
         def ur_block(lat, bottom, lv):

@@ -35,10 +35,7 @@ def stage_errors(tag, image_dtype=None):
     return r
 
 stage_errors("cudnn_tf32")
-stage_errors("cudnn_fp16", torch.float16)
-torch.backends.cudnn.allow_tf32 = False
-stage_errors("cudnn_fp32")
-torch.backends.cudnn.allow_tf32 = True
+
 
 # ---- kernel-time breakdown of the real bench step
 sys.argv = ["bench.py"]
@@ -60,4 +57,5 @@ with torch.no_grad():
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         step(); torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=30, max_name_column_width=70))

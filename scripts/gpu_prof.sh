@@ -3,8 +3,8 @@
 # gather-GEMM launches (isolated script), exported to text/CSV; the .ncu-rep is kept only if small.
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O; rm -f $O/*.ncu-rep
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/launches_mseg3d.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_bench.log 2>&1
+LS3D_PROFILE_RANGE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 6000 --csv \
+    --log-file $O/launches_mseg3d.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --eager-images > $O/ncu_bench.log 2>&1
 LS3D_PRECISE=1 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gather_gemm \
     -o $O/prof_gemm -f python scripts/prof_gemm.py > $O/ncu_gemm.log 2>&1
 ncu -i $O/prof_gemm.ncu-rep --page raw --csv > $O/prof_gemm_raw.csv 2>/dev/null
