@@ -134,16 +134,28 @@ constexpr int CT_E = 96;
 template <int MAXL, class StoreFn>
 __device__ __forceinline__ void tokens_matvec(const float* __restrict__ Wt, const float* __restrict__ bias, int nin,
                                                int nout, const float* in_s, int ld_in, int L, StoreFn store) {
+  // nin is a multiple of 8 and ld_in a multiple of 4 (96 / 48 / 32 here): 8 independent weight loads are in flight per
+  // step and the activations are read as two broadcast float4 per token.
   for (int e = threadIdx.x; e < nout; e += blockDim.x) {
     float acc[MAXL];
     const float b = bias[e];
 #pragma unroll
     for (int l = 0; l < MAXL; ++l) acc[l] = b;
-    for (int c = 0; c < nin; ++c) {
-      const float w = __ldg(Wt + (size_t)c * nout + e);
+    for (int c0 = 0; c0 < nin; c0 += 8) {
+      float w[8];
 #pragma unroll
-      for (int l = 0; l < MAXL; ++l)
-        if (l < L) acc[l] = fmaf(in_s[l * ld_in + c], w, acc[l]);
+      for (int i = 0; i < 8; ++i) w[i] = __ldg(Wt + (size_t)(c0 + i) * nout + e);
+#pragma unroll
+      for (int l = 0; l < MAXL; ++l) {
+        if (l < L) {
+          const float4 x0 = *reinterpret_cast<const float4*>(in_s + l * ld_in + c0);
+          const float4 x1 = *reinterpret_cast<const float4*>(in_s + l * ld_in + c0 + 4);
+          float a = acc[l];
+          a = fmaf(x0.x, w[0], a); a = fmaf(x0.y, w[1], a); a = fmaf(x0.z, w[2], a); a = fmaf(x0.w, w[3], a);
+          a = fmaf(x1.x, w[4], a); a = fmaf(x1.y, w[5], a); a = fmaf(x1.z, w[6], a); a = fmaf(x1.w, w[7], a);
+          acc[l] = a;
+        }
+      }
     }
 #pragma unroll
     for (int l = 0; l < MAXL; ++l)
@@ -251,11 +263,21 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
         const float bb = which ? bv[e] : bk[e];
 #pragma unroll
         for (int l = 0; l < CT_MAXL; ++l) acc[l] = bb;
-        for (int c = 0; c < E; ++c) {
-          const float w = __ldg(Wt + c * E + e);
+        for (int c0 = 0; c0 < E; c0 += 8) {
+          float w[8];
 #pragma unroll
-          for (int l = 0; l < CT_MAXL; ++l)
-            if (l < L) acc[l] = fmaf(mem[l][c], w, acc[l]);
+          for (int i = 0; i < 8; ++i) w[i] = __ldg(Wt + (c0 + i) * E + e);
+#pragma unroll
+          for (int l = 0; l < CT_MAXL; ++l) {
+            if (l < L) {
+              const float4 x0 = *reinterpret_cast<const float4*>(&mem[l][c0]);
+              const float4 x1 = *reinterpret_cast<const float4*>(&mem[l][c0 + 4]);
+              float a = acc[l];
+              a = fmaf(x0.x, w[0], a); a = fmaf(x0.y, w[1], a); a = fmaf(x0.z, w[2], a); a = fmaf(x0.w, w[3], a);
+              a = fmaf(x1.x, w[4], a); a = fmaf(x1.y, w[5], a); a = fmaf(x1.z, w[6], a); a = fmaf(x1.w, w[7], a);
+              acc[l] = a;
+            }
+          }
         }
         const int h = e / dh, d = e % dh;
         float* dst = which ? Vout : Kout;

@@ -392,6 +392,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
     uint32_t soff[B_IT];                               // swizzled smem offsets of (row it*32 + rsub, chunk ch)
 #pragma unroll
     for (int it = 0; it < B_IT; ++it) soff[it] = sw128(it * (N_PROD / 8) + rsub, ch);
+    const int nbg = (p.n_pad + 31) / 32;               // 32-row groups of the W tile
+    uint32_t bmask = 0;                                // groups in which this thread's row exists
+    for (int it = 0; it < nbg; ++it)
+      if (it * 32 + rsub < p.n_pad) bmask |= 1u << it;
+    const size_t wstride = (size_t)32 * p.cin_pad;     // floats between row groups
+    const size_t wsplit = (size_t)p.n_pad * p.cin_pad; // floats from W_hi to W_lo
     int g = 0;                                        // global step counter (ring position), continues across tiles
     int ti = 0;
     const int my_row = tid & (TILE_M - 1);            // thread t loads rulebook row (t & 127) for half of the offsets
@@ -416,7 +422,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
       for (int q = 0; q < (MAX_KOFF + 1) / 2; ++q) {
         const int k = k_lo + q;
         if (k < k_hi) {
-          nb[k * TILE_M + my_row] = jv[q];
+          nb[k * TILE_M + (my_row & 31) * 4 + (my_row >> 5)] = jv[q];
           const uint32_t b = __ballot_sync(0xffffffffu, jv[q] >= 0);
           if (lane == 0) ac[k * 4 + (warp & 3)] = b;
         }
@@ -440,35 +446,31 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_kernel(const ls3d_ge
           const uint32_t a_dst = smem_u32(a_s + s * a_bytes);
           const uint32_t b_dst = smem_u32(b_s + s * b_bytes);
           // ---- A: 128 rows x 8 chunks of 16 B; 8 lanes cover one row (4 full 128 B lines per warp request).
-          // Everything that does not depend on the row is hoisted: source tensor / column select per chunk, swizzled
-          // destination offsets per thread.  Sources are formed first so the copies issue back to back.
+          // The producers are instruction-issue bound, so the per-copy work is pared down: one 16-byte shared load
+          // brings the thread's 4 rulebook entries, a missing row becomes a zero-size copy from row 0 (no pointer
+          // selects), row offsets are 32x32->64-bit multiplies, destination offsets are per-thread constants.
           const int col = c * KCH + ch * 4;
-          const bool col_ok = (col < cin) && !(p.debug_skip & 1);
-          const float* abase = (col < p.c0) ? (p.in0 + col) : (p.in1 + (col - p.c0));
-          const size_t ald = (col < p.c0) ? (size_t)p.ld0 : (size_t)p.ld1;
-          const int* nbk = nb + k * TILE_M + rsub;
-          const float* asrc[A_IT];
-          uint32_t asz[A_IT];
+          if (col < p.cin_pad && !(p.debug_skip & 64)) {           // columns >= cin_pad are never read by the MMA
+            const bool col_ok = (col < cin) && !(p.debug_skip & 1);
+            const bool first = col < p.c0;
+            const float* abase = first ? (p.in0 + col) : (p.in1 + (col - p.c0));
+            const uint32_t ald = first ? (uint32_t)p.ld0 : (uint32_t)p.ld1;
+            const int4 j4 = *reinterpret_cast<const int4*>(nb + k * TILE_M + rsub * 4);
+            const int jr[4] = {j4.x, j4.y, j4.z, j4.w};
 #pragma unroll
-          for (int it = 0; it < A_IT; ++it) {
-            const int j = nbk[it * (N_PROD / 8)];
-            const bool ok = (j >= 0) && col_ok;
-            asrc[it] = ok ? (abase + (size_t)j * ald) : p.in0;
-            asz[it] = ok ? 16u : 0u;
-          }
-          if (!(p.debug_skip & 64)) {
-#pragma unroll
-            for (int it = 0; it < A_IT; ++it) cp_async16(a_dst + soff[it], asrc[it], asz[it]);
+            for (int it = 0; it < A_IT; ++it) {
+              const uint32_t jc = (uint32_t)max(jr[it], 0);
+              cp_async16(a_dst + soff[it], abase + (size_t)jc * ald, (jr[it] >= 0 && col_ok) ? 16u : 0u);
+            }
             // ---- B: n_pad rows x 8 chunks (x2 when split): row it*32 + rsub, chunk ch -> same swizzled offsets
-            const bool bok = (col < p.cin_pad) && !(p.debug_skip & 2);
-            const float* bsrc = wk + (size_t)rsub * p.cin_pad + col;
-            const uint32_t bsz = bok ? 16u : 0u;
-#pragma unroll
-            for (int it = 0; it < B_IT; ++it) {
-              if (it * (N_PROD / 8) + rsub < p.n_pad) {
-                const float* src = bok ? (bsrc + (size_t)it * (N_PROD / 8) * p.cin_pad) : p.w;
-                cp_async16(b_dst + soff[it], src, bsz);
-                if (SPLIT) cp_async16(b_dst + b_half + soff[it], bok ? (src + (size_t)p.n_pad * p.cin_pad) : p.w, bsz);
+            if (!(p.debug_skip & 2)) {
+              const float* bsrc = wk + (size_t)rsub * p.cin_pad + col;
+#pragma unroll 1
+              for (int it = 0; it < nbg; ++it, bsrc += wstride) {
+                if ((bmask >> it) & 1u) {
+                  cp_async16(b_dst + soff[it], bsrc, 16u);
+                  if (SPLIT) cp_async16(b_dst + b_half + soff[it], bsrc + wsplit, 16u);
+                }
               }
             }
           }

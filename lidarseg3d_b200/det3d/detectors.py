@@ -79,6 +79,7 @@ class SegMSeg3DNet(_SegBase):
     image_dtype = None
 
     def _image_branch(self, images, batch_size):
+        self.img_backbone.keep_channel_padding = True      # the image head consumes zero-padded channel maps directly
         if self.image_dtype is not None:
             images = images.to(self.image_dtype)
         img_data = dict(inputs=self.img_backbone(images), batch_size=batch_size)

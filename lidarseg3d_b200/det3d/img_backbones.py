@@ -31,6 +31,41 @@ def _versions(*ts):
     return tuple(t._version for t in ts if t is not None)
 
 
+PAD_CHANNELS = True     # eval/CUDA: zero-pad channel counts to 16-byte multiples (18 -> 20 fp32 / 24 fp16) so cuDNN can use
+                        # its aligned NHWC tensor-core kernels; padded channels stay exactly zero through conv/BN/ReLU/add
+
+
+def _pad_to(c, dtype):
+    q = 16 // torch.empty((), dtype=dtype).element_size()
+    return (c + q - 1) // q * q if PAD_CHANNELS else c
+
+
+def folded(conv, bn, x_channels, dtype):
+    """BatchNorm folded into the conv (eval): weight [Cout_p, Cin_p, kh, kw] channels-last and bias [Cout_p], zero padded;
+    cached on the conv module, refreshed when a parameter / statistic changes."""
+    key = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var) + (dtype, x_channels, PAD_CHANNELS)
+    cache = getattr(conv, "_ls3d_fold", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            w = conv.weight * scale.view(-1, 1, 1, 1)
+            b = bn.bias - bn.running_mean * scale
+            cout, cin = w.shape[0], w.shape[1]
+            cout_p = _pad_to(cout, dtype)
+            assert x_channels >= cin
+            if cout_p != cout or x_channels != cin:
+                wp = w.new_zeros(cout_p, x_channels, w.shape[2], w.shape[3])
+                wp[:cout, :cin] = w
+                bp = b.new_zeros(cout_p)
+                bp[:cout] = b
+                w, b = wp, bp
+            w = w.to(dtype).contiguous(memory_format=torch.channels_last)
+            b = b.to(dtype).contiguous()
+        cache = (key, w, b)
+        conv._ls3d_fold = cache
+    return cache[1], cache[2]
+
+
 def cbr(conv, bn, x, relu, z=None):
     """conv -> BatchNorm -> (+z) -> (ReLU).  Training / CPU: plain modules.  Eval on CUDA: BN folded into the conv weights
     (cached, refreshed when a parameter changes) and run as one cuDNN call."""
@@ -39,16 +74,7 @@ def cbr(conv, bn, x, relu, z=None):
         if z is not None:
             y = y + z
         return torch.relu(y) if relu else y
-    key = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var) + (x.dtype,)
-    cache = getattr(conv, "_ls3d_fold", None)
-    if cache is None or cache[0] != key:
-        with torch.no_grad():
-            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-            w = (conv.weight * scale.view(-1, 1, 1, 1)).to(x.dtype).contiguous(memory_format=torch.channels_last)
-            b = (bn.bias - bn.running_mean * scale).to(x.dtype).contiguous()
-        cache = (key, w, b)
-        conv._ls3d_fold = cache
-    _, w, b = cache
+    w, b = folded(conv, bn, x.shape[1], x.dtype)
     if FUSED_CUDNN and relu and conv.groups == 1:
         if z is None:
             return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, 1)
@@ -288,6 +314,9 @@ class HRNet(nn.Module):
                 else:
                     xs.append(ys[i])
             ys = getattr(self, f"stage{st}")(xs)
+        if not getattr(self, "keep_channel_padding", False):
+            true_c = [c * self.blocks_dict[self.extra["stage4"]["block"]].expansion for c in self.extra["stage4"]["num_channels"]]
+            ys = [y if y.shape[1] == c else y[:, :c] for y, c in zip(ys, true_c)]
         return ys
 
     def train(self, mode=True):

@@ -6,7 +6,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from .img_backbones import _bn, cbr
+from .img_backbones import _bn, cbr, folded
 from .registry import IMG_HEADS
 
 
@@ -56,6 +56,7 @@ class FCNMSeg3DHead(nn.Module):
             assert isinstance(in_channels, (list, tuple)) and isinstance(in_index, (list, tuple))
             assert len(in_channels) == len(in_index)
         self.input_transform, self.in_index = input_transform, in_index
+        self._branch_channels = list(in_channels) if isinstance(in_channels, (list, tuple)) else [in_channels]
         self.in_channels = sum(in_channels) if input_transform == "resize_concat" else in_channels
         self.channels, self.num_classes = channels, num_classes
         self.num_convs, self.concat_input, self.kernel_size = num_convs, concat_input, kernel_size
@@ -74,6 +75,7 @@ class FCNMSeg3DHead(nn.Module):
     def _transform_inputs(self, inputs):
         if self.input_transform == "resize_concat":
             inputs = [inputs[i] for i in self.in_index]
+            inputs = [x if x.shape[1] == c else x[:, :c] for x, c in zip(inputs, self._branch_channels)]
             ups = [F.interpolate(x, size=inputs[0].shape[2:], mode="bilinear", align_corners=self.align_corners)
                    for x in inputs]
             return torch.cat(ups, dim=1)
@@ -81,13 +83,43 @@ class FCNMSeg3DHead(nn.Module):
             return [inputs[i] for i in self.in_index]
         return inputs[self.in_index]
 
+    def _first_conv_per_branch(self, inputs):
+        """resize_concat followed by a 1x1 ConvModule == sum over branches of upsample(conv1x1_b(x_b)) (both linear), then the
+        folded-BN bias and ReLU once: the 270-channel full-resolution concat (decode_head.py:151-160) is never materialised
+        and the 1x1 convolutions run at each branch's native resolution."""
+        cm = self.convs[0]
+        xs = [inputs[i] for i in self.in_index]
+        true_c = [c for c in self._branch_channels]
+        w, b = folded(cm.conv, cm.bn, sum(true_c), xs[0].dtype)
+        y, c0 = None, 0
+        for i, (x, c) in enumerate(zip(xs, true_c)):
+            wi = w[:, c0:c0 + c]
+            if x.shape[1] != c:                                  # channel-padded backbone output
+                wi = torch.nn.functional.pad(wi, (0, 0, 0, 0, 0, x.shape[1] - c))
+            t = F.conv2d(x, wi.contiguous(memory_format=torch.channels_last), b if i == 0 else None)
+            if i > 0:
+                t = F.interpolate(t, size=xs[0].shape[2:], mode="bilinear", align_corners=self.align_corners)
+            y = t if y is None else y + t
+            c0 += c
+        return torch.relu_(y)
+
     def forward(self, batch_dict, return_loss=True, **kwargs):
         if return_loss:
             raise NotImplementedError("lidarseg3d_b200 image head: inference path only (return_loss=False)")
-        x = self._transform_inputs(batch_dict["inputs"])
-        feats = self.convs(x)
+        inputs = batch_dict["inputs"]
+        fast = (self.input_transform == "resize_concat" and self.num_convs > 0 and self.kernel_size == 1 and inputs[0].is_cuda
+                and not self.training and self.convs[0].with_norm and not self.concat_input)
+        if fast:
+            feats = self._first_conv_per_branch(inputs)
+            for m in list(self.convs)[1:]:
+                feats = m(feats)
+        else:
+            x = self._transform_inputs(inputs)
+            feats = self.convs(x)
         if self.concat_input:
             feats = self.conv_cat(torch.cat([x, feats], dim=1))
+        if feats.shape[1] != self.channels:
+            feats = feats[:, :self.channels].contiguous(memory_format=torch.channels_last)
         cs = self.conv_seg
         logits = F.conv2d(feats if self.dropout is None else self.dropout(feats), cs.weight.to(feats.dtype),
                           cs.bias.to(feats.dtype))
