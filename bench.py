@@ -33,6 +33,8 @@ WORKLOADS = {
                               "(BASELINE.json configs[4])"),
     "mseg3d_nuscenes": dict(cfg="mseg3d_nuscenes.py", spec="NUSC", frames_per_gpu=3, cam=True,
                             desc="MSeg3D nuScenes LiDAR + 6-cam GF/SF fusion forward (BASELINE.json configs[2])"),
+    "mseg3d_waymo": dict(cfg="mseg3d_waymo.py", spec="WAYMO", frames_per_gpu=2, cam=True,
+                         desc="MSeg3D Waymo LiDAR + 5-cam GF/SF fusion forward (BASELINE.json configs[3])"),
     "sdseg3d_semantickitti": dict(cfg="sdseg3d_semantickitti.py", spec="KITTI", frames_per_gpu=4, cam=False,
                                   desc="SDSeg3D SemanticKITTI LiDAR-only sparse-conv UNet forward (configs[1])"),
 }
@@ -435,8 +437,17 @@ def main():
         al = [(p["bytes"], p["flops"], p["e0"].elapsed_time(p["e1"])) for p in prof]
         tb, tf, tm = (sum(x[i] for x in sp) for i in range(3))
         ab, af, am = (sum(x[i] for x in al) for i in range(3))
+        # DRAM traffic of the kernel from the committed `ncu --set full` capture (profiles/, one representative LiDAR-like SubM
+        # launch; the per-launch algorithmic bytes of that same launch are next to it for comparison)
+        traffic, traffic_case = None, None
+        try:
+            tc = json.load(open(os.path.join(ROOT, "profiles", "r01_gather_gemm_traffic.json")))["launches"][0]
+            traffic = tc["traffic_bytes"]
+            traffic_case = dict(launch=tc["name"], algorithmic_bytes=tc["algorithmic_bytes"], ncu_duration_us=tc["duration_us"])
+        except Exception:
+            pass
         roof = dict(bound="hbm", kernel="gather_gemm_kernel (sparse SubM/strided/inverse conv launches)", achieved=tb / tm / 1e6,
-                    peak=peak, unit="GB/s", frac=tb / tm / 1e6 / peak, traffic=None,
+                    peak=peak, unit="GB/s", frac=tb / tm / 1e6 / peak, traffic=traffic, traffic_case=traffic_case,
                     peak_source="MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
                     launches_per_step=len(sp) // args.steps, avg_launch_us=tm / max(len(sp), 1) * 1e3,
                     algorithmic_bytes_per_step=tb / args.steps, tflops=tf / tm / 1e9,

@@ -163,6 +163,40 @@ int ls3d_sample_image_features(const float* feat_nhwc, int32_t n_frames, int32_t
                                int32_t round_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SF-Phase: point -> class-token cross attention core.
+ * replaces: SparsePointCorssAttention.forward, attention part (det3d/models/point_heads/context_module.py:320-376);
+ *           the q projection and the output projection around it are ls3d_gather_gemm launches.
+ *   q [n, ld_q] fp32 (n_head * d_head columns used), k / v [n_frames][n_head][n_tok][d_head] from ls3d_class_tokens,
+ *   frame_off[n_frames] int32 first row of each frame; out [n, ld_out]; n_head in {1,2,4,8}, d_head in {16,24,32}
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_token_attention(const float* q, int32_t ld_q, int32_t n, const float* k, const float* v, const int32_t* frame_off,
+                         int32_t n_frames, int32_t n_tok, int32_t n_head, int32_t d_head, float scale, float* out,
+                         int32_t ld_out, int32_t round_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Point -> camera projection (on the CPU, in the data loader, in the reference).
+ * replaces: nuScenes branch of LoadPointCloudFromFile (det3d/datasets/pipelines/loading.py:373-416, view_points :67-103)
+ *           + rescale / normalisation of SegImagePreprocess (det3d/datasets/pipelines/segpreprocess.py:544-565,654-671).
+ *   points [n, ld_p] fp32 with x,y,z at columns xyz_off..xyz_off+2; cam_from_lidar [ncam][4][4], intrinsics [ncam][3][3]
+ *   HOST doubles (row-major); points_cuv [n, 4] = (valid, cam, v, u), cam/v/u normalised to [-1, 1]
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_project_points(const float* points, int32_t ld_p, int32_t xyz_off, int32_t n, const double* cam_from_lidar,
+                        const double* intrinsics, int32_t ncam, int32_t img_h, int32_t img_w, int32_t net_h, int32_t net_w,
+                        float* points_cuv, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Camera stem: multi-resolution branch fusion, out = act(sum_k bilinear_resize(term_k)) on channels-last fp32 maps.
+ * replaces: the per-term resize / add / ReLU loops of HRModule.forward (det3d/models/img_backbones/hrnet.py:205-226) and
+ *           the resize_concat of the decode head (det3d/models/img_heads/decode_head.py:151-160) once its 1x1 ConvModule
+ *           has been applied per branch (fcn_mseg3d_head.py:150-163).
+ *   terms    HOST array of n_terms (<= 4) device pointers, term k = [n_img, term_h[k], term_w[k], C] NHWC; a term with
+ *            term_h == H and term_w == W is added as is, a coarser one is resized with align_corners = False
+ *   out      [n_img, H, W, C]; C a multiple of 4; relu != 0 applies max(., 0) to the sum
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_upsample_sum(const float* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
+                      int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SF-Phase: class embedding aggregation and class-token memory path.
  * replaces: LiDARSemanticFeatureAggregationModule (det3d/models/point_heads/context_module.py:25-53),
  *           CameraSemanticFeatureAggregationModule (det3d/models/img_heads/fcn_mseg3d_head.py:24-51),

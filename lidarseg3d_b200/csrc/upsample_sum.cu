@@ -1,0 +1,94 @@
+// Multi-resolution branch fusion of the camera stem: out = act(sum_k resize(term_k)) in ONE pass over channels-last maps.
+//
+// Replaces the python loops of HRModule.forward (reference det3d/models/img_backbones/hrnet.py:205-226: per output branch,
+// y += x_i | y += resize(conv1x1_bn(x_j)) for coarser j | y += strided convs of finer j, then ReLU) and the
+// resize_concat + first 1x1 ConvModule of the FCN decode head (det3d/models/img_heads/decode_head.py:151-160,
+// fcn_mseg3d_head.py:150-163; the 1x1 convolution commutes with the bilinear resize, so the per-branch convolutions run at
+// native resolution and only their sum is formed at full resolution).  The reference issues one bilinear-upsample kernel,
+// one add and one ReLU per term; here every output element is written once and the coarse terms (<= 1/4 of the pixels)
+// are read through L1/L2.  Bilinear taps follow ATen's align_corners=False rule (src = scale*(dst+0.5)-0.5, clamped at 0).
+// One thread per (pixel, 4 channels): 16-byte loads/stores; HBM-bound: (1 + sum_k hk*wk/(H*W)) reads + 1 write per element.
+#include "common.cuh"
+#include "../../include/ls3d.h"
+
+namespace ls3d {
+
+constexpr int UPS_MAX_TERMS = 4;
+
+struct UpsTerms {
+  const float* p[UPS_MAX_TERMS];
+  int h[UPS_MAX_TERMS], w[UPS_MAX_TERMS];
+  float rh[UPS_MAX_TERMS], rw[UPS_MAX_TERMS];
+  int n;
+};
+
+__device__ __forceinline__ float4 f4_fma(float a, float4 x, float4 acc) {
+  return make_float4(fmaf(a, x.x, acc.x), fmaf(a, x.y, acc.y), fmaf(a, x.z, acc.z), fmaf(a, x.w, acc.w));
+}
+__device__ __forceinline__ float4 f4_scale(float a, float4 x) { return make_float4(a * x.x, a * x.y, a * x.z, a * x.w); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__global__ void __launch_bounds__(256) upsample_sum_kernel(UpsTerms T, int n_img, int H, int W, int C4, int relu,
+                                                           float* __restrict__ out) {
+  const long long total = (long long)n_img * H * W * C4;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(e % C4);
+    long long pix = e / C4;
+    const int x = (int)(pix % W);
+    pix /= W;
+    const int y = (int)(pix % H);
+    const int img = (int)(pix / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < UPS_MAX_TERMS; ++k) {
+      if (k >= T.n) break;
+      const int h = T.h[k], w = T.w[k];
+      const float4* src = reinterpret_cast<const float4*>(T.p[k]) + (size_t)img * h * w * C4 + c4;
+      float4 v;
+      if (h == H && w == W) {
+        v = __ldg(src + ((size_t)y * W + x) * C4);
+      } else {
+        float sy = T.rh[k] * ((float)y + 0.5f) - 0.5f;
+        float sx = T.rw[k] * ((float)x + 0.5f) - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int yp = y0 < h - 1 ? 1 : 0, xp = x0 < w - 1 ? 1 : 0;
+        const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+        const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+        const float4* r0 = src + ((size_t)y0 * w + x0) * C4;
+        const float4* r1 = r0 + (size_t)yp * w * C4;
+        const float4 v00 = __ldg(r0), v01 = __ldg(r0 + (size_t)xp * C4), v10 = __ldg(r1), v11 = __ldg(r1 + (size_t)xp * C4);
+        const float4 top = f4_fma(lx1, v01, f4_scale(lx0, v00));
+        const float4 bot = f4_fma(lx1, v11, f4_scale(lx0, v10));
+        v = f4_fma(ly1, bot, f4_scale(ly0, top));
+      }
+      acc = k == 0 ? v : f4_add(acc, v);
+    }
+    if (relu) acc = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+    reinterpret_cast<float4*>(out)[e] = acc;
+  }
+}
+
+}  // namespace ls3d
+
+extern "C" int ls3d_upsample_sum(const float* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
+                                 int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, float* out, void* stream) {
+  using namespace ls3d;
+  if (n_img <= 0 || H <= 0 || W <= 0) return LS3D_OK;
+  if (!terms || !term_h || !term_w || !out || n_terms < 1 || n_terms > UPS_MAX_TERMS || C <= 0 || (C & 3)) return LS3D_ERR_ARG;
+  UpsTerms T;
+  T.n = n_terms;
+  for (int k = 0; k < n_terms; ++k) {
+    if (!terms[k] || term_h[k] <= 0 || term_w[k] <= 0 || term_h[k] > H || term_w[k] > W) return LS3D_ERR_ARG;
+    T.p[k] = terms[k]; T.h[k] = term_h[k]; T.w[k] = term_w[k];
+    T.rh[k] = (float)term_h[k] / (float)H;
+    T.rw[k] = (float)term_w[k] / (float)W;
+  }
+  const long long total = (long long)n_img * H * W * (C / 4);
+  const long long blocks = (total + 255) / 256;
+  const int grid = (int)(blocks < 148LL * 64 ? blocks : 148LL * 64);     // grid-stride, a multiple of the SM count when large
+  upsample_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 4, relu, out);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}

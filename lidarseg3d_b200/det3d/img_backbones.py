@@ -31,6 +31,7 @@ def _versions(*ts):
     return tuple(t._version for t in ts if t is not None)
 
 
+FUSED_SUM = True        # eval/CUDA/fp32: branch fusion (resize + add + ReLU) in one hand-written kernel (csrc/upsample_sum.cu)
 PAD_CHANNELS = True     # eval/CUDA: zero-pad channel counts to 16-byte multiples (18 -> 20 fp32 / 24 fp16) so cuDNN can use
                         # its aligned NHWC tensor-core kernels; padded channels stay exactly zero through conv/BN/ReLU/add
 
@@ -188,6 +189,10 @@ class HRModule(nn.Module):
         if self.num_branches == 1:
             return [self.branches[0](x[0])]
         x = [self.branches[i](x[i]) for i in range(self.num_branches)]
+        if FUSED_SUM and x[0].is_cuda and not self.training and x[0].dtype == torch.float32 and all(
+                t.shape[1] % 4 == 0 and x[0].shape[2] == t.shape[2] << j and x[0].shape[3] == t.shape[3] << j
+                for j, t in enumerate(x)):
+            return self._forward_fused(x)
         outs = []
         for i in range(len(self.fuse_layers)):
             y = 0
@@ -197,7 +202,9 @@ class HRModule(nn.Module):
                 elif j > i:
                     fl = self.fuse_layers[i][j]                     # conv1x1 + BN + Upsample, then resize (hrnet.py:216-220)
                     t = fl[2](cbr(fl[0], fl[1], x[j], False))
-                    y = y + F.interpolate(t, size=x[i].shape[2:], mode="bilinear", align_corners=False)
+                    if t.shape[2:] != x[i].shape[2:]:            # the reference's second resize; identity when sizes agree
+                        t = F.interpolate(t, size=x[i].shape[2:], mode="bilinear", align_corners=False)
+                    y = y + t
                 else:
                     t = x[j]
                     for seq in self.fuse_layers[i][j]:              # conv3x3 s2 + BN (+ReLU except the last)
@@ -205,6 +212,31 @@ class HRModule(nn.Module):
                     y = y + t
             outs.append(self.relu(y))
         return outs
+
+
+def _forward_fused(self, x):
+    """Eval / CUDA: every output branch = ONE ls3d_upsample_sum launch over its terms in the reference's j order (same-size
+    terms as they are, coarser 1x1-conv outputs resized inside the kernel), ReLU fused."""
+    from .. import ops
+    outs = []
+    for i in range(len(self.fuse_layers)):
+        terms = []
+        for j in range(self.num_branches):
+            if i == j:
+                terms.append(x[j])
+            elif j > i:
+                fl = self.fuse_layers[i][j]
+                terms.append(cbr(fl[0], fl[1], x[j], False))
+            else:
+                t = x[j]
+                for seq in self.fuse_layers[i][j]:
+                    t = cbr(seq[0], seq[1], t, len(seq) == 3)
+                terms.append(t)
+        outs.append(ops.upsample_sum(terms, relu=True))
+    return outs
+
+
+HRModule._forward_fused = _forward_fused
 
 
 @IMG_BACKBONES.register_module

@@ -91,16 +91,20 @@ class FCNMSeg3DHead(nn.Module):
         xs = [inputs[i] for i in self.in_index]
         true_c = [c for c in self._branch_channels]
         w, b = folded(cm.conv, cm.bn, sum(true_c), xs[0].dtype)
-        y, c0 = None, 0
+        terms, c0 = [], 0
         for i, (x, c) in enumerate(zip(xs, true_c)):
             wi = w[:, c0:c0 + c]
             if x.shape[1] != c:                                  # channel-padded backbone output
                 wi = torch.nn.functional.pad(wi, (0, 0, 0, 0, 0, x.shape[1] - c))
-            t = F.conv2d(x, wi.contiguous(memory_format=torch.channels_last), b if i == 0 else None)
-            if i > 0:
-                t = F.interpolate(t, size=xs[0].shape[2:], mode="bilinear", align_corners=self.align_corners)
-            y = t if y is None else y + t
+            terms.append(F.conv2d(x, wi.contiguous(memory_format=torch.channels_last), b if i == 0 else None))
             c0 += c
+        H, W = xs[0].shape[2:]
+        if (not self.align_corners and len(terms) <= 4 and terms[0].dtype == torch.float32 and terms[0].shape[1] % 4 == 0
+                and all(t.shape[2] <= H and t.shape[3] <= W for t in terms)):
+            return ops.upsample_sum(terms, relu=True)            # resize + sum + ReLU in one pass (csrc/upsample_sum.cu)
+        y = terms[0]
+        for t in terms[1:]:
+            y = y + F.interpolate(t, size=(H, W), mode="bilinear", align_corners=self.align_corners)
         return torch.relu_(y)
 
     def forward(self, batch_dict, return_loss=True, **kwargs):

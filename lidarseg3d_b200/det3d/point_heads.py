@@ -319,8 +319,8 @@ class PointSegMSeg3DHead(Prepared):
         tgt = gemm.run(geo, P["proj_point"][0], shift=P["proj_point"][1])
         dh = sf.d_model // sf.nhead
         for i, ly in enumerate(P["layers"]):
-            att = gemm.run(tgt, ly["q"][0], shift=ly["q"][1],
-                           attn=dict(k=K[i], v=V[i], frame_off=point_off, scale=dh ** -0.5))
+            q = gemm.run(tgt, ly["q"][0], shift=ly["q"][1])
+            att = ops.token_attention(q, K[i], V[i], point_off, dh ** -0.5)
             tgt = gemm.run(att, ly["o"][0], shift=ly["o"][1], res=tgt, res_mode=1, ln=(ly["n2"],))
             h = gemm.run(tgt, ly["l1"][0], shift=ly["l1"][1], relu=True)
             lns = (ly["n3"], P["norm_tgt"]) if i == nl - 1 else (ly["n3"],)

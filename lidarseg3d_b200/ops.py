@@ -182,6 +182,50 @@ def sample_image_features(feat_nhwc, points_cuv, point_off, round_out=False):
     return out
 
 
+def project_points(points, cam_from_lidar, intrinsics, img_hw, net_hw, xyz_off=0):
+    """points [N, >=3] fp32 cuda; cam_from_lidar [ncam,4,4], intrinsics [ncam,3,3] (host, float64).  Returns
+    points_cuv [N,4] = (valid, cam, v, u) with the reference's projection rules (loading.py:373-416)."""
+    import numpy as np
+    T = np.ascontiguousarray(np.asarray(cam_from_lidar, dtype=np.float64))
+    K = np.ascontiguousarray(np.asarray(intrinsics, dtype=np.float64))
+    n = points.shape[0]
+    out = _f32(points.device, n, 4)
+    check(capi.lib().ls3d_project_points(ptr(points), points.stride(0), xyz_off, n, T.ctypes.data, K.ctypes.data, T.shape[0],
+                                         img_hw[0], img_hw[1], net_hw[0], net_hw[1], ptr(out), stream_ptr()),
+          "ls3d_project_points")
+    return out
+
+
+def token_attention(q, k, v, frame_off, scale, round_out=False):
+    """q [N, H*dh] fp32; k, v [F, H, L, dh]; frame_off int32 [F] -> softmax(q K^T * scale) V per point and head, [N, H*dh]."""
+    F_, H, L, dh = k.shape
+    n = q.shape[0]
+    out = _f32(q.device, n, H * dh)
+    check(capi.lib().ls3d_token_attention(ptr(q), q.stride(0), n, ptr(k), ptr(v), ptr(frame_off), F_, L, H, dh, float(scale),
+                                          ptr(out), out.stride(0), int(round_out), stream_ptr()), "ls3d_token_attention")
+    return out
+
+
+def upsample_sum(terms, relu=True):
+    """terms: list (<= 4) of [N, C, h_k, w_k] fp32 channels-last CUDA tensors, the FIRST at the output resolution or any of
+    them; output resolution = the largest term.  Returns act(sum_k resize(term_k)) [N, C, H, W] channels-last."""
+    import ctypes
+    N, C = terms[0].shape[:2]
+    H = max(t.shape[2] for t in terms)
+    W = max(t.shape[3] for t in terms)
+    ts = []
+    for t in terms:
+        assert t.dtype == torch.float32 and t.shape[0] == N and t.shape[1] == C
+        ts.append(t.contiguous(memory_format=torch.channels_last))
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=terms[0].device, memory_format=torch.channels_last)
+    k = len(ts)
+    ptrs = (ctypes.c_void_p * k)(*[ptr(t) for t in ts])
+    hs = (ctypes.c_int32 * k)(*[t.shape[2] for t in ts])
+    ws = (ctypes.c_int32 * k)(*[t.shape[3] for t in ts])
+    check(capi.lib().ls3d_upsample_sum(ptrs, hs, ws, k, N, H, W, C, int(relu), ptr(out), stream_ptr()), "ls3d_upsample_sum")
+    return out
+
+
 def class_embed(logits, feats, seg_off, n_frames, max_rows, ncls=None, C=None):
     """softmax over rows per (frame, class) then probs^T @ feats -> [B, ncls, C]."""
     ncls = ncls or logits.shape[1]

@@ -26,5 +26,12 @@ print('launches', sum(v[0] for v in agg.values()), 'total_ns', tot)
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
     print(f'{v[1]/tot*100:6.2f}%  {v[0]:5d}  {v[1]/1e3:10.1f} us  {k}')
 PY
-timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "dense_gemm or trans_vfe or sparse_conv" --timeout 120 2>&1 | tail -3
-timeout 300 python bench.py --workload sdseg3d_semantickitti --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_sdseg3d.log 2>&1; tail -c 700 $O/bench_sdseg3d.log
+
+
+timeout 500 python bench.py --steps 10 --warmup 3 > $O/bench_default_with_cpu.log 2>&1; tail -c 1500 $O/bench_default_with_cpu.log
+timeout 400 python bench.py --workload spconv_sweep --steps 5 --warmup 3 > $O/bench_sweep.log 2>&1; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_sweep.log').read().strip().splitlines()[-1])
+print('sweep value', d['value'], d['roofline'])
+for r in d['sweep']: print({k:(round(v,3) if isinstance(v,float) else v) for k,v in r.items()})
+PY

@@ -79,10 +79,13 @@ def test_sdseg3d_forward_vs_oracle():
     assert float((preds[1]["pred_point_sem_labels"].cpu() == labels[1]).float().mean()) >= 0.999
 
 
-def test_mseg3d_forward_vs_oracle():
+@pytest.mark.parametrize("cfg_name,spec_name", [("mseg3d_nuscenes.py", "NUSC"), ("mseg3d_waymo.py", "WAYMO")])
+def test_mseg3d_forward_vs_oracle(cfg_name, spec_name):
+    """BASELINE.json configs[2] (nuScenes: 17 classes, 6 cameras) and configs[3] (Waymo: 23 classes, 5 cameras, z range
+    [-2, 4]) at a reduced scan / image size the CPU oracle finishes in seconds."""
     from lidarseg3d_b200 import pipeline, synth
-    cfg, m = _build("mseg3d_nuscenes.py")
-    spec = dict(synth.NUSC)
+    cfg, m = _build(cfg_name)
+    spec = dict(getattr(synth, spec_name))
     spec.update(beams=16, azimuths=400)
     hw = (128, 192)
     frames = [synth.lidar_scan(spec, s) for s in (0, 1)]
