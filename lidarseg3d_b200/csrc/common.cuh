@@ -170,6 +170,74 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n) {
   return d;
 }
 
+
+
+// One lane of the (fully active) warp is elected; the compiler keeps single-thread tcgen05 / bulk-copy issue on the uniform
+// datapath when the operands are provably warp-uniform (see bcast0) and the guard is this predicate.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// lane 0's value in every lane; tells the compiler the value is warp-uniform (memory loads are not provably uniform)
+__device__ __forceinline__ uint32_t bcast0(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// ---------------------------------------------------------------- bulk async copy (TMA unit, no tensor map)
+// mbarrier: one arrival + expected transaction bytes
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// contiguous global -> shared copy (bytes % 16 == 0, both 16-byte aligned); completion = complete_tx on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05, bf16 with the A operand in tensor memory
+// D[tmem] (+)= A[tmem] * B[smem], kind::f16 (bf16 operands, fp32 accumulate). One thread issues.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same with A from shared memory
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 instruction descriptor: fp32 accumulate, A/B bf16, both K-major, M=128.
+__device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n) {
+  uint32_t d = 0;
+  d |= 1u << 4;           // c_format = F32
+  d |= 1u << 7;           // a_format = BF16
+  d |= 1u << 10;          // b_format = BF16
+  d |= (n >> 3) << 17;    // N / 8
+  d |= (128u >> 4) << 24; // M / 16
+  return d;
+}
+// two floats -> packed bf16x2 (lo -> bits [0,16), hi -> bits [16,32)), round to nearest even
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

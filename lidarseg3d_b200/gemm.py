@@ -22,9 +22,13 @@ COUNT = None
 DEBUG_SKIP = 0      # development only (see ls3d_gemm_args.debug_skip)
 
 
-# True: error-compensated 3xTF32 everywhere (fp32-level accuracy; default).  False: single-pass TF32 with tf32-rounded
-# activations (faster, ~1e-3 relative error after the full network).
-PRECISE = True
+# Arithmetic engine of every gather-GEMM launch (csrc/gather_gemm*.cu):
+#   2 (default): "bf16x3" - operands split into bf16 hi + lo on the fly, x_hi.W_hi + x_hi.W_lo + x_lo.W_hi with fp32
+#                accumulate (~2^-17 relative error per product; activations stay exact fp32 in HBM)
+#   1 / True   : error-compensated 3xTF32 (~2^-22 per product), the slower reference engine
+#   0 / False  : single-pass TF32 with tf32-rounded activations (~2e-3 relative error after the full network: fails the
+#                1e-3 logit gate, kept for comparison only)
+PRECISE = 2
 
 
 def trunc_tf32(x: torch.Tensor) -> torch.Tensor:
@@ -40,11 +44,13 @@ class PackedWeight:
         assert w_kio.dim() == 3
         koff, cin, cout = w_kio.shape
         self.koff, self.cin, self.cout = koff, cin, cout
-        self.cin_pad = pad_to(cin, 8)
+        self.precise = int(PRECISE)
+        self.cin_pad = pad_to(cin, 16 if self.precise == 2 else 8)
         self.n_pad = pad_to(cout, 16)
-        self.precise = PRECISE
         wt = w_kio.float().permute(0, 2, 1)
-        if self.precise:
+        if self.precise == 2:
+            buf = self._pack_bf16x3(wt)
+        elif self.precise:
             buf = torch.zeros(koff, 2, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
             hi = trunc_tf32(wt)
             buf[:, 0, :cout, :cin] = hi
@@ -53,6 +59,23 @@ class PackedWeight:
             buf = torch.zeros(koff, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
             buf[:, :cout, :cin] = round_tf32(wt)
         self.data = buf.contiguous()
+
+    def _pack_bf16x3(self, wt):
+        """[koff][nchunk][n_pad rows x 128 B]: row n of chunk c = [bf16 hi of W[n, 32c..32c+31] | bf16 lo of the same],
+        stored as the 128B-swizzled shared-memory image (16-byte unit u of row n sits at unit u ^ (n & 7)) so that one
+        contiguous cp.async.bulk per (offset, chunk) lands a ready tcgen05 K-major B tile."""
+        koff, cout, cin = wt.shape
+        nchunk = (self.cin_pad + 31) // 32
+        full = torch.zeros(koff, self.n_pad, nchunk * 32, dtype=torch.float32, device=wt.device)
+        full[:, :cout, :cin] = wt
+        hi = full.to(torch.bfloat16)
+        lo = (full - hi.float()).to(torch.bfloat16)
+        rows = torch.cat([hi.view(koff, self.n_pad, nchunk, 32), lo.view(koff, self.n_pad, nchunk, 32)], dim=-1)
+        rows = rows.permute(0, 2, 1, 3).reshape(koff, nchunk, self.n_pad, 8, 8)          # [.., row, 16B unit, 8 bf16]
+        n = torch.arange(self.n_pad, device=wt.device)
+        u = torch.arange(8, device=wt.device)
+        src = u[None, :] ^ (n[:, None] & 7)                                             # unit stored at position u
+        return rows[:, :, n[:, None], src].contiguous()
 
     @staticmethod
     def from_linear(weight_oi: torch.Tensor):

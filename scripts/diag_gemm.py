@@ -152,11 +152,17 @@ def timing(m, cin, cout, fill, koff=27, iters=20):
     nbr[13] = base
     pw = gemm.PackedWeight(w); out = torch.empty(m, cout, device=dev)
     for _ in range(3): gemm.run(x, pw, nbr=nbr, out=out)
+    torch.cuda.synchronize()
+    # CUDA graph of `iters` launches: the python/ctypes launch path (~30 us) must not bound the measurement
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for _ in range(iters): gemm.run(x, pw, nbr=nbr, out=out)
+    gr.replay(); torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters): gemm.run(x, pw, nbr=nbr, out=out)
+    for _ in range(3): gr.replay()
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    ms = e0.elapsed_time(e1) / iters / 3
     pairs = int((nbr >= 0).sum())
     byts = m * cin * 4 + m * cout * 4 + koff * cin * cout * 4 + pairs * 8
     return dict(m=m, cin=cin, cout=cout, ms=ms, pairs=pairs, gbs=byts / ms / 1e6, gflops=2 * pairs * cin * cout / ms / 1e6)
@@ -168,9 +174,10 @@ def timings():
   except Exception as e:
     traceback.print_exc()
 
-for mode in (True, False):
+MODES = [int(v) for v in os.environ.get("LS3D_MODES", "2,1,0").split(",")]
+for mode in MODES:
     gemm.PRECISE = mode
-    ladder("precise(3xTF32)" if mode else "single-pass TF32")
+    ladder({2: "bf16x3", 1: "precise(3xTF32)", 0: "single-pass TF32"}[mode])
     timings()
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/diag_gemm.json", "w"), indent=1)
