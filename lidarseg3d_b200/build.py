@@ -9,7 +9,11 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--ex
          "-Xcompiler", "-fPIC"]
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, prof=False):
+    """prof=True: development build with in-kernel cycle counters (-DLS3D_PROF) -> _ls3d_prof.so (never loaded by the
+    package unless LS3D_PROF_SO=1 is set)."""
+    if prof:
+        return _build_prof()
     srcs = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")))
     deps = srcs + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + [os.path.join(HERE, "..", "include", "ls3d.h")]
     out = os.path.join(HERE, "_ls3d.so")
@@ -42,6 +46,13 @@ def build(force=False, verbose=False):
             return build(force=True, verbose=verbose)
         raise RuntimeError(f"_ls3d.so does not export {missing}")
     os.replace(tmp, out)            # atomic: a concurrent snapshot never sees a half-written library
+    return out
+
+
+def _build_prof():
+    srcs = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")))
+    out = os.path.join(HERE, "_ls3d_prof.so")
+    subprocess.check_call([NVCC] + FLAGS + ["-DLS3D_PROF", "-shared", "-o", out] + srcs + ["-lcudart"])
     return out
 
 

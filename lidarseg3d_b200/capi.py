@@ -10,6 +10,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ls3d.so")
+if os.environ.get("LS3D_PROF_SO") == "1":       # development: instrumented build (build.build(prof=True))
+    LIB_PATH = os.path.join(_HERE, "_ls3d_prof.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int32

@@ -159,6 +159,16 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// K-major, SWIZZLE_64B (rows of 64 bytes, 8-row groups 512 B apart; 16-byte unit index ^= (row >> 1) & 3)
+__device__ __forceinline__ uint64_t make_desc_k_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
 // kind::tf32 instruction descriptor: fp32 accumulate, A/B tf32, both K-major, M=128.
 __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t n) {
   uint32_t d = 0;

@@ -65,8 +65,9 @@ __device__ __forceinline__ void panel_store(const float* stgw, float* dst, int l
   }
 }
 
+// dual > 0: the accumulator is the sum of two partial tiles, columns [0, n) and [dual, dual + n) (bf16x3 stacked-W mode).
 __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uint32_t trow, const int tile_row0, const int et,
-                                              const float* colv, float* stg_all) {
+                                              const float* colv, float* stg_all, const uint32_t dual = 0) {
   const int lane = et & 31;
   const int row0 = tile_row0 + (et & ~31);             // first global row of this warp's 32-row slice
   const int r = tile_row0 + et;
@@ -91,6 +92,14 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
       float q[DHEAD];
 #pragma unroll
       for (int d = 0; d < DHEAD; ++d) q[d] = __uint_as_float(raw[d]) + colv[COLV + h * DHEAD + d];
+      if (dual) {
+        tmem_ld8(trow + dual + h * DHEAD, raw);
+        tmem_ld8(trow + dual + h * DHEAD + 8, raw + 8);
+        tmem_ld8(trow + dual + h * DHEAD + 16, raw + 16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < DHEAD; ++d) q[d] += __uint_as_float(raw[d]);
+      }
       const float* kh = p.attn_k + ((size_t)(f * p.n_head + h) * L) * DHEAD;
       const float* vh = p.attn_v + ((size_t)(f * p.n_head + h) * L) * DHEAD;
       float sc[MAX_TOK];
@@ -173,6 +182,12 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < PANEL; ++j) v[j] = __uint_as_float(raw[j]);
+    if (dual) {
+      tmem_ld16(trow + dual + c0, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < PANEL; ++j) v[j] += __uint_as_float(raw[j]);
+    }
     if (has_affine) {
 #pragma unroll
       for (int j4 = 0; j4 < PANEL / 4; ++j4) {

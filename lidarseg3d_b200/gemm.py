@@ -61,21 +61,31 @@ class PackedWeight:
         self.data = buf.contiguous()
 
     def _pack_bf16x3(self, wt):
-        """[koff][nchunk][n_pad rows x 128 B]: row n of chunk c = [bf16 hi of W[n, 32c..32c+31] | bf16 lo of the same],
-        stored as the 128B-swizzled shared-memory image (16-byte unit u of row n sits at unit u ^ (n & 7)) so that one
-        contiguous cp.async.bulk per (offset, chunk) lands a ready tcgen05 K-major B tile."""
+        """One contiguous block of n_pad * 128 bytes per (offset, 32-channel chunk), stored as the swizzled shared-memory
+        image so that a single cp.async.bulk lands a ready tcgen05 K-major B tile (csrc/gather_gemm_bf16x3.cu):
+          n_pad <= 96 ("stacked"): 2 n_pad rows of 64 bytes, rows [0, n) = bf16 hi of W[n, 32c..32c+31], rows [n, 2n) = bf16
+                        lo; SWIZZLE_64B: 16-byte unit u of row r sits at unit u ^ ((r >> 1) & 3);
+          n_pad  > 96 : n_pad rows of 128 bytes = [hi (32) | lo (32)]; SWIZZLE_128B: unit u of row r at u ^ (r & 7)."""
         koff, cout, cin = wt.shape
         nchunk = (self.cin_pad + 31) // 32
-        full = torch.zeros(koff, self.n_pad, nchunk * 32, dtype=torch.float32, device=wt.device)
+        n_pad = self.n_pad
+        full = torch.zeros(koff, n_pad, nchunk * 32, dtype=torch.float32, device=wt.device)
         full[:, :cout, :cin] = wt
         hi = full.to(torch.bfloat16)
         lo = (full - hi.float()).to(torch.bfloat16)
-        rows = torch.cat([hi.view(koff, self.n_pad, nchunk, 32), lo.view(koff, self.n_pad, nchunk, 32)], dim=-1)
-        rows = rows.permute(0, 2, 1, 3).reshape(koff, nchunk, self.n_pad, 8, 8)          # [.., row, 16B unit, 8 bf16]
-        n = torch.arange(self.n_pad, device=wt.device)
-        u = torch.arange(8, device=wt.device)
-        src = u[None, :] ^ (n[:, None] & 7)                                             # unit stored at position u
-        return rows[:, :, n[:, None], src].contiguous()
+        hi = hi.view(koff, n_pad, nchunk, 32).permute(0, 2, 1, 3)                          # [koff, nchunk, n, 32]
+        lo = lo.view(koff, n_pad, nchunk, 32).permute(0, 2, 1, 3)
+        if n_pad <= 96:
+            rows = torch.cat([hi, lo], dim=2).reshape(koff, nchunk, 2 * n_pad, 4, 8)      # [.., row, 16B unit, 8 bf16]
+            r = torch.arange(2 * n_pad, device=wt.device)
+            u = torch.arange(4, device=wt.device)
+            src = u[None, :] ^ ((r[:, None] >> 1) & 3)
+        else:
+            rows = torch.cat([hi, lo], dim=3).reshape(koff, nchunk, n_pad, 8, 8)
+            r = torch.arange(n_pad, device=wt.device)
+            u = torch.arange(8, device=wt.device)
+            src = u[None, :] ^ (r[:, None] & 7)
+        return rows[:, :, r[:, None], src].contiguous()
 
     @staticmethod
     def from_linear(weight_oi: torch.Tensor):
