@@ -195,6 +195,23 @@ int ls3d_project_points(const float* points, int32_t ld_p, int32_t xyz_off, int3
  * ------------------------------------------------------------------------------------------------ */
 int ls3d_upsample_sum(const float* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
                       int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, float* out, void* stream);
+/* same on fp16 maps (fp32 arithmetic); C a multiple of 8 */
+int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
+                          int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Camera stem: fused 3x3 / stride 1 / pad 1 convolution + bias (+ residual) (+ ReLU) on channels-last fp16 maps,
+ * tcgen05 tensor cores, fp32 accumulation.
+ * replaces: conv3x3 -> BatchNorm (folded) -> [+ identity] -> ReLU of the HRNet BasicBlocks
+ *           (det3d/models/img_backbones/resnet_mmcv.py:20-100 as used by hrnet.py:78-226), cuDNN in the reference.
+ *   in  [n_img, H, W, cin] fp16, res / out [n_img, H, W, cout] fp16 (res may be NULL); cin, cout multiples of 8 (zero-padded
+ *   channels); w_packed [9][k_pad/8][n_pad][8] fp16 with k_pad / n_pad = cin / cout rounded up to 16, tap = ky*3 + kx,
+ *   element = W[n][8*chunk + e][ky][kx] (zero outside); bias [cout] fp32 or NULL.
+ *   ls3d_conv3x3_f16_smem_bytes: shared memory the launch needs (weights stay resident); > 227 KB = not supported.
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_conv3x3_f16_smem_bytes(int32_t cin, int32_t cout, int64_t* bytes);
+int ls3d_conv3x3_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img,
+                     int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t relu, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SF-Phase: class embedding aggregation and class-token memory path.

@@ -8,6 +8,8 @@
 // one add and one ReLU per term; here every output element is written once and the coarse terms (<= 1/4 of the pixels)
 // are read through L1/L2.  Bilinear taps follow ATen's align_corners=False rule (src = scale*(dst+0.5)-0.5, clamped at 0).
 // One thread per (pixel, 4 channels): 16-byte loads/stores; HBM-bound: (1 + sum_k hk*wk/(H*W)) reads + 1 write per element.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "../../include/ls3d.h"
 
@@ -70,25 +72,111 @@ __global__ void __launch_bounds__(256) upsample_sum_kernel(UpsTerms T, int n_img
   }
 }
 
+// fp16 maps (fp16 camera stem): one thread per (pixel, 8 channels), fp32 arithmetic, 16-byte loads/stores
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld_h8(const uint4* p) {
+  const uint4 u = __ldg(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+  F8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__global__ void __launch_bounds__(256) upsample_sum_f16_kernel(UpsTerms T, int n_img, int H, int W, int C8, int relu,
+                                                               uint4* __restrict__ out) {
+  const long long total = (long long)n_img * H * W * C8;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(e % C8);
+    long long pix = e / C8;
+    const int x = (int)(pix % W);
+    pix /= W;
+    const int y = (int)(pix % H);
+    const int img = (int)(pix / H);
+    F8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < UPS_MAX_TERMS; ++k) {
+      if (k >= T.n) break;
+      const int h = T.h[k], w = T.w[k];
+      const uint4* src = reinterpret_cast<const uint4*>(T.p[k]) + (size_t)img * h * w * C8 + c8;
+      if (h == H && w == W) {
+        const F8 v = ld_h8(src + ((size_t)y * W + x) * C8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc.v[i] += v.v[i];
+      } else {
+        float sy = T.rh[k] * ((float)y + 0.5f) - 0.5f;
+        float sx = T.rw[k] * ((float)x + 0.5f) - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int yp = y0 < h - 1 ? 1 : 0, xp = x0 < w - 1 ? 1 : 0;
+        const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+        const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+        const uint4* r0 = src + ((size_t)y0 * w + x0) * C8;
+        const uint4* r1 = r0 + (size_t)yp * w * C8;
+        const F8 v00 = ld_h8(r0), v01 = ld_h8(r0 + (size_t)xp * C8), v10 = ld_h8(r1), v11 = ld_h8(r1 + (size_t)xp * C8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float top = fmaf(lx1, v01.v[i], lx0 * v00.v[i]);
+          const float bot = fmaf(lx1, v11.v[i], lx0 * v10.v[i]);
+          acc.v[i] += fmaf(ly1, bot, ly0 * top);
+        }
+      }
+    }
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = acc.v[2 * i], b = acc.v[2 * i + 1];
+      if (relu) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      o2[i] = __floats2half2_rn(a, b);
+    }
+    out[e] = o;
+  }
+}
+
 }  // namespace ls3d
 
-extern "C" int ls3d_upsample_sum(const float* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
-                                 int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, float* out, void* stream) {
+static int upsample_sum_launch(const void* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
+                               int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream, int vec) {
   using namespace ls3d;
   if (n_img <= 0 || H <= 0 || W <= 0) return LS3D_OK;
-  if (!terms || !term_h || !term_w || !out || n_terms < 1 || n_terms > UPS_MAX_TERMS || C <= 0 || (C & 3)) return LS3D_ERR_ARG;
+  if (!terms || !term_h || !term_w || !out || n_terms < 1 || n_terms > UPS_MAX_TERMS || C <= 0 || (C % vec)) return LS3D_ERR_ARG;
   UpsTerms T;
   T.n = n_terms;
   for (int k = 0; k < n_terms; ++k) {
     if (!terms[k] || term_h[k] <= 0 || term_w[k] <= 0 || term_h[k] > H || term_w[k] > W) return LS3D_ERR_ARG;
-    T.p[k] = terms[k]; T.h[k] = term_h[k]; T.w[k] = term_w[k];
+    T.p[k] = (const float*)terms[k]; T.h[k] = term_h[k]; T.w[k] = term_w[k];
     T.rh[k] = (float)term_h[k] / (float)H;
     T.rw[k] = (float)term_w[k] / (float)W;
   }
-  const long long total = (long long)n_img * H * W * (C / 4);
+  const long long total = (long long)n_img * H * W * (C / vec);
   const long long blocks = (total + 255) / 256;
   const int grid = (int)(blocks < 148LL * 64 ? blocks : 148LL * 64);     // grid-stride, a multiple of the SM count when large
-  upsample_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 4, relu, out);
+  if (vec == 4)
+    upsample_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 4, relu, (float*)out);
+  else
+    upsample_sum_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 8, relu, (uint4*)out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
+}
+
+extern "C" int ls3d_upsample_sum(const float* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
+                                 int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, float* out, void* stream) {
+  return upsample_sum_launch((const void* const*)terms, term_h, term_w, n_terms, n_img, H, W, C, relu, out, stream, 4);
+}
+
+extern "C" int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
+                                     int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream) {
+  return upsample_sum_launch(terms, term_h, term_w, n_terms, n_img, H, W, C, relu, out, stream, 8);
 }

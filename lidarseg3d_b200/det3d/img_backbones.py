@@ -67,14 +67,51 @@ def folded(conv, bn, x_channels, dtype):
     return cache[1], cache[2]
 
 
+FUSED_CONV3X3 = True    # eval/CUDA/fp16: 3x3 stride-1 convs on the hand-written tcgen05 kernel (csrc/conv3x3_f16.cu)
+
+
+def folded_packed3x3(conv, bn, x_channels):
+    """BN-folded 3x3 weights packed for ls3d_conv3x3_f16 (+ fp32 bias), cached like ``folded``; None when the weights do not
+    fit the kernel's shared memory (the caller then uses cuDNN)."""
+    key = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var) + (x_channels, PAD_CHANNELS)
+    cache = getattr(conv, "_ls3d_fold3", None)
+    if cache is None or cache[0] != key:
+        from .. import ops
+        w, b = folded(conv, bn, x_channels, torch.float32)          # [Cout_p(4), Cin, 3, 3] fp32: re-pad Cout for fp16 maps
+        cout_p = _pad_to(conv.out_channels, torch.float16)
+        if not ops.conv3x3_f16_supported(x_channels, cout_p):
+            cache = (key, None, None, cout_p)
+        else:
+            with torch.no_grad():
+                wp = w.new_zeros(cout_p, x_channels, 3, 3)
+                wp[:conv.out_channels] = w[:conv.out_channels]
+                bp = b.new_zeros(cout_p)
+                bp[:conv.out_channels] = b[:conv.out_channels]
+                cache = (key, ops.pack_conv3x3_f16(wp), bp.float().contiguous(), cout_p)
+        conv._ls3d_fold3 = cache
+    return cache[1], cache[2], cache[3]
+
+
+def _is_plain3x3(conv):
+    return (conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+            and conv.groups == 1)
+
+
 def cbr(conv, bn, x, relu, z=None):
     """conv -> BatchNorm -> (+z) -> (ReLU).  Training / CPU: plain modules.  Eval on CUDA: BN folded into the conv weights
-    (cached, refreshed when a parameter changes) and run as one cuDNN call."""
+    (cached, refreshed when a parameter changes); fp16 3x3 stride-1 convs run on the hand-written tensor-core kernel, the rest
+    as one cuDNN call."""
     if bn.training or not x.is_cuda:
         y = bn(conv(x))
         if z is not None:
             y = y + z
         return torch.relu(y) if relu else y
+    if (FUSED_CONV3X3 and x.dtype == torch.float16 and _is_plain3x3(conv) and x.shape[1] % 8 == 0
+            and x.is_contiguous(memory_format=torch.channels_last)):
+        wp, bp, cout_p = folded_packed3x3(conv, bn, x.shape[1])
+        if wp is not None and (z is None or (z.shape[1] == cout_p and z.is_contiguous(memory_format=torch.channels_last))):
+            from .. import ops
+            return ops.conv3x3_f16(x, wp, bp, res=z, relu=relu, cout=cout_p)
     w, b = folded(conv, bn, x.shape[1], x.dtype)
     if FUSED_CUDNN and relu and conv.groups == 1:
         if z is None:
@@ -189,9 +226,9 @@ class HRModule(nn.Module):
         if self.num_branches == 1:
             return [self.branches[0](x[0])]
         x = [self.branches[i](x[i]) for i in range(self.num_branches)]
-        if FUSED_SUM and x[0].is_cuda and not self.training and x[0].dtype == torch.float32 and all(
-                t.shape[1] % 4 == 0 and x[0].shape[2] == t.shape[2] << j and x[0].shape[3] == t.shape[3] << j
-                for j, t in enumerate(x)):
+        if FUSED_SUM and x[0].is_cuda and not self.training and x[0].dtype in (torch.float32, torch.float16) and all(
+                t.shape[1] % (4 if t.dtype == torch.float32 else 8) == 0 and x[0].shape[2] == t.shape[2] << j
+                and x[0].shape[3] == t.shape[3] << j for j, t in enumerate(x)):
             return self._forward_fused(x)
         outs = []
         for i in range(len(self.fuse_layers)):

@@ -99,7 +99,9 @@ class FCNMSeg3DHead(nn.Module):
             terms.append(F.conv2d(x, wi.contiguous(memory_format=torch.channels_last), b if i == 0 else None))
             c0 += c
         H, W = xs[0].shape[2:]
-        if (not self.align_corners and len(terms) <= 4 and terms[0].dtype == torch.float32 and terms[0].shape[1] % 4 == 0
+        vec = 4 if terms[0].dtype == torch.float32 else 8
+        if (not self.align_corners and len(terms) <= 4 and terms[0].dtype in (torch.float32, torch.float16)
+                and terms[0].shape[1] % vec == 0 and terms[0].is_cuda
                 and all(t.shape[2] <= H and t.shape[3] <= W for t in terms)):
             return ops.upsample_sum(terms, relu=True)            # resize + sum + ReLU in one pass (csrc/upsample_sum.cu)
         y = terms[0]

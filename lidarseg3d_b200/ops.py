@@ -213,16 +213,54 @@ def upsample_sum(terms, relu=True):
     N, C = terms[0].shape[:2]
     H = max(t.shape[2] for t in terms)
     W = max(t.shape[3] for t in terms)
+    dt = terms[0].dtype
+    assert dt in (torch.float32, torch.float16) and C % (4 if dt == torch.float32 else 8) == 0
     ts = []
     for t in terms:
-        assert t.dtype == torch.float32 and t.shape[0] == N and t.shape[1] == C
+        assert t.dtype == dt and t.shape[0] == N and t.shape[1] == C
         ts.append(t.contiguous(memory_format=torch.channels_last))
-    out = torch.empty((N, C, H, W), dtype=torch.float32, device=terms[0].device, memory_format=torch.channels_last)
+    out = torch.empty((N, C, H, W), dtype=dt, device=terms[0].device, memory_format=torch.channels_last)
     k = len(ts)
     ptrs = (ctypes.c_void_p * k)(*[ptr(t) for t in ts])
     hs = (ctypes.c_int32 * k)(*[t.shape[2] for t in ts])
     ws = (ctypes.c_int32 * k)(*[t.shape[3] for t in ts])
-    check(capi.lib().ls3d_upsample_sum(ptrs, hs, ws, k, N, H, W, C, int(relu), ptr(out), stream_ptr()), "ls3d_upsample_sum")
+    if dt == torch.float32:
+        check(capi.lib().ls3d_upsample_sum(ptrs, hs, ws, k, N, H, W, C, int(relu), ptr(out), stream_ptr()), "ls3d_upsample_sum")
+    else:
+        check(capi.lib().ls3d_upsample_sum_f16(ptrs, hs, ws, k, N, H, W, C, int(relu), ptr(out), stream_ptr()),
+              "ls3d_upsample_sum_f16")
+    return out
+
+
+def conv3x3_f16_supported(cin, cout):
+    """The fused fp16 3x3 convolution keeps all 9 taps of the weights in shared memory: true when they fit."""
+    nb = ctypes.c_int64()
+    if cin % 8 or cout % 8:
+        return False
+    check(capi.lib().ls3d_conv3x3_f16_smem_bytes(cin, cout, ctypes.byref(nb)), "ls3d_conv3x3_f16_smem_bytes")
+    return nb.value <= 227 * 1024
+
+
+def pack_conv3x3_f16(w_oihw):
+    """[Cout_p, Cin_p, 3, 3] (BatchNorm folded, zero-padded channels) -> [9][k_pad/8][n_pad][8] fp16 for ls3d_conv3x3_f16."""
+    cout, cin = w_oihw.shape[:2]
+    k_pad, n_pad = (cin + 15) // 16 * 16, (cout + 15) // 16 * 16
+    w = torch.zeros(n_pad, k_pad, 3, 3, dtype=torch.float32, device=w_oihw.device)
+    w[:cout, :cin] = w_oihw.float()
+    w = w.permute(2, 3, 1, 0).reshape(9, k_pad // 8, 8, n_pad).permute(0, 1, 3, 2)       # [tap][chunk][n][8]
+    return w.contiguous().to(torch.float16)
+
+
+def conv3x3_f16(x, w_packed, bias, res=None, relu=True, cout=None):
+    """x [N, Cin, H, W] fp16 channels-last, res [N, Cout, H, W] fp16 channels-last or None -> relu(conv3x3(x) + bias + res)."""
+    N, cin, H, W = x.shape
+    assert x.dtype == torch.float16 and x.is_contiguous(memory_format=torch.channels_last)
+    cout = cout if cout is not None else bias.shape[0]
+    if res is not None:
+        assert res.dtype == torch.float16 and res.shape == (N, cout, H, W) and res.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((N, cout, H, W), dtype=torch.float16, device=x.device, memory_format=torch.channels_last)
+    check(capi.lib().ls3d_conv3x3_f16(ptr(x), ptr(w_packed), ptr(bias), ptr(res), ptr(out), N, H, W, cin, cout, int(relu),
+                                      stream_ptr()), "ls3d_conv3x3_f16")
     return out
 
 

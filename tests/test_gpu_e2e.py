@@ -79,8 +79,10 @@ def test_sdseg3d_forward_vs_oracle():
     assert float((preds[1]["pred_point_sem_labels"].cpu() == labels[1]).float().mean()) >= 0.999
 
 
-@pytest.mark.parametrize("cfg_name,spec_name", [("mseg3d_nuscenes.py", "NUSC"), ("mseg3d_waymo.py", "WAYMO")])
-def test_mseg3d_forward_vs_oracle(cfg_name, spec_name):
+@pytest.mark.parametrize("cfg_name,spec_name,image_dtype", [("mseg3d_nuscenes.py", "NUSC", None),
+                                                            ("mseg3d_waymo.py", "WAYMO", None),
+                                                            ("mseg3d_nuscenes.py", "NUSC", torch.float16)])
+def test_mseg3d_forward_vs_oracle(cfg_name, spec_name, image_dtype):
     """BASELINE.json configs[2] (nuScenes: 17 classes, 6 cameras) and configs[3] (Waymo: 23 classes, 5 cameras, z range
     [-2, 4]) at a reduced scan / image size the CPU oracle finishes in seconds."""
     from lidarseg3d_b200 import pipeline, synth
@@ -95,6 +97,7 @@ def test_mseg3d_forward_vs_oracle(cfg_name, spec_name):
                 nhead=4, nlayer=6, num_convs=2)
     ref = on.mseg3d_forward(sd, ex_cpu, ocfg, return_all=True)
     m = m.to(DEV)
+    m.image_dtype = image_dtype          # fp16: camera branch on fp16 maps (own tcgen05 3x3 kernel); same logits gate
     ex = pipeline.build_example(frames, spec["voxel_size"], spec["pc_range"], images=ex_cpu["images"],
                                 points_cuv=ex_cpu["points_cuv"])
     preds = m(ex, return_loss=False)

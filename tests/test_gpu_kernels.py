@@ -257,6 +257,50 @@ def test_upsample_sum_vs_torch(C, sizes):
     torch.testing.assert_close(ops.upsample_sum(terms, relu=False), ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("C,sizes", [(24, [(32, 48), (16, 24), (8, 12), (4, 6)]), (48, [(30, 44), (15, 22)])])
+def test_upsample_sum_f16_vs_torch(C, sizes):
+    """fp16-storage twin of the fused branch fusion: fp32 arithmetic on fp16 maps, one rounding at the store."""
+    import torch.nn.functional as F
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(6)
+    terms = [torch.randn(2, C, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last) for h, w in sizes]
+    H, W = sizes[0]
+    ref = 0
+    for t in terms:
+        t = t.float()
+        ref = ref + (t if t.shape[2:] == (H, W) else F.interpolate(t, size=(H, W), mode="bilinear", align_corners=False))
+    out = ops.upsample_sum(terms, relu=True)
+    assert out.dtype == torch.float16 and out.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(out.float(), torch.relu(ref), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,res,relu", [(1, 16, 8, 16, 16, False, False), (2, 20, 30, 24, 24, True, True),
+                                                     (1, 40, 60, 40, 40, True, True), (3, 33, 17, 72, 72, False, True),
+                                                     (1, 1, 1, 8, 8, False, True), (2, 7, 129, 24, 40, False, False),
+                                                     (1, 160, 240, 24, 24, True, True)])
+def test_conv3x3_f16_vs_fp64(n, h, w, cin, cout, res, relu):
+    """Fused 3x3 conv + bias (+ residual) (+ ReLU) on fp16 channels-last maps vs an fp64 convolution of the same fp16 operands:
+    the only difference allowed is fp32 accumulation order and the final fp16 rounding (2^-11 relative)."""
+    import torch.nn.functional as F
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(n * 131 + h)
+    x = torch.randn(n, cin, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    z = torch.randn(n, cout, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last) if res else None
+    if not ops.conv3x3_f16_supported(cin, cout):
+        pytest.skip("weights do not fit shared memory")
+    y = ops.conv3x3_f16(x, ops.pack_conv3x3_f16(wt), b, res=z, relu=relu)
+    ref = F.conv2d(x.double(), wt.half().double(), b.double(), padding=1)
+    if z is not None:
+        ref = ref + z.double()
+    if relu:
+        ref = ref.relu()
+    assert y.dtype == torch.float16 and y.is_contiguous(memory_format=torch.channels_last)
+    err = float((y.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 6e-4, err
+
+
 @pytest.mark.parametrize("H,dh,L", [(4, 24, 34), (4, 24, 46), (2, 16, 5), (8, 32, 40)])
 def test_token_attention_vs_fp64(H, dh, L):
     """Class-token cross attention (context_module.py:320-376) vs a float64 softmax(q K^T) V, frames of uneven size with a
