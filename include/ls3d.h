@@ -205,11 +205,14 @@ int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* term_h, const
  * replaces: conv3x3 -> BatchNorm (folded) -> [+ identity] -> ReLU of the HRNet BasicBlocks
  *           (det3d/models/img_backbones/resnet_mmcv.py:20-100 as used by hrnet.py:78-226), cuDNN in the reference.
  *   in  [n_img, H, W, cin] fp16, res / out [n_img, H, W, cout] fp16 (res may be NULL); cin, cout multiples of 8 (zero-padded
- *   channels); w_packed [9][k_pad/8][n_pad][8] fp16 with k_pad / n_pad = cin / cout rounded up to 16, tap = ky*3 + kx,
- *   element = W[n][8*chunk + e][ky][kx] (zero outside); bias [cout] fp32 or NULL.
+ *   channels), all base pointers 16-byte aligned; bias [cout] fp32 or NULL.
+ *   w_packed: ls3d_conv3x3_f16_packed_bytes(cin, cout) bytes written by ls3d_conv3x3_f16_pack from the BatchNorm-folded fp32
+ *   weights [cout][cin][3][3] (the kernel's K order pairs (tap, 8-channel chunk) entries two per MMA; opaque to the caller).
  *   ls3d_conv3x3_f16_smem_bytes: shared memory the launch needs (weights stay resident); > 227 KB = not supported.
  * ------------------------------------------------------------------------------------------------ */
 int ls3d_conv3x3_f16_smem_bytes(int32_t cin, int32_t cout, int64_t* bytes);
+int ls3d_conv3x3_f16_packed_bytes(int32_t cin, int32_t cout, int64_t* bytes);
+int ls3d_conv3x3_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, void* packed, void* stream);
 int ls3d_conv3x3_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img,
                      int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t relu, void* stream);
 

@@ -1,5 +1,5 @@
 // Camera stem: fused 3x3 / stride 1 / pad 1 convolution + folded BatchNorm bias (+ residual) (+ ReLU) on channels-last fp16
-// maps, tcgen05 tensor cores with fp32 accumulation in TMEM.
+// maps, tcgen05 tensor cores with fp32 accumulation in TMEM, all global traffic through the TMA unit.
 //
 // Replaces (eval mode) the conv3x3 -> BN -> [+identity] -> ReLU pairs of the HRNet BasicBlocks, reference
 // det3d/models/img_backbones/resnet_mmcv.py:20-100 as instantiated by hrnet.py:78-226 (4 blocks per branch and module; 64 of
@@ -9,13 +9,18 @@
 // Implicit GEMM without im2col traffic: a persistent CTA walks 16 x 8 output tiles (128 pixels = the UMMA M dimension).
 // The (16+2) x (8+2) input halo of a tile is staged ONCE in shared memory, channel-chunk major ([16-byte chunk][pixel]) -
 // the un-swizzled K-major UMMA layout whose 8-row groups are 8 x-adjacent pixels - so each of the 9 taps is the same buffer
-// read through a shared-memory descriptor whose start address is shifted by (dy * 10 + dx) pixels: 9 * Cin/16 MMAs per tile
-// against weights that stay resident in shared memory for the whole launch.
-//   warps 0-2   loaders : cp.async halo gathers (zero fill outside the image) driven by a per-launch shared-memory table of
-//                         (global offset, halo position) per 16-byte chunk; completion via cp.async.mbarrier.arrive
-//   warp 3      MMA     : one elected thread, tcgen05.mma.kind::f16 M=128 N=Cout K=16, double-buffered accumulators
-//   warps 4-7   epilogue: tcgen05.ld -> + bias (+ residual) -> ReLU -> fp16 -> 16-byte stores; overlaps the next tile's MMAs
-// Bound: HBM (one read of the input, one of the residual, one write) once the ~64-cycle per-MMA operand fetch is hidden.
+// read through a shared-memory descriptor whose start address is shifted by (dy * 10 + dx) pixels.  The K dimension of the
+// GEMM is the list of (tap, 8-channel chunk) pairs; one MMA (K = 16) takes two consecutive list entries wherever they lie in
+// the halo buffer (the descriptor's leading-dimension byte offset is per MMA), so 18 padded channels cost ceil(27 / 2) = 14
+// MMAs per tile rather than 9 * 2.  Weights are packed on the device in that order and stay resident in shared memory.
+//   warp 0      producer: one thread; per tile one 4-D tensor-map copy per channel chunk (box 8 ch x 10 x 18, zero fill outside
+//                         the image = the conv padding) + one for the residual tile, completion on the stage's mbarrier
+//   warp 1      MMA     : one elected thread, tcgen05.mma.kind::f16 M=128 N=Cout K=16, double-buffered accumulators
+//   warps 2-9   epilogue: tcgen05.ld -> + bias + residual (read from the stage) -> ReLU -> fp16, written in place over the
+//                         residual tile, then ONE tensor-map store per tile (clips partial tiles); overlaps the next tile's MMAs
+// Bound: HBM (one read of the input, one of the residual, one write) / the tensor core's shared-memory operand fetch
+// (128 rows x 32 bytes per MMA).
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -27,19 +32,18 @@ namespace c3 {
 constexpr int TW = 8, TH = 16;              // output tile: 8 wide x 16 tall
 constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
 constexpr int HPIX = HALO_W * HALO_H;       // 180 halo pixels
-constexpr int N_LOAD_WARPS = 3;              // warps 0-2 loaders, warp 3 MMA issuer, warps 4-7 epilogue
-constexpr int N_LOAD = N_LOAD_WARPS * 32;
-constexpr int MMA_WARP = N_LOAD_WARPS;
-constexpr int N_THREADS = 8 * 32;
-constexpr int MAX_BUF = 4;
+constexpr int CH_STRIDE = 2944;             // bytes between channel chunks of a halo buffer (180 * 16 rounded up to 128)
+constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2, N_EPI_WARPS = 8;
+constexpr int N_EPI = N_EPI_WARPS * 32;
+constexpr int N_THREADS = (EPI_WARP0 + N_EPI_WARPS) * 32;
+constexpr int MAX_BUF = 8;
 
 struct Args {
-  const __half* in;
-  const __half* w;        // [9][k_pad/8][n_pad][8] fp16 (tap = ky*3+kx, 8 input channels per 16-byte chunk)
+  const __half* w;        // packed weights, see pack kernel
   const float* bias;      // [cout] fp32 or NULL
-  const __half* res;      // [n_img,H,W,cout] or NULL
-  __half* out;            // [n_img,H,W,cout]
-  int n_img, H, W, cin, cout, k_pad, n_pad, relu, tiles_x, tiles_y, n_tiles, nbuf;
+  int has_res;
+  int n_img, H, W, cin, cout, kcg, kc, n_mma, n_pad, relu, tiles_x, tiles_y, n_tiles, nbuf;
+  float inv_tiles_x, inv_tiles_per_img;
 };
 
 // K-major, no swizzle: core matrix = 8 rows x 16 bytes, rows 16 bytes apart; `sbo` between 8-row groups, `lbo` between the
@@ -60,43 +64,112 @@ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n) {
   return d;
 }
 
-__global__ void __launch_bounds__(N_THREADS, 1) conv3x3_f16_kernel(const Args p) {
+// Entry c of the K list: tap = c / kcg, channel chunk = c % kcg; entries past 9 * kcg are the all-zero chunk (index kcg of the
+// halo buffer, never written by the copies).  Byte offset of its first row inside a halo buffer:
+__host__ __device__ __forceinline__ int k_entry_offset(int c, int kcg) {
+  if (c >= 9 * kcg) return kcg * CH_STRIDE;
+  const int tap = c / kcg, kc = c - tap * kcg;
+  return kc * CH_STRIDE + ((tap / 3) * HALO_W + (tap % 3)) * 16;
+}
+// MMA j multiplies K-list entries 2j and 2j+1; the one at the lower shared-memory offset is the first 8 of its 16 K values.
+__host__ __device__ __forceinline__ void mma_entries(int j, int kcg, int& first, int& second) {
+  const int a = 2 * j, b = 2 * j + 1;
+  if (k_entry_offset(a, kcg) <= k_entry_offset(b, kcg)) {
+    first = a;
+    second = b;
+  } else {
+    first = b;
+    second = a;
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 3, %0;" ::"n"(N_EPI) : "memory"); }
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+
+struct TileXY {
+  int img, ty, tx;
+};
+// tile -> (image, tile row, tile column); float quotient + one-step fix-up, exact for tile < 2^22
+__device__ __forceinline__ TileXY tile_coords(int tile, const Args& p) {
+  const int tpi = p.tiles_x * p.tiles_y;
+  int img = (int)((float)tile * p.inv_tiles_per_img);
+  int rem = tile - img * tpi;
+  if (rem < 0) {
+    --img;
+    rem += tpi;
+  } else if (rem >= tpi) {
+    ++img;
+    rem -= tpi;
+  }
+  int ty = (int)((float)rem * p.inv_tiles_x);
+  int tx = rem - ty * p.tiles_x;
+  if (tx < 0) {
+    --ty;
+    tx += p.tiles_x;
+  } else if (tx >= p.tiles_x) {
+    ++ty;
+    tx -= p.tiles_x;
+  }
+  return {img, ty, tx};
+}
+
+__global__ void __launch_bounds__(N_THREADS, 1)
+    conv3x3_f16_kernel(const Args p, const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_res,
+                       const __grid_constant__ CUtensorMap map_out) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int KC = p.k_pad / 8;                             // 16-byte chunks along K (shared memory)
-  const int KCG = p.cin / 8;                              // chunks present in global memory
-  const uint32_t w_bytes = 9u * KC * p.n_pad * 16u;
-  const uint32_t halo_bytes = (uint32_t)KC * HPIX * 16u;
-  uint8_t* w_s = smem;
-  uint8_t* halo_s = w_s + w_bytes;
-  float* bias_s = (float*)(halo_s + p.nbuf * halo_bytes);
-  int2* tab_s = (int2*)(bias_s + p.n_pad);                   // [HPIX * KCG] copy table (tile independent)
-  uint64_t* bars = (uint64_t*)(tab_s + HPIX * KCG);
+  const uint32_t w_bytes = (uint32_t)p.n_mma * 2u * p.n_pad * 16u;
+  const uint32_t halo_bytes = (uint32_t)p.kc * CH_STRIDE;
+  const uint32_t io_bytes = 128u * p.cout * 2u;
+  const uint32_t stage_bytes = halo_bytes + io_bytes;                 // both multiples of 128
+  uint8_t* stage_s = smem;                                             // [nbuf][halo | io tile]
+  uint8_t* w_s = stage_s + (size_t)p.nbuf * stage_bytes;
+  float* bias_s = (float*)(w_s + w_bytes);
+  uint2* tab_s = (uint2*)(bias_s + p.n_pad);                          // per MMA: {A offset in the halo buffer, LBO bytes}
+  uint64_t* bars = (uint64_t*)(tab_s + p.n_mma);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_BUF + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t full_bar0 = smem_u32(bars);                   // halo landed   [nbuf] (32 noinc arrivals)
-  const uint32_t empty_bar0 = smem_u32(bars + MAX_BUF);        // halo consumed [nbuf] (tcgen05.commit)
+  const uint32_t full_bar0 = smem_u32(bars);                   // stage landed  [nbuf] (1 arrival + tx bytes)
+  const uint32_t empty_bar0 = smem_u32(bars + MAX_BUF);        // stage free    [nbuf] (tcgen05.commit + store drained)
   const uint32_t accf_bar0 = smem_u32(bars + 2 * MAX_BUF);     // accumulator full  [2]
   const uint32_t acce_bar0 = smem_u32(bars + 2 * MAX_BUF + 2); // accumulator empty [2]
 
-  // ---- one-time staging: weights (resident), bias, zero K padding of the halo buffers
+  // ---- one-time staging: weights (resident), bias, MMA table, the all-zero K chunk of every halo buffer
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.w);
     uint4* dst = reinterpret_cast<uint4*>(w_s);
     for (uint32_t i = tid; i < w_bytes / 16; i += N_THREADS) dst[i] = __ldg(src + i);
     for (int c = tid; c < p.n_pad; c += N_THREADS) bias_s[c] = (p.bias && c < p.cout) ? __ldg(p.bias + c) : 0.f;
-    // copy i of a tile: 16-byte chunk kc of halo pixel (hy, hx); consecutive i = consecutive chunks of a pixel (coalesced).
-    // .x = element offset from the tile's first halo pixel, .y = hy | hx << 8 | (chunk-major smem slot) << 16
-    for (int i = tid; i < HPIX * KCG; i += N_THREADS) {
-      const int pix = i / KCG, kc = i - pix * KCG;
-      const int hy = pix / HALO_W, hx = pix - hy * HALO_W;
-      tab_s[i] = make_int2((hy * p.W + hx) * p.cin + kc * 8, hy | (hx << 8) | ((kc * HPIX + pix) << 16));
+    for (int j = tid; j < p.n_mma; j += N_THREADS) {
+      int e0, e1;
+      mma_entries(j, p.kcg, e0, e1);
+      const int o0 = k_entry_offset(e0, p.kcg), o1 = k_entry_offset(e1, p.kcg);
+      tab_s[j] = make_uint2((uint32_t)o0, (uint32_t)(o1 - o0));
     }
-    if (KCG < KC) {
-      uint4* h = reinterpret_cast<uint4*>(halo_s);
-      const int per = (KC - KCG) * HPIX;
+    if (p.kcg < p.kc) {
+      const int per = CH_STRIDE / 16;
       for (int i = tid; i < p.nbuf * per; i += N_THREADS)
-        h[(size_t)(i / per) * KC * HPIX + (size_t)KCG * HPIX + (i % per)] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(stage_s + (size_t)(i / per) * stage_bytes + (size_t)p.kcg * CH_STRIDE)[i % per] =
+            make_uint4(0, 0, 0, 0);
     }
   }
   uint32_t tmem_cols = 32;
@@ -104,72 +177,67 @@ __global__ void __launch_bounds__(N_THREADS, 1) conv3x3_f16_kernel(const Args p)
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < MAX_BUF; ++s) {
-        mbar_init(full_bar0 + 8 * s, N_LOAD);
-        mbar_init(empty_bar0 + 8 * s, 1);
+        mbar_init(full_bar0 + 8 * s, 1);
+        mbar_init(empty_bar0 + 8 * s, 2);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(accf_bar0 + 8 * b, 1);
-        mbar_init(acce_bar0 + 8 * b, 128);
+        mbar_init(acce_bar0 + 8 * b, N_EPI);
       }
       fence_mbar_init();
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  } else if (warp == PROD_WARP && lane == 0) {
+    prefetch_map(&map_in);
+    prefetch_map(&map_res);
+    prefetch_map(&map_out);
   }
-  fence_proxy_async_smem();          // the staged weights / zero padding are read by the tensor core (async proxy)
+  fence_proxy_async_smem();          // the staged weights / zero chunk are read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const uint32_t stage0 = smem_u32(stage_s);
 
-  if (warp < N_LOAD_WARPS) {
-    // =========================== halo loaders ===========================
-    int it = 0;
-    const int n_copy = HPIX * KCG;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int b = it % p.nbuf;
-      const uint32_t ph = (uint32_t)(it / p.nbuf) & 1u;
-      mbar_wait(empty_bar0 + 8 * b, ph ^ 1u);
-      const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
-      const int y0 = (rem / p.tiles_x) * TH - 1, x0 = (rem % p.tiles_x) * TW - 1;
-      const uint32_t dst0 = smem_u32(halo_s + (size_t)b * halo_bytes);
-      // first halo pixel of the tile (may lie outside the image: only dereferenced for in-image pixels)
-      const __half* org = p.in + ((size_t)img * p.H * p.W + (long long)y0 * p.W + x0) * p.cin;
-      for (int i = tid; i < n_copy; i += N_LOAD) {
-        const int2 t = tab_s[i];
-        const int gy = y0 + (t.y & 0xff), gx = x0 + ((t.y >> 8) & 0xff);
-        const bool ok = (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
-        cp_async16(dst0 + ((uint32_t)t.y >> 16) * 16u, ok ? org + t.x : p.in, ok ? 16u : 0u);
+  if (warp == PROD_WARP) {
+    // =========================== producer (tensor-map copies) ===========================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)p.kcg * (HPIX * 16u) + (p.has_res ? io_bytes : 0u);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int b = it % p.nbuf;
+        mbar_wait(empty_bar0 + 8 * b, (((uint32_t)(it / p.nbuf)) & 1u) ^ 1u);
+        const TileXY t = tile_coords(tile, p);
+        const uint32_t dst = stage0 + (uint32_t)b * stage_bytes;
+        const uint32_t bar = full_bar0 + 8 * b;
+        mbar_arrive_expect_tx(bar, tx_bytes);
+        for (int kc = 0; kc < p.kcg; ++kc)
+          tma_load_4d(dst + (uint32_t)kc * CH_STRIDE, &map_in, bar, kc * 8, t.tx * TW - 1, t.ty * TH - 1, t.img);
+        if (p.has_res) tma_load_4d(dst + halo_bytes, &map_res, bar, 0, t.tx * TW, t.ty * TH, t.img);
       }
-      cp_async_mbar_arrive_noinc(full_bar0 + 8 * b);
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = make_idesc_f16((uint32_t)p.n_pad);
     const uint32_t tbase = bcast0(tmem_base);
-    const uint32_t w0 = smem_u32(w_s), h0 = smem_u32(halo_s);
-    const int nsl = p.k_pad / 16;
+    const uint32_t w0 = smem_u32(w_s);
+    const uint32_t w_step = 2u * (uint32_t)p.n_pad * 16u;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it % p.nbuf;
       const int ab = it & 1;
       mbar_wait(full_bar0 + 8 * b, (uint32_t)(it / p.nbuf) & 1u);
       mbar_wait(acce_bar0 + 8 * ab, ((uint32_t)(it >> 1) & 1u) ^ 1u);
-      fence_proxy_async_smem();                 // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
       tc_fence_after();
       const uint32_t tacc = tbase + (uint32_t)(ab * p.n_pad);
-      const uint32_t hb = h0 + (uint32_t)b * halo_bytes;
+      const uint32_t hb = stage0 + (uint32_t)b * stage_bytes;
       if (elect_one()) {
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3, dx = tap - dy * 3;
-          for (int j = 0; j < nsl; ++j) {
-            const uint64_t adesc = make_desc_k_nosw(hb + (uint32_t)((2 * j) * HPIX + dy * HALO_W + dx) * 16u, HPIX * 16u,
-                                                    HALO_W * 16u);
-            const uint64_t bdesc = make_desc_k_nosw(w0 + (uint32_t)((tap * KC + 2 * j) * p.n_pad) * 16u,
-                                                    (uint32_t)p.n_pad * 16u, 128u);
-            umma_bf16_ss(tacc, adesc, bdesc, idesc, (tap > 0 || j > 0) ? 1u : 0u);
-          }
+        for (int j = 0; j < p.n_mma; ++j) {
+          const uint2 e = tab_s[j];
+          const uint64_t adesc = make_desc_k_nosw(hb + e.x, e.y, HALO_W * 16u);
+          const uint64_t bdesc = make_desc_k_nosw(w0 + (uint32_t)j * w_step, (uint32_t)p.n_pad * 16u, 128u);
+          umma_bf16_ss(tacc, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
         }
         umma_commit(empty_bar0 + 8 * b);
         umma_commit(accf_bar0 + 8 * ab);
@@ -178,63 +246,136 @@ __global__ void __launch_bounds__(N_THREADS, 1) conv3x3_f16_kernel(const Args p)
     }
   } else {
     // =========================== epilogue ===========================
-    const int q = warp & 3;                       // TMEM lane quarter of this warp
+    const int ew = warp - EPI_WARP0;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id mod 4)
+    const int half = ew >> 2;                     // two warps per quarter split the 16-column groups
     const int m = q * 32 + lane;                  // tile pixel = accumulator row
-    const int py = m >> 3, px = m & 7;
+    const bool leader = (warp == EPI_WARP0 && lane == 0);
+    const int n_groups = p.n_pad >> 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it % p.nbuf;
       const int ab = it & 1;
-      const int img = tile / tiles_per_img, rem = tile % tiles_per_img;
-      const int gy = (rem / p.tiles_x) * TH + py, gx = (rem % p.tiles_x) * TW + px;
-      const bool ok = gy < p.H && gx < p.W;
-      const size_t pix = ((size_t)img * p.H + gy) * p.W + gx;
+      uint8_t* io = stage_s + (size_t)b * stage_bytes + halo_bytes + (size_t)m * p.cout * 2;
+      if (p.has_res) mbar_wait(full_bar0 + 8 * b, (uint32_t)(it / p.nbuf) & 1u);
       mbar_wait(accf_bar0 + 8 * ab, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(ab * p.n_pad) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+      for (int g = half; g < n_groups; g += 2) {
+        const int c0 = g * 16;
         uint32_t raw[16];
         tmem_ld16(trow + c0, raw);
         uint4 rz[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (p.res && ok) {
+        if (p.has_res) {
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8)
-            if (c0 + 8 * g8 < p.cout) rz[g8] = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.cout + c0 + 8 * g8));
+            if (c0 + 8 * g8 < p.cout) rz[g8] = *reinterpret_cast<const uint4*>(io + (c0 + 8 * g8) * 2);
         }
         tmem_ld_wait();
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
           if (c0 + 8 * g8 >= p.cout) continue;
           const __half2* r2 = reinterpret_cast<const __half2*>(&rz[g8]);
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           uint4 o;
           __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int c = c0 + 8 * g8 + 2 * e;
             const float2 rr = __half22float2(r2[e]);
-            float v0 = __uint_as_float(raw[8 * g8 + 2 * e]) + bias_s[c] + rr.x;
-            float v1 = __uint_as_float(raw[8 * g8 + 2 * e + 1]) + bias_s[c + 1] + rr.y;
+            float v0 = __uint_as_float(raw[8 * g8 + 2 * e]) + bb[2 * e] + rr.x;
+            float v1 = __uint_as_float(raw[8 * g8 + 2 * e + 1]) + bb[2 * e + 1] + rr.y;
             if (p.relu) {
               v0 = fmaxf(v0, 0.f);
               v1 = fmaxf(v1, 0.f);
             }
             o2[e] = __floats2half2_rn(v0, v1);
           }
-          if (ok) *reinterpret_cast<uint4*>(p.out + pix * p.cout + c0 + 8 * g8) = o;
+          *reinterpret_cast<uint4*>(io + (c0 + 8 * g8) * 2) = o;
         }
       }
       tc_fence_before();
       mbar_arrive(acce_bar0 + 8 * ab);
+      fence_proxy_async_smem();                   // this thread's output row -> visible to the bulk store (async proxy)
+      bar_sync_epi();
+      if (leader) {
+        const TileXY t = tile_coords(tile, p);
+        tma_store_4d(&map_out, stage0 + (uint32_t)b * stage_bytes + halo_bytes, 0, t.tx * TW, t.ty * TH, t.img);
+        bulk_commit();
+        if (it > 0) {
+          bulk_wait_read<1>();                    // the previous tile's store has drained its stage
+          mbar_arrive(empty_bar0 + 8 * ((it - 1) % p.nbuf));
+        }
+      }
     }
+    if (leader) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-static size_t smem_for(int k_pad, int n_pad, int nbuf) {
-  const size_t KC = k_pad / 8;
-  return 9 * KC * n_pad * 16 + (size_t)nbuf * KC * HPIX * 16 + (size_t)n_pad * 4 + (size_t)HPIX * KC * 8 +
-         (2 * MAX_BUF + 4) * 8 + 16 + 128;
+// BatchNorm-folded fp32 weights [cout_p][cin_p][3][3] -> fp16 [n_mma][2][n_pad][8] in the kernel's K-list order
+__global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int kcg, int n_mma, int n_pad, __half* __restrict__ out) {
+  const int total = n_mma * 2 * n_pad * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7, n = (i >> 3) % n_pad, slot = ((i >> 3) / n_pad) & 1, j = (i >> 3) / n_pad / 2;
+    int e0, e1;
+    mma_entries(j, kcg, e0, e1);
+    const int c = slot ? e1 : e0;
+    float v = 0.f;
+    if (c < 9 * kcg && n < cout) {
+      const int tap = c / kcg, ch = (c - tap * kcg) * 8 + e;
+      if (ch < cin) v = w[((size_t)n * cin + ch) * 9 + tap];
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
+struct Geom {
+  int kcg, kc, n_mma, n_pad;
+};
+static Geom geom(int cin, int cout) {
+  Geom g;
+  g.kcg = cin / 8;
+  g.kc = (g.kcg + 1) / 2 * 2;
+  g.n_mma = (9 * g.kcg + 1) / 2;
+  g.n_pad = (cout + 15) / 16 * 16;
+  return g;
+}
+static size_t smem_for(const Geom& g, int cout, int nbuf) {
+  return (size_t)nbuf * ((size_t)g.kc * CH_STRIDE + 128 * (size_t)cout * 2) + (size_t)g.n_mma * 2 * g.n_pad * 16 +
+         (size_t)g.n_pad * 4 + (size_t)g.n_mma * 8 + (2 * MAX_BUF + 4) * 8 + 16 + 128;
+}
+
+// ---- tensor maps (driver entry point fetched through the runtime: no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// [n_img, H, W, C] fp16 channels-last viewed as the 4-D tensor (C, W, H, n_img) with a (bc, bw, bh, 1) box
+static int make_map(CUtensorMap* m, const void* base, int C, int W, int H, int n_img, int bc, int bw, int bh) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return LS3D_ERR_ARG;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? LS3D_OK : 1000 + (int)r;
 }
 
 }  // namespace c3
@@ -242,8 +383,27 @@ static size_t smem_for(int k_pad, int n_pad, int nbuf) {
 
 extern "C" int ls3d_conv3x3_f16_smem_bytes(int32_t cin, int32_t cout, int64_t* bytes) {
   using namespace ls3d::c3;
-  if (!bytes || cin <= 0 || cout <= 0) return LS3D_ERR_ARG;
-  *bytes = (int64_t)smem_for((cin + 15) / 16 * 16, (cout + 15) / 16 * 16, 2);
+  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7)) return LS3D_ERR_ARG;
+  *bytes = (int64_t)smem_for(geom(cin, cout), cout, 2);
+  return LS3D_OK;
+}
+
+extern "C" int ls3d_conv3x3_f16_packed_bytes(int32_t cin, int32_t cout, int64_t* bytes) {
+  using namespace ls3d::c3;
+  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7)) return LS3D_ERR_ARG;
+  const Geom g = geom(cin, cout);
+  *bytes = (int64_t)g.n_mma * 2 * g.n_pad * 16;
+  return LS3D_OK;
+}
+
+extern "C" int ls3d_conv3x3_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, void* packed, void* stream) {
+  using namespace ls3d::c3;
+  if (!w_oihw || !packed || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7)) return LS3D_ERR_ARG;
+  const Geom g = geom(cin, cout);
+  const int total = g.n_mma * 2 * g.n_pad * 8;
+  pack_kernel<<<ls3d_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, cout, cin, g.kcg, g.n_mma, g.n_pad,
+                                                                        (__half*)packed);
+  LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
 
@@ -253,20 +413,23 @@ extern "C" int ls3d_conv3x3_f16(const void* in, const void* w_packed, const floa
   using namespace ls3d::c3;
   if (n_img <= 0 || H <= 0 || W <= 0) return LS3D_OK;
   if (!in || !w_packed || !out || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7)) return LS3D_ERR_ARG;
+  if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)res) | ((uintptr_t)w_packed)) & 15) return LS3D_ERR_ARG;
+  const Geom g = geom(cin, cout);
   Args a;
-  a.in = (const __half*)in; a.w = (const __half*)w_packed; a.bias = bias; a.res = (const __half*)res; a.out = (__half*)out;
+  a.w = (const __half*)w_packed; a.bias = bias; a.has_res = res != nullptr;
   a.n_img = n_img; a.H = H; a.W = W; a.cin = cin; a.cout = cout; a.relu = relu;
-  a.k_pad = (cin + 15) / 16 * 16;
-  a.n_pad = (cout + 15) / 16 * 16;
+  a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad;
   if (a.n_pad > 256) return LS3D_ERR_ARG;
   a.tiles_x = ls3d_div_up(W, TW);
   a.tiles_y = ls3d_div_up(H, TH);
   const long long nt = (long long)n_img * a.tiles_x * a.tiles_y;
-  if (nt > 0x7fffffffLL) return LS3D_ERR_ARG;
+  if (nt >= (1LL << 22)) return LS3D_ERR_ARG;
   a.n_tiles = (int)nt;
+  a.inv_tiles_x = 1.0f / (float)a.tiles_x;
+  a.inv_tiles_per_img = 1.0f / (float)(a.tiles_x * a.tiles_y);
   a.nbuf = MAX_BUF;
-  while (a.nbuf > 2 && smem_for(a.k_pad, a.n_pad, a.nbuf) > 227 * 1024) --a.nbuf;
-  const size_t smem = smem_for(a.k_pad, a.n_pad, a.nbuf);
+  while (a.nbuf > 2 && smem_for(g, cout, a.nbuf) > 227 * 1024) --a.nbuf;
+  const size_t smem = smem_for(g, cout, a.nbuf);
   if (smem > 227 * 1024) return LS3D_ERR_ARG;           // weights do not fit in shared memory: caller uses the library conv
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -277,8 +440,15 @@ extern "C" int ls3d_conv3x3_f16(const void* in, const void* w_packed, const floa
     cudaError_t e = cudaFuncSetAttribute(conv3x3_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
   }
+  CUtensorMap m_in, m_res, m_out;
+  int rc = make_map(&m_in, in, cin, W, H, n_img, 8, HALO_W, HALO_H);
+  if (rc) return rc;
+  rc = make_map(&m_out, out, cout, W, H, n_img, cout, TW, TH);
+  if (rc) return rc;
+  rc = make_map(&m_res, res ? res : out, cout, W, H, n_img, cout, TW, TH);
+  if (rc) return rc;
   const int grid = a.n_tiles < num_sms ? a.n_tiles : num_sms;
-  conv3x3_f16_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(a);
+  conv3x3_f16_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(a, m_in, m_res, m_out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }

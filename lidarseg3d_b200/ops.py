@@ -242,13 +242,15 @@ def conv3x3_f16_supported(cin, cout):
 
 
 def pack_conv3x3_f16(w_oihw):
-    """[Cout_p, Cin_p, 3, 3] (BatchNorm folded, zero-padded channels) -> [9][k_pad/8][n_pad][8] fp16 for ls3d_conv3x3_f16."""
+    """[Cout_p, Cin_p, 3, 3] (BatchNorm folded, zero-padded channels, both multiples of 8) -> the packed fp16 weight block of
+    ls3d_conv3x3_f16 (packed on the device in the kernel's K order)."""
     cout, cin = w_oihw.shape[:2]
-    k_pad, n_pad = (cin + 15) // 16 * 16, (cout + 15) // 16 * 16
-    w = torch.zeros(n_pad, k_pad, 3, 3, dtype=torch.float32, device=w_oihw.device)
-    w[:cout, :cin] = w_oihw.float()
-    w = w.permute(2, 3, 1, 0).reshape(9, k_pad // 8, 8, n_pad).permute(0, 1, 3, 2)       # [tap][chunk][n][8]
-    return w.contiguous().to(torch.float16)
+    w = w_oihw.detach().float().contiguous()
+    nb = ctypes.c_int64()
+    check(capi.lib().ls3d_conv3x3_f16_packed_bytes(cin, cout, ctypes.byref(nb)), "ls3d_conv3x3_f16_packed_bytes")
+    out = torch.empty(nb.value // 2, dtype=torch.float16, device=w.device)
+    check(capi.lib().ls3d_conv3x3_f16_pack(ptr(w), cin, cout, ptr(out), stream_ptr()), "ls3d_conv3x3_f16_pack")
+    return out
 
 
 def conv3x3_f16(x, w_packed, bias, res=None, relu=True, cout=None):
