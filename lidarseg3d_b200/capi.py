@@ -135,6 +135,18 @@ def kernel_launches():
     return int(sum(KERNELS_PER_CALL.get(k, 0) * v for k, v in COUNTERS.items()))
 
 
+def snapshot():
+    return dict(COUNTERS)
+
+
+def add_replay(before, after):
+    """A CUDA-graph replay re-launches the kernels captured between two snapshots without passing through ctypes again."""
+    for k, v in after.items():
+        d = v - before.get(k, 0)
+        if d > 0:
+            COUNTERS[k] = COUNTERS.get(k, 0) + d
+
+
 def check(status, what):
     if status != 0:
         raise RuntimeError(f"{what} failed with status {status}")

@@ -15,9 +15,10 @@
 // MMAs per tile rather than 9 * 2.  Weights are packed on the device in that order and stay resident in shared memory.
 //   warp 0      producer: one thread; per tile one 4-D tensor-map copy per channel chunk (box 8 ch x 10 x 18, zero fill outside
 //                         the image = the conv padding) + one for the residual tile, completion on the stage's mbarrier
-//   warp 1      MMA     : one elected thread, tcgen05.mma.kind::f16 M=128 N=Cout K=16, double-buffered accumulators
-//   warps 2-9   epilogue: tcgen05.ld -> + bias + residual (read from the stage) -> ReLU -> fp16, written in place over the
-//                         residual tile, then ONE tensor-map store per tile (clips partial tiles); overlaps the next tile's MMAs
+//   warp 1      MMA     : one elected thread, tcgen05.mma.kind::f16 M=128 N=Cout K=16, four accumulators in tensor memory
+//   warps 2-9   epilogue: two teams of 4 warps (even / odd tiles of the CTA): tcgen05.ld -> + bias + residual
+//                         (read from the stage) -> ReLU -> fp16, written in place over the residual tile, then ONE tensor-map
+//                         store per tile (clips partial tiles); overlaps the following tiles' MMAs
 // Bound: HBM (one read of the input, one of the residual, one write) / the tensor core's shared-memory operand fetch
 // (128 rows x 32 bytes per MMA).
 #include <cuda.h>
@@ -33,8 +34,7 @@ constexpr int TW = 8, TH = 16;              // output tile: 8 wide x 16 tall
 constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
 constexpr int HPIX = HALO_W * HALO_H;       // 180 halo pixels
 constexpr int CH_STRIDE = 2944;             // bytes between channel chunks of a halo buffer (180 * 16 rounded up to 128)
-constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2, N_EPI_WARPS = 8;
-constexpr int N_EPI = N_EPI_WARPS * 32;
+constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2, N_EPI_WARPS = 8;   // two epilogue teams of 4 warps alternate tiles
 constexpr int N_THREADS = (EPI_WARP0 + N_EPI_WARPS) * 32;
 constexpr int MAX_BUF = 8;
 
@@ -100,7 +100,7 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 3, %0;" ::"n"(N_EPI) : "memory"); }
+__device__ __forceinline__ void bar_sync_team(int team) { asm volatile("bar.sync %0, 128;" ::"r"(3 + team) : "memory"); }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
@@ -143,15 +143,16 @@ __global__ void __launch_bounds__(N_THREADS, 1)
   uint8_t* stage_s = smem;                                             // [nbuf][halo | io tile]
   uint8_t* w_s = stage_s + (size_t)p.nbuf * stage_bytes;
   float* bias_s = (float*)(w_s + w_bytes);
-  uint2* tab_s = (uint2*)(bias_s + p.n_pad);                          // per MMA: {A offset in the halo buffer, LBO bytes}
+  ulonglong2* tab_s = (ulonglong2*)(bias_s + p.n_pad);               // per MMA: {A descriptor less the stage base, B descriptor}
   uint64_t* bars = (uint64_t*)(tab_s + p.n_mma);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_BUF + 4);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_BUF + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t full_bar0 = smem_u32(bars);                   // stage landed  [nbuf] (1 arrival + tx bytes)
   const uint32_t empty_bar0 = smem_u32(bars + MAX_BUF);        // stage free    [nbuf] (tcgen05.commit + store drained)
-  const uint32_t accf_bar0 = smem_u32(bars + 2 * MAX_BUF);     // accumulator full  [2]
-  const uint32_t acce_bar0 = smem_u32(bars + 2 * MAX_BUF + 2); // accumulator empty [2]
+  const uint32_t accf_bar0 = smem_u32(bars + 2 * MAX_BUF);     // accumulator full  [nacc <= 4]
+  const uint32_t acce_bar0 = smem_u32(bars + 2 * MAX_BUF + 4); // accumulator empty [nacc <= 4]
+  const int nacc = p.n_pad <= 128 ? 4 : 2;                     // accumulators in tensor memory (nacc * n_pad <= 512 columns)
 
   // ---- one-time staging: weights (resident), bias, MMA table, the all-zero K chunk of every halo buffer
   {
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(N_THREADS, 1)
       int e0, e1;
       mma_entries(j, p.kcg, e0, e1);
       const int o0 = k_entry_offset(e0, p.kcg), o1 = k_entry_offset(e1, p.kcg);
-      tab_s[j] = make_uint2((uint32_t)o0, (uint32_t)(o1 - o0));
+      tab_s[j] = make_ulonglong2(make_desc_k_nosw((uint32_t)o0, (uint32_t)(o1 - o0), HALO_W * 16u),
+                                 make_desc_k_nosw(smem_u32(w_s) + (uint32_t)j * 2u * p.n_pad * 16u, (uint32_t)p.n_pad * 16u, 128u));
     }
     if (p.kcg < p.kc) {
       const int per = CH_STRIDE / 16;
@@ -173,16 +175,16 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     }
   }
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * (uint32_t)p.n_pad) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(nacc * p.n_pad)) tmem_cols <<= 1;
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < MAX_BUF; ++s) {
         mbar_init(full_bar0 + 8 * s, 1);
         mbar_init(empty_bar0 + 8 * s, 2);
       }
-      for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < 4; ++b) {
         mbar_init(accf_bar0 + 8 * b, 1);
-        mbar_init(acce_bar0 + 8 * b, N_EPI);
+        mbar_init(acce_bar0 + 8 * b, 128);
       }
       fence_mbar_init();
     }
@@ -204,10 +206,10 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     // =========================== producer (tensor-map copies) ===========================
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)p.kcg * (HPIX * 16u) + (p.has_res ? io_bytes : 0u);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const int b = it % p.nbuf;
-        mbar_wait(empty_bar0 + 8 * b, (((uint32_t)(it / p.nbuf)) & 1u) ^ 1u);
+      int b = 0;
+      uint32_t ph = 1;                                       // parity of the "previous" phase: passes on a fresh barrier
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        mbar_wait(empty_bar0 + 8 * b, ph);
         const TileXY t = tile_coords(tile, p);
         const uint32_t dst = stage0 + (uint32_t)b * stage_bytes;
         const uint32_t bar = full_bar0 + 8 * b;
@@ -215,53 +217,60 @@ __global__ void __launch_bounds__(N_THREADS, 1)
         for (int kc = 0; kc < p.kcg; ++kc)
           tma_load_4d(dst + (uint32_t)kc * CH_STRIDE, &map_in, bar, kc * 8, t.tx * TW - 1, t.ty * TH - 1, t.img);
         if (p.has_res) tma_load_4d(dst + halo_bytes, &map_res, bar, 0, t.tx * TW, t.ty * TH, t.img);
+        if (++b == p.nbuf) {
+          b = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = make_idesc_f16((uint32_t)p.n_pad);
     const uint32_t tbase = bcast0(tmem_base);
-    const uint32_t w0 = smem_u32(w_s);
-    const uint32_t w_step = 2u * (uint32_t)p.n_pad * 16u;
-    int it = 0;
+    int b = 0, it = 0;
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int b = it % p.nbuf;
-      const int ab = it & 1;
-      mbar_wait(full_bar0 + 8 * b, (uint32_t)(it / p.nbuf) & 1u);
-      mbar_wait(acce_bar0 + 8 * ab, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      const int ab = it & (nacc - 1);
+      mbar_wait(full_bar0 + 8 * b, ph);
+      mbar_wait(acce_bar0 + 8 * ab, ((uint32_t)(it / nacc) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t tacc = tbase + (uint32_t)(ab * p.n_pad);
-      const uint32_t hb = stage0 + (uint32_t)b * stage_bytes;
+      const uint64_t hb = (uint64_t)((stage0 + (uint32_t)b * stage_bytes) >> 4);   // start-address field: no carry out of 14 bits
       if (elect_one()) {
+#pragma unroll 2
         for (int j = 0; j < p.n_mma; ++j) {
-          const uint2 e = tab_s[j];
-          const uint64_t adesc = make_desc_k_nosw(hb + e.x, e.y, HALO_W * 16u);
-          const uint64_t bdesc = make_desc_k_nosw(w0 + (uint32_t)j * w_step, (uint32_t)p.n_pad * 16u, 128u);
-          umma_bf16_ss(tacc, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
+          const ulonglong2 e = tab_s[j];
+          umma_bf16_ss(tacc, e.x + hb, e.y, idesc, j > 0 ? 1u : 0u);
         }
         umma_commit(empty_bar0 + 8 * b);
         umma_commit(accf_bar0 + 8 * ab);
       }
       __syncwarp();
+      if (++b == p.nbuf) {
+        b = 0;
+        ph ^= 1u;
+      }
     }
   } else {
     // =========================== epilogue ===========================
     const int ew = warp - EPI_WARP0;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id mod 4)
-    const int half = ew >> 2;                     // two warps per quarter split the 16-column groups
+    const int team = ew >> 2;                     // team 0: even tiles of this CTA (accumulator 0), team 1: odd tiles
     const int m = q * 32 + lane;                  // tile pixel = accumulator row
-    const bool leader = (warp == EPI_WARP0 && lane == 0);
+    const bool leader = ((ew & 3) == 0 && lane == 0);
     const int n_groups = p.n_pad >> 4;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int b = it % p.nbuf;
-      const int ab = it & 1;
+    const bool deep = p.nbuf >= 4;                // a stage may stay occupied until this team's next tile
+    int b = team % p.nbuf, b_prev = 0, it = team;
+    uint32_t ph = (uint32_t)(team / p.nbuf) & 1u;
+    bool first = true;
+    for (int tile = blockIdx.x + team * gridDim.x; tile < p.n_tiles; tile += 2 * gridDim.x, it += 2) {
       uint8_t* io = stage_s + (size_t)b * stage_bytes + halo_bytes + (size_t)m * p.cout * 2;
-      if (p.has_res) mbar_wait(full_bar0 + 8 * b, (uint32_t)(it / p.nbuf) & 1u);
-      mbar_wait(accf_bar0 + 8 * ab, (uint32_t)(it >> 1) & 1u);
-      tc_fence_after();
+      const int ab = it & (nacc - 1);
       const uint32_t trow = tmem_base + (uint32_t)(ab * p.n_pad) + ((uint32_t)(q * 32) << 16);
-      for (int g = half; g < n_groups; g += 2) {
+      if (p.has_res) mbar_wait(full_bar0 + 8 * b, ph);
+      mbar_wait(accf_bar0 + 8 * ab, (uint32_t)(it / nacc) & 1u);
+      tc_fence_after();
+      for (int g = 0; g < n_groups; ++g) {
         const int c0 = g * 16;
         uint32_t raw[16];
         tmem_ld16(trow + c0, raw);
@@ -298,15 +307,27 @@ __global__ void __launch_bounds__(N_THREADS, 1)
       tc_fence_before();
       mbar_arrive(acce_bar0 + 8 * ab);
       fence_proxy_async_smem();                   // this thread's output row -> visible to the bulk store (async proxy)
-      bar_sync_epi();
+      bar_sync_team(team);
       if (leader) {
         const TileXY t = tile_coords(tile, p);
         tma_store_4d(&map_out, stage0 + (uint32_t)b * stage_bytes + halo_bytes, 0, t.tx * TW, t.ty * TH, t.img);
         bulk_commit();
-        if (it > 0) {
-          bulk_wait_read<1>();                    // the previous tile's store has drained its stage
-          mbar_arrive(empty_bar0 + 8 * ((it - 1) % p.nbuf));
+        if (deep) {
+          if (!first) {
+            bulk_wait_read<1>();                  // this team's previous store has drained its stage
+            mbar_arrive(empty_bar0 + 8 * b_prev);
+          }
+        } else {
+          bulk_wait_read<0>();
+          mbar_arrive(empty_bar0 + 8 * b);
         }
+      }
+      first = false;
+      b_prev = b;
+      b += 2;                                     // this team's next tile is two ring slots on
+      while (b >= p.nbuf) {
+        b -= p.nbuf;
+        ph ^= 1u;
       }
     }
     if (leader) bulk_wait_all();
@@ -346,7 +367,7 @@ static Geom geom(int cin, int cout) {
 }
 static size_t smem_for(const Geom& g, int cout, int nbuf) {
   return (size_t)nbuf * ((size_t)g.kc * CH_STRIDE + 128 * (size_t)cout * 2) + (size_t)g.n_mma * 2 * g.n_pad * 16 +
-         (size_t)g.n_pad * 4 + (size_t)g.n_mma * 8 + (2 * MAX_BUF + 4) * 8 + 16 + 128;
+         (size_t)g.n_pad * 4 + (size_t)g.n_mma * 16 + (2 * MAX_BUF + 8) * 8 + 16 + 128;
 }
 
 // ---- tensor maps (driver entry point fetched through the runtime: no link-time libcuda dependency)

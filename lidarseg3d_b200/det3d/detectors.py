@@ -4,6 +4,7 @@ import torch
 from torch import nn
 
 from . import builder
+from .. import capi
 from .registry import DETECTORS
 
 
@@ -102,12 +103,14 @@ class SegMSeg3DNet(_SegBase):
                     self._image_branch(static_in, batch_size)
                 side.synchronize()
                 g = torch.cuda.CUDAGraph()
+                c0 = capi.snapshot()
                 with torch.cuda.graph(g, stream=side):
                     outs = self._image_branch(static_in, batch_size)
-                ent = cache[key] = (g, static_in, outs)
-            g, static_in, outs = ent
+                ent = cache[key] = (g, static_in, outs, (c0, capi.snapshot()))
+            g, static_in, outs, counted = ent
             static_in.copy_(images, non_blocking=True)
             g.replay()
+            capi.add_replay(*counted)                                  # launch accounting: the captured C-ABI kernels ran again
         return outs, side
 
     def forward(self, example, return_loss=True, **kwargs):
@@ -125,15 +128,22 @@ class SegMSeg3DNet(_SegBase):
                 feats, img_logits, cam_emb = self._image_branch(images, batch_size)
             _, c, ho, wo = feats.shape
             data = self._lidar_branch(example)
-            if side is not None:
-                torch.cuda.current_stream().wait_stream(side)
             data["points_cuv"] = example["points_cuv"]
-            data["image_features"] = feats.view(batch_size, num_cams, c, ho, wo) if feats.is_contiguous() else \
-                feats.reshape(batch_size, num_cams, c, ho, wo)
-            data["_ls3d_image_features_nhwc"] = feats.permute(0, 2, 3, 1).contiguous().view(batch_size, num_cams, ho, wo, c)
-            data["image_logits"] = img_logits
-            data["camera_semantic_embeddings"] = cam_emb
             data["metadata"] = example.get("metadata", None)
+
+            def join_images():
+                # Called by the point head right before its first use of the camera outputs: everything it computes from
+                # the LiDAR branch alone (voxel logits, 3-NN devoxelization, GFFM lidar MLP, LiDAR class embeddings) is
+                # enqueued first and overlaps the tail of the camera branch on the side stream.
+                if side is not None:
+                    torch.cuda.current_stream().wait_stream(side)
+                data["image_features"] = feats.view(batch_size, num_cams, c, ho, wo) if feats.is_contiguous() else \
+                    feats.reshape(batch_size, num_cams, c, ho, wo)
+                data["_ls3d_image_features_nhwc"] = feats.permute(0, 2, 3, 1).contiguous().view(batch_size, num_cams, ho, wo, c)
+                data["image_logits"] = img_logits
+                data["camera_semantic_embeddings"] = cam_emb
+
+            data["_ls3d_join_images"] = join_images
             data = self.point_head(batch_dict=data, return_loss=False)
             self.last_batch_dict = data
             return self.point_head.predict(example=example, test_cfg=self.test_cfg)

@@ -295,6 +295,11 @@ class PointSegMSeg3DHead(Prepared):
                                                       batch_dict["_ls3d_pc_range"], B)
         pw, s, b = P["gffm_lidar"]
         fl = gemm.run(f0, pw, scale=s, shift=b, relu=True)
+        lidar_emb = self.lidar_sfam(vf, voxel_logits, voxel_off, B)         # [B, ncls, C]
+        # ---- everything above depends on the LiDAR branch only; the detector defers the camera-branch join to here
+        join = batch_dict.pop("_ls3d_join_images", None)
+        if join is not None:
+            join()
         # image feature maps -> point camera features; invalid rows zeroed by the row mask.  The reference evaluates the
         # pseudo-camera (mimic) MLP on valid points only and pads the others with zeros, so at inference the completed
         # camera feature of an out-of-image point is exactly zero (point_seg_mseg3d_head.py:305-334).
@@ -312,7 +317,6 @@ class PointSegMSeg3DHead(Prepared):
         cam_emb = batch_dict["camera_semantic_embeddings"]
         if cam_emb.dim() == 4:                                              # reference layout [B, C, ncls, 1]
             cam_emb = cam_emb.squeeze(-1).permute(0, 2, 1).contiguous()
-        lidar_emb = self.lidar_sfam(vf, voxel_logits, voxel_off, B)         # [B, ncls, C]
         sf = self.sffm
         nl = len(P["layers"])
         K, V = ops.class_tokens(cam_emb, lidar_emb, P["token_params"], nl, sf.nhead, sf.d_model)

@@ -1,9 +1,10 @@
 #!/bin/bash
 # GPU session: all parity tests (incl. the fp16 camera-branch kernels), then MSeg3D bench lines fp32 vs fp16 camera branch.
 cd "$(dirname "$0")/.."
+python -c "import torch"
 O=gpurun_out; mkdir -p $O
 timeout 700 python -m pytest tests -m gpu -q --timeout 200 > $O/pytest_gpu.log 2>&1; tail -n 25 $O/pytest_gpu.log
-timeout 250 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_mseg3d.log 2>&1
+
 timeout 250 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --image-dtype fp16 > $O/bench_mseg3d_fp16.log 2>&1
 python - <<'PY'
 import json
