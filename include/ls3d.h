@@ -200,6 +200,16 @@ int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* term_h, const
                           int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Camera input preparation: uint8 [n_pixels][3] (HWC images, any batch of them back to back) -> (x / 255 - mean[c]) / std[c]
+ * in IEEE fp32, stored fp32 or fp16 in the same pixel-major order (= channels-last maps).
+ * replaces: image_input_transform (det3d/datasets/pipelines/img_transforms.py:18-29, segpreprocess.py:621-628) + the HWC->CHW
+ *           transpose (segpreprocess.py:637); mean3 / std3 are HOST pointers to 3 floats (cam_attributes[cam]["mean"/"std"]).
+ *   in and out 16-byte aligned.
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_normalize_images_u8(const uint8_t* in, int64_t n_pixels, const float* mean3, const float* std3, void* out,
+                             int32_t out_fp16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Camera stem: fused 3x3 / stride 1 / pad 1 convolution + bias (+ residual) (+ ReLU) on channels-last fp16 maps,
  * tcgen05 tensor cores, fp32 accumulation.
  * replaces: conv3x3 -> BatchNorm (folded) -> [+ identity] -> ReLU of the HRNet BasicBlocks

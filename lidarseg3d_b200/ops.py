@@ -5,6 +5,8 @@ PyTorch is used for device memory and the current CUDA stream only; all arithmet
 """
 import ctypes
 
+import numpy as np
+
 import torch
 
 from . import capi
@@ -204,6 +206,21 @@ def token_attention(q, k, v, frame_off, scale, round_out=False):
     check(capi.lib().ls3d_token_attention(ptr(q), q.stride(0), n, ptr(k), ptr(v), ptr(frame_off), F_, L, H, dh, float(scale),
                                           ptr(out), out.stride(0), int(round_out), stream_ptr()), "ls3d_token_attention")
     return out
+
+
+def normalize_images_u8(images_u8, mean, std, dtype=torch.float32):
+    """uint8 [..., H, W, 3] (HWC images as the loader decodes them) -> (x / 255 - mean) / std as [..., 3, H, W] ``dtype`` maps in
+    channels-last memory (the tensor is a permuted view of the pixel-major result, so no transpose is ever materialised).
+    Reference: image_input_transform (det3d/datasets/pipelines/img_transforms.py:18-29)."""
+    assert images_u8.dtype == torch.uint8 and images_u8.shape[-1] == 3 and images_u8.is_contiguous()
+    assert dtype in (torch.float32, torch.float16)
+    out = torch.empty(images_u8.shape, dtype=dtype, device=images_u8.device)
+    m = (ctypes.c_float * 3)(*[float(v) for v in np.asarray(mean, np.float32).reshape(-1)[:3]])
+    sd = (ctypes.c_float * 3)(*[float(v) for v in np.asarray(std, np.float32).reshape(-1)[:3]])
+    check(capi.lib().ls3d_normalize_images_u8(ptr(images_u8), images_u8.numel() // 3, m, sd, ptr(out),
+                                              int(dtype == torch.float16), stream_ptr()), "ls3d_normalize_images_u8")
+    nd = out.dim()
+    return out.permute(*range(nd - 3), nd - 1, nd - 3, nd - 2)
 
 
 def upsample_sum(terms, relu=True):

@@ -112,6 +112,22 @@ def camera_images(spec, seed, hw=None):
     return np.ascontiguousarray(img + rng.normal(0, 0.1, img.shape).astype(np.float32))
 
 
+# configs/semanticnusc/MSeg3D/semnusc_avgvfe_unetscn3d_hrnetw18_lr1en2_e12.py:19-28 (BGR; the Waymo config reuses them)
+IMG_MEAN = [0.40789654, 0.44719302, 0.47026115]
+IMG_STD = [0.28863828, 0.27408164, 0.27809835]
+
+
+def camera_images_u8(spec, seed, hw=None):
+    """[ncam, h, w, 3] uint8 camera images as the loader holds them after cv2.resize (seeded smooth noise around mid-grey);
+    hw defaults to the network input size."""
+    rng = np.random.default_rng(seed + 7919)
+    h, w = hw or spec["net_hw"]
+    low = rng.normal(0, 1, (spec["ncam"], h // 16 + 1, w // 16 + 1, 3)).astype(np.float32)
+    img = np.kron(low, np.ones((1, 16, 16, 1), np.float32))[:, :h, :w]
+    img = 112.0 + 64.0 * img + rng.normal(0, 6.0, img.shape).astype(np.float32)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+
+
 def grid_shape(spec):
     vs = np.asarray(spec["voxel_size"], np.float32)
     rg = np.asarray(spec["pc_range"], np.float32)

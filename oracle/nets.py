@@ -504,3 +504,15 @@ def predict_labels(out_logits, points, batch_size):
     """predict() non-TTA branch (point_seg_mseg3d_head.py:455-477): argmax, split per frame."""
     lab = torch.argmax(out_logits, dim=1)
     return [lab[points[:, 0] == i] for i in range(batch_size)]
+
+
+def image_input_transform(images_u8, mean, std):
+    """det3d/datasets/pipelines/img_transforms.py:18-29 applied per camera (segpreprocess.py:621-628), then the
+    [.., H, W, 3] -> [.., 3, H, W] transpose of segpreprocess.py:637.  numpy fp32, same operation order."""
+    import numpy as np
+    image = np.asarray(images_u8).astype(np.float32)
+    image = image / 255.0
+    image -= np.asarray(mean, np.float32).reshape(1, 1, 3)
+    image /= np.asarray(std, np.float32).reshape(1, 1, 3)
+    nd = image.ndim
+    return np.ascontiguousarray(image.transpose(*range(nd - 3), nd - 1, nd - 3, nd - 2))

@@ -8,7 +8,7 @@ timeout 700 python -m pytest tests -m gpu -q --timeout 200 > $O/pytest_gpu.log 2
 timeout 250 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --image-dtype fp16 > $O/bench_mseg3d_fp16.log 2>&1
 python - <<'PY'
 import json
-for f in ['bench_mseg3d','bench_mseg3d_fp16']:
+for f in ['bench_mseg3d_fp16']:
     try:
         d=json.loads(open(f'gpurun_out/{f}.log').read().strip().splitlines()[-1])
         print(f, 'value',round(d['value'],1),'ms',round(d['ms_per_step'],2),'e2e',round(d['e2e']['value'],1), 'launches', d['gpu_launches'])

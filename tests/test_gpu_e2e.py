@@ -32,7 +32,7 @@ def _build(cfg_name, seed=0):
     return cfg, m
 
 
-def _cpu_example(frames, spec, with_cam=False, img_hw=None):
+def _cpu_example(frames, spec, with_cam=False, img_hw=None, u8=False):
     from lidarseg3d_b200 import synth
     vox = [ov.points_to_voxel(f, spec["voxel_size"], spec["pc_range"], 5, 300000) for f in frames]
     v, c, n, nv, pts = ov.collate_frames([(a, b, cc, f) for (a, b, cc), f in zip(vox, frames)])
@@ -44,7 +44,11 @@ def _cpu_example(frames, spec, with_cam=False, img_hw=None):
         if img_hw:
             s2["net_hw"] = img_hw
         ex["points_cuv"] = torch.from_numpy(np.concatenate([synth.project_points(f[:, :3], s2) for f in frames]))
-        ex["images"] = torch.from_numpy(np.stack([synth.camera_images(s2, b, s2["net_hw"]) for b in range(B)]))
+        if u8:      # raw uint8 images; the oracle normalises them the reference's way (img_transforms.py:18-29) on the CPU
+            ex["images_u8"] = torch.from_numpy(np.stack([synth.camera_images_u8(s2, b, s2["net_hw"]) for b in range(B)]))
+            ex["images"] = torch.from_numpy(on.image_input_transform(ex["images_u8"].numpy(), synth.IMG_MEAN, synth.IMG_STD))
+        else:
+            ex["images"] = torch.from_numpy(np.stack([synth.camera_images(s2, b, s2["net_hw"]) for b in range(B)]))
     return ex
 
 
@@ -79,10 +83,12 @@ def test_sdseg3d_forward_vs_oracle():
     assert float((preds[1]["pred_point_sem_labels"].cpu() == labels[1]).float().mean()) >= 0.999
 
 
-@pytest.mark.parametrize("cfg_name,spec_name,image_dtype", [("mseg3d_nuscenes.py", "NUSC", None),
-                                                            ("mseg3d_waymo.py", "WAYMO", None),
-                                                            ("mseg3d_nuscenes.py", "NUSC", torch.float16)])
-def test_mseg3d_forward_vs_oracle(cfg_name, spec_name, image_dtype):
+@pytest.mark.parametrize("cfg_name,spec_name,image_dtype,u8", [("mseg3d_nuscenes.py", "NUSC", None, False),
+                                                               ("mseg3d_waymo.py", "WAYMO", None, False),
+                                                               ("mseg3d_nuscenes.py", "NUSC", torch.float16, False),
+                                                               ("mseg3d_nuscenes.py", "NUSC", torch.float16, True),
+                                                               ("mseg3d_waymo.py", "WAYMO", None, True)])
+def test_mseg3d_forward_vs_oracle(cfg_name, spec_name, image_dtype, u8):
     """BASELINE.json configs[2] (nuScenes: 17 classes, 6 cameras) and configs[3] (Waymo: 23 classes, 5 cameras, z range
     [-2, 4]) at a reduced scan / image size the CPU oracle finishes in seconds."""
     from lidarseg3d_b200 import pipeline, synth
@@ -91,15 +97,20 @@ def test_mseg3d_forward_vs_oracle(cfg_name, spec_name, image_dtype):
     spec.update(beams=16, azimuths=400)
     hw = (128, 192)
     frames = [synth.lidar_scan(spec, s) for s in (0, 1)]
-    ex_cpu = _cpu_example(frames, spec, with_cam=True, img_hw=hw)
+    ex_cpu = _cpu_example(frames, spec, with_cam=True, img_hw=hw, u8=u8)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     ocfg = dict(voxel_size=spec["voxel_size"], pc_range=spec["pc_range"], hrnet_extra=cfg.model.img_backbone.extra,
                 nhead=4, nlayer=6, num_convs=2)
     ref = on.mseg3d_forward(sd, ex_cpu, ocfg, return_all=True)
     m = m.to(DEV)
     m.image_dtype = image_dtype          # fp16: camera branch on fp16 maps (own tcgen05 3x3 kernel); same logits gate
-    ex = pipeline.build_example(frames, spec["voxel_size"], spec["pc_range"], images=ex_cpu["images"],
-                                points_cuv=ex_cpu["points_cuv"])
+    if u8:      # bench.py's path: uint8 images uploaded and normalised on the device in the camera branch's storage type
+        ex = pipeline.build_example(frames, spec["voxel_size"], spec["pc_range"], images_u8=ex_cpu["images_u8"],
+                                    img_mean=synth.IMG_MEAN, img_std=synth.IMG_STD, image_dtype=image_dtype or torch.float32,
+                                    points_cuv=ex_cpu["points_cuv"])
+    else:
+        ex = pipeline.build_example(frames, spec["voxel_size"], spec["pc_range"], images=ex_cpu["images"],
+                                    points_cuv=ex_cpu["points_cuv"])
     preds = m(ex, return_loss=False)
     bd = m.last_batch_dict
     # stage-by-stage (helps localise a failure), then the north-star gate on the logits

@@ -257,6 +257,25 @@ def test_upsample_sum_vs_torch(C, sizes):
     torch.testing.assert_close(ops.upsample_sum(terms, relu=False), ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 20, 32, 3), (1, 7, 5, 3), (6, 64, 96, 3)])
+def test_normalize_images_u8_bit_exact(shape):
+    """uint8 HWC -> (x / 255 - mean) / std: fp32 output bit-exact vs the numpy restatement of image_input_transform
+    (img_transforms.py:18-29), fp16 output = that result rounded once; both are channels-last views [.., 3, H, W]."""
+    from lidarseg3d_b200 import synth
+    from oracle import nets as on
+    ops, _ = _ops()
+    rng = np.random.default_rng(11)
+    u8 = rng.integers(0, 256, shape, dtype=np.uint8)
+    ref = on.image_input_transform(u8, synth.IMG_MEAN, synth.IMG_STD)
+    out = ops.normalize_images_u8(torch.from_numpy(u8).to(DEV), synth.IMG_MEAN, synth.IMG_STD, torch.float32)
+    assert tuple(out.shape) == ref.shape
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    out16 = ops.normalize_images_u8(torch.from_numpy(u8).to(DEV), synth.IMG_MEAN, synth.IMG_STD, torch.float16)
+    assert torch.equal(out16.cpu(), torch.from_numpy(ref).half())
+    flat = out16.reshape(-1, 3, shape[-3], shape[-2])
+    assert flat.is_contiguous(memory_format=torch.channels_last) or flat.shape[0] == 1
+
+
 @pytest.mark.parametrize("C,sizes", [(24, [(32, 48), (16, 24), (8, 12), (4, 6)]), (48, [(30, 44), (15, 22)])])
 def test_upsample_sum_f16_vs_torch(C, sizes):
     """fp16-storage twin of the fused branch fusion: fp32 arithmetic on fp16 maps, one rounding at the store."""
