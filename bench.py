@@ -167,8 +167,8 @@ def cpu_forward_once(wl, spec, cfg, sd, batch, nframes=1):
 
 def run_cpu(wl, spec, cfg, model, batches, steps, warmup, budget_s):
     """Time the oracle port on all host cores, one frame per step, inside a wall-clock budget."""
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = min(os.cpu_count() or 1, 32)       # more intra-op threads than this slow the small CPU kernels down (measured:
+    torch.set_num_threads(cores)               # 47 s / frame with 128 threads against 11 s with 8)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     if wl["cam"]:                                   # the loader's normalisation (img_transforms.py:18-29) is outside the timed part
         from oracle import nets as on

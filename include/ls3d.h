@@ -156,11 +156,12 @@ int ls3d_three_interpolate(const float* feat, int32_t ld_f, int32_t C, const flo
  * Camera feature sampling.
  * replaces: PointSegMSeg3DHead.get_points_image_feature (F.grid_sample 3-D, bilinear, zeros,
  *           align_corners=True; det3d/models/point_heads/point_seg_mseg3d_head.py:200-236).
- *   feat_nhwc [n_frames, ncam, H, W, C] fp32;  points_cuv [n, 4] = (valid, cam, v, u) in [-1, 1]
+ *   feat_nhwc [n_frames, ncam, H, W, C] fp32 (feat_fp16 = 0) or fp16 (feat_fp16 = 1, fp32 arithmetic);
+ *   points_cuv [n, 4] = (valid, cam, v, u) in [-1, 1]; out [n, C] fp32
  * ------------------------------------------------------------------------------------------------ */
-int ls3d_sample_image_features(const float* feat_nhwc, int32_t n_frames, int32_t ncam, int32_t H, int32_t W, int32_t C,
-                               const float* points_cuv, int32_t n, const int32_t* point_off, float* out, int32_t ld_out,
-                               int32_t round_out, void* stream);
+int ls3d_sample_image_features(const void* feat_nhwc, int32_t feat_fp16, int32_t n_frames, int32_t ncam, int32_t H, int32_t W,
+                               int32_t C, const float* points_cuv, int32_t n, const int32_t* point_off, float* out,
+                               int32_t ld_out, int32_t round_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SF-Phase: point -> class-token cross attention core.
@@ -185,19 +186,21 @@ int ls3d_project_points(const float* points, int32_t ld_p, int32_t xyz_off, int3
                         float* points_cuv, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Camera stem: multi-resolution branch fusion, out = act(sum_k bilinear_resize(term_k)) on channels-last fp32 maps.
+ * Camera stem: multi-resolution branch fusion, out = act(bias + sum_k bilinear_resize(term_k)) on channels-last fp32 maps.
  * replaces: the per-term resize / add / ReLU loops of HRModule.forward (det3d/models/img_backbones/hrnet.py:205-226) and
  *           the resize_concat of the decode head (det3d/models/img_heads/decode_head.py:151-160) once its 1x1 ConvModule
  *           has been applied per branch (fcn_mseg3d_head.py:150-163).
  *   terms    HOST array of n_terms (<= 4) device pointers, term k = [n_img, term_h[k], term_w[k], C] NHWC; a term with
  *            term_h == H and term_w == W is added as is, a coarser one is resized with align_corners = False
+ *   bias     [C] fp32 on the device or NULL: added once per output element (the summed folded-BatchNorm shifts of the
+ *            bias-free convolutions behind the terms; a per-channel constant commutes with the resize)
  *   out      [n_img, H, W, C]; C a multiple of 4; relu != 0 applies max(., 0) to the sum
  * ------------------------------------------------------------------------------------------------ */
 int ls3d_upsample_sum(const float* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
-                      int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, float* out, void* stream);
+                      int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, float* out, void* stream);
 /* same on fp16 maps (fp32 arithmetic); C a multiple of 8 */
 int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
-                          int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream);
+                          int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera input preparation: uint8 [n_pixels][3] (HWC images, any batch of them back to back) -> (x / 255 - mean[c]) / std[c]
@@ -232,13 +235,14 @@ int ls3d_conv3x3_f16(const void* in, const void* w_packed, const float* bias, co
  *           CameraSemanticFeatureAggregationModule (det3d/models/img_heads/fcn_mseg3d_head.py:24-51),
  *           memory side of SemanticFeatureFusionModule / TransformerDecoderLayer.forward_post
  *           (context_module.py:101-109,211-227,337-339).
+ *   logits [rows][ld_l], feats [rows][ld_f]: both fp32 (in_fp16 = 0) or both fp16 (in_fp16 = 1; fp32 arithmetic)
  *   emb  [n_frames][ncls][C];  K, V [n_layer][n_frames][n_head][2*ncls][d_model/n_head]
  * ------------------------------------------------------------------------------------------------ */
 int ls3d_class_embed_workspace_bytes(int32_t n_frames, int32_t max_rows_per_frame, int32_t ncls, int32_t C,
                                      int64_t* bytes);
-int ls3d_class_embed(const float* logits, int32_t ld_l, int32_t ncls, const float* feats, int32_t ld_f, int32_t C,
-                     const int32_t* seg_off, int32_t n_frames, int32_t max_rows_per_frame, void* workspace, float* emb,
-                     void* stream);
+int ls3d_class_embed(const void* logits, int32_t ld_l, int32_t ncls, const void* feats, int32_t ld_f, int32_t C,
+                     int32_t in_fp16, const int32_t* seg_off, int32_t n_frames, int32_t max_rows_per_frame, void* workspace,
+                     float* emb, void* stream);
 int ls3d_class_tokens(const float* emb1, int32_t C1, const float* emb2, int32_t C2, int32_t ncls, int32_t n_frames,
                       const float* params, int32_t n_layer, int32_t n_head, int32_t d_model, float* K, float* V,
                       float* mem_out, void* stream);

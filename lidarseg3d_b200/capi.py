@@ -86,18 +86,18 @@ _SIGNATURES = {
     "ls3d_rulebook_scatter": ([P, I, I, I, I, P, I, P, P, P, P, P], ctypes.c_int),
     "ls3d_three_nn_grid": ([P, I, I, P, P, I, I, I, I, P, P, P, P, P, P, P, P, P, P], ctypes.c_int),
     "ls3d_three_interpolate": ([P, I, I, P, P, I, P, I, I, P], ctypes.c_int),
-    "ls3d_sample_image_features": ([P, I, I, I, I, I, P, I, P, P, I, I, P], ctypes.c_int),
+    "ls3d_sample_image_features": ([P, I, I, I, I, I, I, P, I, P, P, I, I, P], ctypes.c_int),
     "ls3d_project_points": ([P, I, I, I, P, P, I, I, I, I, I, P, P], ctypes.c_int),
     "ls3d_token_attention": ([P, I, I, P, P, P, I, I, I, I, ctypes.c_float, P, I, I, P], ctypes.c_int),
-    "ls3d_upsample_sum": ([P, P, P, I, I, I, I, I, I, P, P], ctypes.c_int),
+    "ls3d_upsample_sum": ([P, P, P, I, I, I, I, I, I, P, P, P], ctypes.c_int),
     "ls3d_normalize_images_u8": ([P, L, P, P, P, I, P], ctypes.c_int),
-    "ls3d_upsample_sum_f16": ([P, P, P, I, I, I, I, I, I, P, P], ctypes.c_int),
+    "ls3d_upsample_sum_f16": ([P, P, P, I, I, I, I, I, I, P, P, P], ctypes.c_int),
     "ls3d_conv3x3_f16_smem_bytes": ([I, I, PL], ctypes.c_int),
     "ls3d_conv3x3_f16_packed_bytes": ([I, I, PL], ctypes.c_int),
     "ls3d_conv3x3_f16_pack": ([P, I, I, P, P], ctypes.c_int),
     "ls3d_conv3x3_f16": ([P, P, P, P, P, I, I, I, I, I, I, P], ctypes.c_int),
     "ls3d_class_embed_workspace_bytes": ([I, I, I, I, PL], ctypes.c_int),
-    "ls3d_class_embed": ([P, I, I, P, I, I, P, I, I, P, P, P], ctypes.c_int),
+    "ls3d_class_embed": ([P, I, I, P, I, I, I, P, I, I, P, P, P], ctypes.c_int),
     "ls3d_class_tokens": ([P, I, P, I, I, I, P, I, I, I, P, P, P, P], ctypes.c_int),
 }
 EXPORTS = ["ls3d_gather_gemm"] + list(_SIGNATURES)

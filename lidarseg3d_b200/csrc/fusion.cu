@@ -11,6 +11,8 @@
 //                       embedding sets, then per layer self-attention over the 2*ncls tokens + LayerNorm,
 //                       and the k/v projections consumed by the point cross-attention.  The memory never
 //                       depends on the points, so all layers run in one launch (one CTA per frame).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "../../include/ls3d.h"
 
@@ -36,33 +38,49 @@ static __global__ void fill_f32_kernel(float* p, int n, float v) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = v;
 }
 
+__device__ __forceinline__ float ce_ld(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ce_ld(const __half* p) { return __half2float(__ldg(p)); }
+
 // pass 1: per (frame, class) max over rows.  grid = (chunks, frames)
-__global__ void ce_max_kernel(const float* __restrict__ logits, int ld_l, int ncls, const int* __restrict__ seg_off,
+template <typename T>
+__global__ void ce_max_kernel(const T* __restrict__ logits, int ld_l, int ncls, const int* __restrict__ seg_off,
                               float* __restrict__ cmax /* [B][ncls] init -inf */) {
   const int b = blockIdx.y;
   const int r0 = seg_off[b], r1 = seg_off[b + 1];
   const int start = r0 + blockIdx.x * CE_ROWS;
   if (start >= r1) return;
   const int end = min(start + CE_ROWS, r1);
-  __shared__ float smax[CE_MAXCLS];
-  if (threadIdx.x < CE_MAXCLS) smax[threadIdx.x] = -INFINITY;
-  __syncthreads();
-  // thread t handles class (t % ncls_pad) of rows strided
-  for (int c = 0; c < ncls; ++c) {
-    float m = -INFINITY;
-    for (int r = start + threadIdx.x; r < end; r += blockDim.x) m = fmaxf(m, __ldg(logits + (size_t)r * ld_l + c));
-#pragma unroll
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomic_max_f(&smax[c], m);
+  // lane = class (ncls <= 32), warp = row group: a warp reads the ncls contiguous logits of one row per step
+  __shared__ float smax8[8][CE_MAXCLS];
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  float m = -INFINITY;
+  if (c < ncls) {
+#pragma unroll 4
+    for (int r = start + rg; r < end; r += 8) m = fmaxf(m, ce_ld(logits + (size_t)r * ld_l + c));
   }
+  smax8[rg][c] = m;
   __syncthreads();
-  if (threadIdx.x < ncls) atomic_max_f(&cmax[b * ncls + threadIdx.x], smax[threadIdx.x]);
+  if (threadIdx.x < ncls) {
+    float v = smax8[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) v = fmaxf(v, smax8[k][threadIdx.x]);
+    atomic_max_f(&cmax[b * ncls + threadIdx.x], v);
+  }
 }
 
-// pass 2: partial sums  part[b][chunk][cls][C+1] = sum_r e * [feat | 1]
-__global__ void ce_partial_kernel(const float* __restrict__ logits, int ld_l, int ncls, const float* __restrict__ feats,
-                                  int ld_f, int C, const int* __restrict__ seg_off, const float* __restrict__ cmax,
-                                  float* __restrict__ part, int nchunk) {
+// pass 2: partial sums  part[b][chunk][cls][C+1] = sum_r e * [feat | 1]   (probs^T @ [feats | 1] before normalisation)
+// Register-tiled outer product: a thread owns a 6-class x 4-channel block of the [ncls, C+1] result for one slice of the
+// rows, so each staged row costs it 6 scalar + 1 float4 shared-memory reads for 24 FMAs; slices are summed at the end.
+constexpr int CE_TR = 32;                       // rows staged per step
+constexpr int CE_CG = 6, CE_HG = 4;             // classes / channels per thread
+constexpr int CE_SE_LD = (CE_MAXCLS + CE_CG - 1) / CE_CG * CE_CG;          // 36
+constexpr int CE_SF_LD = (CE_MAXC + 1 + CE_HG - 1) / CE_HG * CE_HG;        // 68
+constexpr int CE_RED = 6144;                    // floats of cross-slice reduction space
+template <typename T>
+__global__ void __launch_bounds__(256) ce_partial_kernel(const T* __restrict__ logits, int ld_l, int ncls,
+                                                         const T* __restrict__ feats, int ld_f, int C,
+                                                         const int* __restrict__ seg_off, const float* __restrict__ cmax,
+                                                         float* __restrict__ part, int nchunk) {
   const int b = blockIdx.y;
   const int r0 = seg_off[b], r1 = seg_off[b + 1];
   const int start = r0 + blockIdx.x * CE_ROWS;
@@ -73,35 +91,67 @@ __global__ void ce_partial_kernel(const float* __restrict__ logits, int ld_l, in
     return;
   }
   const int end = min(start + CE_ROWS, r1);
-  __shared__ float se[32][CE_MAXCLS];
-  __shared__ float sf[32][CE_MAXC + 1];
-  // each thread owns up to 4 accumulators (cls, ch) with ch in [0, C] (ch == C -> denominator)
-  float acc[8];
-  int acls[8], ach[8];
-  int na = 0;
-  for (int a = threadIdx.x; a < nacc && na < 8; a += blockDim.x) {
-    acls[na] = a / (C + 1); ach[na] = a % (C + 1); acc[na] = 0.f; ++na;
-  }
-  for (int t0 = start; t0 < end; t0 += 32) {
-    const int nr = min(32, end - t0);
-    for (int q = threadIdx.x; q < 32 * ncls; q += blockDim.x) {
+  __shared__ __align__(16) float se[CE_TR][CE_SE_LD];
+  __shared__ __align__(16) float sf[CE_TR][CE_SF_LD];
+  __shared__ float red[CE_RED];
+  __shared__ float smx[CE_MAXCLS];
+  const int n_cg = (ncls + CE_CG - 1) / CE_CG, n_hg = (C + 1 + CE_HG - 1) / CE_HG;
+  const int per_slice = n_cg * n_hg;                       // threads per row slice (<= 6 * 17 = 102)
+  int n_slices = blockDim.x / per_slice;
+  while (n_slices * per_slice * CE_CG * CE_HG > CE_RED) --n_slices;
+  const int slice = threadIdx.x / per_slice, t = threadIdx.x % per_slice;
+  const bool active = slice < n_slices;
+  const int cg = t / n_hg, hg = t % n_hg;
+  float acc[CE_CG][CE_HG];
+#pragma unroll
+  for (int i = 0; i < CE_CG; ++i)
+#pragma unroll
+    for (int j = 0; j < CE_HG; ++j) acc[i][j] = 0.f;
+  // zero the padding once (classes >= ncls, channels > C): they are multiplied but never stored
+  for (int q = threadIdx.x; q < CE_TR * CE_SE_LD; q += blockDim.x) (&se[0][0])[q] = 0.f;
+  for (int q = threadIdx.x; q < CE_TR * CE_SF_LD; q += blockDim.x) (&sf[0][0])[q] = 0.f;
+  if (threadIdx.x < ncls) smx[threadIdx.x] = __ldg(cmax + b * ncls + threadIdx.x);
+  __syncthreads();
+  for (int t0 = start; t0 < end; t0 += CE_TR) {
+    const int nr = min(CE_TR, end - t0);
+    for (int q = threadIdx.x; q < CE_TR * ncls; q += blockDim.x) {
       const int r = q / ncls, c = q % ncls;
-      se[r][c] = r < nr ? __expf(__ldg(logits + (size_t)(t0 + r) * ld_l + c) - __ldg(cmax + b * ncls + c)) : 0.f;
+      se[r][c] = r < nr ? __expf(ce_ld(logits + (size_t)(t0 + r) * ld_l + c) - smx[c]) : 0.f;
     }
-    for (int q = threadIdx.x; q < 32 * (C + 1); q += blockDim.x) {
+    for (int q = threadIdx.x; q < CE_TR * (C + 1); q += blockDim.x) {
       const int r = q / (C + 1), c = q % (C + 1);
-      sf[r][c] = r < nr ? (c < C ? __ldg(feats + (size_t)(t0 + r) * ld_f + c) : 1.f) : 0.f;
+      sf[r][c] = r < nr ? (c < C ? ce_ld(feats + (size_t)(t0 + r) * ld_f + c) : 1.f) : 0.f;
     }
     __syncthreads();
-    for (int k = 0; k < na; ++k) {
-      float a = acc[k];
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) a = fmaf(se[r][acls[k]], sf[r][ach[k]], a);
-      acc[k] = a;
+    if (active) {
+      for (int r = slice; r < CE_TR; r += n_slices) {
+        const float4 f = *reinterpret_cast<const float4*>(&sf[r][hg * CE_HG]);
+        const float fv[CE_HG] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int i = 0; i < CE_CG; ++i) {
+          const float e = se[r][cg * CE_CG + i];
+#pragma unroll
+          for (int j = 0; j < CE_HG; ++j) acc[i][j] = fmaf(e, fv[j], acc[i][j]);
+        }
+      }
     }
     __syncthreads();
   }
-  for (int k = 0; k < na; ++k) dst[acls[k] * (C + 1) + ach[k]] = acc[k];
+  // cross-slice sum (fixed order: deterministic)
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < CE_CG; ++i)
+#pragma unroll
+      for (int j = 0; j < CE_HG; ++j) red[(slice * per_slice + t) * (CE_CG * CE_HG) + i * CE_HG + j] = acc[i][j];
+  }
+  __syncthreads();
+  for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
+    const int cls = a / (C + 1), ch = a % (C + 1);
+    const int tt = (cls / CE_CG) * n_hg + ch / CE_HG, k = (cls % CE_CG) * CE_HG + ch % CE_HG;
+    float v = 0.f;
+    for (int sl = 0; sl < n_slices; ++sl) v += red[(sl * per_slice + tt) * (CE_CG * CE_HG) + k];
+    dst[a] = v;
+  }
 }
 
 // pass 3: emb[b][cls][c] = sum_chunks num / sum_chunks den
@@ -174,9 +224,13 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
   const int dh = E / n_head;
   extern __shared__ float ct_smem[];
   float (*mem)[E] = reinterpret_cast<float (*)[E]>(ct_smem);                       // [L][E]
-  float (*qkv)[3 * E] = reinterpret_cast<float (*)[3 * E]>(ct_smem + L * E);       // [L][3E]
-  float (*att)[E] = reinterpret_cast<float (*)[E]>(ct_smem + L * E + L * 3 * E);   // [L][E]
-  float* scb = ct_smem + L * E + L * 3 * E + L * E;                                // [H][L][L+1]
+  // q|k|v rows are 3E + 1 floats apart: the score loop reads k of 32 different tokens in one warp instruction (a 3E stride
+  // would put them all in one bank); att starts on a 16-byte boundary again (it is read as float4)
+  constexpr int QS = 3 * E + 1;
+  const int qkv_floats = (L * QS + 3) & ~3;
+  float (*qkv)[QS] = reinterpret_cast<float (*)[QS]>(ct_smem + L * E);             // [L][3E+1]
+  float (*att)[E] = reinterpret_cast<float (*)[E]>(ct_smem + L * E + qkv_floats);  // [L][E]
+  float* scb = ct_smem + L * E + qkv_floats + L * E;                               // [H][L][L+1]
 #define SC(h, i, j) scb[((h) * L + (i)) * (L + 1) + (j)]
   const float* P1t = params;
   const float* b1 = P1t + C1 * E;
@@ -304,21 +358,27 @@ extern "C" int ls3d_class_embed_workspace_bytes(int32_t n_frames, int32_t max_ro
   return LS3D_OK;
 }
 
-extern "C" int ls3d_class_embed(const float* logits, int32_t ld_l, int32_t ncls, const float* feats, int32_t ld_f, int32_t C,
-                                const int32_t* seg_off, int32_t n_frames, int32_t max_rows_per_frame, void* workspace,
-                                float* emb, void* stream) {
+extern "C" int ls3d_class_embed(const void* logits, int32_t ld_l, int32_t ncls, const void* feats, int32_t ld_f, int32_t C,
+                                int32_t in_fp16, const int32_t* seg_off, int32_t n_frames, int32_t max_rows_per_frame,
+                                void* workspace, float* emb, void* stream) {
   using namespace ls3d;
   if (!logits || !feats || !seg_off || !workspace || !emb || ncls > CE_MAXCLS || C > CE_MAXC || ncls < 1)
     return LS3D_ERR_ARG;
-  if (ncls * (C + 1) > 8 * 256) return LS3D_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int nchunk = ls3d_div_up(max_rows_per_frame > 0 ? max_rows_per_frame : 1, CE_ROWS);
   float* cmax = (float*)workspace;
   float* part = cmax + (size_t)n_frames * ncls;
   fill_f32_kernel<<<1, 256, 0, st>>>(cmax, n_frames * ncls, -INFINITY);
   dim3 grid(nchunk, n_frames);
-  ce_max_kernel<<<grid, 256, 0, st>>>(logits, ld_l, ncls, seg_off, cmax);
-  ce_partial_kernel<<<grid, 256, 0, st>>>(logits, ld_l, ncls, feats, ld_f, C, seg_off, cmax, part, nchunk);
+  if (in_fp16) {
+    ce_max_kernel<__half><<<grid, 256, 0, st>>>((const __half*)logits, ld_l, ncls, seg_off, cmax);
+    ce_partial_kernel<__half><<<grid, 256, 0, st>>>((const __half*)logits, ld_l, ncls, (const __half*)feats, ld_f, C, seg_off,
+                                                   cmax, part, nchunk);
+  } else {
+    ce_max_kernel<float><<<grid, 256, 0, st>>>((const float*)logits, ld_l, ncls, seg_off, cmax);
+    ce_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)logits, ld_l, ncls, (const float*)feats, ld_f, C, seg_off,
+                                                  cmax, part, nchunk);
+  }
   ce_final_kernel<<<n_frames, 256, 0, st>>>(part, nchunk, ncls, C, emb);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
@@ -332,7 +392,7 @@ extern "C" int ls3d_class_tokens(const float* emb1, int32_t C1, const float* emb
       d_model % n_head)
     return LS3D_ERR_ARG;
   const int L = 2 * ncls;
-  const size_t smem = ((size_t)L * CT_E * 5 + (size_t)n_head * L * (L + 1)) * 4;
+  const size_t smem = ((size_t)L * CT_E * 2 + (((size_t)L * (3 * CT_E + 1) + 3) & ~(size_t)3) + (size_t)n_head * L * (L + 1)) * 4;
   cudaError_t e = cudaFuncSetAttribute(class_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   class_tokens_kernel<<<n_frames, 512, smem, (cudaStream_t)stream>>>(emb1, C1, emb2, C2, ncls, params, n_layer, n_head, K,

@@ -8,6 +8,8 @@
 // [B, ncam, H, W, C] so one point's tap is one contiguous 4*C-byte read; half a warp handles a point.
 // Rows of invalid points (points_cuv[:,0] != 1) are written as zeros (the reference scatters the valid
 // rows into a zero tensor, point_seg_mseg3d_head.py:314-320).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "../../include/ls3d.h"
 
@@ -20,7 +22,16 @@ __device__ __forceinline__ int frame_of_row(const int* off, int nf, int i) {
   return f;
 }
 
-__global__ void sample_image_kernel(const float* __restrict__ feat, int ncam, int H, int W, int C,
+__device__ __forceinline__ float4 ld_feat4(const float* p) { return ldg_f4(p); }
+__device__ __forceinline__ float4 ld_feat4(const __half* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename T>
+__global__ void sample_image_kernel(const T* __restrict__ feat, int ncam, int H, int W, int C,
                                     const float* __restrict__ cuv, int n, const int* __restrict__ point_off, int n_frames,
                                     float* __restrict__ out, int ld_out, int rnd) {
   const int lane16 = threadIdx.x & 15;
@@ -58,7 +69,7 @@ __global__ void sample_image_kernel(const float* __restrict__ feat, int ncam, in
           const float wx = dx ? tx : 1.f - tx;
           if ((unsigned)z < (unsigned)ncam && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
             const float wgt = wx * wy * wz;
-            const float4 v = ldg_f4(feat + ((((size_t)f * ncam + z) * H + y) * W + x) * C + c * 4);
+            const float4 v = ld_feat4(feat + ((((size_t)f * ncam + z) * H + y) * W + x) * C + c * 4);
             acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y);
             acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
           }
@@ -72,15 +83,19 @@ __global__ void sample_image_kernel(const float* __restrict__ feat, int ncam, in
 
 }  // namespace ls3d
 
-extern "C" int ls3d_sample_image_features(const float* feat_nhwc, int32_t n_frames, int32_t ncam, int32_t H, int32_t W,
-                                          int32_t C, const float* points_cuv, int32_t n, const int32_t* point_off,
+extern "C" int ls3d_sample_image_features(const void* feat_nhwc, int32_t feat_fp16, int32_t n_frames, int32_t ncam, int32_t H,
+                                          int32_t W, int32_t C, const float* points_cuv, int32_t n, const int32_t* point_off,
                                           float* out, int32_t ld_out, int32_t round_out, void* stream) {
   using namespace ls3d;
   if (n <= 0) return LS3D_OK;
   if (!feat_nhwc || !points_cuv || !point_off || !out || (C & 3) || (ld_out & 3) || ncam < 1) return LS3D_ERR_ARG;
   const long long threads = (long long)n * 16;
-  sample_image_kernel<<<ls3d_div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(feat_nhwc, ncam, H, W, C, points_cuv, n,
-                                                                                   point_off, n_frames, out, ld_out, round_out);
+  if (feat_fp16)
+    sample_image_kernel<__half><<<ls3d_div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)feat_nhwc, ncam, H, W, C, points_cuv, n, point_off, n_frames, out, ld_out, round_out);
+  else
+    sample_image_kernel<float><<<ls3d_div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)feat_nhwc, ncam, H, W, C, points_cuv, n, point_off, n_frames, out, ld_out, round_out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }

@@ -1,4 +1,6 @@
-// Multi-resolution branch fusion of the camera stem: out = act(sum_k resize(term_k)) in ONE pass over channels-last maps.
+// Multi-resolution branch fusion of the camera stem: out = act(bias + sum_k resize(term_k)) in ONE pass over channels-last maps
+// (bias = the summed folded-BatchNorm shifts of the bias-free convolutions that produced the terms: a per-channel constant
+// commutes with the bilinear resize, whose taps sum to one).
 //
 // Replaces the python loops of HRModule.forward (reference det3d/models/img_backbones/hrnet.py:205-226: per output branch,
 // y += x_i | y += resize(conv1x1_bn(x_j)) for coarser j | y += strided convs of finer j, then ReLU) and the
@@ -31,7 +33,7 @@ __device__ __forceinline__ float4 f4_scale(float a, float4 x) { return make_floa
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 __global__ void __launch_bounds__(256) upsample_sum_kernel(UpsTerms T, int n_img, int H, int W, int C4, int relu,
-                                                           float* __restrict__ out) {
+                                                           const float* __restrict__ bias, float* __restrict__ out) {
   const long long total = (long long)n_img * H * W * C4;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(e % C4);
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(256) upsample_sum_kernel(UpsTerms T, int n_img
     pix /= W;
     const int y = (int)(pix % H);
     const int img = (int)(pix / H);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < UPS_MAX_TERMS; ++k) {
       if (k >= T.n) break;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(256) upsample_sum_kernel(UpsTerms T, int n_img
         const float4 bot = f4_fma(lx1, v11, f4_scale(lx0, v10));
         v = f4_fma(ly1, bot, f4_scale(ly0, top));
       }
-      acc = k == 0 ? v : f4_add(acc, v);
+      acc = f4_add(acc, v);
     }
     if (relu) acc = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
     reinterpret_cast<float4*>(out)[e] = acc;
@@ -89,7 +91,7 @@ __device__ __forceinline__ F8 ld_h8(const uint4* p) {
   return r;
 }
 __global__ void __launch_bounds__(256) upsample_sum_f16_kernel(UpsTerms T, int n_img, int H, int W, int C8, int relu,
-                                                               uint4* __restrict__ out) {
+                                                               const float* __restrict__ bias, uint4* __restrict__ out) {
   const long long total = (long long)n_img * H * W * C8;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(e % C8);
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(256) upsample_sum_f16_kernel(UpsTerms T, int n
     const int img = (int)(pix / H);
     F8 acc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+    for (int i = 0; i < 8; ++i) acc.v[i] = bias ? __ldg(bias + c8 * 8 + i) : 0.f;
 #pragma unroll
     for (int k = 0; k < UPS_MAX_TERMS; ++k) {
       if (k >= T.n) break;
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(256) upsample_sum_f16_kernel(UpsTerms T, int n
 }  // namespace ls3d
 
 static int upsample_sum_launch(const void* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
-                               int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream, int vec) {
+                               int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, void* out, void* stream,
+                               int vec) {
   using namespace ls3d;
   if (n_img <= 0 || H <= 0 || W <= 0) return LS3D_OK;
   if (!terms || !term_h || !term_w || !out || n_terms < 1 || n_terms > UPS_MAX_TERMS || C <= 0 || (C % vec)) return LS3D_ERR_ARG;
@@ -164,19 +167,21 @@ static int upsample_sum_launch(const void* const* terms, const int32_t* term_h, 
   const long long blocks = (total + 255) / 256;
   const int grid = (int)(blocks < 148LL * 64 ? blocks : 148LL * 64);     // grid-stride, a multiple of the SM count when large
   if (vec == 4)
-    upsample_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 4, relu, (float*)out);
+    upsample_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 4, relu, bias, (float*)out);
   else
-    upsample_sum_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 8, relu, (uint4*)out);
+    upsample_sum_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 8, relu, bias, (uint4*)out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
 
 extern "C" int ls3d_upsample_sum(const float* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
-                                 int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, float* out, void* stream) {
-  return upsample_sum_launch((const void* const*)terms, term_h, term_w, n_terms, n_img, H, W, C, relu, out, stream, 4);
+                                 int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, float* out,
+                                 void* stream) {
+  return upsample_sum_launch((const void* const*)terms, term_h, term_w, n_terms, n_img, H, W, C, relu, bias, out, stream, 4);
 }
 
 extern "C" int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
-                                     int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, void* out, void* stream) {
-  return upsample_sum_launch(terms, term_h, term_w, n_terms, n_img, H, W, C, relu, out, stream, 8);
+                                     int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, void* out,
+                                     void* stream) {
+  return upsample_sum_launch(terms, term_h, term_w, n_terms, n_img, H, W, C, relu, bias, out, stream, 8);
 }

@@ -97,6 +97,14 @@ def _is_plain3x3(conv):
             and conv.groups == 1)
 
 
+def conv_deferred_bias(conv, bn, x):
+    """conv -> BatchNorm (folded) WITHOUT the shift: returns (conv(x, w_folded), shift fp32 [Cout_p]).  For the linear terms
+    of a branch fusion: the caller sums the shifts of all terms and ls3d_upsample_sum adds them once (a library convolution
+    with a bias and no activation would run a separate elementwise add over every output map)."""
+    w, b = folded(conv, bn, x.shape[1], x.dtype)
+    return F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation, conv.groups), b
+
+
 def cbr(conv, bn, x, relu, z=None):
     """conv -> BatchNorm -> (+z) -> (ReLU).  Training / CPU: plain modules.  Eval on CUDA: BN folded into the conv weights
     (cached, refreshed when a parameter changes); fp16 3x3 stride-1 convs run on the hand-written tensor-core kernel, the rest
@@ -253,23 +261,36 @@ class HRModule(nn.Module):
 
 def _forward_fused(self, x):
     """Eval / CUDA: every output branch = ONE ls3d_upsample_sum launch over its terms in the reference's j order (same-size
-    terms as they are, coarser 1x1-conv outputs resized inside the kernel), ReLU fused."""
+    terms as they are, coarser 1x1-conv outputs resized inside the kernel), the terms' folded-BN shifts summed into one bias
+    vector (cached) that the kernel adds once, ReLU fused."""
     from .. import ops
     outs = []
+    cache = self.__dict__.setdefault("_ls3d_fuse_bias", {})
     for i in range(len(self.fuse_layers)):
-        terms = []
+        terms, shifts = [], []
         for j in range(self.num_branches):
             if i == j:
                 terms.append(x[j])
             elif j > i:
                 fl = self.fuse_layers[i][j]
-                terms.append(cbr(fl[0], fl[1], x[j], False))
+                t, b = conv_deferred_bias(fl[0], fl[1], x[j])
+                terms.append(t)
+                shifts.append(b)
             else:
                 t = x[j]
                 for seq in self.fuse_layers[i][j]:
-                    t = cbr(seq[0], seq[1], t, len(seq) == 3)
+                    if len(seq) == 3:
+                        t = cbr(seq[0], seq[1], t, True)
+                    else:
+                        t, b = conv_deferred_bias(seq[0], seq[1], t)
+                        shifts.append(b)
                 terms.append(t)
-        outs.append(ops.upsample_sum(terms, relu=True))
+        key = tuple((b.data_ptr(), b._version) for b in shifts)
+        ent = cache.get(i)
+        if ent is None or ent[0] != key:
+            with torch.no_grad():
+                ent = cache[i] = (key, torch.stack([b.float() for b in shifts]).sum(0).contiguous() if shifts else None)
+        outs.append(ops.upsample_sum(terms, relu=True, bias=ent[1]))
     return outs
 
 

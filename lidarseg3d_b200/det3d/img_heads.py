@@ -96,14 +96,15 @@ class FCNMSeg3DHead(nn.Module):
             wi = w[:, c0:c0 + c]
             if x.shape[1] != c:                                  # channel-padded backbone output
                 wi = torch.nn.functional.pad(wi, (0, 0, 0, 0, 0, x.shape[1] - c))
-            terms.append(F.conv2d(x, wi.contiguous(memory_format=torch.channels_last), b if i == 0 else None))
+            terms.append((x, wi.contiguous(memory_format=torch.channels_last)))
             c0 += c
         H, W = xs[0].shape[2:]
-        vec = 4 if terms[0].dtype == torch.float32 else 8
-        if (not self.align_corners and len(terms) <= 4 and terms[0].dtype in (torch.float32, torch.float16)
-                and terms[0].shape[1] % vec == 0 and terms[0].is_cuda
-                and all(t.shape[2] <= H and t.shape[3] <= W for t in terms)):
-            return ops.upsample_sum(terms, relu=True)            # resize + sum + ReLU in one pass (csrc/upsample_sum.cu)
+        vec = 4 if xs[0].dtype == torch.float32 else 8
+        if (not self.align_corners and len(terms) <= 4 and xs[0].dtype in (torch.float32, torch.float16)
+                and w.shape[0] % vec == 0 and xs[0].is_cuda and all(t.shape[2] <= H and t.shape[3] <= W for t in xs)):
+            # bias-free per-branch 1x1 convolutions; resize + sum + folded-BN shift + ReLU in one pass (csrc/upsample_sum.cu)
+            return ops.upsample_sum([F.conv2d(x, wi) for x, wi in terms], relu=True, bias=b.float().contiguous())
+        terms = [F.conv2d(x, wi, b if i == 0 else None) for i, (x, wi) in enumerate(terms)]
         y = terms[0]
         for t in terms[1:]:
             y = y + F.interpolate(t, size=(H, W), mode="bilinear", align_corners=self.align_corners)
@@ -129,8 +130,7 @@ class FCNMSeg3DHead(nn.Module):
         cs = self.conv_seg
         logits = F.conv2d(feats if self.dropout is None else self.dropout(feats), cs.weight.to(feats.dtype),
                           cs.bias.to(feats.dtype))
-        if feats.dtype != torch.float32:               # fp16 image branch: hand fp32 maps to the fusion kernels
-            feats, logits = feats.float(), logits.float()
+        # fp16 camera branch: the class-embedding and point-sampling kernels read the fp16 maps directly (fp32 arithmetic)
         emb = self.camera_sfam(feats, logits, batch_dict["batch_size"])
         self.forward_ret_dict["image_logits"] = logits
         batch_dict["image_logits"] = logits

@@ -174,11 +174,13 @@ def three_interpolate(feat, d2, idx, C=None, round_out=False):
 
 # ------------------------------------------------------------------------------------------ sampling / SF-Phase
 def sample_image_features(feat_nhwc, points_cuv, point_off, round_out=False):
-    """feat_nhwc [B, ncam, H, W, C] contiguous fp32; points_cuv [N,4]; returns [N, C] (zeros on invalid rows)."""
+    """feat_nhwc [B, ncam, H, W, C] contiguous fp32 or fp16; points_cuv [N,4]; returns [N, C] fp32 (zeros on invalid rows)."""
     B, ncam, H, W, C = feat_nhwc.shape
     n = points_cuv.shape[0]
+    assert feat_nhwc.dtype in (torch.float32, torch.float16) and feat_nhwc.is_contiguous()
     out = _f32(feat_nhwc.device, n, C)
-    check(capi.lib().ls3d_sample_image_features(ptr(feat_nhwc), B, ncam, H, W, C, ptr(points_cuv.contiguous()), n,
+    check(capi.lib().ls3d_sample_image_features(ptr(feat_nhwc), int(feat_nhwc.dtype == torch.float16), B, ncam, H, W, C,
+                                                ptr(points_cuv.contiguous()), n,
                                                 ptr(point_off), ptr(out), out.stride(0), int(round_out),
                                                 stream_ptr()), "ls3d_sample_image_features")
     return out
@@ -223,7 +225,7 @@ def normalize_images_u8(images_u8, mean, std, dtype=torch.float32):
     return out.permute(*range(nd - 3), nd - 1, nd - 3, nd - 2)
 
 
-def upsample_sum(terms, relu=True):
+def upsample_sum(terms, relu=True, bias=None):
     """terms: list (<= 4) of [N, C, h_k, w_k] fp32 channels-last CUDA tensors, the FIRST at the output resolution or any of
     them; output resolution = the largest term.  Returns act(sum_k resize(term_k)) [N, C, H, W] channels-last."""
     import ctypes
@@ -241,10 +243,13 @@ def upsample_sum(terms, relu=True):
     ptrs = (ctypes.c_void_p * k)(*[ptr(t) for t in ts])
     hs = (ctypes.c_int32 * k)(*[t.shape[2] for t in ts])
     ws = (ctypes.c_int32 * k)(*[t.shape[3] for t in ts])
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == C and bias.is_contiguous() and bias.device == out.device
     if dt == torch.float32:
-        check(capi.lib().ls3d_upsample_sum(ptrs, hs, ws, k, N, H, W, C, int(relu), ptr(out), stream_ptr()), "ls3d_upsample_sum")
+        check(capi.lib().ls3d_upsample_sum(ptrs, hs, ws, k, N, H, W, C, int(relu), ptr(bias), ptr(out), stream_ptr()),
+              "ls3d_upsample_sum")
     else:
-        check(capi.lib().ls3d_upsample_sum_f16(ptrs, hs, ws, k, N, H, W, C, int(relu), ptr(out), stream_ptr()),
+        check(capi.lib().ls3d_upsample_sum_f16(ptrs, hs, ws, k, N, H, W, C, int(relu), ptr(bias), ptr(out), stream_ptr()),
               "ls3d_upsample_sum_f16")
     return out
 
@@ -291,7 +296,9 @@ def class_embed(logits, feats, seg_off, n_frames, max_rows, ncls=None, C=None):
     check(capi.lib().ls3d_class_embed_workspace_bytes(n_frames, max_rows, ncls, C, ctypes.byref(nb)), "class_embed_ws")
     ws = torch.empty(nb.value, dtype=torch.uint8, device=logits.device)
     emb = _f32(logits.device, n_frames, ncls, C)
-    check(capi.lib().ls3d_class_embed(ptr(logits), logits.stride(0), ncls, ptr(feats), feats.stride(0), C, ptr(seg_off),
+    assert logits.dtype == feats.dtype and logits.dtype in (torch.float32, torch.float16)
+    check(capi.lib().ls3d_class_embed(ptr(logits), logits.stride(0), ncls, ptr(feats), feats.stride(0), C,
+                                      int(logits.dtype == torch.float16), ptr(seg_off),
                                       n_frames, max_rows, ptr(ws), ptr(emb), stream_ptr()), "ls3d_class_embed")
     return emb
 

@@ -1,6 +1,7 @@
 #!/bin/bash
 # ncu launch list (gpu__time_duration) of two timed MSeg3D bench steps + per-kernel summary.
 cd "$(dirname "$0")/.."
+python -c "import torch"
 O=gpurun_out; mkdir -p $O
 LS3D_PROFILE_RANGE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 6000 --csv \
     --log-file $O/launches_mseg3d.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --eager-images > $O/ncu_bench.log 2>&1
