@@ -1,8 +1,9 @@
 """HRNet behind the IMG_BACKBONES registry (reference det3d/models/img_backbones/hrnet.py:229-704,
 resnet_mmcv.py:20-313).  Same constructor kwargs and state-dict names (mmseg HRNet naming).
 
-SURVEY.md section 8: the camera stem is "*-adjacent" - it runs on cuDNN through PyTorch (channels-last, BatchNorm folded
-into the convolutions at inference); hand-written stem kernels are a "next" row (8f rank 3).
+Channels-last, BatchNorm folded into the convolutions at inference.  fp16 maps (``image_dtype=torch.float16``): every 3x3
+stride-1 conv+BN(+residual)+ReLU runs on csrc/conv3x3_f16.cu and every branch fusion on csrc/upsample_sum.cu; the stem,
+stride-2, 1x1 and 144-channel convolutions stay on cuDNN (own kernels for those are a next row).
 """
 import warnings
 
