@@ -228,6 +228,14 @@ int ls3d_conv3x3_f16_packed_bytes(int32_t cin, int32_t cout, int64_t* bytes);
 int ls3d_conv3x3_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, void* packed, void* stream);
 int ls3d_conv3x3_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img,
                      int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t relu, void* stream);
+/* the same kernel for ksize = 3 (above) or ksize = 1 (1x1 / stride 1 / pad 0: only the centre of the halo enters the K list;
+ * weights [cout][cin][1][1]) - the 1x1 convolutions of the HRNet fuse layers / Bottlenecks (hrnet.py:156-204,
+ * resnet_mmcv.py:103-225) and of the FCN decode head (fcn_mseg3d_head.py:150-163), cuBLAS/cuDNN in the reference */
+int ls3d_conv_f16_smem_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes);
+int ls3d_conv_f16_packed_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes);
+int ls3d_conv_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream);
+int ls3d_conv_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img, int32_t H,
+                  int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SF-Phase: class embedding aggregation and class-token memory path.

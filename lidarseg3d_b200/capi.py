@@ -92,6 +92,10 @@ _SIGNATURES = {
     "ls3d_upsample_sum": ([P, P, P, I, I, I, I, I, I, P, P, P], ctypes.c_int),
     "ls3d_normalize_images_u8": ([P, L, P, P, P, I, P], ctypes.c_int),
     "ls3d_upsample_sum_f16": ([P, P, P, I, I, I, I, I, I, P, P, P], ctypes.c_int),
+    "ls3d_conv_f16_smem_bytes": ([I, I, I, PL], ctypes.c_int),
+    "ls3d_conv_f16_packed_bytes": ([I, I, I, PL], ctypes.c_int),
+    "ls3d_conv_f16_pack": ([P, I, I, I, P, P], ctypes.c_int),
+    "ls3d_conv_f16": ([P, P, P, P, P, I, I, I, I, I, I, I, P], ctypes.c_int),
     "ls3d_conv3x3_f16_smem_bytes": ([I, I, PL], ctypes.c_int),
     "ls3d_conv3x3_f16_packed_bytes": ([I, I, PL], ctypes.c_int),
     "ls3d_conv3x3_f16_pack": ([P, I, I, P, P], ctypes.c_int),
@@ -128,7 +132,7 @@ KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_voxelize": 8, "ls3d_vfe_descrip
                     "ls3d_vfe_token_max": 1, "ls3d_grid_build": 4, "ls3d_grid_build_strided": 4, "ls3d_grid_enumerate": 1,
                     "ls3d_rulebook_gather": 1, "ls3d_rulebook_scatter": 1, "ls3d_three_nn_grid": 2,
                     "ls3d_three_interpolate": 1, "ls3d_sample_image_features": 1, "ls3d_project_points": 1, "ls3d_upsample_sum": 1, "ls3d_upsample_sum_f16": 1,
-                    "ls3d_conv3x3_f16": 1, "ls3d_conv3x3_f16_pack": 1, "ls3d_normalize_images_u8": 1, "ls3d_token_attention": 1, "ls3d_class_embed": 4,
+                    "ls3d_conv3x3_f16": 1, "ls3d_conv3x3_f16_pack": 1, "ls3d_conv_f16": 1, "ls3d_conv_f16_pack": 1, "ls3d_normalize_images_u8": 1, "ls3d_token_attention": 1, "ls3d_class_embed": 4,
                     "ls3d_class_tokens": 1}
 
 

@@ -70,17 +70,19 @@ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n) {
   return d;
 }
 
-// Entry c of the K list: tap = c / kcg, channel chunk = c % kcg; entries past 9 * kcg are the all-zero chunk (index kcg of the
+// ntap = 9 (3x3) or 1 (1x1: the same kernel reading only the centre of the halo).
+// Entry c of the K list: tap = c / kcg, channel chunk = c % kcg; entries past ntap * kcg are the all-zero chunk (index kcg of the
 // halo buffer, never written by the copies).  Byte offset of its first row inside a halo buffer:
-__host__ __device__ __forceinline__ int k_entry_offset(int c, int kcg) {
-  if (c >= 9 * kcg) return kcg * CH_STRIDE;
-  const int tap = c / kcg, kc = c - tap * kcg;
+__host__ __device__ __forceinline__ int k_entry_offset(int c, int kcg, int ntap) {
+  if (c >= ntap * kcg) return kcg * CH_STRIDE;
+  const int t = c / kcg, kc = c - t * kcg;
+  const int tap = ntap == 1 ? 4 : t;                     // 1x1: the centre tap
   return kc * CH_STRIDE + ((tap / 3) * HALO_W + (tap % 3)) * 16;
 }
 // MMA j multiplies K-list entries 2j and 2j+1; the one at the lower shared-memory offset is the first 8 of its 16 K values.
-__host__ __device__ __forceinline__ void mma_entries(int j, int kcg, int& first, int& second) {
+__host__ __device__ __forceinline__ void mma_entries(int j, int kcg, int ntap, int& first, int& second) {
   const int a = 2 * j, b = 2 * j + 1;
-  if (k_entry_offset(a, kcg) <= k_entry_offset(b, kcg)) {
+  if (k_entry_offset(a, kcg, ntap) <= k_entry_offset(b, kcg, ntap)) {
     first = a;
     second = b;
   } else {
@@ -341,18 +343,19 @@ __global__ void __launch_bounds__(N_THREADS, 1)
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// BatchNorm-folded fp32 weights [cout_p][cin_p][3][3] -> fp16 [n_mma][2][n_pad][8] in the kernel's K-list order
-__global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int kcg, int n_mma, int n_pad, __half* __restrict__ out) {
+// BatchNorm-folded fp32 weights [cout_p][cin_p][k][k] (k*k = ntap) -> fp16 [n_mma][2][n_pad][8] in the kernel's K-list order
+__global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int kcg, int ntap, int n_mma, int n_pad,
+                            __half* __restrict__ out) {
   const int total = n_mma * 2 * n_pad * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 7, n = (i >> 3) % n_pad, slot = ((i >> 3) / n_pad) & 1, j = (i >> 3) / n_pad / 2;
     int e0, e1;
-    mma_entries(j, kcg, e0, e1);
+    mma_entries(j, kcg, ntap, e0, e1);
     const int c = slot ? e1 : e0;
     float v = 0.f;
-    if (c < 9 * kcg && n < cout) {
+    if (c < ntap * kcg && n < cout) {
       const int tap = c / kcg, ch = (c - tap * kcg) * 8 + e;
-      if (ch < cin) v = w[((size_t)n * cin + ch) * 9 + tap];
+      if (ch < cin) v = w[((size_t)n * cin + ch) * ntap + tap];
     }
     out[i] = __float2half_rn(v);
   }
@@ -361,11 +364,11 @@ __global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int 
 struct Geom {
   int kcg, kc, n_mma, n_pad;
 };
-static Geom geom(int cin, int cout) {
+static Geom geom(int cin, int cout, int ntap) {
   Geom g;
   g.kcg = cin / 8;
   g.kc = (g.kcg + 1) / 2 * 2;
-  g.n_mma = (9 * g.kcg + 1) / 2;
+  g.n_mma = (ntap * g.kcg + 1) / 2;
   g.n_pad = (cout + 15) / 16 * 16;
   return g;
 }
@@ -406,40 +409,43 @@ static int make_map(CUtensorMap* m, const void* base, int C, int W, int H, int n
 }  // namespace c3
 }  // namespace ls3d
 
-extern "C" int ls3d_conv3x3_f16_smem_bytes(int32_t cin, int32_t cout, int64_t* bytes) {
+static int ntap_of(int ksize) { return ksize == 3 ? 9 : ksize == 1 ? 1 : 0; }
+
+extern "C" int ls3d_conv_f16_smem_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes) {
   using namespace ls3d::c3;
-  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7)) return LS3D_ERR_ARG;
-  *bytes = (int64_t)smem_for(geom(cin, cout), cout, 2);
+  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  *bytes = (int64_t)smem_for(geom(cin, cout, ntap_of(ksize)), cout, 2);
   return LS3D_OK;
 }
 
-extern "C" int ls3d_conv3x3_f16_packed_bytes(int32_t cin, int32_t cout, int64_t* bytes) {
+extern "C" int ls3d_conv_f16_packed_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes) {
   using namespace ls3d::c3;
-  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7)) return LS3D_ERR_ARG;
-  const Geom g = geom(cin, cout);
+  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  const Geom g = geom(cin, cout, ntap_of(ksize));
   *bytes = (int64_t)g.n_mma * 2 * g.n_pad * 16;
   return LS3D_OK;
 }
 
-extern "C" int ls3d_conv3x3_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, void* packed, void* stream) {
+extern "C" int ls3d_conv_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream) {
   using namespace ls3d::c3;
-  if (!w_oihw || !packed || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7)) return LS3D_ERR_ARG;
-  const Geom g = geom(cin, cout);
+  if (!w_oihw || !packed || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  const Geom g = geom(cin, cout, ntap_of(ksize));
   const int total = g.n_mma * 2 * g.n_pad * 8;
-  pack_kernel<<<ls3d_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, cout, cin, g.kcg, g.n_mma, g.n_pad,
-                                                                        (__half*)packed);
+  pack_kernel<<<ls3d_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, cout, cin, g.kcg, ntap_of(ksize), g.n_mma,
+                                                                        g.n_pad, (__half*)packed);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
 
-extern "C" int ls3d_conv3x3_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out,
-                                int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t relu, void* stream) {
+extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img,
+                             int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream) {
   using namespace ls3d;
   using namespace ls3d::c3;
   if (n_img <= 0 || H <= 0 || W <= 0) return LS3D_OK;
-  if (!in || !w_packed || !out || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7)) return LS3D_ERR_ARG;
+  if (!in || !w_packed || !out || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  const int ntap = ntap_of(ksize);
   if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)res) | ((uintptr_t)w_packed)) & 15) return LS3D_ERR_ARG;
-  const Geom g = geom(cin, cout);
+  const Geom g = geom(cin, cout, ntap);
   Args a;
   a.w = (const __half*)w_packed; a.bias = bias; a.has_res = res != nullptr;
   a.n_img = n_img; a.H = H; a.W = W; a.cin = cin; a.cout = cout; a.relu = relu;
@@ -447,8 +453,8 @@ extern "C" int ls3d_conv3x3_f16(const void* in, const void* w_packed, const floa
   if (a.n_pad > 256 || g.n_mma > MAX_MMA) return LS3D_ERR_ARG;
   for (int j = 0; j < g.n_mma; ++j) {
     int e0, e1;
-    mma_entries(j, g.kcg, e0, e1);
-    const int o0 = k_entry_offset(e0, g.kcg), o1 = k_entry_offset(e1, g.kcg);
+    mma_entries(j, g.kcg, ntap, e0, e1);
+    const int o0 = k_entry_offset(e0, g.kcg, ntap), o1 = k_entry_offset(e1, g.kcg, ntap);
     a.a_lo[j] = ((uint32_t)o0 >> 4) | (((uint32_t)(o1 - o0) >> 4) << 16);
   }
   a.tiles_x = ls3d_div_up(W, TW);
@@ -482,4 +488,19 @@ extern "C" int ls3d_conv3x3_f16(const void* in, const void* w_packed, const floa
   conv3x3_f16_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(a, m_in, m_res, m_out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
+}
+
+// the 3x3 entry points (ksize = 3)
+extern "C" int ls3d_conv3x3_f16_smem_bytes(int32_t cin, int32_t cout, int64_t* bytes) {
+  return ls3d_conv_f16_smem_bytes(cin, cout, 3, bytes);
+}
+extern "C" int ls3d_conv3x3_f16_packed_bytes(int32_t cin, int32_t cout, int64_t* bytes) {
+  return ls3d_conv_f16_packed_bytes(cin, cout, 3, bytes);
+}
+extern "C" int ls3d_conv3x3_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, void* packed, void* stream) {
+  return ls3d_conv_f16_pack(w_oihw, cin, cout, 3, packed, stream);
+}
+extern "C" int ls3d_conv3x3_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out,
+                                int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t relu, void* stream) {
+  return ls3d_conv_f16(in, w_packed, bias, res, out, n_img, H, W, cin, cout, 3, relu, stream);
 }

@@ -68,59 +68,83 @@ def folded(conv, bn, x_channels, dtype):
     return cache[1], cache[2]
 
 
-FUSED_CONV3X3 = True    # eval/CUDA/fp16: 3x3 stride-1 convs on the hand-written tcgen05 kernel (csrc/conv3x3_f16.cu)
+FUSED_CONV3X3 = True    # eval/CUDA/fp16: 3x3 and 1x1 stride-1 convs on the hand-written tcgen05 kernel (csrc/conv3x3_f16.cu)
 
 
-def folded_packed3x3(conv, bn, x_channels):
-    """BN-folded 3x3 weights packed for ls3d_conv3x3_f16 (+ fp32 bias), cached like ``folded``; None when the weights do not
-    fit the kernel's shared memory (the caller then uses cuDNN)."""
+def folded_packed(conv, bn, x_channels):
+    """BN-folded 3x3 / 1x1 weights packed for ls3d_conv_f16 (+ fp32 shift), cached like ``folded``; None when the weights do
+    not fit the kernel's shared memory (the caller then uses cuDNN)."""
     key = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var) + (x_channels, PAD_CHANNELS)
     cache = getattr(conv, "_ls3d_fold3", None)
     if cache is None or cache[0] != key:
         from .. import ops
-        w, b = folded(conv, bn, x_channels, torch.float32)          # [Cout_p(4), Cin, 3, 3] fp32: re-pad Cout for fp16 maps
+        k = conv.kernel_size[0]
         cout_p = _pad_to(conv.out_channels, torch.float16)
-        if not ops.conv3x3_f16_supported(x_channels, cout_p):
+        if not ops.conv_f16_supported(x_channels, cout_p, k):
             cache = (key, None, None, cout_p)
         else:
             with torch.no_grad():
-                wp = w.new_zeros(cout_p, x_channels, 3, 3)
-                wp[:conv.out_channels] = w[:conv.out_channels]
+                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                w = (conv.weight * scale.view(-1, 1, 1, 1)).float()
+                b = (bn.bias - bn.running_mean * scale).float()
+                wp = w.new_zeros(cout_p, x_channels, k, k)
+                wp[:conv.out_channels, :conv.in_channels] = w
                 bp = b.new_zeros(cout_p)
-                bp[:conv.out_channels] = b[:conv.out_channels]
-                cache = (key, ops.pack_conv3x3_f16(wp), bp.float().contiguous(), cout_p)
+                bp[:conv.out_channels] = b
+                cache = (key, ops.pack_conv_f16(wp), bp.contiguous(), cout_p)
         conv._ls3d_fold3 = cache
     return cache[1], cache[2], cache[3]
 
 
-def _is_plain3x3(conv):
-    return (conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
-            and conv.groups == 1)
+def _is_plain(conv):
+    """3x3 / stride 1 / pad 1 or 1x1 / stride 1 / pad 0: the shapes csrc/conv3x3_f16.cu serves."""
+    k = conv.kernel_size
+    return (k in ((3, 3), (1, 1)) and conv.stride == (1, 1) and conv.padding == (k[0] // 2, k[0] // 2)
+            and conv.dilation == (1, 1) and conv.groups == 1)
+
+
+# 1x1 convolutions: the kernel serves them (parity-tested), but inside the MSeg3D step routing them away from the library
+# GEMM was measured slower on every map size (196.3 frames/s with the library against 191-193): each call is one more
+# persistent 148-CTA launch competing with the concurrent LiDAR branch (its sparse-conv launches went from 99 to 128 us), for
+# work the library already runs near its bandwidth bound.  Off by default; LS3D_OWN_1X1_MIN_PIXELS=<n> routes 1x1
+# convolutions on maps of at least n pixels to the own kernel.
+OWN_1X1_MIN_PIXELS = int(__import__("os").environ.get("LS3D_OWN_1X1_MIN_PIXELS", 1 << 62))
+
+
+def _own_conv_ok(conv, x):
+    if not (FUSED_CONV3X3 and x.dtype == torch.float16 and _is_plain(conv) and x.shape[1] % 8 == 0
+            and x.is_contiguous(memory_format=torch.channels_last)):
+        return False
+    return conv.kernel_size == (3, 3) or x.shape[0] * x.shape[2] * x.shape[3] >= OWN_1X1_MIN_PIXELS
 
 
 def conv_deferred_bias(conv, bn, x):
     """conv -> BatchNorm (folded) WITHOUT the shift: returns (conv(x, w_folded), shift fp32 [Cout_p]).  For the linear terms
     of a branch fusion: the caller sums the shifts of all terms and ls3d_upsample_sum adds them once (a library convolution
     with a bias and no activation would run a separate elementwise add over every output map)."""
+    if _own_conv_ok(conv, x):
+        wp, bp, cout_p = folded_packed(conv, bn, x.shape[1])
+        if wp is not None:
+            from .. import ops
+            return ops.conv_f16(x, wp, None, relu=False, cout=cout_p, ksize=conv.kernel_size[0]), bp
     w, b = folded(conv, bn, x.shape[1], x.dtype)
     return F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation, conv.groups), b
 
 
 def cbr(conv, bn, x, relu, z=None):
     """conv -> BatchNorm -> (+z) -> (ReLU).  Training / CPU: plain modules.  Eval on CUDA: BN folded into the conv weights
-    (cached, refreshed when a parameter changes); fp16 3x3 stride-1 convs run on the hand-written tensor-core kernel, the rest
+    (cached, refreshed when a parameter changes); fp16 3x3 / 1x1 stride-1 convs run on the hand-written tensor-core kernel, the rest
     as one cuDNN call."""
     if bn.training or not x.is_cuda:
         y = bn(conv(x))
         if z is not None:
             y = y + z
         return torch.relu(y) if relu else y
-    if (FUSED_CONV3X3 and x.dtype == torch.float16 and _is_plain3x3(conv) and x.shape[1] % 8 == 0
-            and x.is_contiguous(memory_format=torch.channels_last)):
-        wp, bp, cout_p = folded_packed3x3(conv, bn, x.shape[1])
+    if _own_conv_ok(conv, x):
+        wp, bp, cout_p = folded_packed(conv, bn, x.shape[1])
         if wp is not None and (z is None or (z.shape[1] == cout_p and z.is_contiguous(memory_format=torch.channels_last))):
             from .. import ops
-            return ops.conv3x3_f16(x, wp, bp, res=z, relu=relu, cout=cout_p)
+            return ops.conv_f16(x, wp, bp, res=z, relu=relu, cout=cout_p, ksize=conv.kernel_size[0])
     w, b = folded(conv, bn, x.shape[1], x.dtype)
     if FUSED_CUDNN and relu and conv.groups == 1:
         if z is None:

@@ -103,7 +103,20 @@ class FCNMSeg3DHead(nn.Module):
         if (not self.align_corners and len(terms) <= 4 and xs[0].dtype in (torch.float32, torch.float16)
                 and w.shape[0] % vec == 0 and xs[0].is_cuda and all(t.shape[2] <= H and t.shape[3] <= W for t in xs)):
             # bias-free per-branch 1x1 convolutions; resize + sum + folded-BN shift + ReLU in one pass (csrc/upsample_sum.cu)
-            return ops.upsample_sum([F.conv2d(x, wi) for x, wi in terms], relu=True, bias=b.float().contiguous())
+            from .img_backbones import OWN_1X1_MIN_PIXELS
+            if xs[0].dtype == torch.float16 and all(x.shape[1] % 8 == 0 and ops.conv_f16_supported(x.shape[1], w.shape[0], 1)
+                                                     for x in xs):
+                # 1x1 per-branch convolutions on the own tensor-core kernel (packed weights cached per folded tensor)
+                ck = (w.data_ptr(), w._version, tuple(x.shape[1] for x in xs))
+                ent = self.__dict__.get("_ls3d_branch_packed")
+                if ent is None or ent[0] != ck:
+                    ent = self.__dict__["_ls3d_branch_packed"] = (ck, [ops.pack_conv_f16(wi.float()) for _, wi in terms])
+                ys = [ops.conv_f16(x.contiguous(memory_format=torch.channels_last), pk, None, relu=False, cout=w.shape[0], ksize=1)
+                      if x.shape[0] * x.shape[2] * x.shape[3] >= OWN_1X1_MIN_PIXELS else F.conv2d(x, wi)
+                      for (x, wi), pk in zip(terms, ent[1])]
+            else:
+                ys = [F.conv2d(x, wi) for x, wi in terms]
+            return ops.upsample_sum(ys, relu=True, bias=b.float().contiguous())
         terms = [F.conv2d(x, wi, b if i == 0 else None) for i, (x, wi) in enumerate(terms)]
         y = terms[0]
         for t in terms[1:]:

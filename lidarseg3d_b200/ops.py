@@ -254,13 +254,43 @@ def upsample_sum(terms, relu=True, bias=None):
     return out
 
 
-def conv3x3_f16_supported(cin, cout):
-    """The fused fp16 3x3 convolution keeps all 9 taps of the weights in shared memory: true when they fit."""
+def conv_f16_supported(cin, cout, ksize=3):
+    """The fused fp16 convolution keeps all taps of the weights in shared memory: true when they (and two stages) fit."""
     nb = ctypes.c_int64()
-    if cin % 8 or cout % 8:
+    if cin % 8 or cout % 8 or cin > 256 or cout > 256:
         return False
-    check(capi.lib().ls3d_conv3x3_f16_smem_bytes(cin, cout, ctypes.byref(nb)), "ls3d_conv3x3_f16_smem_bytes")
+    check(capi.lib().ls3d_conv_f16_smem_bytes(cin, cout, ksize, ctypes.byref(nb)), "ls3d_conv_f16_smem_bytes")
     return nb.value <= 227 * 1024
+
+
+def conv3x3_f16_supported(cin, cout):
+    return conv_f16_supported(cin, cout, 3)
+
+
+def pack_conv_f16(w_oihw):
+    """[Cout_p, Cin_p, k, k] (k = 1 or 3; BatchNorm folded, zero-padded channels, both multiples of 8) -> the packed fp16
+    weight block of ls3d_conv_f16 (packed on the device in the kernel's K order)."""
+    cout, cin, k = w_oihw.shape[:3]
+    w = w_oihw.detach().float().contiguous()
+    nb = ctypes.c_int64()
+    check(capi.lib().ls3d_conv_f16_packed_bytes(cin, cout, k, ctypes.byref(nb)), "ls3d_conv_f16_packed_bytes")
+    out = torch.empty(nb.value // 2, dtype=torch.float16, device=w.device)
+    check(capi.lib().ls3d_conv_f16_pack(ptr(w), cin, cout, k, ptr(out), stream_ptr()), "ls3d_conv_f16_pack")
+    return out
+
+
+def conv_f16(x, w_packed, bias, res=None, relu=True, cout=None, ksize=3):
+    """x [N, Cin, H, W] fp16 channels-last, res [N, Cout, H, W] fp16 channels-last or None, bias fp32 [Cout] or None
+    -> act(conv_kxk(x) + bias + res), k = ksize (stride 1, same size)."""
+    N, cin, H, W = x.shape
+    assert x.dtype == torch.float16 and x.is_contiguous(memory_format=torch.channels_last)
+    cout = cout if cout is not None else bias.shape[0]
+    if res is not None:
+        assert res.dtype == torch.float16 and res.shape == (N, cout, H, W) and res.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((N, cout, H, W), dtype=torch.float16, device=x.device, memory_format=torch.channels_last)
+    check(capi.lib().ls3d_conv_f16(ptr(x), ptr(w_packed), ptr(bias), ptr(res), ptr(out), N, H, W, cin, cout, ksize, int(relu),
+                                   stream_ptr()), "ls3d_conv_f16")
+    return out
 
 
 def pack_conv3x3_f16(w_oihw):

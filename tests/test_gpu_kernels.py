@@ -320,6 +320,30 @@ def test_conv3x3_f16_vs_fp64(n, h, w, cin, cout, res, relu):
     assert err <= 6e-4, err
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,res,relu", [(2, 20, 30, 24, 48, False, True), (1, 40, 60, 72, 24, False, False),
+                                                     (3, 33, 17, 64, 256, True, True), (1, 160, 240, 48, 48, False, True),
+                                                     (2, 5, 3, 8, 8, False, False)])
+def test_conv1x1_f16_vs_fp64(n, h, w, cin, cout, res, relu):
+    """The same kernel with a one-tap K list (1x1 convolutions of the fuse layers / Bottlenecks / FCN head), bias optional."""
+    import torch.nn.functional as F
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(n * 17 + h)
+    x = torch.randn(n, cin, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV) if relu else None
+    z = torch.randn(n, cout, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last) if res else None
+    if not ops.conv_f16_supported(cin, cout, 1):
+        pytest.skip("weights do not fit shared memory")
+    y = ops.conv_f16(x, ops.pack_conv_f16(wt), b, res=z, relu=relu, cout=cout, ksize=1)
+    ref = F.conv2d(x.double(), wt.half().double(), None if b is None else b.double())
+    if z is not None:
+        ref = ref + z.double()
+    if relu:
+        ref = ref.relu()
+    err = float((y.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 6e-4, err
+
+
 @pytest.mark.parametrize("H,dh,L", [(4, 24, 34), (4, 24, 46), (2, 16, 5), (8, 32, 40)])
 def test_token_attention_vs_fp64(H, dh, L):
     """Class-token cross attention (context_module.py:320-376) vs a float64 softmax(q K^T) V, frames of uneven size with a
