@@ -458,10 +458,13 @@ def main():
         try:
             tc = json.load(open(os.path.join(ROOT, "profiles", "r01_gather_gemm_traffic.json")))["launches"][0]
             traffic = tc["traffic_bytes"]
-            traffic_case = dict(launch=tc["name"], algorithmic_bytes=tc["algorithmic_bytes"], ncu_duration_us=tc["duration_us"])
+            traffic_case = dict(launch=tc["name"], algorithmic_bytes=tc["algorithmic_bytes"], ncu_duration_us=tc["duration_us"],
+                                captured_kernel=tc.get("kernel"),
+                                note="ncu --set full capture of the 3xTF32 engine revision of the gather-GEMM (same gather / "
+                                     "rulebook / output traffic pattern as the bf16x3 engine timed here; not re-captured)")
         except Exception:
             pass
-        roof = dict(bound="hbm", kernel="gather_gemm_kernel (sparse SubM/strided/inverse conv launches)", achieved=tb / tm / 1e6,
+        roof = dict(bound="hbm", kernel="gather_gemm_bf16x3_kernel (sparse SubM/strided/inverse conv launches)", achieved=tb / tm / 1e6,
                     peak=peak, unit="GB/s", frac=tb / tm / 1e6 / peak, traffic=traffic, traffic_case=traffic_case,
                     peak_source="MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
                     launches_per_step=len(sp) // args.steps, avg_launch_us=tm / max(len(sp), 1) * 1e3,

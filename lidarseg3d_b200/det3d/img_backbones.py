@@ -5,6 +5,7 @@ Channels-last, BatchNorm folded into the convolutions at inference.  fp16 maps (
 stride-1 conv+BN(+residual)+ReLU runs on csrc/conv3x3_f16.cu and every branch fusion on csrc/upsample_sum.cu; the stem,
 stride-2, 1x1 and 144-channel convolutions stay on cuDNN (own kernels for those are a next row).
 """
+import os
 import warnings
 
 import torch
@@ -108,7 +109,7 @@ def _is_plain(conv):
 # persistent 148-CTA launch competing with the concurrent LiDAR branch (its sparse-conv launches went from 99 to 128 us), for
 # work the library already runs near its bandwidth bound.  Off by default; LS3D_OWN_1X1_MIN_PIXELS=<n> routes 1x1
 # convolutions on maps of at least n pixels to the own kernel.
-OWN_1X1_MIN_PIXELS = int(__import__("os").environ.get("LS3D_OWN_1X1_MIN_PIXELS", 1 << 62))
+OWN_1X1_MIN_PIXELS = int(os.environ.get("LS3D_OWN_1X1_MIN_PIXELS", 1 << 62))
 
 
 def _own_conv_ok(conv, x):

@@ -1,10 +1,10 @@
 #!/bin/bash
-# ncu launch list (gpu__time_duration) of two timed MSeg3D bench steps + per-kernel summary.
+# ncu launch list (gpu__time_duration) of one timed MSeg3D bench step + per-kernel summary.
 cd "$(dirname "$0")/.."
 python -c "import torch"
 O=gpurun_out; mkdir -p $O
 LS3D_PROFILE_RANGE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 6000 --csv \
-    --log-file $O/launches_mseg3d.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --eager-images > $O/ncu_bench.log 2>&1
+    --log-file $O/launches_mseg3d.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --eager-images > $O/ncu_bench.log 2>&1
 python - <<'PY'
 import csv, collections
 rows = list(csv.reader(l for l in open('gpurun_out/launches_mseg3d.csv') if l.startswith('"')))
@@ -16,7 +16,7 @@ for r in rows[1:]:
     except Exception:
         pass
 tot = sum(v[1] for v in agg.values())
-out = [f'launches {sum(v[0] for v in agg.values())} total {tot/1e3:.1f} us (serialised, cold) -> {tot/2e6:.2f} ms per step']
+out = [f'launches {sum(v[0] for v in agg.values())} total {tot/1e3:.1f} us (serialised, cold) -> {tot/1e6:.2f} ms per step']
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     out.append(f'{v[1]/1e3:10.1f} us {v[1]/tot*100:6.2f}%  n={v[0]:5d}  {k}')
 open('gpurun_out/launches_summary.txt', 'w').write('\n'.join(out) + '\n')
