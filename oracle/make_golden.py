@@ -307,8 +307,65 @@ def gen_modules():
     print("modules:", {k: (tuple(v["out"].shape) if isinstance(v, dict) and "out" in v else "...") for k, v in fx.items()})
 
 
+def gen_losses():
+    """Training losses from the reference's own det3d/core/utils/loss_utils.py + the loss assembly of
+    the reference MSeg3D point head (forward_ret_dict filled by hand) -> tests/golden/ref_losses.pt."""
+    for k in [k for k in sys.modules if k.startswith("det3d")]:
+        del sys.modules[k]
+    install_stubs()
+    _mod("det3d.core.utils.box_utils")
+    lu = load_ref("det3d.core.utils.loss_utils", "det3d/core/utils/loss_utils.py")
+    g = torch.Generator().manual_seed(4321)
+    fx = {"cases": []}
+    for n, c, p_ignore in ((500, 17, 0.2), (64, 5, 0.5), (1000, 23, 0.0), (7, 4, 0.6)):
+        logits = torch.randn(n, c, generator=g) * 2
+        labels = torch.randint(0, c, (n,), generator=g)
+        labels[torch.rand(n, generator=g) < p_ignore] = 0
+        probas = torch.softmax(logits, -1)
+        fx["cases"].append(dict(logits=logits, labels=labels,
+                                lovasz_ignore0=lu.lovasz_softmax(probas, labels, ignore=0),
+                                lovasz_noignore=lu.lovasz_softmax(probas, labels),
+                                ce_ignore0=nn.CrossEntropyLoss(ignore_index=0)(logits, labels)))
+    # dense (image) form [B, C, H, W]
+    logits4 = torch.randn(2, 6, 9, 11, generator=g)
+    labels4 = torch.randint(0, 6, (2, 9, 11), generator=g)
+    fx["dense"] = dict(logits=logits4, labels=labels4, lovasz=lu.lovasz_softmax(torch.softmax(logits4, 1), labels4),
+                       lovasz_per_image=lu.lovasz_softmax(torch.softmax(logits4, 1), labels4, per_image=True))
+    # point-head assembly through the reference head object
+    R = load_reference_modules()
+    sys.modules["det3d.core.utils.loss_utils"].lovasz_softmax = lu.lovasz_softmax
+    R["mhead"].lovasz_softmax = lu.lovasz_softmax
+    head = R["mhead"].PointSegMSeg3DHead(class_agnostic=False, num_class=17, model_cfg=HEAD_CFG)
+    vl, pl = torch.randn(300, 17, generator=g), torch.randn(800, 17, generator=g)
+    vlab, plab = torch.randint(0, 17, (300,), generator=g), torch.randint(0, 17, (800,), generator=g)
+    pc, cam = torch.randn(500, 64, generator=g), torch.randn(500, 64, generator=g)
+    head.forward_ret_dict = dict(voxel_logits=vl, voxel_sem_labels=vlab, out_logits=pl, point_sem_labels=plab,
+                                 point_features_pcamera=pc, point_features_camera=cam)
+    loss, parts = head.get_loss()
+    fx["point_head"] = dict(voxel_logits=vl, voxel_labels=vlab, out_logits=pl, point_labels=plab, pcamera=pc, camera=cam,
+                            loss=loss.detach(), parts={k: v.clone() for k, v in parts.items()})
+    # image-head loss (fcn_mseg3d_head.py:202-244) through the reference head object
+    fcn = R["fcn"].FCNMSeg3DHead(in_channels=[4, 8, 16, 32], in_index=(0, 1, 2, 3), channels=8, num_classes=5,
+                                 input_transform="resize_concat", kernel_size=1, num_convs=2, concat_input=False,
+                                 dropout_ratio=-1, norm_cfg=dict(type="BN", requires_grad=True), align_corners=False,
+                                 ignore_index=0, loss_weight=0.5, lovasz_loss_weight=-1.0)
+    il = torch.randn(4, 5, 16, 24, generator=g)
+    ilab = torch.randint(0, 5, (4, 1, 64, 96), generator=g).float()
+    ilab[torch.rand(ilab.shape, generator=g) < 0.9] = 0         # sparse point-wise supervision
+    fcn.forward_ret_dict = dict(image_logits=il, image_sem_labels=ilab)
+    iloss, iparts = fcn.get_loss()
+    fx["image_head"] = dict(image_logits=il, image_sem_labels=ilab, loss=iloss.detach(),
+                            parts={k: v.clone() for k, v in iparts.items()})
+    torch.save(fx, os.path.join(OUT, "ref_losses.pt"))
+    print("losses:", [float(c["lovasz_ignore0"]) for c in fx["cases"]], float(loss), float(iloss))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--losses-only" in sys.argv:
+        gen_losses()
+        sys.exit(0)
     gen_voxelize()
     gen_modules()
+    gen_losses()
     print(sorted((f, os.path.getsize(os.path.join(OUT, f))) for f in os.listdir(OUT)))
