@@ -288,7 +288,8 @@ def run_sweep(args):
         print(json.dumps(dict(metric="sparse_conv_subm_algorithmic_gbs", unit="GB/s", value=agg, n_gpus=args.gpus, steps=args.steps,
                               warmup=max(args.warmup, 3), ms_per_step=float(np.mean([r["ms"] for r in head])) if head else None,
                               higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic",
-                              dtype="3xTF32 (fp32-equivalent) multiply / fp32 accumulate" if gemm.PRECISE else "tf32",
+                              dtype={2: "fp32 activations, error-compensated bf16x3 tensor-core products (fp32-equivalent), fp32 accumulate",
+                                     1: "3xTF32 (fp32-equivalent) multiply / fp32 accumulate", 0: "tf32"}[int(gemm.PRECISE)],
                               config=dict(workload="spconv_sweep", description=WORKLOADS["spconv_sweep"]["desc"],
                                           l2="inputs larger than L2 (>= 640 MB of features per launch)",
                                           value_is="mean SubM algorithmic GB/s over the sweep, summed over ranks (replicas)"),

@@ -84,7 +84,7 @@ def test_trans_vfe_vs_reference_golden(ref_modules):
     m.load_state_dict(seeded_fill(m.state_dict()))
     m = m.to(DEV).eval()
     out = m(fx["voxels"].to(DEV), fx["num"].to(DEV)).cpu()
-    # error-compensated 3xTF32 tensor-core GEMMs, fp32 accumulate: 1e-4 of the output scale
+    # error-compensated (bf16x3 / 3xTF32) tensor-core GEMMs, fp32 accumulate: 1e-4 of the output scale
     scale = float(fx["out"].abs().max())
     assert float((out - fx["out"]).abs().max()) <= 1e-4 * scale
 
@@ -139,7 +139,8 @@ def test_sparse_conv_vs_oracle_and_dense():
     nbr = ops.rulebook_gather(g, coords, (3, 3, 3), (1, 1, 1), (1, 1, 1))
     out = gemm.run(feats.to(DEV), gemm.PackedWeight(w.reshape(27, C, Co).to(DEV)), nbr=nbr).cpu()
     ref = osp.sparse_conv(feats.double(), w.double(), osp.subm_rulebook(idx, shape, 3))
-    # error-compensated 3xTF32 (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi), fp32 accumulate: 2e-5 of the output scale
+    # error-compensated split products (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi; bf16x3 by default), fp32 accumulate: 2e-5 of the
+    # output scale
     assert float((out.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
     dense = torch.zeros(B, C, *shape, dtype=torch.float64)
     dense[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]] = feats.double()
@@ -422,4 +423,4 @@ def test_mseg3d_head_vs_reference_golden(ref_modules):
     ref = fx["out_logits"]
     rel = float((out - ref).abs().max() / ref.abs().max())
     agree = float((out.argmax(1) == ref.argmax(1)).float().mean())
-    assert rel <= 1e-4 and agree >= 0.999, (rel, agree)          # 3xTF32 GEMM chain vs the reference module's fp32 output
+    assert rel <= 1e-4 and agree >= 0.999, (rel, agree)          # compensated GEMM chain vs the reference module's fp32 output
