@@ -1,5 +1,8 @@
 """Functional CPU restatement (PyTorch fp32) of the reference's SegNet / SegMSeg3DNet forward.
 
+TEST INFRASTRUCTURE ONLY: the checker for tests/, __graft_entry__.smoke() and bench.py's CPU baseline / reference arm;
+nothing under lidarseg3d_b200/ imports it and the product path has no CPU fallback.
+
 Each function takes the flat ``state_dict`` of the reference model (parameter names as in the reference,
 SURVEY.md Appendix C) plus the tensors of the ``example`` dict and returns what the reference module
 returns.  Eval mode only (BatchNorm running statistics, Dropout = identity).

@@ -1,5 +1,8 @@
 """Sparse 3-D convolution oracle: spconv 1.x semantics restated on the CPU (numpy + torch).
 
+TEST INFRASTRUCTURE ONLY: the checker for tests/, __graft_entry__.smoke() and bench.py's CPU baseline / reference arm;
+nothing under lidarseg3d_b200/ imports it and the product path has no CPU fallback.
+
 spconv 1.x @ fad3000249d27ca918f2655ff73c41f39b0f3127 is a third-party dependency of the reference
 (docs/INSTALL.md:88-99) whose source is NOT under /root/reference; its published algorithm
 (rulebook = "indice pairs" per kernel offset, then gather -> mm -> scatter-add per offset) is restated

@@ -1,5 +1,8 @@
 """Hard voxelization oracle (numpy).
 
+TEST INFRASTRUCTURE ONLY: the checker for tests/, __graft_entry__.smoke() and bench.py's CPU baseline / reference arm;
+nothing under lidarseg3d_b200/ imports it and the product path has no CPU fallback.
+
 Restates ``points_to_voxel`` / ``_points_to_voxel_reverse_kernel``
 (reference det3d/ops/point_cloud/point_cloud_ops.py:7-55,112-184) as called by ``VoxelGenerator.generate``
 (det3d/core/input/voxel_generator.py:5-30) from ``SegVoxelization`` (det3d/datasets/pipelines/
