@@ -91,3 +91,33 @@ def test_shipped_configs_build():
         cfg = Config.fromfile(os.path.join(ROOT, "configs", name))
         m = build_detector(cfg.model, train_cfg=None, test_cfg=cfg.test_cfg)
         assert sum(p.numel() for p in m.parameters()) > 1e6
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Every `int ls3d_*(...)` prototype of include/ls3d.h is bound in capi with the same number of arguments (a drifted
+    ctypes signature would otherwise only show up as a crash on the GPU box)."""
+    import re
+    from lidarseg3d_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "ls3d.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\bint\s+(ls3d_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) >= 30
+    for name, args in protos:
+        n = len([a for a in args.split(",") if a.strip() and a.strip() != "void"])
+        if name == "ls3d_gather_gemm":
+            assert n == 2                                   # (const ls3d_gemm_args*, void* stream): bound by hand in capi._declare
+            continue
+        assert name in capi._SIGNATURES, f"{name} is declared in ls3d.h but not bound in capi._SIGNATURES"
+        assert len(capi._SIGNATURES[name][0]) == n, (name, n, len(capi._SIGNATURES[name][0]))
+    assert set(capi._SIGNATURES) <= {p[0] for p in protos}, set(capi._SIGNATURES) - {p[0] for p in protos}
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no module of the package (or bench.py's product arm imports) may reference it."""
+    import re
+    pkg = os.path.join(ROOT, "lidarseg3d_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(d, f)
