@@ -1,55 +1,52 @@
-"""Builders mirroring det3d/models/builder.py:19-63 (a list cfg becomes nn.Sequential)."""
+"""Builder entry points with the names and semantics of det3d/models/builder.py:19-63.
+
+``build`` turns a cfg dict into an object through its registry; a list of cfg dicts becomes an ``nn.Sequential`` of the
+built items (builder.py:19-24).  The public ``build_<kind>(cfg)`` functions are generated from one table so that the mapping
+kind -> registry lives in a single place; ``build_detector`` additionally forwards ``train_cfg`` / ``test_cfg`` as default
+constructor arguments (builder.py:62-63, called from tools/train.py:139 and tools/dist_test.py:128).
+"""
 from torch import nn
 
-from .registry import (BACKBONES, DETECTORS, HEADS, IMG_BACKBONES, IMG_HEADS, LOSSES, NECKS, POINT_HEADS, READERS,
-                       ROI_HEAD, SECOND_STAGE, build_from_cfg)
+from . import registry as _reg
+from .registry import build_from_cfg
 
 
 def build(cfg, registry, default_args=None):
-    if isinstance(cfg, list):
-        return nn.Sequential(*[build_from_cfg(c, registry, default_args) for c in cfg])
-    return build_from_cfg(cfg, registry, default_args)
+    if not isinstance(cfg, list):
+        return build_from_cfg(cfg, registry, default_args)
+    return nn.Sequential(*(build_from_cfg(item, registry, default_args) for item in cfg))
 
 
-def build_second_stage_module(cfg):
-    return build(cfg, SECOND_STAGE)
+_KINDS = {
+    "reader": _reg.READERS,
+    "backbone": _reg.BACKBONES,
+    "img_backbone": _reg.IMG_BACKBONES,
+    "img_head": _reg.IMG_HEADS,
+    "neck": _reg.NECKS,
+    "head": _reg.HEADS,
+    "loss": _reg.LOSSES,
+    "point_head": _reg.POINT_HEADS,
+    "roi_head": _reg.ROI_HEAD,
+    "second_stage_module": _reg.SECOND_STAGE,
+}
 
 
-def build_roi_head(cfg):
-    return build(cfg, ROI_HEAD)
+def _make_builder(kind, registry):
+    def builder(cfg):
+        return build(cfg, registry)
+
+    builder.__name__ = builder.__qualname__ = "build_" + kind
+    builder.__doc__ = "Build a {} from its cfg dict (or a list of them) through the {!r} registry.".format(kind, registry.name)
+    return builder
 
 
-def build_reader(cfg):
-    return build(cfg, READERS)
-
-
-def build_backbone(cfg):
-    return build(cfg, BACKBONES)
-
-
-def build_img_backbone(cfg):
-    return build(cfg, IMG_BACKBONES)
-
-
-def build_img_head(cfg):
-    return build(cfg, IMG_HEADS)
-
-
-def build_neck(cfg):
-    return build(cfg, NECKS)
-
-
-def build_head(cfg):
-    return build(cfg, HEADS)
-
-
-def build_loss(cfg):
-    return build(cfg, LOSSES)
-
-
-def build_point_head(cfg):
-    return build(cfg, POINT_HEADS)
+for _kind, _registry in _KINDS.items():
+    globals()["build_" + _kind] = _make_builder(_kind, _registry)
+del _kind, _registry
 
 
 def build_detector(cfg, train_cfg=None, test_cfg=None):
-    return build(cfg, DETECTORS, dict(train_cfg=train_cfg, test_cfg=test_cfg))
+    return build(cfg, _reg.DETECTORS, {"train_cfg": train_cfg, "test_cfg": test_cfg})
+
+
+__all__ = ["build", "build_detector"] + ["build_" + k for k in _KINDS]

@@ -1,69 +1,66 @@
-"""Plugin registry mirroring the reference's det3d.utils.registry (det3d/utils/registry.py:6-78) and the
-model registries (det3d/models/registry.py:3-16): same names, argument meaning and error behaviour."""
+"""Name -> class plugin registry with the behaviour of the reference's det3d.utils.registry (det3d/utils/registry.py:6-78)
+and the model registries of det3d/models/registry.py:3-16.
+
+Contract kept:
+  * ``@REG.register_module`` on a class stores it under ``cls.__name__`` and returns the class; a non-class raises
+    ``TypeError``; a duplicate name raises ``KeyError("<name> is already registered in <registry>")``.
+  * ``REG.get(name)`` returns the class or ``None``; ``REG.name`` / ``REG.module_dict`` are read-only views.
+  * ``build_from_cfg(cfg, registry, default_args)``: ``cfg["type"]`` is a registered name or a class, the remaining keys are
+    constructor kwargs, ``default_args`` only fill keys that are missing; an unknown name raises
+    ``KeyError("<type> is not in the <registry> registry")``, any other ``type`` value raises ``TypeError``.
+"""
 import inspect
 
 
-class Registry(object):
+class Registry:
     def __init__(self, name):
         self._name = name
-        self._module_dict = dict()
+        self._module_dict = {}
+
+    name = property(lambda self: self._name)
+    module_dict = property(lambda self: self._module_dict)
 
     def __repr__(self):
-        return "{}(name={}, items={})".format(self.__class__.__name__, self._name, list(self._module_dict.keys()))
-
-    @property
-    def name(self):
-        return self._name
-
-    @property
-    def module_dict(self):
-        return self._module_dict
+        return "{}(name={}, items={})".format(type(self).__name__, self._name, list(self._module_dict))
 
     def get(self, key):
-        return self._module_dict.get(key, None)
+        return self._module_dict.get(key)
 
     def _register_module(self, module_class):
         if not inspect.isclass(module_class):
             raise TypeError("module must be a class, but got {}".format(type(module_class)))
-        module_name = module_class.__name__
-        if module_name in self._module_dict:
-            raise KeyError("{} is already registered in {}".format(module_name, self.name))
-        self._module_dict[module_name] = module_class
+        key = module_class.__name__
+        if key in self._module_dict:
+            raise KeyError("{} is already registered in {}".format(key, self._name))
+        self._module_dict[key] = module_class
 
     def register_module(self, cls):
         self._register_module(cls)
         return cls
 
 
-def build_from_cfg(cfg, registry, default_args=None):
-    """cfg: dict with "type" (registered name or class); other keys -> constructor kwargs;
-    default_args only fill missing keys; unknown type -> KeyError (registry.py:49-78)."""
-    assert isinstance(cfg, dict) and "type" in cfg
-    assert isinstance(default_args, dict) or default_args is None
-    args = dict(cfg)
-    obj_type = args.pop("type")
-    if isinstance(obj_type, str):
-        obj_cls = registry.get(obj_type)
-        if obj_cls is None:
-            raise KeyError("{} is not in the {} registry".format(obj_type, registry.name))
-    elif inspect.isclass(obj_type):
-        obj_cls = obj_type
-    else:
+def _resolve(obj_type, registry):
+    if inspect.isclass(obj_type):
+        return obj_type
+    if not isinstance(obj_type, str):
         raise TypeError("type must be a str or valid type, but got {}".format(type(obj_type)))
-    if default_args is not None:
-        for name, value in default_args.items():
-            args.setdefault(name, value)
-    return obj_cls(**args)
+    found = registry.get(obj_type)
+    if found is None:
+        raise KeyError("{} is not in the {} registry".format(obj_type, registry.name))
+    return found
 
 
-READERS = Registry("reader")
-BACKBONES = Registry("backbone")
-IMG_BACKBONES = Registry("img_backbone")
-IMG_HEADS = Registry("img_head")
-NECKS = Registry("neck")
-HEADS = Registry("head")
-LOSSES = Registry("loss")
-DETECTORS = Registry("detector")
-SECOND_STAGE = Registry("second_stage")
-ROI_HEAD = Registry("roi_head")
-POINT_HEADS = Registry("point_head")
+def build_from_cfg(cfg, registry, default_args=None):
+    assert isinstance(cfg, dict) and "type" in cfg
+    assert default_args is None or isinstance(default_args, dict)
+    kwargs = {k: v for k, v in cfg.items() if k != "type"}
+    cls = _resolve(cfg["type"], registry)
+    for k, v in (default_args or {}).items():
+        kwargs.setdefault(k, v)
+    return cls(**kwargs)
+
+
+# det3d/models/registry.py:3-16
+(READERS, BACKBONES, IMG_BACKBONES, IMG_HEADS, NECKS, HEADS, LOSSES, DETECTORS, SECOND_STAGE, ROI_HEAD,
+ POINT_HEADS) = (Registry(n) for n in ("reader", "backbone", "img_backbone", "img_head", "neck", "head", "loss", "detector",
+                                       "second_stage", "roi_head", "point_head"))
