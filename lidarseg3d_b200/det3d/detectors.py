@@ -88,7 +88,7 @@ class SegMSeg3DNet(_SegBase):
         return img_data["image_features"], img_data["image_logits"], img_data.get("camera_semantic_embeddings", None)
 
     def _image_branch_graphed(self, images, batch_size):
-        key = (tuple(images.shape), images.device.index, batch_size)
+        key = (tuple(images.shape), images.dtype, self.image_dtype, images.device.index, batch_size)
         cache = self.__dict__.setdefault("_img_graphs", {})
         ent = cache.get(key)
         side = self.__dict__.setdefault("_img_stream", None)
