@@ -105,12 +105,15 @@ class _Sp:
 
 
 def unet_scn3d(sd, p, voxel_features, voxel_coords, input_shape_xyz, voxel_size, pc_range,
-               with_conv_out=True, last_pad=0, return_levels=False):
+               with_conv_out=True, last_pad=0, return_levels=False, backend=None):
     """UNetSCN3D.forward (det3d/models/backbones/scn_unet.py:189-249) with spconv semantics from oracle.sparse.
-    ``p`` is the key prefix (e.g. 'backbone.').  Returns (conv_point_features [M,C], conv_point_coords [M,4])."""
+    ``p`` is the key prefix (e.g. 'backbone.').  Returns (conv_point_features [M,C], conv_point_coords [M,4]).
+    ``backend``: None = oracle.sparse (numpy rulebooks, the parity ground truth); oracle.torch_backend = the same algorithm in
+    pure torch on the device of the inputs (the spconv-style GPU baseline)."""
     EPS = 1e-3                                                                      # scn_unet.py:86
     shape1 = tuple(int(v) for v in (np.array(input_shape_xyz[::-1]) + [1, 0, 0]))   # scn_unet.py:203
-    idx1 = voxel_coords.numpy().astype(np.int32)
+    osp = backend if backend is not None else globals()["osp"]
+    idx1 = voxel_coords.numpy().astype(np.int32) if backend is None else backend.as_indices(voxel_coords)
     rb = {}                                                                         # indice_key -> table
 
     def subm_key(key, indices, shape):
@@ -170,9 +173,11 @@ def unet_scn3d(sd, p, voxel_features, voxel_coords, input_shape_xyz, voxel_size,
     up1 = ur_block(levels[1], up2, 1, None)
 
     # get_voxel_centers (det3d/core/utils/common_utils.py:74-90)
-    centers = (torch.as_tensor(idx1[:, [3, 2, 1]]).float() + 0.5) * torch.tensor(voxel_size).float() \
-        + torch.tensor(pc_range[0:3]).float()
-    coords = torch.cat([torch.as_tensor(idx1[:, 0:1]).float(), centers], dim=1)
+    dev = voxel_features.device
+    idx1_t = torch.as_tensor(idx1).to(dev)
+    centers = (idx1_t[:, [3, 2, 1]].float() + 0.5) * torch.tensor(voxel_size, device=dev).float() \
+        + torch.tensor(pc_range[0:3], device=dev).float()
+    coords = torch.cat([idx1_t[:, 0:1].float(), centers], dim=1)
     if return_levels:
         return up1, coords, dict(levels=levels, up4=up4, up3=up3, up2=up2, rulebooks=rb, down=down, **extra)
     return up1, coords
@@ -219,7 +224,7 @@ def three_nn(unknown, known):
     return torch.from_numpy(d2o), torch.from_numpy(ido)
 
 
-def three_interpolate_wrap(new_coords, coords, features, batch_size):
+def three_interpolate_wrap(new_coords, coords, features, batch_size, three_nn_fn=None):
     """three_interpolate_wrap (det3d/models/point_heads/point_utils.py:8-52): per frame 3-NN between raw points
     and voxel centres, weights 1/(sqrt(d2)+1e-8) normalised, weighted sum of the 3 feature rows
     (three_interpolate_kernel_fast, interpolate_gpu.cu:84-104)."""
@@ -227,7 +232,7 @@ def three_interpolate_wrap(new_coords, coords, features, batch_size):
     for i in range(batch_size):
         m = coords[:, 0] == i
         nm = new_coords[:, 0] == i
-        d2, idx = three_nn(new_coords[nm][:, 1:4].contiguous(), coords[m][:, 1:4].contiguous())
+        d2, idx = (three_nn_fn or three_nn)(new_coords[nm][:, 1:4].contiguous(), coords[m][:, 1:4].contiguous())
         dist = torch.sqrt(d2)
         recip = 1.0 / (dist + 1e-8)
         w = recip / recip.sum(dim=1, keepdim=True)
@@ -247,10 +252,10 @@ def _convcls(sd, p, x, first):
     return _lin(sd, f"{p}.{i}", x)
 
 
-def batchloss_head(sd, p, conv_point_features, conv_point_coords, points, batch_size):
+def batchloss_head(sd, p, conv_point_features, conv_point_coords, points, batch_size, three_nn_fn=None):
     """PointSegBatchlossHead.forward (det3d/models/point_heads/point_seg_batchloss_head.py:122-168)."""
     conv_logits = _convcls(sd, p + "conv_cls_layers", conv_point_features, 0)
-    f = three_interpolate_wrap(points, conv_point_coords, conv_point_features, batch_size)
+    f = three_interpolate_wrap(points, conv_point_coords, conv_point_features, batch_size, three_nn_fn)
     f = torch.relu(_bn(sd, p + "conv_align_layers.1", _lin(sd, p + "conv_align_layers.0", f), 1e-6))
     return _convcls(sd, p + "out_cls_layers", f, 0), conv_logits
 
@@ -315,23 +320,23 @@ def sample_image_features(image_features, points_cuv, batch_idx):
     return torch.cat(outs, 0)
 
 
-def mseg3d_head(sd, p, batch, nhead, nlayer, return_all=False):
+def mseg3d_head(sd, p, batch, nhead, nlayer, return_all=False, three_nn_fn=None):
     """PointSegMSeg3DHead.forward (point_seg_mseg3d_head.py:240-376), return_loss=False.
     batch: conv_point_features, conv_point_coords, points [N,4], points_cuv [N,4], image_features
     [B,ncam,C,h,w], camera_semantic_embeddings [B,C,ncls,1], batch_size."""
     B = batch["batch_size"]
     vf, vc, pts = batch["conv_point_features"], batch["conv_point_coords"], batch["points"]
     voxel_logits = _convcls(sd, p + "voxel_cls_layers", vf, 1)                      # index 0 = Dropout
-    f0 = three_interpolate_wrap(pts, vc, vf, B)
+    f0 = three_interpolate_wrap(pts, vc, vf, B, three_nn_fn)
     fl = torch.relu(_bn(sd, p + "gffm_lidar.1", _lin(sd, p + "gffm_lidar.0", f0), 1e-6))
     cuv = batch["points_cuv"]
     valid = cuv[:, 0] == 1
     fc0 = sample_image_features(batch["image_features"], cuv[valid], pts[:, 0][valid])
     fc = torch.relu(_bn(sd, p + "gffm_camera.1", _lin(sd, p + "gffm_camera.0", fc0), 1e-6))
     fpc = _convcls(sd, p + "lidar_camera_mimic_layer", fl[valid], 0)
-    cam_pad = torch.zeros(valid.shape[0], fc.shape[1])
+    cam_pad = torch.zeros(valid.shape[0], fc.shape[1], device=fc.device)
     cam_pad[valid] = fc
-    pcam_pad = torch.zeros(valid.shape[0], fpc.shape[1])
+    pcam_pad = torch.zeros(valid.shape[0], fpc.shape[1], device=fpc.device)
     pcam_pad[valid] = fpc
     # NOTE the reference computes the mimic layer on valid points only, so invalid points get ZERO pseudo
     # camera features (point_seg_mseg3d_head.py:305-334): where(valid, cam, pcam_pad0) -> 0 for invalid rows.
@@ -462,7 +467,7 @@ def fcn_head(sd, p, inputs, batch_size, num_convs=2):
 
 
 # ------------------------------------------------------------------------------------------ detectors
-def segnet_forward(sd, example, cfg):
+def segnet_forward(sd, example, cfg, backend=None):
     """SegNet.forward(return_loss=False) up to out_logits (det3d/models/detectors/seg_net.py:51-107).
     cfg: dict(voxel_size, pc_range, reader=dict(type, num_head, num_layers))."""
     B = len(example["num_voxels"])
@@ -475,12 +480,13 @@ def segnet_forward(sd, example, cfg):
     else:
         vf = mean_vfe(example["voxels"], example["num_points"])
     feats, coords = unet_scn3d(sd, "backbone.", vf, example["coordinates"], list(example["shape"][0]),
-                               cfg["voxel_size"], cfg["pc_range"])
-    out, conv_logits = batchloss_head(sd, "point_head.", feats, coords, pts, B)
+                               cfg["voxel_size"], cfg["pc_range"], backend=backend)
+    out, conv_logits = batchloss_head(sd, "point_head.", feats, coords, pts, B,
+                                      three_nn_fn=backend.three_nn if backend is not None else None)
     return out
 
 
-def mseg3d_forward(sd, example, cfg, return_all=False):
+def mseg3d_forward(sd, example, cfg, return_all=False, backend=None):
     """SegMSeg3DNet.forward(return_loss=False) up to out_logits (det3d/models/detectors/seg_mseg3d_net.py:47-147).
     cfg: dict(voxel_size, pc_range, hrnet_extra, nhead, nlayer, num_convs)."""
     B = len(example["num_voxels"])
@@ -492,11 +498,12 @@ def mseg3d_forward(sd, example, cfg, return_all=False):
     image_features = feat.view(B, ncam, feat.shape[1], feat.shape[2], feat.shape[3])
     vf = improved_mean_vfe(example["voxels"], example["num_points"])
     feats, coords = unet_scn3d(sd, "backbone.", vf, example["coordinates"], list(example["shape"][0]),
-                               cfg["voxel_size"], cfg["pc_range"])
+                               cfg["voxel_size"], cfg["pc_range"], backend=backend)
     batch = dict(batch_size=B, conv_point_features=feats, conv_point_coords=coords, points=pts,
                  points_cuv=example["points_cuv"], image_features=image_features,
                  camera_semantic_embeddings=cam_emb)
-    r = mseg3d_head(sd, "point_head.", batch, cfg["nhead"], cfg["nlayer"], return_all=return_all)
+    r = mseg3d_head(sd, "point_head.", batch, cfg["nhead"], cfg["nlayer"], return_all=return_all,
+                    three_nn_fn=backend.three_nn if backend is not None else None)
     if return_all:
         r.update(image_features=image_features, image_logits=logits, camera_semantic_embeddings=cam_emb,
                  conv_point_features=feats, conv_point_coords=coords, voxel_features=vf)
