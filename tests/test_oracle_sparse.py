@@ -78,3 +78,47 @@ def test_three_nn_ties_and_small_sets():
     assert idx.tolist() == [[0, 1, 2]] and d2.tolist() == [[0.0, 1.0, 1.0]]        # ties -> lowest index
     d2, idx = on.three_nn(torch.tensor([[0.5, 0, 0]]), known[:2])
     assert idx.tolist() == [[0, 1, 0]] and np.isinf(d2[0, 2].item())
+
+
+# ---------------------------------------------------------------------------------------------- property tests
+from hypothesis import given, settings, strategies as hst   # noqa: E402
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=hst.integers(0, 10 ** 6), n=hst.integers(0, 60), D=hst.integers(1, 6), H=hst.integers(1, 7), W=hst.integers(1, 7),
+       ks=hst.tuples(hst.sampled_from([1, 3]), hst.sampled_from([1, 3]), hst.sampled_from([1, 3])),
+       st=hst.tuples(hst.integers(1, 2), hst.integers(1, 2), hst.integers(1, 2)),
+       pd=hst.tuples(hst.integers(0, 1), hst.integers(0, 1), hst.integers(0, 1)), B=hst.integers(1, 2))
+def test_rulebooks_equal_dictionary_enumeration(seed, n, D, H, W, ks, st, pd, B):
+    """Vectorised rulebook builders (numpy oracle and its torch twin) == the independent O(N*K) dictionary enumeration for
+    random small grids, kernel shapes, strides and paddings - including empty inputs, 1-cell grids and fully dense grids."""
+    from oracle import torch_backend as tb
+    rng = np.random.default_rng(seed)
+    cells = B * D * H * W
+    n = min(n, cells)
+    flat = rng.choice(cells, size=n, replace=False)
+    idx = np.stack([flat // (D * H * W), (flat // (H * W)) % D, (flat // W) % H, flat % W], 1).astype(np.int32).reshape(-1, 4)
+    shape = (D, H, W)
+    osh = osp.out_shape(shape, ks, st, pd)
+    if min(osh) < 1:
+        return
+    # SubM (only defined for odd kernels; spconv pads k // 2)
+    want_out, want_pairs = osp.rulebook_dict(idx, shape, ks, (1, 1, 1), tuple(k // 2 for k in ks), subm=True)
+    nbr = osp.subm_rulebook(idx, shape, ks)
+    assert osp.pairs_of(nbr) == want_pairs
+    if n:
+        np.testing.assert_array_equal(tb.subm_rulebook(torch.from_numpy(idx), shape, ks).numpy(), nbr)
+    if n == 0:
+        return
+    # strided conv: output sites in ascending linear order, pairs as enumerated
+    want_out, want_pairs = osp.rulebook_dict(idx, shape, ks, st, pd, subm=False)
+    oi, oshape, nb = osp.strided_rulebook(idx, shape, ks, st, pd)
+    assert tuple(oshape) == tuple(osh)
+    assert [tuple(int(v) for v in r) for r in oi] == [tuple(r) for r in want_out]
+    assert osp.pairs_of(nb) == want_pairs
+    oi_t, _, nb_t = tb.strided_rulebook(torch.from_numpy(idx), shape, ks, st, pd)
+    np.testing.assert_array_equal(oi_t.numpy(), oi)
+    np.testing.assert_array_equal(nb_t.numpy(), nb)
+    # the inverse table is the exact swap
+    up = osp.invert_rulebook(nb, n)
+    assert {(k, j, i) for (k, i, j) in osp.pairs_of(nb)} == osp.pairs_of(up)
