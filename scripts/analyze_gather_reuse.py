@@ -40,3 +40,29 @@ for name in ("NUSC", "KITTI"):
         print(f"{name:6s} {order_name:30s} rows {M:7d} pairs/row {pairs / M:5.2f} | gathered rows per output row: "
               f"per pair {pairs / M:5.2f}, per (kz,ky) run {per_run / M:5.2f}, distinct per tile {per_tile / M:5.2f} | "
               f"steps/tile now {steps_now / (M / 128):5.1f}, runs/tile {steps_run / (M / 128):4.1f}")
+
+
+# ---- all four UNet levels: distinct input rows per 128-row tile (sizes the shared-memory stage of the next engine revision)
+print()
+for name in ("NUSC", "KITTI"):
+    spec = getattr(synth, name)
+    frames = [synth.lidar_scan(spec, s) for s in range(2)]
+    vox = [ov.points_to_voxel(f, spec["voxel_size"], spec["pc_range"], 5, 300000) for f in frames]
+    v, c, n, nv, pts = ov.collate_frames([(a, b, cc, f) for (a, b, cc), f in zip(vox, frames)])
+    g = synth.grid_shape(spec)
+    shape = (int(g[2]) + 1, int(g[1]), int(g[0]))
+    idx = c.astype(np.int32)
+    pads = {2: (1, 1, 1), 3: (1, 1, 1), 4: (0, 1, 1)}
+    chans = {1: 32, 2: 64, 3: 128, 4: 128}
+    for lv in (1, 2, 3, 4):
+        if lv > 1:
+            idx, shape, _ = osp.strided_rulebook(idx, shape, 3, 2, pads[lv])
+        nbr = osp.subm_rulebook(idx, shape, 3)
+        M = nbr.shape[1]
+        d = []
+        for t0 in range(0, M, 128):
+            blk = nbr[:, t0:t0 + 128]
+            d.append(np.unique(blk[blk >= 0]).size)
+        d = np.asarray(d)
+        print(f"{name:6s} level {lv}: rows {M:6d} tiles {d.size:4d} pairs/row {(nbr >= 0).sum() / M:5.2f} distinct rows per tile: mean "
+              f"{d.mean():6.1f} p95 {np.percentile(d, 95):6.1f} max {d.max():4d} -> {d.max() * chans[lv] * 4 / 1024:6.1f} KB fp32 at C={chans[lv]}")
