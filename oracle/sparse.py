@@ -178,3 +178,71 @@ def rulebook_dict(indices, spatial_shape, ksize, stride, padding, subm):
                         pairs.add((k, i, j))
                     k += 1
     return [c for c, _ in sorted(outs.items(), key=lambda t: t[1])], pairs
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Tile plan for a gather-once sparse convolution (design prototype for the next gather-GEMM revision):
+# output rows are grouped into spatially compact tiles, every tile lists the DISTINCT input rows it needs and addresses them
+# through a local index table, so a kernel can stage those rows on chip once and serve all kernel offsets from the stage.
+def morton_order(indices):
+    """Permutation that sorts sites by (batch, Morton code of (z, y, x)): consecutive rows form compact 3-D blocks."""
+    idx = np.asarray(indices).astype(np.int64)
+
+    def part(v):
+        v = v.astype(np.uint64) & np.uint64(0x1fffff)
+        v = (v | (v << np.uint64(32))) & np.uint64(0x1f00000000ffff)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x1f0000ff0000ff)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x100f00f00f00f00f)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x10c30c30c30c30c3)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+        return v
+    code = part(idx[:, 3]) | (part(idx[:, 2]) << np.uint64(1)) | (part(idx[:, 1]) << np.uint64(2))
+    return np.lexsort((code, idx[:, 0]))
+
+
+def tile_plan(nbr, out_order=None, tile=128):
+    """nbr [K, M_out] (input row per offset and output row, -1 = none) -> plan:
+        out_rows [T, tile]      output row handled by each tile slot (-1 = padding), tiles follow ``out_order``
+        stage_off [T + 1]       CSR offsets into stage_rows
+        stage_rows [S]          distinct input rows of each tile, ascending
+        local [T, K, tile]      uint16 position of the pair's input row inside the tile's stage, 0xFFFF = none
+    Every pair (k, in, out) of the rulebook appears exactly once."""
+    K, M = nbr.shape
+    order = np.arange(M) if out_order is None else np.asarray(out_order)
+    T = (M + tile - 1) // tile
+    out_rows = np.full((T, tile), -1, dtype=np.int64)
+    out_rows.reshape(-1)[:M] = order
+    stage_off = np.zeros(T + 1, dtype=np.int64)
+    stage_rows, local = [], np.full((T, K, tile), 0xFFFF, dtype=np.uint16)
+    for t in range(T):
+        cols = out_rows[t][out_rows[t] >= 0]
+        blk = nbr[:, cols]                                       # [K, n]
+        rows = np.unique(blk[blk >= 0])
+        assert rows.size < 0xFFFF
+        stage_rows.append(rows)
+        stage_off[t + 1] = stage_off[t] + rows.size
+        pos = np.searchsorted(rows, np.where(blk >= 0, blk, rows[0] if rows.size else 0))
+        local[t, :, :cols.size] = np.where(blk >= 0, pos, 0xFFFF).astype(np.uint16)
+    return dict(out_rows=out_rows, stage_off=stage_off,
+                stage_rows=np.concatenate(stage_rows) if stage_rows else np.zeros(0, np.int64), local=local, tile=tile)
+
+
+def sparse_conv_tiled(features, weight, plan, n_out):
+    """The same convolution as ``sparse_conv`` evaluated tile by tile from a staged copy of the tile's distinct input rows
+    (what the planned kernel does: stage once, then one [tile x Cin] x [Cin x Cout] product per kernel offset)."""
+    K = plan["local"].shape[1]
+    w = weight.reshape(K, weight.shape[-2], weight.shape[-1])
+    out = torch.zeros(n_out, w.shape[2], dtype=features.dtype)
+    zero = torch.zeros(1, features.shape[1], dtype=features.dtype)
+    for t in range(plan["out_rows"].shape[0]):
+        rows = plan["stage_rows"][plan["stage_off"][t]:plan["stage_off"][t + 1]]
+        stage = torch.cat([features[torch.as_tensor(rows, dtype=torch.long)], zero], 0)      # last row = the "none" row
+        loc = torch.as_tensor(plan["local"][t].astype(np.int64))
+        loc = torch.where(loc == 0xFFFF, torch.full_like(loc, stage.shape[0] - 1), loc)      # [K, tile]
+        acc = torch.zeros(plan["tile"], w.shape[2], dtype=features.dtype)
+        for k in range(K):
+            acc += stage[loc[k]] @ w[k]
+        cols = plan["out_rows"][t]
+        ok = cols >= 0
+        out[torch.as_tensor(cols[ok], dtype=torch.long)] = acc[torch.as_tensor(np.nonzero(ok)[0], dtype=torch.long)]
+    return out

@@ -122,3 +122,33 @@ def test_rulebooks_equal_dictionary_enumeration(seed, n, D, H, W, ks, st, pd, B)
     # the inverse table is the exact swap
     up = osp.invert_rulebook(nb, n)
     assert {(k, j, i) for (k, i, j) in osp.pairs_of(nb)} == osp.pairs_of(up)
+
+
+@pytest.mark.parametrize("use_morton", [False, True])
+def test_tile_plan_gather_once_equals_per_pair_conv(use_morton):
+    """The gather-once tile plan (design prototype of the next gather-GEMM revision) reproduces the per-pair sparse
+    convolution exactly and lists every rulebook pair once."""
+    rng = np.random.default_rng(7)
+    shape, n, C, Co = (12, 24, 24), 1500, 8, 6
+    cells = rng.choice(2 * shape[0] * shape[1] * shape[2], size=n, replace=False)
+    D, H, W = shape
+    idx = np.stack([cells // (D * H * W), (cells // (H * W)) % D, (cells // W) % H, cells % W], 1).astype(np.int32)
+    nbr = osp.subm_rulebook(idx, shape, 3)
+    order = osp.morton_order(idx) if use_morton else None
+    plan = osp.tile_plan(nbr, order, tile=128)
+    # every pair exactly once
+    pairs = set()
+    for t in range(plan["out_rows"].shape[0]):
+        rows = plan["stage_rows"][plan["stage_off"][t]:plan["stage_off"][t + 1]]
+        k, s = np.nonzero(plan["local"][t] != 0xFFFF)
+        for kk, ss in zip(k.tolist(), s.tolist()):
+            p = (kk, int(rows[plan["local"][t, kk, ss]]), int(plan["out_rows"][t, ss]))
+            assert p not in pairs
+            pairs.add(p)
+    assert pairs == osp.pairs_of(nbr)
+    g = torch.Generator().manual_seed(3)
+    f = torch.randn(n, C, generator=g)
+    w = torch.randn(27, C, Co, generator=g)
+    torch.testing.assert_close(osp.sparse_conv_tiled(f, w, plan, n), osp.sparse_conv(f, w, nbr), rtol=1e-5, atol=1e-5)
+    if use_morton:      # compact tiles stage fewer rows than row-order tiles
+        assert plan["stage_rows"].size < osp.tile_plan(nbr, None, 128)["stage_rows"].size
