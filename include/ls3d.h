@@ -204,7 +204,8 @@ int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* term_h, const
 
 /* ------------------------------------------------------------------------------------------------
  * Camera input preparation: uint8 [n_pixels][3] (HWC images, any batch of them back to back) -> (x / 255 - mean[c]) / std[c]
- * in IEEE fp32, stored fp32 or fp16 in the same pixel-major order (= channels-last maps).
+ * in IEEE fp32 (mean / std as fp32: within 1 ulp per operation of the reference's numpy, whose in-place ops promote its
+ * python-float mean / std to fp64), stored fp32 or fp16 in the same pixel-major order (= channels-last maps).
  * replaces: image_input_transform (det3d/datasets/pipelines/img_transforms.py:18-29, segpreprocess.py:621-628) + the HWC->CHW
  *           transpose (segpreprocess.py:637); mean3 / std3 are HOST pointers to 3 floats (cam_attributes[cam]["mean"/"std"]).
  *   in and out 16-byte aligned.

@@ -360,12 +360,39 @@ def gen_losses():
     print("losses:", [float(c["lovasz_ignore0"]) for c in fx["cases"]], float(loss), float(iloss))
 
 
+def gen_image_norm():
+    """image_input_transform of the reference (det3d/datasets/pipelines/img_transforms.py:18-29; cv2 is only needed by
+    other functions of that file and is stubbed when absent) on random uint8 images -> tests/golden/ref_image_norm.npz."""
+    import types
+    if "cv2" not in sys.modules:
+        try:
+            import cv2  # noqa: F401
+        except Exception:
+            sys.modules["cv2"] = types.SimpleNamespace(INTER_NEAREST=0, INTER_LINEAR=1, INTER_CUBIC=2, INTER_AREA=3,
+                                                       INTER_LANCZOS4=4)
+    spec = importlib.util.spec_from_file_location("ref_img_transforms",
+                                                  os.path.join(REF, "det3d/datasets/pipelines/img_transforms.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rng = np.random.default_rng(99)
+    img = rng.integers(0, 256, (3, 20, 32, 3), dtype=np.uint8)
+    mean = [0.40789654, 0.44719302, 0.47026115]          # configs/semanticnusc/MSeg3D/...e12.py:19-20
+    std = [0.28863828, 0.27408164, 0.27809835]
+    out = np.stack([m.image_input_transform(img[i], mean=mean, std=std).astype(np.float32) for i in range(img.shape[0])])
+    np.savez_compressed(os.path.join(OUT, "ref_image_norm.npz"), images_u8=img, mean=np.array(mean), std=np.array(std), out=out)
+    print("image_norm", out.shape, out.dtype, float(out.mean()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--image-norm-only" in sys.argv:
+        gen_image_norm()
+        sys.exit(0)
     if "--losses-only" in sys.argv:
         gen_losses()
         sys.exit(0)
     gen_voxelize()
     gen_modules()
     gen_losses()
+    gen_image_norm()
     print(sorted((f, os.path.getsize(os.path.join(OUT, f))) for f in os.listdir(OUT)))

@@ -518,7 +518,9 @@ def predict_labels(out_logits, points, batch_size):
 
 def image_input_transform(images_u8, mean, std):
     """det3d/datasets/pipelines/img_transforms.py:18-29 applied per camera (segpreprocess.py:621-628), then the
-    [.., H, W, 3] -> [.., 3, H, W] transpose of segpreprocess.py:637.  numpy fp32, same operation order."""
+    [.., H, W, 3] -> [.., 3, H, W] transpose of segpreprocess.py:637.  numpy fp32, same operation order; mean / std are
+    rounded to fp32 first (the reference's in-place ops promote its python-float lists to fp64 and round the result back, so
+    the two differ by at most 1 fp32 ulp per operation - tests/test_oracle_golden.py pins that bound)."""
     import numpy as np
     image = np.asarray(images_u8).astype(np.float32)
     image = image / 255.0
