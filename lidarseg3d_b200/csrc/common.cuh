@@ -14,6 +14,32 @@
 
 static inline int ls3d_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-device caches (a process may drive several GPUs: attributes and opt-ins are per device ordinal).
+static inline int ls3d_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= 64) ? 0 : dev;
+}
+static inline int ls3d_num_sms() {
+  static int cache[64] = {0};
+  const int dev = ls3d_current_device();
+  if (cache[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
+  }
+  return cache[dev];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize opt-in, once per (kernel, device); `done` = a static bool[64] of the caller
+template <typename K>
+static inline cudaError_t ls3d_optin_smem(K kernel, bool* done, int bytes = 227 * 1024) {
+  const int dev = ls3d_current_device();
+  if (done[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[dev] = true;
+  return e;
+}
+
 namespace ls3d {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -468,15 +468,10 @@ extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* 
   while (a.nbuf > 2 && smem_for(g, cout, a.nbuf) > 227 * 1024) --a.nbuf;
   const size_t smem = smem_for(g, cout, a.nbuf);
   if (smem > 227 * 1024) return LS3D_ERR_ARG;           // weights do not fit in shared memory: caller uses the library conv
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-  }
+  const int num_sms = ls3d_num_sms();
+  static bool optin[64] = {false};
+  cudaError_t eo = ls3d_optin_smem(conv3x3_f16_kernel, optin);
+  if (eo != cudaSuccess) return (int)eo;
   CUtensorMap m_in, m_res, m_out;
   int rc = make_map(&m_in, in, cin, W, H, n_img, 8, HALO_W, HALO_H);
   if (rc) return rc;

@@ -331,14 +331,11 @@ extern "C" int ls3d_gather_gemm(const ls3d_gemm_args* a, void* stream) {
       return LS3D_ERR_ARG;
   }
   if (a->n_ln < 0 || a->n_ln > 2) return LS3D_ERR_ARG;
+  if (a->red0 && (!a->red1 || (a->red_c & 3) || (a->ld_red0 & 3) || (a->ld_red1 & 3) || a->cout != a->red_c ||
+                  a->epi != LS3D_EPI_LINEAR))
+    return LS3D_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = ls3d_num_sms();
   if (a->precise == 2) return ls3d_gather_gemm_bf16x3_launch(a, num_sms, stream);
   const int ntiles = ls3d_div_up(a->m_out, TILE_M);
   const int grid = ntiles < num_sms ? ntiles : num_sms;          // persistent: one CTA per SM

@@ -457,12 +457,9 @@ int ls3d_gather_gemm_bf16x3_launch(const ls3d_gemm_args* a, int num_sms, void* s
   if (smem > 227 * 1024) return LS3D_ERR_ARG;
   const int ntiles = ls3d_div_up(a->m_out, TILE_M);
   const int grid = ntiles < num_sms ? ntiles : num_sms;          // persistent: one CTA per SM
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(gather_gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    smem_set = 227 * 1024;
-  }
+  static bool optin[64] = {false};
+  cudaError_t e = ls3d_optin_smem(gather_gemm_bf16x3_kernel, optin);
+  if (e != cudaSuccess) return (int)e;
   gather_gemm_bf16x3_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(*a, cfg);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;

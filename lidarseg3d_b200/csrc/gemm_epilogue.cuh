@@ -210,14 +210,19 @@ __device__ __forceinline__ void epilogue_tile(const ls3d_gemm_args& p, const uin
       for (int j = 0; j < PANEL; ++j) v[j] += rv[j];
     }
     if (p.red0 && live) {
-      // cat = [red0 (red_c ch) | red1 (red_c ch)] ; out[col] += cat[2col] + cat[2col+1]: 32 consecutive source columns
+      // cat = [red0 (red_c ch) | red1 (red_c ch)] ; out[col] += cat[2col] + cat[2col+1].  The source tensor is chosen per
+      // 4-column group, so any red_c % 4 == 0 works (a 16-column panel may straddle red0 | red1: SCALING_RATIO 1 or 3).
       const int c2 = 2 * c0;
-      const float* src = (c2 < p.red_c) ? (p.red0 + (size_t)r * p.ld_red0 + c2) : (p.red1 + (size_t)r * p.ld_red1 + (c2 - p.red_c));
+      const float* s0 = p.red0 + (size_t)r * p.ld_red0;
+      const float* s1 = p.red1 + (size_t)r * p.ld_red1 - p.red_c;
 #pragma unroll
       for (int j2 = 0; j2 < PANEL / 2; ++j2) {
-        const float4 t = ldg_f4(src + j2 * 4);
-        v[j2 * 2] += t.x + t.y;
-        v[j2 * 2 + 1] += t.z + t.w;
+        const int cc = c2 + j2 * 4;
+        if (cc < 2 * p.red_c) {
+          const float4 t = ldg_f4((cc < p.red_c ? s0 : s1) + cc);
+          v[j2 * 2] += t.x + t.y;
+          v[j2 * 2 + 1] += t.z + t.w;
+        }
       }
     }
     if (w < PANEL) {

@@ -32,7 +32,7 @@ __device__ __forceinline__ long long cell_of(const GridDesc& g, int b, int z, in
 
 // row of the active site at (b,z,y,x) or -1
 __device__ __forceinline__ int grid_lookup(const GridDesc& g, int b, int z, int y, int x) {
-  if ((unsigned)z >= (unsigned)g.D || (unsigned)y >= (unsigned)g.H || (unsigned)x >= (unsigned)g.W) return -1;
+  if ((unsigned)b >= (unsigned)g.B || (unsigned)z >= (unsigned)g.D || (unsigned)y >= (unsigned)g.H || (unsigned)x >= (unsigned)g.W) return -1;
   const long long c = cell_of(g, b, z, y, x);
   const uint2 w = __ldg(&g.words[c >> 5]);
   const unsigned bit = 1u << (c & 31);
@@ -45,6 +45,9 @@ __global__ void grid_set_kernel(const int* __restrict__ coords, int m, uint2* wo
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int4 c = *reinterpret_cast<const int4*>(coords + (size_t)i * 4);
+  // a site outside (B, D, H, W) (example voxelized with another range / shape than the backbone's) is left out of the
+  // bitmap - it then takes no part in any rulebook - instead of writing out of bounds
+  if ((unsigned)c.x >= (unsigned)B || (unsigned)c.y >= (unsigned)D || (unsigned)c.z >= (unsigned)H || (unsigned)c.w >= (unsigned)W) return;
   const long long cell = (((long long)c.x * D + c.y) * H + c.z) * W + c.w;
   atomicOr(&words[cell >> 5].x, 1u << (cell & 31));
 }
@@ -54,6 +57,7 @@ __global__ void grid_perm_kernel(const int* __restrict__ coords, int m, const ui
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int4 c = *reinterpret_cast<const int4*>(coords + (size_t)i * 4);
+  if ((unsigned)c.x >= (unsigned)B || (unsigned)c.y >= (unsigned)D || (unsigned)c.z >= (unsigned)H || (unsigned)c.w >= (unsigned)W) return;
   const long long cell = (((long long)c.x * D + c.y) * H + c.z) * W + c.w;
   const uint2 w = words[cell >> 5];
   const unsigned bit = 1u << (cell & 31);
@@ -65,11 +69,12 @@ struct ConvGeom {
 };
 
 // mark every output cell reachable from an active input site
-__global__ void grid_mark_strided_kernel(const int* __restrict__ coords, int m, ConvGeom g, uint2* owords, int oD,
+__global__ void grid_mark_strided_kernel(const int* __restrict__ coords, int m, ConvGeom g, uint2* owords, int B, int oD,
                                          int oH, int oW) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int4 c = *reinterpret_cast<const int4*>(coords + (size_t)i * 4);
+  if ((unsigned)c.x >= (unsigned)B) return;
   for (int kz = 0; kz < g.k[0]; ++kz) {
     const int nz = c.y + g.p[0] - kz;
     if (nz < 0 || nz % g.s[0]) continue;
@@ -196,7 +201,7 @@ extern "C" int ls3d_grid_build_strided(const int32_t* in_coords, int32_t m_in, i
   cudaMemsetAsync(out_words, 0, nw * 8, st);
   if (m_in > 0)
     grid_mark_strided_kernel<<<ls3d_div_up(m_in, 256), 256, 0, st>>>(in_coords, m_in, make_geom(ksize, stride, pad),
-                                                                    (uint2*)out_words, oD, oH, oW);
+                                                                    (uint2*)out_words, B, oD, oH, oW);
   int e = rank_words((uint2*)out_words, nw, (int*)scratch, total_out, st);
   if (e) return e;
   LS3D_LAUNCH_CHECK();

@@ -79,6 +79,32 @@ class SegMSeg3DNet(_SegBase):
     # branches are bandwidth bound).
     image_dtype = None
 
+    # ---- the captured camera-branch graphs hold pointers to BN-folded / packed weight tensors: drop them whenever the
+    # parameters, their device / dtype or the train / eval mode can have changed (same events as common.Prepared)
+    def _drop_image_graphs(self):
+        self.__dict__.pop("_img_graphs", None)
+
+    def _apply(self, fn, *a, **k):
+        self._drop_image_graphs()
+        self.__dict__.pop("_img_stream", None)
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._drop_image_graphs()
+        return super().load_state_dict(*a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._drop_image_graphs()
+        return super()._load_from_state_dict(*a, **k)
+
+    def train(self, mode=True):
+        self._drop_image_graphs()
+        return super().train(mode)
+
+    def _param_fingerprint(self):
+        """Versions of every camera-branch parameter / buffer: in-place updates (optimizer steps, copy_) also invalidate."""
+        return tuple(t._version for m in (self.img_backbone, self.img_head) for t in list(m.parameters()) + list(m.buffers()))
+
     def _image_branch(self, images, batch_size):
         self.img_backbone.keep_channel_padding = True      # the image head consumes zero-padded channel maps directly
         if self.image_dtype is not None:
@@ -90,6 +116,10 @@ class SegMSeg3DNet(_SegBase):
     def _image_branch_graphed(self, images, batch_size):
         key = (tuple(images.shape), images.dtype, self.image_dtype, images.device.index, batch_size)
         cache = self.__dict__.setdefault("_img_graphs", {})
+        fp = self._param_fingerprint()
+        if self.__dict__.get("_img_graphs_fp") != fp:
+            cache.clear()
+            self.__dict__["_img_graphs_fp"] = fp
         ent = cache.get(key)
         side = self.__dict__.setdefault("_img_stream", None)
         if side is None:

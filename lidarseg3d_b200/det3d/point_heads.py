@@ -84,13 +84,21 @@ def _predict(out_logits, example, test_cfg):
         ntta = test_cfg.get("num_tta_tranforms", 4)
         if test_cfg.get("merge_type", "ArithmeticMean") != "ArithmeticMean":
             raise NotImplementedError
+        assert batch_size % ntta == 0, f"TTA: batch_size {batch_size} is not a multiple of num_tta_tranforms {ntta}"
         metas = example["metadata"][:ntta * batch_size:ntta] if has_meta else [None] * batch_size
         probs = torch.softmax(out_logits, dim=-1)
         per = [probs[stack_points[:, 0] == i] for i in range(batch_size)]
+        left = 0
         for g, i in enumerate(range(0, batch_size, ntta)):
             merged = torch.stack(per[i:i + ntta], 0).mean(0)
-            ret_list.append({"metadata": metas[g] if g < len(metas) else None,
-                             "pred_point_sem_labels": torch.argmax(merged, dim=1)})
+            ret = {"metadata": metas[g] if g < len(metas) else None, "pred_point_sem_labels": torch.argmax(merged, dim=1)}
+            if "point_sem_labels" in example:
+                # the reference slices the stacked labels by the cumulated point counts of the merged frames
+                # (point_seg_mseg3d_head.py:441-451)
+                right = left + per[i].shape[0]
+                ret["point_sem_labels"] = example["point_sem_labels"][left:right]
+                left = right
+            ret_list.append(ret)
     else:
         metas = example["metadata"] if has_meta else [None] * batch_size
         labels = torch.argmax(out_logits, dim=1)

@@ -360,6 +360,179 @@ def gen_losses():
     print("losses:", [float(c["lovasz_ignore0"]) for c in fx["cases"]], float(loss), float(iloss))
 
 
+
+# ----------------------------------------------------------------------------------------------- backbones / detectors
+def unet_fill(sd):
+    """seeded_fill, then every 5-D sparse-conv weight [kz,ky,kx,Cin,Cout] redrawn with fan_in = K*Cin (activations of O(1)
+    through the 37 convs of the UNet; seeded_fill's generic fan-in is far too large for that layout)."""
+    out = seeded_fill(sd)
+    for name, t in out.items():
+        if t.dim() == 5:
+            g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+            fan_in = int(np.prod(t.shape[:4]))
+            out[name] = (torch.randn(t.shape, generator=g) * (2.0 / fan_in) ** 0.5).to(t.dtype)
+    return out
+
+
+def surface_scene(seed, n, feat, half_xy=3.1, z_lo=-1.9, z_hi=1.9):
+    """Points on a few noisy planes (dense local neighbourhoods, so SubM / strided rulebooks have many pairs)."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for _ in range(4):
+        m = n // 4
+        xy = rng.uniform(-half_xy, half_xy, (m, 2))
+        a, b, c = rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), rng.uniform(-1.0, 1.0)
+        z = np.clip(a * xy[:, 0] + b * xy[:, 1] + c + rng.normal(0, 0.03, m), z_lo, z_hi)
+        parts.append(np.concatenate([xy, z[:, None]], 1))
+    xyz = np.concatenate(parts, 0)
+    extra = rng.uniform(0, 1, (xyz.shape[0], feat - 3))
+    return np.concatenate([xyz, extra], 1).astype(np.float32)
+
+
+SMALL_RANGE = [-3.2, -3.2, -2.0, 3.2, 3.2, 2.0]
+SMALL_VOXEL = [0.1, 0.1, 0.1]
+
+
+def load_reference_detectors():
+    """The reference's scn_unet.py / scn.py / detectors on the spconv shim (oracle/spconv_shim.py)."""
+    from oracle import spconv_shim
+    for k in [k for k in sys.modules if k.startswith("det3d")]:
+        del sys.modules[k]
+    R = load_reference_modules()
+    spconv_shim.install()
+    _mod("pycocotools")
+    _mod("pycocotools.mask")
+    sys.modules["pycocotools"].mask = sys.modules["pycocotools.mask"]
+    _mod("det3d.torchie.trainer", load_checkpoint=None)
+    sys.modules["det3d.torchie"].trainer = sys.modules["det3d.torchie.trainer"]
+    _mod("det3d.models.utils.finetune_utils", FrozenBatchNorm2d=None)
+    cu = load_ref("det3d.core.utils.common_utils", "det3d/core/utils/common_utils.py")
+    sys.modules["det3d.core.utils"].common_utils = cu
+    for pkg in ["det3d.models.backbones", "det3d.models.detectors"]:
+        m = _mod(pkg)
+        m.__path__ = [os.path.join(REF, *pkg.split("."))]
+    load_ref("det3d.models.builder", "det3d/models/builder.py")
+    R["scn_unet"] = load_ref("det3d.models.backbones.scn_unet", "det3d/models/backbones/scn_unet.py")
+    R["scn"] = load_ref("det3d.models.backbones.scn", "det3d/models/backbones/scn.py")
+    load_ref("det3d.models.detectors.base", "det3d/models/detectors/base.py")
+    load_ref("det3d.models.detectors.single_stage", "det3d/models/detectors/single_stage.py")
+    R["seg_net"] = load_ref("det3d.models.detectors.seg_net", "det3d/models/detectors/seg_net.py")
+    R["seg_mseg3d_net"] = load_ref("det3d.models.detectors.seg_mseg3d_net", "det3d/models/detectors/seg_mseg3d_net.py")
+    R["builder"] = sys.modules["det3d.models.builder"]
+    return R
+
+
+def _example(frames, feat, with_cam=None):
+    """example dict through the reference's numba voxelizer + collate rules (oracle.voxelize.collate_frames)."""
+    from oracle import voxelize as ov
+    spec = importlib.util.spec_from_file_location("ref_pco", os.path.join(REF, "det3d/ops/point_cloud/point_cloud_ops.py"))
+    pco = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pco)
+    vox = [pco.points_to_voxel(f, np.array(SMALL_VOXEL, np.float32), np.array(SMALL_RANGE, np.float32), 5, True, 300000)
+           for f in frames]
+    v, c, n, nv, pts = ov.collate_frames([(a, b, cc, f) for (a, b, cc), f in zip(vox, frames)])
+    grid = np.round((np.array(SMALL_RANGE[3:], np.float32) - np.array(SMALL_RANGE[:3], np.float32))
+                    / np.array(SMALL_VOXEL, np.float32)).astype(np.int64)
+    return dict(voxels=torch.from_numpy(v), coordinates=torch.from_numpy(c), num_points=torch.from_numpy(n),
+                num_voxels=torch.from_numpy(nv), shape=np.stack([grid] * len(frames)), points=torch.from_numpy(pts),
+                metadata=[dict(token=i) for i in range(len(frames))])
+
+
+def gen_backbones():
+    """Run the reference's OWN UNetSCN3D.forward / SegNet.forward / SegMSeg3DNet.forward / predict() on the spconv shim
+    -> tests/golden/ref_backbones.pt (pins oracle/nets.py::unet_scn3d, segnet_forward, mseg3d_forward, the TTA merge and
+    the state-dict key sets)."""
+    R = load_reference_detectors()
+    from lidarseg3d_b200.det3d import Config
+    fx = {}
+    g = torch.Generator().manual_seed(77)
+    with torch.no_grad():
+        # ---- UNetSCN3D alone, SCALING_RATIO 2 (shipped configs) and 1 (constructor default; red_c = 16)
+        frames = [surface_scene(11, 1600, 5), surface_scene(12, 1200, 5)]
+        ex = _example(frames, 5)
+        vf = torch.randn(ex["voxels"].shape[0], 13, generator=g)
+        for ratio in (2, 1):
+            net = R["scn_unet"].UNetSCN3D(num_input_features=13, voxel_size=SMALL_VOXEL, point_cloud_range=SMALL_RANGE,
+                                         model_cfg=dict(SCALING_RATIO=ratio), ds_factor=8, us_factor=8).eval()
+            net.load_state_dict(unet_fill(net.state_dict()))
+            bd = net(dict(voxel_features=vf.clone(), voxel_coords=ex["coordinates"], batch_size=2, input_shape=ex["shape"][0]))
+            ms = bd["multi_scale_3d_features"]
+            fx[f"unet_r{ratio}"] = dict(
+                voxel_features=vf, coordinates=ex["coordinates"], input_shape=ex["shape"][0],
+                conv_point_features=bd["conv_point_features"], conv_point_coords=bd["conv_point_coords"],
+                encoded_features=bd["encoded_spconv_tensor"].features, encoded_indices=bd["encoded_spconv_tensor"].indices,
+                encoded_shape=list(bd["encoded_spconv_tensor"].spatial_shape),
+                multi_scale={k: dict(features=v.features, indices=v.indices, shape=list(v.spatial_shape)) for k, v in ms.items()},
+                keys=sorted(net.state_dict().keys()))
+        # ---- SegNet (SDSeg3D SemanticKITTI model section of the reference config, small range)
+        cfg = Config.fromfile(os.path.join(REF, "configs/semantickitti/SDSeg3D/semkitti_transVFE_unetscn3d_batchloss_e10.py"))
+        mc = cfg.model
+        mc["backbone"]["voxel_size"], mc["backbone"]["point_cloud_range"] = SMALL_VOXEL, SMALL_RANGE
+        mc["pretrained"] = None
+        det = R["builder"].build_detector(mc, train_cfg=None, test_cfg=cfg.test_cfg).eval()
+        det.load_state_dict(unet_fill(det.state_dict()))
+
+        class _Seq(nn.Module):
+            def __init__(self, layers):
+                super().__init__()
+                self.layers = layers
+
+            def forward(self, x):
+                for l in self.layers:
+                    x = l(x)
+                return x
+        det.reader.chunck = _Seq(det.reader.chunck.layers)          # torch>=2 is_causal drift (SURVEY App. D 19a)
+        frames4 = [surface_scene(21, 1400, 4), surface_scene(22, 1000, 4)]
+        ex4 = _example(frames4, 4)
+        preds = det(ex4, return_loss=False)
+        fx["segnet"] = dict(example={k: v for k, v in ex4.items()}, out_logits=det.point_head.forward_ret_dict["out_logits"],
+                            labels=[p["pred_point_sem_labels"] for p in preds],
+                            keys=sorted(k.replace("chunck.layers.layers.", "chunck.layers.") for k in det.state_dict().keys()))
+        # ---- SegMSeg3DNet (MSeg3D nuScenes model section of the reference config, small range, 2 cameras of 64x96)
+        cfg = Config.fromfile(os.path.join(REF, "configs/semanticnusc/MSeg3D/semnusc_avgvfe_unetscn3d_hrnetw18_lr1en2_e12.py"))
+        mc = cfg.model
+        mc["backbone"]["voxel_size"], mc["backbone"]["point_cloud_range"] = SMALL_VOXEL, SMALL_RANGE
+        mc["pretrained"] = None
+        mc["img_backbone"]["pretrained"] = None
+        mc["img_backbone"]["init_cfg"] = None
+        det = R["builder"].build_detector(mc, train_cfg=None, test_cfg=cfg.test_cfg)
+        det.eval()
+        for m in det.modules():
+            m.training = False                                      # the reference HRNet.train() returns None
+        det.load_state_dict(unet_fill(det.state_dict()))
+        B, ncam = 2, 2
+        npts = ex["points"].shape[0]
+        cuv = torch.rand(npts, 4, generator=g) * 2 - 1
+        cuv[:, 0] = (torch.rand(npts, generator=g) > 0.3).float()
+        cuv[:, 1] = torch.randint(0, ncam, (npts,), generator=g).float() / (ncam - 1) * 2 - 1
+        ex5 = dict(ex)
+        ex5["points_cuv"] = cuv
+        ex5["images"] = torch.randn(B, ncam, 3, 64, 96, generator=g)
+        preds = det(ex5, return_loss=False)
+        fx["mseg3d"] = dict(example=ex5, out_logits=det.point_head.forward_ret_dict["out_logits"],
+                            voxel_logits=det.point_head.forward_ret_dict["voxel_logits"],
+                            labels=[p["pred_point_sem_labels"] for p in preds], keys=sorted(det.state_dict().keys()))
+        # ---- TTA merge (point_seg_mseg3d_head.py:398-453): 4 variants of 2 frames, same point count inside a group
+        ntta, nf, n_each, ncls = 4, 2, [37, 53], 17
+        rows, logits = [], []
+        for f in range(nf):
+            for t in range(ntta):
+                b = f * ntta + t
+                rows.append(torch.cat([torch.full((n_each[f], 1), float(b)), torch.rand(n_each[f], 3, generator=g)], 1))
+                logits.append(torch.randn(n_each[f], ncls, generator=g))
+        pts_tta, log_tta = torch.cat(rows), torch.cat(logits)
+        exT = dict(num_voxels=torch.zeros(nf * ntta), points=pts_tta, metadata=[dict(token=i) for i in range(nf * ntta)],
+                   point_sem_labels=torch.randint(0, ncls, (pts_tta.shape[0],), generator=g))
+        head = det.point_head
+        head.forward_ret_dict = dict(out_logits=log_tta)
+        rt = head.predict(example=exT, test_cfg=dict(tta_flag=True, merge_type="ArithmeticMean", num_tta_tranforms=ntta))
+        fx["tta"] = dict(points=pts_tta, out_logits=log_tta, point_sem_labels=exT["point_sem_labels"], ntta=ntta,
+                         ret=[dict(metadata=r["metadata"], pred=r["pred_point_sem_labels"], gt=r["point_sem_labels"]) for r in rt])
+    torch.save(fx, os.path.join(OUT, "ref_backbones.pt"))
+    print("backbones:", {k: (tuple(v["conv_point_features"].shape) if "conv_point_features" in v else
+                             tuple(v["out_logits"].shape)) for k, v in fx.items()})
+
+
 def gen_image_norm():
     """image_input_transform of the reference (det3d/datasets/pipelines/img_transforms.py:18-29; cv2 is only needed by
     other functions of that file and is stubbed when absent) on random uint8 images -> tests/golden/ref_image_norm.npz."""
@@ -388,6 +561,9 @@ if __name__ == "__main__":
     if "--image-norm-only" in sys.argv:
         gen_image_norm()
         sys.exit(0)
+    if "--backbones-only" in sys.argv:
+        gen_backbones()
+        sys.exit(0)
     if "--losses-only" in sys.argv:
         gen_losses()
         sys.exit(0)
@@ -395,4 +571,5 @@ if __name__ == "__main__":
     gen_modules()
     gen_losses()
     gen_image_norm()
+    gen_backbones()
     print(sorted((f, os.path.getsize(os.path.join(OUT, f))) for f in os.listdir(OUT)))
