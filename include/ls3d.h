@@ -145,6 +145,12 @@ int ls3d_rulebook_scatter(const void* out_words, int32_t B, int32_t oD, int32_t 
  *   idx are GLOBAL voxel rows (reference: per-frame rows; subtract voxel_off[frame] to compare);
  *   dist2 = squared distances (reference three_nn returns sqrt of these).
  * ------------------------------------------------------------------------------------------------ */
+/* Reference-signature twin: any point sets, b batches of n unknown / m known points [b, n|m, 3]; dist2 [b, n, 3] squared
+ * distances, idx [b, n, 3] per-batch rows - exactly what three_nn_wrapper_fast(b, n, m, unknown, known, dist2, idx) fills
+ * (interpolate.cpp:17-30; sequential strict-'<' scan, slots never filled keep (inf, 0)).  The lattice version below is the
+ * fast path of the forward; this one is the drop-in for other callers of the pointnet2 extension. */
+int ls3d_three_nn(int32_t b, int32_t n, int32_t m, const float* unknown, const float* known, float* dist2, int32_t* idx,
+                  void* stream);
 int ls3d_three_nn_grid(const float* points, int32_t ld_p, int32_t n, const void* words, const int32_t* perm, int32_t B,
                        int32_t D, int32_t H, int32_t W, const float* voxel_size_xyz, const float* range_min_xyz,
                        const int32_t* point_off, const int32_t* voxel_off, const int32_t* voxel_coords, int32_t* todo,
@@ -184,6 +190,11 @@ int ls3d_token_attention(const float* q, int32_t ld_q, int32_t n, const float* k
 int ls3d_project_points(const float* points, int32_t ld_p, int32_t xyz_off, int32_t n, const double* cam_from_lidar,
                         const double* intrinsics, int32_t ncam, int32_t img_h, int32_t img_w, int32_t net_h, int32_t net_w,
                         float* points_cuv, void* stream);
+/* Same with the loader's two-stage chain lidar -> global -> camera (info["ref_to_global"] [4][4], then
+ * info["cams_from_global"][cam] [ncam][4][4]; loading.py:386-395), each stage rounded to fp64 like the numpy original. */
+int ls3d_project_points_global(const float* points, int32_t ld_p, int32_t xyz_off, int32_t n, const double* ref_to_global,
+                               const double* cams_from_global, const double* intrinsics, int32_t ncam, int32_t img_h,
+                               int32_t img_w, int32_t net_h, int32_t net_w, float* points_cuv, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera stem: multi-resolution branch fusion, out = act(bias + sum_k bilinear_resize(term_k)) on channels-last fp32 maps.
@@ -212,6 +223,19 @@ int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* term_h, const
  * ------------------------------------------------------------------------------------------------ */
 int ls3d_normalize_images_u8(const uint8_t* in, int64_t n_pixels, const float* mean3, const float* std3, void* out,
                              int32_t out_fp16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Camera input: cv2.resize (uint8, INTER_LINEAR, bit-exact with OpenCV's fixed-point algorithm) fused with the normalisation.
+ * replaces: cv2.resize in image_and_points_cp_and_label_resize (det3d/datasets/pipelines/img_transforms.py:78-99, called
+ *           per camera by SegImagePreprocess.__call__, segpreprocess.py:544-565) followed by image_input_transform
+ *           (img_transforms.py:18-29; segpreprocess.py:621-628) and the HWC -> CHW transpose (:637).
+ *   in  [n_img, in_h, in_w, 3] uint8 (raw decoded camera images, e.g. 900 x 1600)
+ *   out [n_img, out_h, out_w, 3]: out_kind 0 = normalised fp32, 1 = normalised fp16 (channels-last stem input),
+ *                                 2 = resized uint8 only (mean3 / std3 ignored, may be NULL)
+ *   mean3 / std3: HOST pointers to 3 floats.
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_resize_images_u8(const uint8_t* in, int32_t n_img, int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w,
+                          const float* mean3, const float* std3, void* out, int32_t out_kind, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera stem: fused 3x3 / stride 1 / pad 1 convolution + bias (+ residual) (+ ReLU) on channels-last fp16 maps,

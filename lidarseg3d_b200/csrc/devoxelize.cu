@@ -214,7 +214,58 @@ __global__ void three_interpolate_kernel(const float* __restrict__ feat, int ld_
   *reinterpret_cast<float4*>(out + (size_t)i * ld_out + c) = acc;
 }
 
+// Reference-signature 3-NN (any point sets, no lattice): the sequential strict-'<' scan of three_nn_kernel_fast with the
+// known points staged through shared memory in 256-point tiles (every thread of the block walks the same tile).
+__global__ void three_nn_tiled_kernel(int n, int m, const float* __restrict__ unknown, const float* __restrict__ known,
+                                      float* __restrict__ dist2_out, int* __restrict__ idx_out) {
+  __shared__ float sk[256 * 3];
+  const int b = blockIdx.y;
+  unknown += (size_t)b * n * 3;
+  known += (size_t)b * m * 3;
+  dist2_out += (size_t)b * n * 3;
+  idx_out += (size_t)b * n * 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const float ux = live ? unknown[(size_t)i * 3] : 0.f, uy = live ? unknown[(size_t)i * 3 + 1] : 0.f,
+              uz = live ? unknown[(size_t)i * 3 + 2] : 0.f;
+  // the reference initialises best = 1e40 (inf as float) and idx = 0 and inserts on strict '<' only
+  float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int k0 = 0; k0 < m; k0 += 256) {
+    const int cnt = min(256, m - k0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt * 3; t += blockDim.x) sk[t] = known[(size_t)k0 * 3 + t];
+    __syncthreads();
+    for (int k = 0; k < cnt; ++k) {
+      const float d = dist2(ux, uy, uz, sk[k * 3], sk[k * 3 + 1], sk[k * 3 + 2]);
+      if (d < b1) {
+        b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k0 + k;
+      } else if (d < b2) {
+        b3 = b2; i3 = i2; b2 = d; i2 = k0 + k;
+      } else if (d < b3) {
+        b3 = d; i3 = k0 + k;
+      }
+    }
+  }
+  if (live) {
+    dist2_out[(size_t)i * 3] = b1; dist2_out[(size_t)i * 3 + 1] = b2; dist2_out[(size_t)i * 3 + 2] = b3;
+    idx_out[(size_t)i * 3] = i1; idx_out[(size_t)i * 3 + 1] = i2; idx_out[(size_t)i * 3 + 2] = i3;
+  }
+}
+
 }  // namespace ls3d
+
+// drop-in for three_nn_wrapper_fast(b, n, m, unknown, known, dist2, idx) (pointnet2_api.cpp:10-24, interpolate.cpp:17-30)
+extern "C" int ls3d_three_nn(int32_t b, int32_t n, int32_t m, const float* unknown, const float* known, float* dist2,
+                             int32_t* idx, void* stream) {
+  using namespace ls3d;
+  if (b <= 0 || n <= 0) return LS3D_OK;
+  if (!unknown || !known || !dist2 || !idx || m < 0) return LS3D_ERR_ARG;
+  dim3 grid(ls3d_div_up(n, 256), b);
+  three_nn_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}
 
 extern "C" int ls3d_three_nn_grid(const float* points, int32_t ld_p, int32_t n, const void* words, const int32_t* perm,
                                   int32_t B, int32_t D, int32_t H, int32_t W, const float* voxel_size_xyz,

@@ -83,6 +83,7 @@ class SegMSeg3DNet(_SegBase):
     # parameters, their device / dtype or the train / eval mode can have changed (same events as common.Prepared)
     def _drop_image_graphs(self):
         self.__dict__.pop("_img_graphs", None)
+        self.__dict__.pop("_img_tensors", None)
 
     def _apply(self, fn, *a, **k):
         self._drop_image_graphs()
@@ -103,7 +104,11 @@ class SegMSeg3DNet(_SegBase):
 
     def _param_fingerprint(self):
         """Versions of every camera-branch parameter / buffer: in-place updates (optimizer steps, copy_) also invalidate."""
-        return tuple(t._version for m in (self.img_backbone, self.img_head) for t in list(m.parameters()) + list(m.buffers()))
+        ts = self.__dict__.get("_img_tensors")
+        if ts is None:
+            ts = self.__dict__["_img_tensors"] = [t for m in (self.img_backbone, self.img_head)
+                                                  for t in list(m.parameters()) + list(m.buffers())]
+        return tuple(t._version for t in ts)
 
     def _image_branch(self, images, batch_size):
         self.img_backbone.keep_channel_padding = True      # the image head consumes zero-padded channel maps directly

@@ -29,6 +29,7 @@ DEBUG_SKIP = 0      # development only (see ls3d_gemm_args.debug_skip)
 #   0 / False  : single-pass TF32 with tf32-rounded activations (~2e-3 relative error after the full network: fails the
 #                1e-3 logit gate, kept for comparison only)
 PRECISE = 2
+ENGINE_NAME = "gather_gemm_bf16x3_kernel"      # kernel behind PRECISE = 2 (bench.py's roofline label)
 
 
 def trunc_tf32(x: torch.Tensor) -> torch.Tensor:

@@ -163,6 +163,17 @@ def three_nn_grid(points, grid, voxel_size, range_min, point_off, voxel_off, vox
     return d2, idx
 
 
+def three_nn(unknown, known):
+    """Reference-signature 3-NN (three_nn_wrapper_fast): unknown [B, N, 3], known [B, M, 3] -> (dist2 [B, N, 3] squared,
+    idx [B, N, 3] int32 per-batch rows)."""
+    unknown, known = unknown.contiguous(), known.contiguous()
+    B, N, _ = unknown.shape
+    d2, idx = _f32(unknown.device, B, N, 3), _i32(unknown.device, B, N, 3)
+    check(capi.lib().ls3d_three_nn(B, N, known.shape[1], ptr(unknown), ptr(known), ptr(d2), ptr(idx), stream_ptr()),
+          "ls3d_three_nn")
+    return d2, idx
+
+
 def three_interpolate(feat, d2, idx, C=None, round_out=False):
     C = C or feat.shape[1]
     n = idx.shape[0]
@@ -186,18 +197,48 @@ def sample_image_features(feat_nhwc, points_cuv, point_off, round_out=False):
     return out
 
 
-def project_points(points, cam_from_lidar, intrinsics, img_hw, net_hw, xyz_off=0):
+def project_points(points, cam_from_lidar, intrinsics, img_hw, net_hw, xyz_off=0, ref_to_global=None):
     """points [N, >=3] fp32 cuda; cam_from_lidar [ncam,4,4], intrinsics [ncam,3,3] (host, float64).  Returns
-    points_cuv [N,4] = (valid, cam, v, u) with the reference's projection rules (loading.py:373-416)."""
+    points_cuv [N,4] = (valid, cam, v, u) with the reference's projection rules (loading.py:373-416).
+    ``ref_to_global`` [4,4]: the first argument then holds the loader's ``cams_from_global`` and the two-stage chain
+    lidar -> global -> camera is evaluated like the numpy original (loading.py:386-395)."""
     import numpy as np
     T = np.ascontiguousarray(np.asarray(cam_from_lidar, dtype=np.float64))
     K = np.ascontiguousarray(np.asarray(intrinsics, dtype=np.float64))
     n = points.shape[0]
     out = _f32(points.device, n, 4)
-    check(capi.lib().ls3d_project_points(ptr(points), points.stride(0), xyz_off, n, T.ctypes.data, K.ctypes.data, T.shape[0],
-                                         img_hw[0], img_hw[1], net_hw[0], net_hw[1], ptr(out), stream_ptr()),
-          "ls3d_project_points")
+    if ref_to_global is None:
+        check(capi.lib().ls3d_project_points(ptr(points), points.stride(0), xyz_off, n, T.ctypes.data, K.ctypes.data, T.shape[0],
+                                             img_hw[0], img_hw[1], net_hw[0], net_hw[1], ptr(out), stream_ptr()),
+              "ls3d_project_points")
+    else:
+        G = np.ascontiguousarray(np.asarray(ref_to_global, dtype=np.float64))
+        check(capi.lib().ls3d_project_points_global(ptr(points), points.stride(0), xyz_off, n, G.ctypes.data, T.ctypes.data,
+                                                    K.ctypes.data, T.shape[0], int(img_hw[0]), int(img_hw[1]), int(net_hw[0]),
+                                                    int(net_hw[1]), ptr(out), stream_ptr()), "ls3d_project_points_global")
     return out
+
+
+def resize_images_u8(images_u8, net_hw, mean=None, std=None, dtype=torch.float32):
+    """uint8 [..., H, W, 3] raw camera images -> cv2.resize(img, (net_w, net_h)) (bit-exact with OpenCV's uint8 INTER_LINEAR),
+    then, unless ``dtype`` is torch.uint8, (x / 255 - mean) / std as [..., 3, net_h, net_w] ``dtype`` maps in channels-last
+    memory (a permuted view, like normalize_images_u8).  Reference: img_transforms.py:78-99 + :18-29."""
+    assert images_u8.dtype == torch.uint8 and images_u8.shape[-1] == 3 and images_u8.is_contiguous()
+    H, W = images_u8.shape[-3], images_u8.shape[-2]
+    n_img = images_u8.numel() // (H * W * 3)
+    oh, ow = int(net_hw[0]), int(net_hw[1])
+    kind = {torch.float32: 0, torch.float16: 1, torch.uint8: 2}[dtype]
+    out = torch.empty(images_u8.shape[:-3] + (oh, ow, 3), dtype=dtype, device=images_u8.device)
+    m = sd = None
+    if kind != 2:
+        m = (ctypes.c_float * 3)(*[float(v) for v in np.asarray(mean, np.float32).reshape(-1)[:3]])
+        sd = (ctypes.c_float * 3)(*[float(v) for v in np.asarray(std, np.float32).reshape(-1)[:3]])
+    check(capi.lib().ls3d_resize_images_u8(ptr(images_u8), n_img, H, W, oh, ow, m, sd, ptr(out), kind, stream_ptr()),
+          "ls3d_resize_images_u8")
+    if kind == 2:
+        return out
+    nd = out.dim()
+    return out.permute(*range(nd - 3), nd - 1, nd - 3, nd - 2)
 
 
 def token_attention(q, k, v, frame_off, scale, round_out=False):

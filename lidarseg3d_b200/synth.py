@@ -1,9 +1,8 @@
 """Synthetic nuScenes- / SemanticKITTI- / Waymo-shaped inputs.
 
 There are no datasets in the build container or on the GPU box: scans come from a seeded ring-lidar scene model
-(ground plane + random vertical walls), cameras from a seeded pinhole rig; ``points_cuv`` follows the reference's
-CPU projection rules (det3d/datasets/pipelines/loading.py:373-416: depth > 0, 1-pixel margin, later cameras
-overwrite earlier ones; normalisation det3d/datasets/pipelines/segpreprocess.py:654-671).
+(ground plane + random vertical walls), cameras from a seeded pinhole rig + ego pose (``calibration``).  The projection
+itself is NOT here: the product projects on the GPU (csrc/project.cu) and the checker is oracle/camera.py.
 """
 import numpy as np
 
@@ -74,33 +73,18 @@ def camera_rig(spec):
     return rigs
 
 
-def project_points(points_xyz, spec):
-    """points_cp [N,3] = (cam_id starting at 1, u, v) with -100 where no camera sees the point
-    (loading.py:384-413), then points_cuv [N,4] = (valid, cam, v, u) normalised to [-1,1] on the resized image
-    (segpreprocess.py:544-565,654-671)."""
-    H, W = spec["img_hw"]
-    n = points_xyz.shape[0]
-    uv_all = np.ones([n, 3], dtype=np.float32) * -100
-    hom = np.concatenate([points_xyz.astype(np.float64), np.ones([n, 1])], 1).T
-    for cam_id, (T, K) in enumerate(camera_rig(spec)):
-        pc = (T @ hom)[:3]
-        with np.errstate(divide="ignore", invalid="ignore"):
-            uv = (K @ pc) / pc[2:3]
-        uv = uv.T
-        mask = (pc[2] > 0) & (uv[:, 0] > 1) & (uv[:, 0] < W - 1) & (uv[:, 1] > 1) & (uv[:, 1] < H - 1)
-        uv_all[mask, :2] = uv[mask, :2]
-        uv_all[mask, 2] = float(cam_id) + 1
-    cp = uv_all[:, [2, 0, 1]].copy()
-    nh, nw = spec["net_hw"]
-    cp[:, 1] *= nw / W
-    cp[:, 2] *= nh / H
-    cuv = np.zeros([n, 3], dtype=np.float32)
-    ncam = spec["ncam"]
-    cuv[:, 0] = (cp[:, 0] - 1) / (ncam - 1) * 2 - 1 if ncam > 1 else 0
-    cuv[:, 1] = cp[:, 2] / (nh - 1) * 2 - 1
-    cuv[:, 2] = cp[:, 1] / (nw - 1) * 2 - 1
-    valid = (cp[:, 0:1] > 0).astype(np.float32)
-    return np.concatenate([valid, cuv], 1).astype(np.float32)
+def calibration(spec, seed=0):
+    """The calibration record of one frame as the reference's info dict holds it (loading.py:386-388): ref_to_global [4,4]
+    (a seeded ego pose), cams_from_global [ncam,4,4], cam_intrinsics [ncam,3,3], plus the raw image size."""
+    rng = np.random.default_rng(seed + 104729)
+    a = rng.uniform(-np.pi, np.pi)
+    G = np.eye(4)
+    G[:3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    G[:3, 3] = [rng.uniform(-2000, 2000), rng.uniform(-2000, 2000), rng.uniform(-5, 5)]
+    Ginv = np.linalg.inv(G)
+    rig = camera_rig(spec)
+    return dict(ref_to_global=G, cams_from_global=np.stack([T @ Ginv for T, _ in rig]),
+                intrinsics=np.stack([K for _, K in rig]), img_hw=tuple(spec["img_hw"]))
 
 
 def camera_images(spec, seed, hw=None):

@@ -533,6 +533,79 @@ def gen_backbones():
                              tuple(v["out_logits"].shape)) for k, v in fx.items()})
 
 
+
+def gen_camera_inputs():
+    """Drive the reference's OWN LoadPointCloudFromFile (SemanticNuscDataset branch, loading.py:361-416) and
+    SegImagePreprocess (segpreprocess.py:388-676, val mode: cv2.resize + normalisation + points_cuv) on a synthetic frame
+    -> tests/golden/ref_camera_inputs.npz (pins oracle/camera.py; raw images are regenerated from their seed by the tests)."""
+    import hashlib
+    import tempfile
+    from lidarseg3d_b200 import synth
+    for k in [k for k in sys.modules if k.startswith("det3d")]:
+        del sys.modules[k]
+    install_stubs()
+    load_ref("det3d.utils.registry", "det3d/utils/registry.py")
+    Registry = sys.modules["det3d.utils.registry"].Registry
+    _mod("pycocotools")
+    _mod("pycocotools.mask")
+    if "turtle" not in sys.modules:          # loading.py:2 has a stray `from turtle import shape` (needs tkinter)
+        _mod("turtle", shape=None)
+    sys.modules["det3d.core"].box_np_ops = _mod("det3d.core.box_np_ops")
+    for pkg in ["det3d.datasets", "det3d.datasets.pipelines", "det3d.core.sampler", "det3d.core.input", "det3d.ops.point_cloud"]:
+        m = _mod(pkg)
+        m.__path__ = [os.path.join(REF, *pkg.split("."))]
+    _mod("det3d.datasets.registry", PIPELINES=Registry("pipeline"))
+    _mod("det3d.core.sampler.segpreprocess")
+    sys.modules["det3d.core.sampler"].segpreprocess = sys.modules["det3d.core.sampler.segpreprocess"]
+    load_ref("det3d.ops.point_cloud.point_cloud_ops", "det3d/ops/point_cloud/point_cloud_ops.py")
+    load_ref("det3d.core.input.voxel_generator", "det3d/core/input/voxel_generator.py")
+    load_ref("det3d.datasets.pipelines.img_transforms", "det3d/datasets/pipelines/img_transforms.py")
+    ld = load_ref("det3d.datasets.pipelines.loading", "det3d/datasets/pipelines/loading.py")
+    sp = load_ref("det3d.datasets.pipelines.segpreprocess", "det3d/datasets/pipelines/segpreprocess.py")
+
+    spec = dict(synth.NUSC)
+    spec.update(beams=16, azimuths=500)
+    pts = synth.lidar_scan(spec, 4242)
+    rig = synth.camera_rig(spec)
+    # a non-trivial ego pose so that the lidar -> global -> camera chain of the loader is exercised
+    a = 0.3
+    G = np.eye(4)
+    G[:3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    G[:3, 3] = [431.5, -1207.25, 3.5]
+    Ginv = np.linalg.inv(G)
+    chans = ["CAM_FRONT", "CAM_FRONT_RIGHT", "CAM_BACK_RIGHT", "CAM_BACK", "CAM_BACK_LEFT", "CAM_FRONT_LEFT"]
+    cams_from_global = {c: T @ Ginv for c, (T, K) in zip(chans, rig)}
+    intr = {c: K for c, (T, K) in zip(chans, rig)}
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "frame.bin")
+        pts.astype(np.float32).tofile(path)
+        loader = ld.LoadPointCloudFromFile(dataset="SemanticNuscDataset", use_img=True)
+        res = dict(lidar=dict(nsweeps=1), cam=dict(chan=chans), mode="val")
+        info = dict(lidar_path=path, cams_from_global=cams_from_global, cam_intrinsics=intr, ref_to_global=G)
+        res, info = loader(res, info)
+    points_cp = res["lidar"]["points_cp"].copy()
+    img_seed = 31
+    raw = synth.camera_images_u8(spec, img_seed, hw=spec["img_hw"])                       # [6, 900, 1600, 3] uint8
+    names = [str(i + 1) for i in range(len(chans))]
+    res["images"] = [raw[i] for i in range(len(chans))]
+    res["cam"].update(names=names, annotations=None, resized_shape=(spec["net_hw"][1], spec["net_hw"][0]),
+                      attributes={n: dict(mean=synth.IMG_MEAN, std=synth.IMG_STD) for n in names})
+    from lidarseg3d_b200.det3d.config import ConfigDict
+    pre = sp.SegImagePreprocess(cfg=ConfigDict(shuffle_points=False), save_img_for_tta=True)
+    res, info = pre(res, info)
+    resized = np.stack(res["images_for_tta"])                                              # [6, 640, 960, 3] uint8 (cv2.resize)
+    np.savez_compressed(
+        os.path.join(OUT, "ref_camera_inputs.npz"), points=pts, ref_to_global=G,
+        cams_from_global=np.stack([cams_from_global[c] for c in chans]), intrinsics=np.stack([intr[c] for c in chans]),
+        img_hw=np.array(spec["img_hw"]), net_hw=np.array(spec["net_hw"]), points_cp=points_cp,
+        points_cuv=res["lidar"]["points_cuv"].astype(np.float32), img_seed=img_seed,
+        resized_sha256=np.frombuffer(hashlib.sha256(resized.tobytes()).digest(), np.uint8),
+        resized_rows=resized[:, ::40].copy(), raw_sha256=np.frombuffer(hashlib.sha256(raw.tobytes()).digest(), np.uint8),
+        images_norm_rows=res["images"][:, :, ::80].astype(np.float32))
+    v = res["lidar"]["points_cuv"][:, 0]
+    print("camera_inputs: points", pts.shape, "valid", float(v.mean()), "resized", resized.shape)
+
+
 def gen_image_norm():
     """image_input_transform of the reference (det3d/datasets/pipelines/img_transforms.py:18-29; cv2 is only needed by
     other functions of that file and is stubbed when absent) on random uint8 images -> tests/golden/ref_image_norm.npz."""
@@ -561,6 +634,9 @@ if __name__ == "__main__":
     if "--image-norm-only" in sys.argv:
         gen_image_norm()
         sys.exit(0)
+    if "--camera-only" in sys.argv:
+        gen_camera_inputs()
+        sys.exit(0)
     if "--backbones-only" in sys.argv:
         gen_backbones()
         sys.exit(0)
@@ -572,4 +648,5 @@ if __name__ == "__main__":
     gen_losses()
     gen_image_norm()
     gen_backbones()
+    gen_camera_inputs()
     print(sorted((f, os.path.getsize(os.path.join(OUT, f))) for f in os.listdir(OUT)))

@@ -43,7 +43,11 @@ def _cpu_example(frames, spec, with_cam=False, img_hw=None, u8=False):
         s2 = dict(spec)
         if img_hw:
             s2["net_hw"] = img_hw
-        ex["points_cuv"] = torch.from_numpy(np.concatenate([synth.project_points(f[:, :3], s2) for f in frames]))
+        from oracle import camera as oc
+        cbs = [synth.calibration(s2, b) for b in range(B)]
+        ex["points_cuv"] = torch.from_numpy(np.concatenate([
+            oc.project_points(f[:, :3], cb["ref_to_global"], cb["cams_from_global"], cb["intrinsics"], cb["img_hw"], s2["net_hw"])
+            for f, cb in zip(frames, cbs)]))
         if u8:      # raw uint8 images; the oracle normalises them the reference's way (img_transforms.py:18-29) on the CPU
             ex["images_u8"] = torch.from_numpy(np.stack([synth.camera_images_u8(s2, b, s2["net_hw"]) for b in range(B)]))
             ex["images"] = torch.from_numpy(on.image_input_transform(ex["images_u8"].numpy(), synth.IMG_MEAN, synth.IMG_STD))
@@ -123,3 +127,32 @@ def test_mseg3d_forward_vs_oracle(cfg_name, spec_name, image_dtype, u8):
     assert rel(dbg["geo_fused"], ref["geo_fused"]) <= 2e-3
     _check_logits(bd["out_logits"].cpu(), ref["out_logits"], 1e-3, 0.999)
     assert len(preds) == 2
+
+
+@pytest.mark.parametrize("image_dtype", [torch.float32, torch.float16])
+def test_mseg3d_full_size_parity_one_frame(image_dtype):
+    """The BENCHMARKED configuration (32-beam ~30 k-point scan, 6 raw 900x1600 uint8 images resized to 640x960 on the
+    device, GPU projection) through bench.py's own parity block, one frame: the gate the bench line carries
+    (logits 1e-3 relative, >= 99.9 % argmax, bit-exact voxels)."""
+    import sys
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        import bench
+    finally:
+        sys.argv = argv
+    from lidarseg3d_b200 import synth
+    wl = bench.WORKLOADS["mseg3d_nuscenes"]
+    spec = synth.NUSC
+    cfg, model = bench.build_model(wl)
+    model = model.to(DEV)
+    batch = bench.make_batches(wl, spec, 1, 1, 0, n_image_sets=1)[0]
+    name = "fp32" if image_dtype == torch.float32 else "fp16cam"
+    parity, _, _ = bench.parity_block(wl, spec, cfg, model, batch, 1, lambda b, dt: bench.gpu_forward(wl, spec, model, b, dt, DEV),
+                                      [(name, image_dtype)])
+    m = parity["modes"][name]
+    assert m["coords_bit_exact"]
+    assert m["points_cuv_cam_valid_mismatches"] <= 2 and m["points_cuv_max_abs_diff"] <= 2e-6
+    if image_dtype == torch.float32:
+        assert m["resized_images_bit_exact"]
+    assert m["rel_err"] <= 1e-3 and m["argmax_agreement"] >= 0.999, m
+    assert parity["ok"]

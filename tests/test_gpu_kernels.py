@@ -147,13 +147,6 @@ def test_sparse_conv_vs_oracle_and_dense():
     dref = torch.nn.functional.conv3d(dense, w.double().permute(4, 3, 0, 1, 2), padding=1)
     dref = dref[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]]
     assert float((out.double() - dref).abs().max()) <= 2e-5 * float(dref.abs().max())
-    # single-pass TF32 mode (tf32-representable activations): 2e-3 of the output scale
-    gemm.PRECISE = False
-    try:
-        out1 = gemm.run(gemm.round_tf32(feats.to(DEV)), gemm.PackedWeight(w.reshape(27, C, Co).to(DEV)), nbr=nbr).cpu()
-    finally:
-        gemm.PRECISE = True
-    assert float((out1.double() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
 
 
 @pytest.mark.parametrize("m,cin,cout", [(3000, 64, 16), (3000, 32, 48), (3000, 40, 80), (70000, 96, 17), (130, 16, 32)])
@@ -220,25 +213,6 @@ def test_sample_image_features_vs_grid_sample():
     ref = on.sample_image_features(img, cuv[valid], bidx[valid])
     torch.testing.assert_close(out[valid], ref, rtol=1e-5, atol=1e-5)
     assert float(out[~valid].abs().max()) == 0.0
-
-
-@pytest.mark.parametrize("spec_name", ["NUSC", "WAYMO"])
-def test_project_points_vs_reference_rules(spec_name):
-    """GPU projection vs the numpy restatement of loading.py:373-416 + segpreprocess.py:654-671 (lidarseg3d_b200/synth.py)."""
-    ops, _ = _ops()
-    from lidarseg3d_b200 import synth
-    spec = getattr(synth, spec_name)
-    pts = synth.lidar_scan(synth.NUSC, 11)
-    ref = synth.project_points(pts[:, :3], spec)
-    rig = synth.camera_rig(spec)
-    out = ops.project_points(torch.from_numpy(pts).to(DEV), [t for t, _ in rig], [k for _, k in rig], spec["img_hw"],
-                             spec["net_hw"]).cpu().numpy()
-    # camera choice / validity are exact except for points within float rounding of the 1-pixel margin
-    same = (out[:, 0] == ref[:, 0]) & (out[:, 1] == ref[:, 1])
-    assert same.mean() > 0.9999
-    v = same & (ref[:, 0] == 1)
-    assert 0.3 < v.mean() < 1.0
-    np.testing.assert_allclose(out[v, 2:], ref[v, 2:], rtol=0, atol=2e-6)
 
 
 @pytest.mark.parametrize("C,sizes", [(20, [(32, 48), (16, 24), (8, 12), (4, 6)]), (48, [(30, 44), (15, 22)]), (36, [(16, 24), (16, 24), (8, 12)])])
