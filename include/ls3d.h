@@ -67,10 +67,26 @@ typedef struct ls3d_gemm_args {
   int32_t round_out;  /* 1: store outputs rounded to tf32 (cvt.rna); only useful with precise=0, where the  */
                       /* operands of the next GEMM are truncated to tf32 by the tensor core               */
   int32_t debug_skip; /* development only, must be 0: bit0 no A gathers, bit1 no W loads, bit2 no MMA, bit3 no epilogue */
-  int32_t precise;    /* 1: error-compensated 3xTF32 (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi), fp32-level accuracy */
+  int32_t precise;    /* 2 (default engine): error-compensated bf16x3 - operands split on chip into bf16 hi + lo,        */
+                      /*    x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, fp32 accumulate (~2^-17 per product, fp32-equivalent);    */
+                      /*    `w` = ls3d_gemm_pack_bf16x3 image.  1: 3xTF32, 0: single-pass TF32 (comparison engines)      */
+  /* Tile plan of the rulebook `nbr` (ls3d_tile_plan_build; NULL = gather per pair).  With a plan, sparse launches run    */
+  /* on the gather-once engine (csrc/gather_gemm_once.cu): distinct input rows of a tile staged once, all offsets served  */
+  /* from shared memory.  The plan is a pure function of `nbr` and is cached with it (spconv's indice_key cache).         */
+  const int32_t* plan_hdr;
+  const uint16_t* plan_local;
+  const int32_t* plan_pool;
 } ls3d_gemm_args;
 
 int ls3d_gather_gemm(const ls3d_gemm_args* args, void* stream);
+
+/* Tile plan of a rulebook table nbr[koff][m_out] (see ls3d_gemm_args.plan_*): per 128-row output tile the sorted list of
+ * distinct input rows (in `pool`), the uint16 position table local[tile][k][128] and a 32-int header {n_pass, per pass:
+ * offset mask, pool base, row count}.  Buffers are sized by ls3d_tile_plan_bytes and owned by the caller (16-byte aligned);
+ * pool_counter is one device int of scratch. */
+int ls3d_tile_plan_bytes(int32_t koff, int32_t m_out, int64_t* hdr_bytes, int64_t* local_bytes, int64_t* pool_bytes);
+int ls3d_tile_plan_build(const int32_t* nbr, int32_t koff, int32_t m_out, int32_t* hdr, void* local, int32_t* pool,
+                         int32_t* pool_counter, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Hard voxelization of a batch of frames (bit-exact with the reference's numba voxelizer).

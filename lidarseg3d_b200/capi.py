@@ -41,6 +41,7 @@ class GemmArgs(ctypes.Structure):
         ("attn_scale", c_float),
         ("row_mask", c_void_p), ("ld_mask", c_int),
         ("out", c_void_p), ("ld_out", c_int), ("round_out", c_int), ("debug_skip", c_int), ("precise", c_int),
+        ("plan_hdr", c_void_p), ("plan_local", c_void_p), ("plan_pool", c_void_p),
     ]
 
 
@@ -73,6 +74,8 @@ P, I, L = c_void_p, c_int, ctypes.c_int64
 PL = ctypes.POINTER(ctypes.c_int64)
 # name -> (argtypes, restype): one row per prototype of include/ls3d.h
 _SIGNATURES = {
+    "ls3d_tile_plan_bytes": ([I, I, PL, PL, PL], ctypes.c_int),
+    "ls3d_tile_plan_build": ([P, I, I, P, P, P, P, P], ctypes.c_int),
     "ls3d_voxelize_workspace_bytes": ([L, I, I, PL], ctypes.c_int),
     "ls3d_voxelize": ([P, I, I, P, I, P, P, I, I, P, L, P, P, P, P, P, P, P], ctypes.c_int),
     "ls3d_vfe_descriptor": ([P, P, I, I, I, I, P, I, I, P], ctypes.c_int),
@@ -131,7 +134,7 @@ def stream_ptr():
 
 # C-ABI calls since the last COUNTERS.clear(), and the (lower-bound) number of kernels each call launches
 COUNTERS = {}
-KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_voxelize": 8, "ls3d_vfe_descriptor": 1, "ls3d_vfe_token_attn": 1,
+KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_tile_plan_build": 1, "ls3d_voxelize": 8, "ls3d_vfe_descriptor": 1, "ls3d_vfe_token_attn": 1,
                     "ls3d_vfe_token_max": 1, "ls3d_grid_build": 4, "ls3d_grid_build_strided": 4, "ls3d_grid_enumerate": 1,
                     "ls3d_rulebook_gather": 1, "ls3d_rulebook_scatter": 1, "ls3d_three_nn_grid": 2, "ls3d_three_nn": 1,
                     "ls3d_three_interpolate": 1, "ls3d_sample_image_features": 1, "ls3d_project_points": 1, "ls3d_project_points_global": 1,

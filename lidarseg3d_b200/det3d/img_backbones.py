@@ -46,9 +46,15 @@ def _pad_to(c, dtype):
 def folded(conv, bn, x_channels, dtype):
     """BatchNorm folded into the conv (eval): weight [Cout_p, Cin_p, kh, kw] channels-last and bias [Cout_p], zero padded;
     cached on the conv module, refreshed when a parameter / statistic changes."""
-    key = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var) + (dtype, x_channels, PAD_CHANNELS)
-    cache = getattr(conv, "_ls3d_fold", None)
-    if cache is None or cache[0] != key:
+    # one entry per (dtype, channel padding): a captured CUDA graph of one camera-map mode keeps reading its own folded
+    # tensors while another mode runs (replacing a single shared entry freed memory a graph still pointed to)
+    ver = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    store = conv.__dict__.setdefault("_ls3d_fold", {})
+    if store.get("ver") != ver:
+        store.clear()
+        store["ver"] = ver
+    cache = store.get((dtype, x_channels, PAD_CHANNELS))
+    if cache is None:
         with torch.no_grad():
             scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
             w = conv.weight * scale.view(-1, 1, 1, 1)
@@ -64,8 +70,7 @@ def folded(conv, bn, x_channels, dtype):
                 w, b = wp, bp
             w = w.to(dtype).contiguous(memory_format=torch.channels_last)
             b = b.to(dtype).contiguous()
-        cache = (key, w, b)
-        conv._ls3d_fold = cache
+        cache = store[(dtype, x_channels, PAD_CHANNELS)] = (None, w, b)
     return cache[1], cache[2]
 
 
@@ -75,14 +80,18 @@ FUSED_CONV3X3 = True    # eval/CUDA/fp16: 3x3 and 1x1 stride-1 convs on the hand
 def folded_packed(conv, bn, x_channels):
     """BN-folded 3x3 / 1x1 weights packed for ls3d_conv_f16 (+ fp32 shift), cached like ``folded``; None when the weights do
     not fit the kernel's shared memory (the caller then uses cuDNN)."""
-    key = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var) + (x_channels, PAD_CHANNELS)
-    cache = getattr(conv, "_ls3d_fold3", None)
-    if cache is None or cache[0] != key:
+    ver = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    store = conv.__dict__.setdefault("_ls3d_fold3", {})
+    if store.get("ver") != ver:
+        store.clear()
+        store["ver"] = ver
+    cache = store.get((x_channels, PAD_CHANNELS))
+    if cache is None:
         from .. import ops
         k = conv.kernel_size[0]
         cout_p = _pad_to(conv.out_channels, torch.float16)
         if not ops.conv_f16_supported(x_channels, cout_p, k):
-            cache = (key, None, None, cout_p)
+            cache = (None, None, None, cout_p)
         else:
             with torch.no_grad():
                 scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
@@ -92,8 +101,8 @@ def folded_packed(conv, bn, x_channels):
                 wp[:conv.out_channels, :conv.in_channels] = w
                 bp = b.new_zeros(cout_p)
                 bp[:conv.out_channels] = b
-                cache = (key, ops.pack_conv_f16(wp), bp.contiguous(), cout_p)
-        conv._ls3d_fold3 = cache
+                cache = (None, ops.pack_conv_f16(wp), bp.contiguous(), cout_p)
+        store[(x_channels, PAD_CHANNELS)] = cache
     return cache[1], cache[2], cache[3]
 
 
@@ -311,11 +320,13 @@ def _forward_fused(self, x):
                         t, b = conv_deferred_bias(seq[0], seq[1], t)
                         shifts.append(b)
                 terms.append(t)
-        key = tuple((b.data_ptr(), b._version) for b in shifts)
-        ent = cache.get(i)
-        if ent is None or ent[0] != key:
+        key = (i,) + tuple((b.data_ptr(), b._version) for b in shifts)      # one entry per camera-map mode (see ``folded``)
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) > 32:
+                cache.clear()
             with torch.no_grad():
-                ent = cache[i] = (key, torch.stack([b.float() for b in shifts]).sum(0).contiguous() if shifts else None)
+                ent = cache[key] = (key, torch.stack([b.float() for b in shifts]).sum(0).contiguous() if shifts else None)
         outs.append(ops.upsample_sum(terms, relu=True, bias=ent[1]))
     return outs
 

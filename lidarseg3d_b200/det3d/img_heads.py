@@ -108,9 +108,12 @@ class FCNMSeg3DHead(nn.Module):
                                                      for x in xs):
                 # 1x1 per-branch convolutions on the own tensor-core kernel (packed weights cached per folded tensor)
                 ck = (w.data_ptr(), w._version, tuple(x.shape[1] for x in xs))
-                ent = self.__dict__.get("_ls3d_branch_packed")
-                if ent is None or ent[0] != ck:
-                    ent = self.__dict__["_ls3d_branch_packed"] = (ck, [ops.pack_conv_f16(wi.float()) for _, wi in terms])
+                store = self.__dict__.setdefault("_ls3d_branch_packed", {})     # one entry per folded weight (camera-map mode)
+                ent = store.get(ck)
+                if ent is None:
+                    if len(store) > 8:
+                        store.clear()
+                    ent = store[ck] = (ck, [ops.pack_conv_f16(wi.float()) for _, wi in terms])
                 ys = [ops.conv_f16(x.contiguous(memory_format=torch.channels_last), pk, None, relu=False, cout=w.shape[0], ksize=1)
                       if x.shape[0] * x.shape[2] * x.shape[3] >= OWN_1X1_MIN_PIXELS else F.conv2d(x, wi)
                       for (x, wi), pk in zip(terms, ent[1])]

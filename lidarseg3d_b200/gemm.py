@@ -1,7 +1,9 @@
 """Host side of the tcgen05 gather-GEMM (csrc/gather_gemm.cu): weight packing + launch helper."""
+import os
+
 import torch
 
-from . import capi
+from . import capi, ops as _ops
 
 
 def round_tf32(x: torch.Tensor) -> torch.Tensor:
@@ -29,7 +31,10 @@ DEBUG_SKIP = 0      # development only (see ls3d_gemm_args.debug_skip)
 #   0 / False  : single-pass TF32 with tf32-rounded activations (~2e-3 relative error after the full network: fails the
 #                1e-3 logit gate, kept for comparison only)
 PRECISE = 2
-ENGINE_NAME = "gather_gemm_bf16x3_kernel"      # kernel behind PRECISE = 2 (bench.py's roofline label)
+# Sparse launches (nbr given) of the bf16x3 engine run on the gather-once kernel (csrc/gather_gemm_once.cu) with the tile
+# plan of their rulebook; False = per-pair gather kernel (csrc/gather_gemm_bf16x3.cu), which also serves the dense Linears.
+USE_PLAN = os.environ.get("LS3D_USE_PLAN", "1") == "1"
+ENGINE_NAME = "gather_gemm_once_kernel" if USE_PLAN else "gather_gemm_bf16x3_kernel"      # bench.py's roofline label
 
 
 def trunc_tf32(x: torch.Tensor) -> torch.Tensor:
@@ -116,6 +121,10 @@ def run(x0, pw: PackedWeight, *, x1=None, nbr=None, m_out=None, scale=None, shif
         assert nbr.dtype == torch.int32 and nbr.is_contiguous() and nbr.shape[0] == pw.koff
         m = nbr.shape[1]
         a.nbr = capi.ptr(nbr)
+        if USE_PLAN and pw.precise == 2 and attn is None and m > 0:
+            plan = _ops.tile_plan(nbr)
+            assert plan.m_out == m and plan.koff == pw.koff
+            a.plan_hdr, a.plan_local, a.plan_pool = capi.ptr(plan.hdr), capi.ptr(plan.local), capi.ptr(plan.pool)
     else:
         m = x0.shape[0]
     if m_out is not None:

@@ -148,6 +148,33 @@ def rulebook_scatter(out_grid, in_coords, ksize, stride, pad):
     return nbr
 
 
+class TilePlan:
+    """Gather-once plan of a rulebook table (ls3d_tile_plan_build; csrc/gather_gemm_once.cu)."""
+
+    def __init__(self, nbr):
+        K, m = nbr.shape
+        hb, lb, pb = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(capi.lib().ls3d_tile_plan_bytes(K, m, ctypes.byref(hb), ctypes.byref(lb), ctypes.byref(pb)), "ls3d_tile_plan_bytes")
+        dev = nbr.device
+        self.hdr = torch.empty(hb.value // 4, dtype=torch.int32, device=dev)
+        self.local = torch.empty(lb.value // 2, dtype=torch.int16, device=dev)
+        self.pool = torch.empty(pb.value // 4, dtype=torch.int32, device=dev)
+        self.counter = torch.empty(1, dtype=torch.int32, device=dev)
+        self.koff, self.m_out = K, m
+        check(capi.lib().ls3d_tile_plan_build(ptr(nbr), K, m, ptr(self.hdr), ptr(self.local), ptr(self.pool), ptr(self.counter),
+                                              stream_ptr()), "ls3d_tile_plan_build")
+
+
+def tile_plan(nbr):
+    """The plan of ``nbr`` [K, m] int32, built once and cached on the tensor (a rulebook is reused by 6-9 convolutions)."""
+    plan = getattr(nbr, "_ls3d_plan", None)
+    if plan is None:
+        assert nbr.dtype == torch.int32 and nbr.is_contiguous()
+        plan = TilePlan(nbr)
+        nbr._ls3d_plan = plan
+    return plan
+
+
 # ------------------------------------------------------------------------------------------ devoxelize
 def three_nn_grid(points, grid, voxel_size, range_min, point_off, voxel_off, voxel_coords):
     """Exact 3-NN of points [N, >=4] (b,x,y,z) among the voxel centres of ``grid`` (level 1).

@@ -230,3 +230,83 @@ def test_argument_validation():
     ok = torch.randn(n, 32, device=DEV)                                   # red_c = 32 != cout = 24
     with pytest.raises(RuntimeError):
         gemm.run(x, w, red=(ok, ok))
+
+
+def _plan_views(plan, K, m):
+    T = (m + 127) // 128
+    hdr = plan.hdr.cpu().numpy()[:T * 32].reshape(T, 32)
+    local = plan.local.cpu().numpy().view(np.uint16)[:T * K * 128].reshape(T, K, 128)
+    return hdr, local, plan.pool.cpu().numpy()
+
+
+def test_tile_plan_bit_exact_vs_oracle_single_pass():
+    """LiDAR-like rulebook: every tile fits one pass, and the device plan equals oracle/sparse.py::tile_plan bit for bit
+    (ascending distinct rows per tile, uint16 local positions)."""
+    ops, _ = _mods()
+    B, shape = 2, (21, 64, 64)
+    idx = _clustered_sites(4, B, shape, 7000)
+    coords = torch.from_numpy(idx).to(DEV)
+    grid = ops.grid_from_coords(coords, B, shape, need_perm=True)
+    nbr = ops.rulebook_gather(grid, coords, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+    plan = ops.TilePlan(nbr)
+    K, m = nbr.shape
+    hdr, local, pool = _plan_views(plan, K, m)
+    ref = osp.tile_plan(nbr.cpu().numpy())
+    assert (hdr[:, 0] == 1).all()
+    for t in range(hdr.shape[0]):
+        kmask, base, cnt = hdr[t, 1], hdr[t, 2], hdr[t, 3]
+        rows = ref["stage_rows"][ref["stage_off"][t]:ref["stage_off"][t + 1]]
+        assert cnt == rows.size and np.array_equal(pool[base:base + cnt], rows), t
+        assert np.array_equal(local[t], ref["local"][t]), t
+        active = [k for k in range(K) if (ref["local"][t, k] != 0xFFFF).any()]
+        assert kmask == sum(1 << k for k in active) or (not active and kmask == 1)
+
+
+def test_tile_plan_multi_pass_is_a_partition():
+    """A dense random table (each tile touches > 512 distinct rows) must be cut into passes over disjoint offset ranges, each
+    staging <= 512 sorted distinct rows through which every pair of its offsets is addressable."""
+    ops, _ = _mods()
+    g = torch.Generator().manual_seed(8)
+    K, m, rows_in = 27, 1000, 50000
+    nbr = _random_table(g, K, m, rows_in, 0.6)
+    nbr[5] = -1                                          # an empty offset belongs to no pass
+    plan = ops.TilePlan(nbr.to(DEV))
+    hdr, local, pool = _plan_views(plan, K, m)
+    nb = nbr.numpy()
+    multi = 0
+    for t in range(hdr.shape[0]):
+        n_pass = hdr[t, 0]
+        assert 1 <= n_pass <= 8
+        multi += n_pass > 1
+        seen = 0
+        r0, r1 = t * 128, min(m, t * 128 + 128)
+        for p in range(n_pass):
+            kmask, base, cnt = int(hdr[t, 1 + 3 * p]), int(hdr[t, 2 + 3 * p]), int(hdr[t, 3 + 3 * p])
+            assert cnt <= 512 and (kmask & seen) == 0 and base % 4 == 0
+            seen |= kmask
+            rows = pool[base:base + cnt]
+            assert (np.diff(rows) > 0).all()
+            for k in range(K):
+                if not (kmask >> k) & 1:
+                    continue
+                e = nb[k, r0:r1]
+                l = local[t, k, :r1 - r0].astype(np.int64)
+                assert ((l == 0xFFFF) == (e < 0)).all()
+                ok = e >= 0
+                assert (l[ok] < cnt).all() and np.array_equal(rows[l[ok]], e[ok])
+            assert (local[t, :, r1 - r0:] == 0xFFFF).all()
+        want = sum(1 << k for k in range(K) if (nb[k, r0:r1] >= 0).any())
+        assert seen == want
+    assert multi > 0
+
+
+def test_multi_pass_convolution():
+    """The convolution kernel over a plan with several passes per tile (dense random table) and 2 K chunks."""
+    _, gemm = _mods()
+    g = torch.Generator().manual_seed(12)
+    rows_in, m_out, cin, cout = 40000, 900, 64, 64
+    x = torch.randn(rows_in, cin, generator=g)
+    w = torch.randn(27, cin, cout, generator=g) / (27 * cin) ** 0.5
+    nbr = _random_table(g, 27, m_out, rows_in, 0.7)
+    out = gemm.run(x.to(DEV), gemm.PackedWeight(w.to(DEV)), nbr=nbr.to(DEV))
+    _close(out, _ref_from_table(x, w, nbr))
