@@ -228,6 +228,11 @@ int ls3d_upsample_sum(const float* const* terms, const int32_t* term_h, const in
 /* same on fp16 maps (fp32 arithmetic); C a multiple of 8 */
 int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
                           int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, void* out, void* stream);
+int ls3d_upsample_sum_dual(const float* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
+                           int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, float* out,
+                           void* out16, void* stream);   /* fp32 result + its fp16 operand copy in one pass */
+/* fp16 (round-to-nearest-even) copy of n fp32 values, n a multiple of 4: the tensor-core operand copy of an fp32 map */
+int ls3d_cast_f16(const float* in, void* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera input preparation: uint8 [n_pixels][3] (HWC images, any batch of them back to back) -> (x / 255 - mean[c]) / std[c]
@@ -277,6 +282,24 @@ int ls3d_conv_f16_packed_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t
 int ls3d_conv_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream);
 int ls3d_conv_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img, int32_t H,
                   int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream);
+/* fp32 feature maps with fp16 tensor-core operands ("fp32 residual stream"): in16 = fp16 operand copy of the input map,
+ * res32 (may be NULL) / out32 = fp32 maps, out16 = fp16 operand copy of the result for the next convolution.  The
+ * multiplications see the 11-bit significand a TF32 tensor-core convolution (the reference's stock cuDNN path) sees;
+ * accumulation, bias, residual, ReLU and the stored maps are fp32.
+ *   out32 == NULL: operand-only result (only out16 is written, res32 must be NULL): a map that only feeds the next convolution
+ *                  (conv1 of a BasicBlock).
+ *   w_split != 0 : w_packed holds SPLIT weights [W_hi ; W_lo] (ls3d_conv_f16_pack_split: fp16(w) and fp16(w - fp16(w)) stacked
+ *                  along N, one MMA per K slice over 2 n_pad columns, the epilogue adds the halves): the fp32 weights enter
+ *                  exactly (2^-22), so the only rounding left is the RNE fp16 operand copy of the activations - an unbiased,
+ *                  spatially incoherent error (measured on the CPU oracle, scripts/sim_operand_rounding.py: 3.4e-5 on the
+ *                  logits against 3.6e-4 when the weights are rounded too).  Needs 2 n_pad <= 256 and twice the resident weight
+ *                  bytes (ls3d_conv_f16_split_supported). */
+int ls3d_conv_f16_dual(const void* in16, const void* w_packed, const float* bias, const float* res32, float* out32, void* out16,
+                       int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu,
+                       int32_t w_split, void* stream);
+int ls3d_conv_f16_dual_smem_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes);
+int ls3d_conv_f16_split_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t dual, int32_t* supported);
+int ls3d_conv_f16_pack_split(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SF-Phase: class embedding aggregation and class-token memory path.

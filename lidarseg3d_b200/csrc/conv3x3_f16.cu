@@ -43,6 +43,10 @@ struct Args {
   const __half* w;        // packed weights, see pack kernel
   const float* bias;      // [cout] fp32 or NULL
   int has_res;
+  int dual;               // 1: fp32 residual / output maps + an fp16 operand copy of the output (see ls3d_conv_f16_dual)
+  int nb;                 // rows of the B operand = accumulator columns per tile: n_pad, or 2 n_pad with split weights
+                          // ([W_hi ; W_lo] stacked along N: exact fp32 weights at the cost of a wider MMA, the epilogue adds
+                          // the two halves)
   int n_img, H, W, cin, cout, kcg, kc, n_mma, n_pad, relu, tiles_x, tiles_y, n_tiles, nbuf;
   float inv_tiles_x, inv_tiles_per_img;
   // per MMA: low word of the A descriptor less the stage base = (offset of the lower K entry >> 4) | (LBO >> 4) << 16.
@@ -142,11 +146,12 @@ __device__ __forceinline__ TileXY tile_coords(int tile, const Args& p) {
 
 __global__ void __launch_bounds__(N_THREADS, 1)
     conv3x3_f16_kernel(const Args p, const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_res,
-                       const __grid_constant__ CUtensorMap map_out) {
+                       const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t w_bytes = (uint32_t)p.n_mma * 2u * p.n_pad * 16u;
+  const uint32_t w_bytes = (uint32_t)p.n_mma * 2u * p.nb * 16u;
   const uint32_t halo_bytes = (uint32_t)p.kc * CH_STRIDE;
-  const uint32_t io_bytes = 128u * p.cout * 2u;
+  const uint32_t io32_bytes = p.dual ? 128u * p.cout * 4u : 0u;      // dual: fp32 residual / output tile, then the fp16 copy
+  const uint32_t io_bytes = io32_bytes + 128u * p.cout * 2u;
   const uint32_t stage_bytes = halo_bytes + io_bytes;                 // both multiples of 128
   uint8_t* stage_s = smem;                                             // [nbuf][halo | io tile]
   uint8_t* w_s = stage_s + (size_t)p.nbuf * stage_bytes;
@@ -159,7 +164,8 @@ __global__ void __launch_bounds__(N_THREADS, 1)
   const uint32_t empty_bar0 = smem_u32(bars + MAX_BUF);        // stage free    [nbuf] (tcgen05.commit + store drained)
   const uint32_t accf_bar0 = smem_u32(bars + 2 * MAX_BUF);     // accumulator full  [nacc <= 4]
   const uint32_t acce_bar0 = smem_u32(bars + 2 * MAX_BUF + 4); // accumulator empty [nacc <= 4]
-  const int nacc = p.n_pad <= 128 ? 4 : 2;                     // accumulators in tensor memory (nacc * n_pad <= 512 columns)
+  const int nacc = p.nb <= 128 ? 4 : 2;                        // accumulators in tensor memory (nacc * nb <= 512 columns)
+  const uint32_t lo_col = p.nb > p.n_pad ? (uint32_t)p.n_pad : 0u;   // split weights: column offset of the W_lo partial sums
 
   // ---- one-time staging: weights (resident), bias, the all-zero K chunk of every halo buffer
   {
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     }
   }
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(nacc * p.n_pad)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(nacc * p.nb)) tmem_cols <<= 1;
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < MAX_BUF; ++s) {
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
       }
       for (int b = 0; b < 4; ++b) {
         mbar_init(accf_bar0 + 8 * b, 1);
-        mbar_init(acce_bar0 + 8 * b, 128);
+        mbar_init(acce_bar0 + 8 * b, 4);             // one arrival per epilogue warp of the team
       }
       fence_mbar_init();
     }
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     prefetch_map(&map_in);
     prefetch_map(&map_res);
     prefetch_map(&map_out);
+    if (p.dual) prefetch_map(&map_out16);
   }
   fence_proxy_async_smem();          // the staged weights / zero chunk are read by the tensor core (async proxy)
   tc_fence_before();
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
   if (warp == PROD_WARP) {
     // =========================== producer (tensor-map copies) ===========================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)p.kcg * (HPIX * 16u) + (p.has_res ? io_bytes : 0u);
+      const uint32_t tx_bytes = (uint32_t)p.kcg * (HPIX * 16u) + (p.has_res ? (p.dual ? io32_bytes : io_bytes) : 0u);
       int b = 0;
       uint32_t ph = 1;                                       // parity of the "previous" phase: passes on a fresh barrier
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -225,12 +232,12 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = make_idesc_f16((uint32_t)p.n_pad);
+    const uint32_t idesc = make_idesc_f16((uint32_t)p.nb);
     const uint32_t tbase = bcast0(tmem_base);
     const uint32_t a_hi = ((HALO_W * 16u) >> 4) | (1u << 14);       // SBO (8-row group pitch) | descriptor version
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
-    const uint32_t b_lo0 = (smem_u32(w_s) >> 4) | ((((uint32_t)p.n_pad * 16u) >> 4) << 16);
-    const uint32_t b_step = 2u * (uint32_t)p.n_pad;                 // one MMA's weights: [2][n_pad][16 B]
+    const uint32_t b_lo0 = (smem_u32(w_s) >> 4) | ((((uint32_t)p.nb * 16u) >> 4) << 16);
+    const uint32_t b_step = 2u * (uint32_t)p.nb;                    // one MMA's weights: [2][nb][16 B]
     int b = 0, it = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
       mbar_wait(full_bar0 + 8 * b, ph);
       mbar_wait(acce_bar0 + 8 * ab, ((uint32_t)(it / nacc) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t tacc = tbase + (uint32_t)(ab * p.n_pad);
+      const uint32_t tacc = tbase + (uint32_t)(ab * p.nb);
       // all operands warp-uniform: kernel parameters, loop counters, lane-0 broadcasts (start-address field: no carry out
       // of its 14 bits)
       const uint32_t a_base = (stage0 + (uint32_t)b * stage_bytes) >> 4;
@@ -272,14 +279,61 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     for (int tile = blockIdx.x + team * gridDim.x; tile < p.n_tiles; tile += 2 * gridDim.x, it += 2) {
       uint8_t* io = stage_s + (size_t)b * stage_bytes + halo_bytes + (size_t)m * p.cout * 2;
       const int ab = it & (nacc - 1);
-      const uint32_t trow = tmem_base + (uint32_t)(ab * p.n_pad) + ((uint32_t)(q * 32) << 16);
+      const uint32_t trow = tmem_base + (uint32_t)(ab * p.nb) + ((uint32_t)(q * 32) << 16);
       if (p.has_res) mbar_wait(full_bar0 + 8 * b, ph);
       mbar_wait(accf_bar0 + 8 * ab, (uint32_t)(it / nacc) & 1u);
       tc_fence_after();
+      if (p.dual) {
+        // fp32 residual stream: acc + bias + residual (fp32, read from the stage) -> ReLU -> fp32 in place + fp16 operand copy
+        float* io32 = reinterpret_cast<float*>(stage_s + (size_t)b * stage_bytes + halo_bytes) + (size_t)m * p.cout;
+        __half* io16 = reinterpret_cast<__half*>(stage_s + (size_t)b * stage_bytes + halo_bytes + io32_bytes) + (size_t)m * p.cout;
+        for (int g = 0; g < n_groups; ++g) {
+          const int c0 = g * 16;
+          uint32_t raw[16], raw2[16];
+          tmem_ld16(trow + c0, raw);
+          if (lo_col) tmem_ld16(trow + lo_col + c0, raw2);
+          float4 rr[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            rr[q4] = (p.has_res && c0 + 4 * q4 < p.cout) ? *reinterpret_cast<const float4*>(io32 + c0 + 4 * q4)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          tmem_ld_wait();
+          if (lo_col) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(__uint_as_float(raw[e]) + __uint_as_float(raw2[e]));
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            if (c0 + 8 * g8 >= p.cout) continue;
+            float v[8];
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8 + 4 * q4);
+              const float4 r4 = rr[2 * g8 + q4];
+              v[4 * q4 + 0] = __uint_as_float(raw[8 * g8 + 4 * q4 + 0]) + bb.x + r4.x;
+              v[4 * q4 + 1] = __uint_as_float(raw[8 * g8 + 4 * q4 + 1]) + bb.y + r4.y;
+              v[4 * q4 + 2] = __uint_as_float(raw[8 * g8 + 4 * q4 + 2]) + bb.z + r4.z;
+              v[4 * q4 + 3] = __uint_as_float(raw[8 * g8 + 4 * q4 + 3]) + bb.w + r4.w;
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            *reinterpret_cast<float4*>(io32 + c0 + 8 * g8) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(io32 + c0 + 8 * g8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            uint4 o;
+            __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            *reinterpret_cast<uint4*>(io16 + c0 + 8 * g8) = o;
+          }
+        }
+      } else
       for (int g = 0; g < n_groups; ++g) {
         const int c0 = g * 16;
-        uint32_t raw[16];
+        uint32_t raw[16], raw2[16];
         tmem_ld16(trow + c0, raw);
+        if (lo_col) tmem_ld16(trow + lo_col + c0, raw2);
         uint4 rz[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
         if (p.has_res) {
 #pragma unroll
@@ -287,6 +341,10 @@ __global__ void __launch_bounds__(N_THREADS, 1)
             if (c0 + 8 * g8 < p.cout) rz[g8] = *reinterpret_cast<const uint4*>(io + (c0 + 8 * g8) * 2);
         }
         tmem_ld_wait();
+        if (lo_col) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(__uint_as_float(raw[e]) + __uint_as_float(raw2[e]));
+        }
 #pragma unroll
         for (int g8 = 0; g8 < 2; ++g8) {
           if (c0 + 8 * g8 >= p.cout) continue;
@@ -311,12 +369,15 @@ __global__ void __launch_bounds__(N_THREADS, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(acce_bar0 + 8 * ab);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar0 + 8 * ab);
       fence_proxy_async_smem();                   // this thread's output row -> visible to the bulk store (async proxy)
       bar_sync_team(team);
       if (leader) {
         const TileXY t = tile_coords(tile, p);
         tma_store_4d(&map_out, stage0 + (uint32_t)b * stage_bytes + halo_bytes, 0, t.tx * TW, t.ty * TH, t.img);
+        if (p.dual)
+          tma_store_4d(&map_out16, stage0 + (uint32_t)b * stage_bytes + halo_bytes + io32_bytes, 0, t.tx * TW, t.ty * TH, t.img);
         bulk_commit();
         if (deep) {
           if (!first) {
@@ -344,11 +405,14 @@ __global__ void __launch_bounds__(N_THREADS, 1)
 }
 
 // BatchNorm-folded fp32 weights [cout_p][cin_p][k][k] (k*k = ntap) -> fp16 [n_mma][2][n_pad][8] in the kernel's K-list order
-__global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int kcg, int ntap, int n_mma, int n_pad,
+// split: [n_mma][2][2 n_pad][8], rows [0, n_pad) = fp16(w), rows [n_pad, 2 n_pad) = fp16(w - fp16(w)) (w_hi + w_lo = w to 2^-22)
+__global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int kcg, int ntap, int n_mma, int n_pad, int split,
                             __half* __restrict__ out) {
-  const int total = n_mma * 2 * n_pad * 8;
+  const int nb = split ? 2 * n_pad : n_pad;
+  const int total = n_mma * 2 * nb * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i & 7, n = (i >> 3) % n_pad, slot = ((i >> 3) / n_pad) & 1, j = (i >> 3) / n_pad / 2;
+    const int e = i & 7, row = (i >> 3) % nb, slot = ((i >> 3) / nb) & 1, j = (i >> 3) / nb / 2;
+    const int n = row < n_pad ? row : row - n_pad;
     int e0, e1;
     mma_entries(j, kcg, ntap, e0, e1);
     const int c = slot ? e1 : e0;
@@ -357,6 +421,7 @@ __global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int 
       const int tap = c / kcg, ch = (c - tap * kcg) * 8 + e;
       if (ch < cin) v = w[((size_t)n * cin + ch) * ntap + tap];
     }
+    if (row >= n_pad) v = v - __half2float(__float2half_rn(v));
     out[i] = __float2half_rn(v);
   }
 }
@@ -372,10 +437,12 @@ static Geom geom(int cin, int cout, int ntap) {
   g.n_pad = (cout + 15) / 16 * 16;
   return g;
 }
-static size_t smem_for(const Geom& g, int cout, int nbuf) {
-  return (size_t)nbuf * ((size_t)g.kc * CH_STRIDE + 128 * (size_t)cout * 2) + (size_t)g.n_mma * 2 * g.n_pad * 16 +
-         (size_t)g.n_pad * 4 + (2 * MAX_BUF + 8) * 8 + 16 + 128;
+static size_t smem_for(const Geom& g, int cout, int nbuf, int dual = 0, int split = 0) {
+  return (size_t)nbuf * ((size_t)g.kc * CH_STRIDE + 128 * (size_t)cout * (dual ? 6 : 2)) +
+         (size_t)g.n_mma * 2 * g.n_pad * (split ? 2 : 1) * 16 + (size_t)g.n_pad * 4 + (2 * MAX_BUF + 8) * 8 + 16 + 128;
 }
+// split weights need 2 n_pad <= 256 accumulator columns per tile and twice the resident weight bytes
+static bool split_ok(const Geom& g, int cout, int dual) { return 2 * g.n_pad <= 256 && smem_for(g, cout, 2, dual, 1) <= 227 * 1024; }
 
 // ---- tensor maps (driver entry point fetched through the runtime: no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -393,14 +460,14 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 // [n_img, H, W, C] fp16 channels-last viewed as the 4-D tensor (C, W, H, n_img) with a (bc, bw, bh, 1) box
-static int make_map(CUtensorMap* m, const void* base, int C, int W, int H, int n_img, int bc, int bw, int bh) {
+static int make_map(CUtensorMap* m, const void* base, int C, int W, int H, int n_img, int bc, int bw, int bh, int es_bytes = 2) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return LS3D_ERR_ARG;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
-  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * es_bytes, (cuuint64_t)W * C * es_bytes, (cuuint64_t)H * W * C * es_bytes};
   const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   const cuuint32_t es[4] = {1, 1, 1, 1};
-  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+  const CUresult r = fn(m, es_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? LS3D_OK : 1000 + (int)r;
@@ -426,31 +493,49 @@ extern "C" int ls3d_conv_f16_packed_bytes(int32_t cin, int32_t cout, int32_t ksi
   return LS3D_OK;
 }
 
-extern "C" int ls3d_conv_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream) {
+static int pack_launch(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, int split, void* packed, void* stream) {
   using namespace ls3d::c3;
   if (!w_oihw || !packed || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
   const Geom g = geom(cin, cout, ntap_of(ksize));
-  const int total = g.n_mma * 2 * g.n_pad * 8;
+  if (split && 2 * g.n_pad > 256) return LS3D_ERR_ARG;
+  const int total = g.n_mma * 2 * g.n_pad * (split ? 2 : 1) * 8;
   pack_kernel<<<ls3d_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, cout, cin, g.kcg, ntap_of(ksize), g.n_mma,
-                                                                        g.n_pad, (__half*)packed);
+                                                                        g.n_pad, split, (__half*)packed);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
 
-extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img,
-                             int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream) {
+extern "C" int ls3d_conv_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream) {
+  return pack_launch(w_oihw, cin, cout, ksize, 0, packed, stream);
+}
+
+// split weights [W_hi ; W_lo] (twice ls3d_conv_f16_packed_bytes); *supported = 0 when the shape has no split configuration
+extern "C" int ls3d_conv_f16_split_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t dual, int32_t* supported) {
+  using namespace ls3d::c3;
+  if (!supported || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  *supported = split_ok(geom(cin, cout, ntap_of(ksize)), cout, dual) ? 1 : 0;
+  return LS3D_OK;
+}
+extern "C" int ls3d_conv_f16_pack_split(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream) {
+  return pack_launch(w_oihw, cin, cout, ksize, 1, packed, stream);
+}
+
+static int conv_launch(const void* in, const void* w_packed, const float* bias, const void* res, void* out, void* out16, int dual,
+                       int split, int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream) {
   using namespace ls3d;
   using namespace ls3d::c3;
   if (n_img <= 0 || H <= 0 || W <= 0) return LS3D_OK;
   if (!in || !w_packed || !out || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  if (dual && !out16) return LS3D_ERR_ARG;
   const int ntap = ntap_of(ksize);
-  if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)res) | ((uintptr_t)w_packed)) & 15) return LS3D_ERR_ARG;
+  if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)res) | ((uintptr_t)w_packed) | ((uintptr_t)out16)) & 15) return LS3D_ERR_ARG;
   const Geom g = geom(cin, cout, ntap);
   Args a;
-  a.w = (const __half*)w_packed; a.bias = bias; a.has_res = res != nullptr;
+  a.w = (const __half*)w_packed; a.bias = bias; a.has_res = res != nullptr; a.dual = dual;
   a.n_img = n_img; a.H = H; a.W = W; a.cin = cin; a.cout = cout; a.relu = relu;
   a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad;
-  if (a.n_pad > 256 || g.n_mma > MAX_MMA) return LS3D_ERR_ARG;
+  a.nb = split ? 2 * g.n_pad : g.n_pad;
+  if (a.nb > 256 || g.n_mma > MAX_MMA) return LS3D_ERR_ARG;
   for (int j = 0; j < g.n_mma; ++j) {
     int e0, e1;
     mma_entries(j, g.kcg, ntap, e0, e1);
@@ -465,23 +550,52 @@ extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* 
   a.inv_tiles_x = 1.0f / (float)a.tiles_x;
   a.inv_tiles_per_img = 1.0f / (float)(a.tiles_x * a.tiles_y);
   a.nbuf = MAX_BUF;
-  while (a.nbuf > 2 && smem_for(g, cout, a.nbuf) > 227 * 1024) --a.nbuf;
-  const size_t smem = smem_for(g, cout, a.nbuf);
+  while (a.nbuf > 2 && smem_for(g, cout, a.nbuf, dual, split) > 227 * 1024) --a.nbuf;
+  const size_t smem = smem_for(g, cout, a.nbuf, dual, split);
   if (smem > 227 * 1024) return LS3D_ERR_ARG;           // weights do not fit in shared memory: caller uses the library conv
   const int num_sms = ls3d_num_sms();
   static bool optin[64] = {false};
   cudaError_t eo = ls3d_optin_smem(conv3x3_f16_kernel, optin);
   if (eo != cudaSuccess) return (int)eo;
-  CUtensorMap m_in, m_res, m_out;
+  CUtensorMap m_in, m_res, m_out, m_out16;
+  const int es = dual ? 4 : 2;
   int rc = make_map(&m_in, in, cin, W, H, n_img, 8, HALO_W, HALO_H);
   if (rc) return rc;
-  rc = make_map(&m_out, out, cout, W, H, n_img, cout, TW, TH);
+  rc = make_map(&m_out, out, cout, W, H, n_img, cout, TW, TH, es);
   if (rc) return rc;
-  rc = make_map(&m_res, res ? res : out, cout, W, H, n_img, cout, TW, TH);
+  rc = make_map(&m_res, res ? res : out, cout, W, H, n_img, cout, TW, TH, es);
+  if (rc) return rc;
+  rc = make_map(&m_out16, dual ? out16 : out, cout, W, H, n_img, cout, TW, TH, 2);
   if (rc) return rc;
   const int grid = a.n_tiles < num_sms ? a.n_tiles : num_sms;
-  conv3x3_f16_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(a, m_in, m_res, m_out);
+  conv3x3_f16_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(a, m_in, m_res, m_out, m_out16);
   LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}
+
+extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img,
+                             int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream) {
+  return conv_launch(in, w_packed, bias, res, out, nullptr, 0, 0, n_img, H, W, cin, cout, ksize, relu, stream);
+}
+
+// fp32 feature maps with fp16 tensor-core operands: `in` is the fp16 operand copy of the input map, `res` / `out` are fp32
+// maps (the residual stream never leaves fp32), `out16` receives the fp16 operand copy of the result for the next convolution.
+// out32 == NULL: operand-only result (out16 alone is written; res32 must be NULL) - a map that only feeds the next convolution.
+// w_split: w_packed comes from ls3d_conv_f16_pack_split (exact fp32 weights as fp16 hi + lo).
+extern "C" int ls3d_conv_f16_dual(const void* in16, const void* w_packed, const float* bias, const float* res32, float* out32,
+                                  void* out16, int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize,
+                                  int32_t relu, int32_t w_split, void* stream) {
+  if (!out32) {
+    if (res32 || !out16) return LS3D_ERR_ARG;
+    return conv_launch(in16, w_packed, bias, nullptr, out16, nullptr, 0, w_split ? 1 : 0, n_img, H, W, cin, cout, ksize, relu, stream);
+  }
+  return conv_launch(in16, w_packed, bias, res32, out32, out16, 1, w_split ? 1 : 0, n_img, H, W, cin, cout, ksize, relu, stream);
+}
+
+extern "C" int ls3d_conv_f16_dual_smem_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes) {
+  using namespace ls3d::c3;
+  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  *bytes = (int64_t)smem_for(geom(cin, cout, ntap_of(ksize)), cout, 2, 1);
   return LS3D_OK;
 }
 

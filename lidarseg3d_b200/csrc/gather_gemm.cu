@@ -316,6 +316,7 @@ static size_t smem_bytes_for(int stages, int n_pad, int koff, int nsplit) {
 
 int ls3d_gather_gemm_bf16x3_launch(const ls3d_gemm_args* a, int num_sms, void* stream);   // gather_gemm_bf16x3.cu
 int ls3d_gather_gemm_once_launch(const ls3d_gemm_args* a, int num_sms, void* stream);     // gather_gemm_once.cu
+int ls3d_gather_gemm_once_fits(const ls3d_gemm_args* a);
 
 extern "C" int ls3d_gather_gemm(const ls3d_gemm_args* a, void* stream) {
   using namespace ls3d;
@@ -337,7 +338,7 @@ extern "C" int ls3d_gather_gemm(const ls3d_gemm_args* a, void* stream) {
     return LS3D_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int num_sms = ls3d_num_sms();
-  if (a->precise == 2 && a->nbr && a->plan_hdr) return ls3d_gather_gemm_once_launch(a, num_sms, stream);
+  if (a->precise == 2 && a->nbr && a->plan_hdr && ls3d_gather_gemm_once_fits(a)) return ls3d_gather_gemm_once_launch(a, num_sms, stream);
   if (a->precise == 2) return ls3d_gather_gemm_bf16x3_launch(a, num_sms, stream);
   const int ntiles = ls3d_div_up(a->m_out, TILE_M);
   const int grid = ntiles < num_sms ? ntiles : num_sms;          // persistent: one CTA per SM

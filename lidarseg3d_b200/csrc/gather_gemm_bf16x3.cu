@@ -105,14 +105,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_bf16x3_kernel(const 
     if (lane == 0) {
       for (int s = 0; s < MAXR; ++s) {
         mbar_init(land_bar0 + 8 * s, 32);
-        mbar_init(rawe_bar0 + 8 * s, 128);
-        mbar_init(afull_bar0 + 8 * s, 128);
+        mbar_init(rawe_bar0 + 8 * s, 4);             // one arrival per splitter warp: 128 per-thread arrivals on one
+        mbar_init(afull_bar0 + 8 * s, 4);            // shared-memory word serialise (~250 cycles per barrier and step)
         mbar_init(aempty_bar0 + 8 * s, 1);
         mbar_init(wfull_bar0 + 8 * s, 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(accf_bar0 + 8 * b, 1);
-        mbar_init(acce_bar0 + 8 * b, 128);
+        mbar_init(acce_bar0 + 8 * b, 4);
         mbar_init(nbre_bar0 + 8 * b, 4);
         mbar_init(nbrl_bar0 + 8 * b, 1);
       }
@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_bf16x3_kernel(const 
           lo[2 * cch] = pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xFFFF0000u));
           lo[2 * cch + 1] = pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xFFFF0000u));
         }
-        mbar_arrive(rawe_bar0 + 8 * rr.idx);            // the raw stage may be refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rawe_bar0 + 8 * rr.idx);   // the raw stage may be refilled
         PROF_ADD(0);
         PROF_T0;
         mbar_wait(aempty_bar0 + 8 * tr.idx, tr.ph ^ 1u);
@@ -238,7 +239,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_bf16x3_kernel(const 
         tmem_st_wait();
         PROF_ADD(3);
         tc_fence_before();
-        mbar_arrive(afull_bar0 + 8 * tr.idx);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(afull_bar0 + 8 * tr.idx);
       }
     }
 #ifdef LS3D_PROF
@@ -407,7 +409,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_bf16x3_kernel(const 
       const uint32_t trow = tmem_base + (uint32_t)(buf * cfg.acc_stride) + ((uint32_t)(q * 32) << 16);
       if (!(p.debug_skip & 8)) epilogue_tile(p, trow, tile * TILE_M, et, colv, stg, cfg.stack ? (uint32_t)p.n_pad : 0u);
       tc_fence_before();
-      mbar_arrive(acce_bar0 + 8 * buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar0 + 8 * buf);
     }
 #ifdef LS3D_PROF
     pacc_[1] = clock64() - pstart_;

@@ -25,6 +25,8 @@
 //   warps 4-11  splitters : two groups of four (thread = tile row = TMEM lane), alternate steps: stage -> TMEM A slot
 //   warps 12-15 epilogue  : gemm_epilogue.cuh
 //   warp  16    MMA issuer, warp 17 W loader (one elected thread each), warp 18 plan loader (one tile ahead)
+#include <cstdlib>
+
 #include "gemm_epilogue.cuh"
 #include "scan.cuh"
 
@@ -46,6 +48,23 @@ constexpr int N_THREADS = 19 * 32;
 constexpr int MAXR = 8;
 constexpr int A_SLOT_COLS = 32;
 
+// Development instrumentation (nvcc -DLS3D_PROF): event timeline of CTA 0 - (role, event, counter, clock64) records.
+#ifdef LS3D_PROF
+constexpr int TRACE_CAP = 2048;
+__device__ unsigned long long g_trace[8 * TRACE_CAP];
+__device__ unsigned int g_trace_n[8];
+#define TRACE(role, ev, idx)                                                                                    \
+  do {                                                                                                          \
+    if (blockIdx.x == 0 && trc_ < TRACE_CAP) {                                                                  \
+      g_trace[(role) * TRACE_CAP + trc_] = ((unsigned long long)(ev) << 56) | ((unsigned long long)((idx) & 0xFFFF) << 40) | \
+                                           ((unsigned long long)clock64() & 0xFFFFFFFFFFull);                   \
+      g_trace_n[role] = ++trc_;                                                                                 \
+    }                                                                                                           \
+  } while (0)
+#else
+#define TRACE(role, ev, idx)
+#endif
+
 struct Ring {
   int n, idx;
   uint32_t ph;
@@ -60,6 +79,7 @@ struct Ring {
 
 struct Cfg {
   int ts;               // steps in flight (TMEM A slot + W smem stage each)
+  int grp;              // offsets per step (A slot = grp x 32 TMEM columns, W stage = grp chunks)
   int a_col0;           // first TMEM column of the A slots
   int stack;            // W chunk = [W_hi ; W_lo] stacked along N
   int acc_stride;       // TMEM columns per accumulator buffer
@@ -218,8 +238,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
   const uint32_t w_bytes = (uint32_t)p.n_pad * 128u;
   const uint32_t local_bytes = (uint32_t)p.koff * TILE_M * 2u;
   uint8_t* stage_s = smem;                                          // [2][S_CAP][128]
-  uint8_t* w_s = stage_s + 2 * STAGE_BYTES;                         // [ts][w_bytes]
-  uint16_t* local_s = (uint16_t*)(w_s + cfg.ts * w_bytes);          // [2][koff][128]
+  uint8_t* w_s = stage_s + 2 * STAGE_BYTES;                         // [ts][grp][w_bytes]
+  uint16_t* local_s = (uint16_t*)(w_s + cfg.ts * cfg.grp * w_bytes); // [2][koff][128]
   int* hdr_s = (int*)((uint8_t*)local_s + 2 * local_bytes);         // [2][HDR_INTS]
   uint64_t* bars = (uint64_t*)(hdr_s + 2 * HDR_INTS);
   uint32_t* tmem_slot = (uint32_t*)(bars + 4 * MAXR + 16);
@@ -229,13 +249,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+#ifdef LS3D_PROF
+  unsigned int trc_ = 0;                        // per-thread record counter (each role is traced by one thread)
+#endif
   const int cin = p.c0 + p.c1;
   const int nchunk = (p.cin_pad + KCH - 1) / KCH;
   const int ntiles = (p.m_out + TILE_M - 1) / TILE_M;
 
-  const uint32_t afull_bar0 = smem_u32(bars);                    // bf16 A slot written      [ts]  (128 splitters)
+  const uint32_t full_bar0 = smem_u32(bars);                     // step operands ready [ts]: 4 splitter warps (A slot written) +
+                                                                 // the W loader's arrive.expect_tx (W chunks landed)
   const uint32_t aempty_bar0 = smem_u32(bars + MAXR);            // A slot + W stage consumed [ts] (tcgen05.commit)
-  const uint32_t wfull_bar0 = smem_u32(bars + 2 * MAXR);         // W chunk landed           [ts]  (expect_tx)
   const uint32_t accf_bar0 = smem_u32(bars + 3 * MAXR);          // accumulator full  [2]
   const uint32_t acce_bar0 = smem_u32(bars + 3 * MAXR + 2);      // accumulator empty [2]
   const uint32_t sfull_bar0 = smem_u32(bars + 3 * MAXR + 4);     // stage buffer filled   [2] (4 stager warps)
@@ -247,13 +270,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < MAXR; ++s) {
-        mbar_init(afull_bar0 + 8 * s, 128);
+        mbar_init(full_bar0 + 8 * s, 5);
         mbar_init(aempty_bar0 + 8 * s, 1);
-        mbar_init(wfull_bar0 + 8 * s, 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(accf_bar0 + 8 * b, 1);
-        mbar_init(acce_bar0 + 8 * b, 128);
+        mbar_init(acce_bar0 + 8 * b, 4);
         mbar_init(sfull_bar0 + 8 * b, 4);
         mbar_init(sempty_bar0 + 8 * b, 8);
         mbar_init(pfull_bar0 + 8 * b, 1);
@@ -269,6 +291,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_a0 = tmem_base + (uint32_t)cfg.a_col0;
+  if (tid == N_THREADS - 1) TRACE(7, 0, 0);
 
   if (warp < SPLIT_WARP0) {
     // =========================== stagers ===========================
@@ -283,6 +306,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const int pb = ti & 1;
       mbar_wait(pfull_bar0 + 8 * pb, (uint32_t)(ti >> 1) & 1u);
+      if (tid == 0) TRACE(0, 0, ti);
       const int* h = hdr_s + pb * HDR_INTS;
       const int n_pass = h[0];
       for (int ps = 0; ps < n_pass; ++ps) {
@@ -294,6 +318,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
         for (int c = 0; c < nchunk; ++c, ++sg) {
           const int sb = sg & 1;
           mbar_wait(sempty_bar0 + 8 * sb, ((sg >> 1) & 1u) ^ 1u);
+          if (tid == 0) TRACE(0, 1, sg);
           uint8_t* st = stage_s + sb * STAGE_BYTES;
           const int col = c * KCH + q * 8;             // first of this thread's 8 channels
           // the 8 channels never straddle in0 | in1 (c0 is a multiple of 4, handled per 16-byte half below)
@@ -308,7 +333,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
               for (int hf = 0; hf < 2; ++hf) {
                 const int cc = col + hf * 4;
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (id >= 0 && cc < cin) {
+                if (id >= 0 && cc < cin && !(p.debug_skip & 1)) {
                   const char* src = (cc < p.c0) ? base0 + (size_t)id * ldb0 + (size_t)cc * 4
                                                 : base1 + (size_t)id * ldb1 + (size_t)(cc - p.c0) * 4;
                   t = __ldg(reinterpret_cast<const float4*>(src));
@@ -336,6 +361,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(sfull_bar0 + 8 * sb);
+          if (tid == 0) TRACE(0, 2, sg);
         }
       }
       __syncwarp();
@@ -343,9 +369,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
     }
   } else if (warp < EPI_WARP0) {
     // =========================== splitters ===========================
+    // A STEP = up to cfg.grp active offsets of one (pass, chunk): one handshake (slot wait, full arrival, commit) per step
+    // instead of per offset - the issue / synchronisation cost of a step (~550 cycles, measured with the CTA-0 timeline)
+    // is what bounded the one-offset-per-step version, not the tensor pipe or the shared-memory copies.
     const int grp = (warp - SPLIT_WARP0) >> 2;         // steps with (g & 1) == grp
     const int row = ((warp & 3) << 5) | lane;          // tile row == TMEM lane
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t slot_cols = (uint32_t)(cfg.grp * A_SLOT_COLS);
     Ring tr(cfg.ts);
     int g = 0, ti = 0;
     uint32_t sg = 0;
@@ -360,34 +390,46 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
         for (int c = 0; c < nchunk; ++c, ++sg) {
           const int sb = sg & 1;
           mbar_wait(sfull_bar0 + 8 * sb, (sg >> 1) & 1u);
+          if (lane == 0 && (warp & 3) == 0) TRACE(1 + grp, 0, sg);
           const uint8_t* st = stage_s + sb * STAGE_BYTES;
-          for (int k = 0; k < p.koff; ++k) {
-            if (!((kmask >> k) & 1u)) continue;
+          uint32_t km = kmask;
+          while (km) {
             if ((g & 1) == grp) {
-              const uint32_t s = loc[k * TILE_M];
-              uint32_t hi[16], lo[16];
-              if (s != NONE16) {
-                const uint8_t* rowp = st + s * 128;
-                const uint32_t x = s & 7u;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const uint4 a = *reinterpret_cast<const uint4*>(rowp + ((u ^ x) << 4));
-                  const uint4 b = *reinterpret_cast<const uint4*>(rowp + (((4 + u) ^ x) << 4));
-                  hi[4 * u] = a.x; hi[4 * u + 1] = a.y; hi[4 * u + 2] = a.z; hi[4 * u + 3] = a.w;
-                  lo[4 * u] = b.x; lo[4 * u + 1] = b.y; lo[4 * u + 2] = b.z; lo[4 * u + 3] = b.w;
-                }
-              } else {
-#pragma unroll
-                for (int u = 0; u < 16; ++u) hi[u] = lo[u] = 0u;
-              }
+              if (lane == 0 && (warp & 3) == 0) TRACE(1 + grp, 1, g);
               mbar_wait(aempty_bar0 + 8 * tr.idx, tr.ph ^ 1u);
+              if (lane == 0 && (warp & 3) == 0) TRACE(1 + grp, 2, g);
               tc_fence_after();
-              const uint32_t ta = tmem_a0 + lane_addr + (uint32_t)(tr.idx * A_SLOT_COLS);
-              tmem_st16(ta, hi);
-              tmem_st16(ta + 16, lo);
+              uint32_t ta = tmem_a0 + lane_addr + (uint32_t)tr.idx * slot_cols;
+              for (int j = 0; j < cfg.grp && km; ++j, ta += A_SLOT_COLS) {
+                const int k = __ffs(km) - 1;
+                km &= km - 1;
+                if (p.debug_skip & 2) continue;
+                const uint32_t s = loc[k * TILE_M];
+                uint32_t hi[16], lo[16];
+                if (s != NONE16) {
+                  const uint8_t* rowp = st + s * 128;
+                  const uint32_t x = s & 7u;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(rowp + ((u ^ x) << 4));
+                    const uint4 b = *reinterpret_cast<const uint4*>(rowp + (((4 + u) ^ x) << 4));
+                    hi[4 * u] = a.x; hi[4 * u + 1] = a.y; hi[4 * u + 2] = a.z; hi[4 * u + 3] = a.w;
+                    lo[4 * u] = b.x; lo[4 * u + 1] = b.y; lo[4 * u + 2] = b.z; lo[4 * u + 3] = b.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int u = 0; u < 16; ++u) hi[u] = lo[u] = 0u;
+                }
+                tmem_st16(ta, hi);
+                tmem_st16(ta + 16, lo);
+              }
               tmem_st_wait();
               tc_fence_before();
-              mbar_arrive(afull_bar0 + 8 * tr.idx);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(full_bar0 + 8 * tr.idx);
+              if (lane == 0 && (warp & 3) == 0) TRACE(1 + grp, 3, g);
+            } else {
+              for (int j = 0; j < cfg.grp && km; ++j) km &= km - 1;
             }
             ++g;
             tr.next();
@@ -406,6 +448,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
     const uint32_t tbase = bcast0(tmem_base);
     const uint32_t ta0 = tbase + (uint32_t)cfg.a_col0;
     const uint32_t ws0 = smem_u32(w_s);
+    const uint32_t slot_cols = (uint32_t)(cfg.grp * A_SLOT_COLS);
+    const uint32_t wstage_bytes = (uint32_t)cfg.grp * w_bytes;
     Ring tr(cfg.ts);
     int ti = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
@@ -416,43 +460,54 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
       const int n_pass = (int)bcast0((uint32_t)h[0]);
       const uint32_t acc_use = cfg.n_acc == 2 ? (uint32_t)(ti >> 1) : (uint32_t)ti;
       mbar_wait(acce_bar0 + 8 * buf, (acc_use & 1u) ^ 1u);     // epilogue drained this accumulator
+      if (lane == 0) TRACE(3, 3, ti);
       tc_fence_after();
       const uint32_t tacc = tbase + (uint32_t)(buf * cfg.acc_stride);
       int nst = 0;
-      for (int ps = 0; ps < n_pass; ++ps) nst += __popc(bcast0((uint32_t)h[1 + 3 * ps])) * nchunk;
+      for (int ps = 0; ps < n_pass; ++ps)
+        nst += ((__popc(bcast0((uint32_t)h[1 + 3 * ps])) + cfg.grp - 1) / cfg.grp) * nchunk;
       int st = 0;
       for (int ps = 0; ps < n_pass; ++ps) {
         const uint32_t kmask = bcast0((uint32_t)h[1 + 3 * ps]);
         for (int c = 0; c < nchunk; ++c) {
           const int nsl = min(KCH, p.cin_pad - c * KCH) / 16;
-          for (int k = 0; k < p.koff; ++k) {
-            if (!((kmask >> k) & 1u)) continue;
-            mbar_wait(afull_bar0 + 8 * tr.idx, tr.ph);
-            mbar_wait(wfull_bar0 + 8 * tr.idx, tr.ph);
+          uint32_t km = kmask;
+          while (km) {
+            int cnt = 0;
+            for (; cnt < cfg.grp && km; ++cnt) km &= km - 1;
+            mbar_wait(full_bar0 + 8 * tr.idx, tr.ph);
+            if (lane == 0) TRACE(3, 0, st);
             tc_fence_after();
-            const uint64_t bdesc = cfg.stack ? make_desc_k_sw64(ws0 + (uint32_t)tr.idx * w_bytes)
-                                             : make_desc_k_sw128(ws0 + (uint32_t)tr.idx * w_bytes);
-            const uint32_t a_hi = ta0 + (uint32_t)(tr.idx * A_SLOT_COLS);
-            const uint32_t a_lo = a_hi + 16;
+            const uint32_t wst = ws0 + (uint32_t)tr.idx * wstage_bytes;
+            const uint32_t a_slot = ta0 + (uint32_t)tr.idx * slot_cols;
             if (elect_one()) {
-              if (cfg.stack) {
-                for (int j = 0; j < nsl; ++j) {
-                  const uint64_t o = (uint64_t)(2 * j);
-                  umma_bf16_ts(tacc, a_hi + 8 * j, bdesc + o, idesc2, (st > 0 || j > 0) ? 1u : 0u);
-                  umma_bf16_ts(tacc, a_lo + 8 * j, bdesc + o, idesc, 1u);
-                }
-              } else {
-                for (int j = 0; j < nsl; ++j) {
-                  const uint64_t o = (uint64_t)(2 * j);
-                  umma_bf16_ts(tacc, a_hi + 8 * j, bdesc + o, idesc, (st > 0 || j > 0) ? 1u : 0u);
-                  umma_bf16_ts(tacc, a_hi + 8 * j, bdesc + 4 + o, idesc, 1u);
-                  umma_bf16_ts(tacc, a_lo + 8 * j, bdesc + o, idesc, 1u);
+              if (!(p.debug_skip & 4)) {
+                for (int m = 0; m < cnt; ++m) {
+                  const uint64_t bdesc = cfg.stack ? make_desc_k_sw64(wst + (uint32_t)m * w_bytes)
+                                                   : make_desc_k_sw128(wst + (uint32_t)m * w_bytes);
+                  const uint32_t a_hi = a_slot + (uint32_t)(m * A_SLOT_COLS);
+                  const uint32_t a_lo = a_hi + 16;
+                  if (cfg.stack) {
+                    for (int j = 0; j < nsl; ++j) {
+                      const uint64_t o = (uint64_t)(2 * j);
+                      umma_bf16_ts(tacc, a_hi + 8 * j, bdesc + o, idesc2, (st > 0 || m > 0 || j > 0) ? 1u : 0u);
+                      umma_bf16_ts(tacc, a_lo + 8 * j, bdesc + o, idesc, 1u);
+                    }
+                  } else {
+                    for (int j = 0; j < nsl; ++j) {
+                      const uint64_t o = (uint64_t)(2 * j);
+                      umma_bf16_ts(tacc, a_hi + 8 * j, bdesc + o, idesc, (st > 0 || m > 0 || j > 0) ? 1u : 0u);
+                      umma_bf16_ts(tacc, a_hi + 8 * j, bdesc + 4 + o, idesc, 1u);
+                      umma_bf16_ts(tacc, a_lo + 8 * j, bdesc + o, idesc, 1u);
+                    }
+                  }
                 }
               }
               umma_commit(aempty_bar0 + 8 * tr.idx);
               if (st == nst - 1) umma_commit(accf_bar0 + 8 * buf);
             }
             __syncwarp();
+            if (lane == 0) TRACE(3, 2, st);
             ++st;
             tr.next();
           }
@@ -463,26 +518,38 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
     }
   } else if (warp == W_WARP) {
     // =========================== W loader ===========================
+    // lane m of the warp issues the copy of the step's m-th offset (bulk-copy issue costs ~500 cycles per thread)
     Ring wr(cfg.ts);
     int ti = 0;
     const uint8_t* wg = reinterpret_cast<const uint8_t*>(p.w);
+    const uint32_t wstage_bytes = (uint32_t)cfg.grp * w_bytes;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const int pb = ti & 1;
       mbar_wait(pfull_bar0 + 8 * pb, (uint32_t)(ti >> 1) & 1u);
-      if (lane == 0) {
-        const int* h = hdr_s + pb * HDR_INTS;
-        const int n_pass = h[0];
-        for (int ps = 0; ps < n_pass; ++ps) {
-          const uint32_t kmask = (uint32_t)h[1 + 3 * ps];
-          for (int c = 0; c < nchunk; ++c)
-            for (int k = 0; k < p.koff; ++k) {
-              if (!((kmask >> k) & 1u)) continue;
-              mbar_wait(aempty_bar0 + 8 * wr.idx, wr.ph ^ 1u);
-              mbar_arrive_expect_tx(wfull_bar0 + 8 * wr.idx, w_bytes);
-              bulk_g2s(smem_u32(w_s + wr.idx * w_bytes), wg + ((size_t)k * nchunk + c) * w_bytes, w_bytes,
-                       wfull_bar0 + 8 * wr.idx);
-              wr.next();
+      const int* h = hdr_s + pb * HDR_INTS;
+      const int n_pass = (int)bcast0((uint32_t)h[0]);
+      for (int ps = 0; ps < n_pass; ++ps) {
+        const uint32_t kmask = bcast0((uint32_t)h[1 + 3 * ps]);
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t km = kmask;
+          while (km) {
+            int cnt = 0, myk = -1;
+            for (; cnt < cfg.grp && km; ++cnt) {
+              if (cnt == lane) myk = __ffs(km) - 1;
+              km &= km - 1;
             }
+            mbar_wait(aempty_bar0 + 8 * wr.idx, wr.ph ^ 1u);
+            if (lane == 0) {
+              TRACE(4, 0, cnt);
+              if (p.debug_skip & 16) mbar_arrive(full_bar0 + 8 * wr.idx);
+              else mbar_arrive_expect_tx(full_bar0 + 8 * wr.idx, (uint32_t)cnt * w_bytes);
+            }
+            __syncwarp();
+            if (myk >= 0 && !(p.debug_skip & 16))
+              bulk_g2s(smem_u32(w_s) + (uint32_t)wr.idx * wstage_bytes + (uint32_t)lane * w_bytes,
+                       wg + ((size_t)myk * nchunk + c) * w_bytes, w_bytes, full_bar0 + 8 * wr.idx);
+            wr.next();
+          }
         }
       }
       __syncwarp();
@@ -496,6 +563,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
       const int pb = ti & 1;
       mbar_wait(pempty_bar0 + 8 * pb, ((uint32_t)(ti >> 1) & 1u) ^ 1u);
       if (lane == 0) {
+        TRACE(5, 0, ti);
         mbar_arrive_expect_tx(pfull_bar0 + 8 * pb, local_bytes + HDR_INTS * 4u);
         bulk_g2s(smem_u32(hdr_s + pb * HDR_INTS), p.plan_hdr + (size_t)tile * HDR_INTS, HDR_INTS * 4u, pfull_bar0 + 8 * pb);
         bulk_g2s(smem_u32((uint8_t*)local_s + pb * local_bytes), p.plan_local + (size_t)tile * p.koff * TILE_M, local_bytes,
@@ -522,22 +590,26 @@ __global__ void __launch_bounds__(N_THREADS, 1) gather_gemm_once_kernel(const ls
       const int buf = cfg.n_acc == 2 ? (ti & 1) : 0;
       const uint32_t acc_use = cfg.n_acc == 2 ? (uint32_t)(ti >> 1) : (uint32_t)ti;
       mbar_wait(accf_bar0 + 8 * buf, acc_use & 1u);
+      if (et == 0) TRACE(6, 0, ti);
       tc_fence_after();
       const uint32_t trow = tmem_base + (uint32_t)(buf * cfg.acc_stride) + ((uint32_t)(q * 32) << 16);
-      epilogue_tile(p, trow, tile * TILE_M, et, colv, stg, cfg.stack ? (uint32_t)p.n_pad : 0u);
+      if (!(p.debug_skip & 8)) epilogue_tile(p, trow, tile * TILE_M, et, colv, stg, cfg.stack ? (uint32_t)p.n_pad : 0u);
       tc_fence_before();
-      mbar_arrive(acce_bar0 + 8 * buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar0 + 8 * buf);
+      if (et == 0) TRACE(6, 1, ti);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (tid == N_THREADS - 1) TRACE(7, 1, 0);
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-static size_t smem_bytes_for(int ts, int n_pad, int koff) {
+static size_t smem_bytes_for(int ts, int grp, int n_pad, int koff) {
   size_t b = 1024;  // alignment slack
-  b += (size_t)2 * STAGE_BYTES + (size_t)ts * n_pad * 128;
+  b += (size_t)2 * STAGE_BYTES + (size_t)ts * grp * n_pad * 128;
   b += (size_t)2 * koff * TILE_M * 2 + 2 * HDR_INTS * 4;
   b += (4 * MAXR + 16) * 8 + 16 + 32;
   b += (size_t)(6 * COLV + TILE_M * STG_LD) * 4;
@@ -546,6 +618,19 @@ static size_t smem_bytes_for(int ts, int n_pad, int koff) {
 
 }  // namespace once
 }  // namespace ls3d
+
+#ifdef LS3D_PROF
+// development: reset / read the CTA-0 event trace (8 roles x TRACE_CAP records, then the 8 counts)
+extern "C" int ls3d_debug_once_trace_reset() {
+  unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  return (int)cudaMemcpyToSymbol(ls3d::once::g_trace_n, z, sizeof(z));
+}
+extern "C" int ls3d_debug_once_trace(unsigned long long* host_out, unsigned int* counts) {
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, ls3d::once::g_trace, sizeof(unsigned long long) * 8 * ls3d::once::TRACE_CAP);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemcpyFromSymbol(counts, ls3d::once::g_trace_n, sizeof(unsigned int) * 8);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------------------------ C ABI
 extern "C" int ls3d_tile_plan_bytes(int32_t koff, int32_t m_out, int64_t* hdr_bytes, int64_t* local_bytes, int64_t* pool_bytes) {
@@ -572,6 +657,14 @@ extern "C" int ls3d_tile_plan_build(const int32_t* nbr, int32_t koff, int32_t m_
   return LS3D_OK;
 }
 
+// does the gather-once kernel have a shared-memory configuration for this launch?  (n_pad 256 with 27 offsets does not:
+// ls3d_gather_gemm then runs the per-pair engine on the same rulebook)
+int ls3d_gather_gemm_once_fits(const ls3d_gemm_args* a) {
+  using namespace ls3d::once;
+  return a->cin_pad % 16 == 0 && a->n_pad <= 256 && a->epi == LS3D_EPI_LINEAR &&
+         smem_bytes_for(2, 1, a->n_pad, a->koff) <= 227 * 1024;
+}
+
 // called by ls3d_gather_gemm (gather_gemm.cu) for launches that carry a tile plan, after the common argument checks
 int ls3d_gather_gemm_once_launch(const ls3d_gemm_args* a, int num_sms, void* stream) {
   using namespace ls3d;
@@ -586,12 +679,23 @@ int ls3d_gather_gemm_once_launch(const ls3d_gemm_args* a, int num_sms, void* str
   const int acc_cols = cfg.n_acc * cfg.acc_stride;
   cfg.a_col0 = acc_cols <= 256 ? 256 : 384;
   if (acc_cols > 384) return LS3D_ERR_ARG;     // n_pad 256 stacked never happens (stack needs n_pad <= 96); 256 -> 1 x 256
-  int ts_max = (512 - cfg.a_col0) / A_SLOT_COLS;
+  // offsets per step: as many as leave >= 2 steps in flight in the TMEM columns and the shared memory that remain
+  static int grp_env = -1;
+  if (grp_env < 0) {
+    const char* e = getenv("LS3D_ONCE_GROUP");
+    grp_env = e ? atoi(e) : 0;
+  }
+  const int avail_cols = 512 - cfg.a_col0;
+  cfg.grp = grp_env > 0 ? grp_env : 4;
+  if (cfg.grp > a->koff) cfg.grp = a->koff;
+  while (cfg.grp > 1 && (avail_cols / (cfg.grp * A_SLOT_COLS) < 2 || smem_bytes_for(2, cfg.grp, a->n_pad, a->koff) > 227 * 1024))
+    --cfg.grp;
+  int ts_max = avail_cols / (cfg.grp * A_SLOT_COLS);
   if (ts_max > MAXR) ts_max = MAXR;
   cfg.ts = ts_max;
-  while (cfg.ts > 2 && smem_bytes_for(cfg.ts, a->n_pad, a->koff) > 227 * 1024) --cfg.ts;
-  const size_t smem = smem_bytes_for(cfg.ts, a->n_pad, a->koff);
-  if (smem > 227 * 1024) return LS3D_ERR_ARG;
+  while (cfg.ts > 2 && smem_bytes_for(cfg.ts, cfg.grp, a->n_pad, a->koff) > 227 * 1024) --cfg.ts;
+  const size_t smem = smem_bytes_for(cfg.ts, cfg.grp, a->n_pad, a->koff);
+  if (smem > 227 * 1024 || cfg.ts < 1) return LS3D_ERR_ARG;
   const int ntiles = ls3d_div_up(a->m_out, TILE_M);
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   static bool optin[64] = {false};

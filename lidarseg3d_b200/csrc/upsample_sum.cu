@@ -33,7 +33,8 @@ __device__ __forceinline__ float4 f4_scale(float a, float4 x) { return make_floa
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 __global__ void __launch_bounds__(256) upsample_sum_kernel(UpsTerms T, int n_img, int H, int W, int C4, int relu,
-                                                           const float* __restrict__ bias, float* __restrict__ out) {
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           uint2* __restrict__ out16) {
   const long long total = (long long)n_img * H * W * C4;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(e % C4);
@@ -71,6 +72,12 @@ __global__ void __launch_bounds__(256) upsample_sum_kernel(UpsTerms T, int n_img
     }
     if (relu) acc = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
     reinterpret_cast<float4*>(out)[e] = acc;
+    if (out16) {                                  // fp16 operand copy of the fused map (fp32 residual-stream mode)
+      uint2 o;
+      *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(acc.x, acc.y);
+      *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(acc.z, acc.w);
+      out16[e] = o;
+    }
   }
 }
 
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(256) upsample_sum_f16_kernel(UpsTerms T, int n
 
 static int upsample_sum_launch(const void* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
                                int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, void* out, void* stream,
-                               int vec) {
+                               int vec, void* out16 = nullptr) {
   using namespace ls3d;
   if (n_img <= 0 || H <= 0 || W <= 0) return LS3D_OK;
   if (!terms || !term_h || !term_w || !out || n_terms < 1 || n_terms > UPS_MAX_TERMS || C <= 0 || (C % vec)) return LS3D_ERR_ARG;
@@ -167,7 +174,7 @@ static int upsample_sum_launch(const void* const* terms, const int32_t* term_h, 
   const long long blocks = (total + 255) / 256;
   const int grid = (int)(blocks < 148LL * 64 ? blocks : 148LL * 64);     // grid-stride, a multiple of the SM count when large
   if (vec == 4)
-    upsample_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 4, relu, bias, (float*)out);
+    upsample_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 4, relu, bias, (float*)out, (uint2*)out16);
   else
     upsample_sum_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n_img, H, W, C / 8, relu, bias, (uint4*)out);
   LS3D_LAUNCH_CHECK();
@@ -184,4 +191,36 @@ extern "C" int ls3d_upsample_sum_f16(const void* const* terms, const int32_t* te
                                      int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, void* out,
                                      void* stream) {
   return upsample_sum_launch(terms, term_h, term_w, n_terms, n_img, H, W, C, relu, bias, out, stream, 8);
+}
+
+// fp32 maps + an fp16 operand copy of the result (the input of the next tensor-core convolution), one pass
+extern "C" int ls3d_upsample_sum_dual(const float* const* terms, const int32_t* term_h, const int32_t* term_w, int32_t n_terms,
+                                      int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t relu, const float* bias, float* out,
+                                      void* out16, void* stream) {
+  if (!out16 || (((uintptr_t)out16) & 7)) return LS3D_ERR_ARG;
+  return upsample_sum_launch((const void* const*)terms, term_h, term_w, n_terms, n_img, H, W, C, relu, bias, out, stream, 4, out16);
+}
+
+// fp16 operand copy of an fp32 map (fp32 residual-stream mode: maps produced by a library convolution enter the own kernels)
+namespace ls3d {
+__global__ void __launch_bounds__(256) cast_f16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + e);
+    uint2 o;
+    *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(v.z, v.w);
+    out[e] = o;
+  }
+}
+}  // namespace ls3d
+
+extern "C" int ls3d_cast_f16(const float* in, void* out, int64_t n, void* stream) {
+  if (n <= 0) return LS3D_OK;
+  if (!in || !out || (n & 3) || (((uintptr_t)in) & 15) || (((uintptr_t)out) & 7)) return LS3D_ERR_ARG;
+  const long long n4 = n / 4;
+  const long long blocks = (n4 + 255) / 256;
+  const int grid = (int)(blocks < 148LL * 32 ? blocks : 148LL * 32);
+  ls3d::cast_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)in, (uint2*)out, n4);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
 }

@@ -76,7 +76,9 @@ class SegMSeg3DNet(_SegBase):
     use_image_graph = True
     # None = fp32 storage with TF32 tensor-core convolutions (cuDNN default).  torch.float16 = fp16 storage and operands with
     # fp32 accumulation: the same 10-bit operand mantissa as TF32 at half the memory traffic (the high-resolution HRNet
-    # branches are bandwidth bound).
+    # branches are bandwidth bound).  "dual" = fp32 maps (the residual stream, every stored activation, bias / residual / ReLU
+    # arithmetic stay fp32) whose convolutions read an fp16 OPERAND COPY written by the producing kernel: the products see the
+    # same 11-bit significand as the TF32 tensor-core convolutions of the stock reference path, on the own tcgen05 kernels.
     image_dtype = None
 
     # ---- the captured camera-branch graphs hold pointers to BN-folded / packed weight tensors: drop them whenever the
@@ -112,7 +114,9 @@ class SegMSeg3DNet(_SegBase):
 
     def _image_branch(self, images, batch_size):
         self.img_backbone.keep_channel_padding = True      # the image head consumes zero-padded channel maps directly
-        if self.image_dtype is not None:
+        dual = isinstance(self.image_dtype, str) and self.image_dtype == "dual"
+        self.img_backbone.dual_maps = dual
+        if self.image_dtype is not None and not dual:
             images = images.to(self.image_dtype)
         img_data = dict(inputs=self.img_backbone(images), batch_size=batch_size)
         img_data = self.img_head(batch_dict=img_data, return_loss=False)

@@ -43,7 +43,28 @@ def _pad_to(c, dtype):
     return (c + q - 1) // q * q if PAD_CHANNELS else c
 
 
-def folded(conv, bn, x_channels, dtype):
+class DualMap:
+    """A camera feature map of the "fp32 residual stream" mode: the fp32 map and / or its fp16 tensor-core operand copy.
+    ``f32`` is None for a map that only ever feeds an own convolution (conv1 of a BasicBlock); ``f16`` is produced by the
+    writing kernel when it is an own one, else on first use (ls3d_cast_f16)."""
+    __slots__ = ("f32", "_f16")
+
+    def __init__(self, f32=None, f16=None):
+        self.f32, self._f16 = f32, f16
+
+    @property
+    def f16(self):
+        if self._f16 is None:
+            from .. import ops
+            self._f16 = ops.cast_f16(self.f32)
+        return self._f16
+
+    @property
+    def shape(self):
+        return (self.f32 if self.f32 is not None else self._f16).shape
+
+
+def folded(conv, bn, x_channels, dtype, pad_dtype=None):
     """BatchNorm folded into the conv (eval): weight [Cout_p, Cin_p, kh, kw] channels-last and bias [Cout_p], zero padded;
     cached on the conv module, refreshed when a parameter / statistic changes."""
     # one entry per (dtype, channel padding): a captured CUDA graph of one camera-map mode keeps reading its own folded
@@ -53,14 +74,15 @@ def folded(conv, bn, x_channels, dtype):
     if store.get("ver") != ver:
         store.clear()
         store["ver"] = ver
-    cache = store.get((dtype, x_channels, PAD_CHANNELS))
+    pad_dtype = pad_dtype or dtype
+    cache = store.get((dtype, x_channels, PAD_CHANNELS, pad_dtype))
     if cache is None:
         with torch.no_grad():
             scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
             w = conv.weight * scale.view(-1, 1, 1, 1)
             b = bn.bias - bn.running_mean * scale
             cout, cin = w.shape[0], w.shape[1]
-            cout_p = _pad_to(cout, dtype)
+            cout_p = _pad_to(cout, pad_dtype)
             assert x_channels >= cin
             if cout_p != cout or x_channels != cin:
                 wp = w.new_zeros(cout_p, x_channels, w.shape[2], w.shape[3])
@@ -70,14 +92,14 @@ def folded(conv, bn, x_channels, dtype):
                 w, b = wp, bp
             w = w.to(dtype).contiguous(memory_format=torch.channels_last)
             b = b.to(dtype).contiguous()
-        cache = store[(dtype, x_channels, PAD_CHANNELS)] = (None, w, b)
+        cache = store[(dtype, x_channels, PAD_CHANNELS, pad_dtype)] = (None, w, b)
     return cache[1], cache[2]
 
 
 FUSED_CONV3X3 = True    # eval/CUDA/fp16: 3x3 and 1x1 stride-1 convs on the hand-written tcgen05 kernel (csrc/conv3x3_f16.cu)
 
 
-def folded_packed(conv, bn, x_channels):
+def folded_packed(conv, bn, x_channels, dual=False):
     """BN-folded 3x3 / 1x1 weights packed for ls3d_conv_f16 (+ fp32 shift), cached like ``folded``; None when the weights do
     not fit the kernel's shared memory (the caller then uses cuDNN)."""
     ver = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
@@ -85,13 +107,16 @@ def folded_packed(conv, bn, x_channels):
     if store.get("ver") != ver:
         store.clear()
         store["ver"] = ver
-    cache = store.get((x_channels, PAD_CHANNELS))
+    cache = store.get((x_channels, PAD_CHANNELS, dual))
     if cache is None:
         from .. import ops
         k = conv.kernel_size[0]
         cout_p = _pad_to(conv.out_channels, torch.float16)
-        if not ops.conv_f16_supported(x_channels, cout_p, k):
+        other = store.get((x_channels, PAD_CHANNELS, not dual))
+        if not (ops.conv_f16_dual_supported if dual else ops.conv_f16_supported)(x_channels, cout_p, k):
             cache = (None, None, None, cout_p)
+        elif other is not None and other[1] is not None:
+            cache = other                                        # same packed block serves both kernels
         else:
             with torch.no_grad():
                 scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
@@ -102,7 +127,7 @@ def folded_packed(conv, bn, x_channels):
                 bp = b.new_zeros(cout_p)
                 bp[:conv.out_channels] = b
                 cache = (None, ops.pack_conv_f16(wp), bp.contiguous(), cout_p)
-        store[(x_channels, PAD_CHANNELS)] = cache
+        store[(x_channels, PAD_CHANNELS, dual)] = cache
     return cache[1], cache[2], cache[3]
 
 
@@ -119,6 +144,7 @@ def _is_plain(conv):
 # work the library already runs near its bandwidth bound.  Off by default; LS3D_OWN_1X1_MIN_PIXELS=<n> routes 1x1
 # convolutions on maps of at least n pixels to the own kernel.
 OWN_1X1_MIN_PIXELS = int(os.environ.get("LS3D_OWN_1X1_MIN_PIXELS", 1 << 62))
+OWN_1X1_DUAL_MIN_PIXELS = int(os.environ.get("LS3D_OWN_1X1_DUAL_MIN_PIXELS", 1 << 62))      # same switch, fp32-map mode
 
 
 def _own_conv_ok(conv, x):
@@ -128,7 +154,7 @@ def _own_conv_ok(conv, x):
     return conv.kernel_size == (3, 3) or x.shape[0] * x.shape[2] * x.shape[3] >= OWN_1X1_MIN_PIXELS
 
 
-def conv_deferred_bias(conv, bn, x):
+def conv_deferred_bias(conv, bn, x, dual=False):
     """conv -> BatchNorm (folded) WITHOUT the shift: returns (conv(x, w_folded), shift fp32 [Cout_p]).  For the linear terms
     of a branch fusion: the caller sums the shifts of all terms and ls3d_upsample_sum adds them once (a library convolution
     with a bias and no activation would run a separate elementwise add over every output map)."""
@@ -137,14 +163,95 @@ def conv_deferred_bias(conv, bn, x):
         if wp is not None:
             from .. import ops
             return ops.conv_f16(x, wp, None, relu=False, cout=cout_p, ksize=conv.kernel_size[0]), bp
-    w, b = folded(conv, bn, x.shape[1], x.dtype)
+    w, b = folded(conv, bn, x.shape[1], x.dtype, pad_dtype=torch.float16 if dual else None)
     return F.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation, conv.groups), b
 
 
-def cbr(conv, bn, x, relu, z=None):
+DUAL_EXACT_WEIGHTS = os.environ.get("LS3D_DUAL_EXACT_WEIGHTS", "1") == "1"
+
+
+def folded_packed_dual(conv, bn, x_channels):
+    """BN-folded weights of a 3x3 / 1x1 stride-1 convolution packed for ls3d_conv_f16_dual.  Returns (mode, w, w_lo, bias,
+    cout_p): mode "split" = one launch on split weights [W_hi ; W_lo]; "hilo" = the shape has no split configuration (the
+    doubled weight block does not fit shared memory): two launches, W_hi then W_lo accumulated through the fp32 residual
+    input; "plain" = fp16-rounded weights (DUAL_EXACT_WEIGHTS off); None = not served by the own kernel."""
+    ver = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    store = conv.__dict__.setdefault("_ls3d_fold3", {})
+    if store.get("ver") != ver:
+        store.clear()
+        store["ver"] = ver
+    key = ("dualpk", x_channels, PAD_CHANNELS, DUAL_EXACT_WEIGHTS)
+    ent = store.get(key)
+    if ent is None:
+        from .. import ops
+        k = conv.kernel_size[0]
+        cout_p = _pad_to(conv.out_channels, torch.float16)
+        if not ops.conv_f16_dual_supported(x_channels, cout_p, k):
+            ent = (None, None, None, None, cout_p)
+        else:
+            with torch.no_grad():
+                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                w = (conv.weight * scale.view(-1, 1, 1, 1)).float()
+                b = (bn.bias - bn.running_mean * scale).float()
+                wp = w.new_zeros(cout_p, x_channels, k, k)
+                wp[:conv.out_channels, :conv.in_channels] = w
+                bp = b.new_zeros(cout_p)
+                bp[:conv.out_channels] = b
+                bp = bp.contiguous()
+                if not DUAL_EXACT_WEIGHTS:
+                    ent = ("plain", ops.pack_conv_f16(wp), None, bp, cout_p)
+                elif ops.conv_f16_split_supported(x_channels, cout_p, k, dual=True):
+                    ent = ("split", ops.pack_conv_f16_split(wp), None, bp, cout_p)
+                else:
+                    hi = wp.half().float()
+                    ent = ("hilo", ops.pack_conv_f16(hi), ops.pack_conv_f16(wp - hi), bp, cout_p)
+        store[key] = ent
+    return ent
+
+
+def _cbr_dual(conv, bn, x, relu, z, want):
+    """cbr on DualMaps (fp32 maps, fp16 tensor-core operands).  want: "f16" = the result only feeds an own convolution (no fp32
+    map is written), "both" = fp32 map + operand copy, "f32" = fp32 map (operand copy on demand)."""
+    from .. import ops
+    C = x.shape[1]
+    if (FUSED_CONV3X3 and _is_plain(conv) and C % 8 == 0 and
+            (conv.kernel_size == (3, 3) or x.shape[0] * x.shape[2] * x.shape[3] >= OWN_1X1_DUAL_MIN_PIXELS)):
+        k = conv.kernel_size[0]
+        mode, wp, wlo, bp, cout_p = folded_packed_dual(conv, bn, C)
+        if mode is not None and (z is None or z.shape[1] == cout_p):
+            z32 = None if z is None else z.f32
+            if mode == "hilo":
+                t32, _ = ops.conv_f16_dual(x.f16, wp, bp, res32=z32, relu=False, cout=cout_p, ksize=k)
+                o32, o16 = ops.conv_f16_dual(x.f16, wlo, None, res32=t32, relu=relu, cout=cout_p, ksize=k)
+            else:
+                o32, o16 = ops.conv_f16_dual(x.f16, wp, bp, res32=z32, relu=relu, cout=cout_p, ksize=k, split=mode == "split",
+                                             want32=not (want == "f16" and z is None))
+            return DualMap(o32, o16)
+    w, b = folded(conv, bn, C, torch.float32, pad_dtype=torch.float16)
+    xf, zf = x.f32, (None if z is None else z.f32)
+    if FUSED_CUDNN and relu and conv.groups == 1:
+        if zf is None:
+            return DualMap(torch.cudnn_convolution_relu(xf, w, b, conv.stride, conv.padding, conv.dilation, 1))
+        return DualMap(torch.cudnn_convolution_add_relu(xf, w, zf, 1.0, b, conv.stride, conv.padding, conv.dilation, 1))
+    y = F.conv2d(xf, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if zf is not None:
+        y = y + zf
+    return DualMap(torch.relu_(y) if relu else y)
+
+
+def own_dual_ok(conv, channels):
+    """Will _cbr_dual run ``conv`` on the own kernel (so that its input may be an operand-only map)?"""
+    from .. import ops
+    return (FUSED_CONV3X3 and _is_plain(conv) and conv.kernel_size == (3, 3) and channels % 8 == 0
+            and ops.conv_f16_dual_supported(channels, _pad_to(conv.out_channels, torch.float16), 3))
+
+
+def cbr(conv, bn, x, relu, z=None, want="both"):
     """conv -> BatchNorm -> (+z) -> (ReLU).  Training / CPU: plain modules.  Eval on CUDA: BN folded into the conv weights
     (cached, refreshed when a parameter changes); fp16 3x3 / 1x1 stride-1 convs run on the hand-written tensor-core kernel, the rest
     as one cuDNN call."""
+    if isinstance(x, DualMap):
+        return _cbr_dual(conv, bn, x, relu, z, want)
     if bn.training or not x.is_cuda:
         y = bn(conv(x))
         if z is not None:
@@ -180,7 +287,10 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         idt = x if self.downsample is None else cbr(self.downsample[0], self.downsample[1], x, False)
-        out = cbr(self.conv1, self.bn1, x, True)
+        want = "both"
+        if isinstance(x, DualMap) and own_dual_ok(self.conv2, _pad_to(self.conv1.out_channels, torch.float16)):
+            want = "f16"                                          # conv1's result is only ever conv2's operand
+        out = cbr(self.conv1, self.bn1, x, True, want=want)
         return cbr(self.conv2, self.bn2, out, True, z=idt)
 
 
@@ -269,6 +379,8 @@ class HRModule(nn.Module):
         if self.num_branches == 1:
             return [self.branches[0](x[0])]
         x = [self.branches[i](x[i]) for i in range(self.num_branches)]
+        if isinstance(x[0], DualMap):
+            return self._forward_fused(x)
         if FUSED_SUM and x[0].is_cuda and not self.training and x[0].dtype in (torch.float32, torch.float16) and all(
                 t.shape[1] % (4 if t.dtype == torch.float32 else 8) == 0 and x[0].shape[2] == t.shape[2] << j
                 and x[0].shape[3] == t.shape[3] << j for j, t in enumerate(x)):
@@ -301,6 +413,9 @@ def _forward_fused(self, x):
     from .. import ops
     outs = []
     cache = self.__dict__.setdefault("_ls3d_fuse_bias", {})
+    dual = isinstance(x[0], DualMap)
+    if dual:                                  # the linear fusion terms are fp32 maps; library 1x1 / stride-2 convs read them
+        x = [t.f32 for t in x]
     for i in range(len(self.fuse_layers)):
         terms, shifts = [], []
         for j in range(self.num_branches):
@@ -308,16 +423,16 @@ def _forward_fused(self, x):
                 terms.append(x[j])
             elif j > i:
                 fl = self.fuse_layers[i][j]
-                t, b = conv_deferred_bias(fl[0], fl[1], x[j])
+                t, b = conv_deferred_bias(fl[0], fl[1], x[j], dual)
                 terms.append(t)
                 shifts.append(b)
             else:
                 t = x[j]
                 for seq in self.fuse_layers[i][j]:
                     if len(seq) == 3:
-                        t = cbr(seq[0], seq[1], t, True)
+                        t = cbr(seq[0], seq[1], DualMap(t), True).f32 if dual else cbr(seq[0], seq[1], t, True)
                     else:
-                        t, b = conv_deferred_bias(seq[0], seq[1], t)
+                        t, b = conv_deferred_bias(seq[0], seq[1], t, dual)
                         shifts.append(b)
                 terms.append(t)
         key = (i,) + tuple((b.data_ptr(), b._version) for b in shifts)      # one entry per camera-map mode (see ``folded``)
@@ -327,7 +442,10 @@ def _forward_fused(self, x):
                 cache.clear()
             with torch.no_grad():
                 ent = cache[key] = (key, torch.stack([b.float() for b in shifts]).sum(0).contiguous() if shifts else None)
-        outs.append(ops.upsample_sum(terms, relu=True, bias=ent[1]))
+        if dual:
+            outs.append(DualMap(*ops.upsample_sum_dual(terms, relu=True, bias=ent[1])))
+        else:
+            outs.append(ops.upsample_sum(terms, relu=True, bias=ent[1]))
     return outs
 
 
@@ -424,6 +542,9 @@ class HRNet(nn.Module):
     def forward(self, x):
         x = cbr(self.conv1, self.bn1, x, True)
         x = cbr(self.conv2, self.bn2, x, True)
+        dual = getattr(self, "dual_maps", False) and x.is_cuda and not self.training and x.dtype == torch.float32
+        if dual:
+            x = DualMap(x)
         x = self.layer1(x)
         ys = [x]
         for st in (2, 3, 4):
@@ -441,6 +562,8 @@ class HRNet(nn.Module):
                 else:
                     xs.append(ys[i])
             ys = getattr(self, f"stage{st}")(xs)
+        if dual:
+            ys = [y.f32 for y in ys]
         if not getattr(self, "keep_channel_padding", False):
             true_c = [c * self.blocks_dict[self.extra["stage4"]["block"]].expansion for c in self.extra["stage4"]["num_channels"]]
             ys = [y if y.shape[1] == c else y[:, :c] for y, c in zip(ys, true_c)]

@@ -361,6 +361,85 @@ def conv_f16(x, w_packed, bias, res=None, relu=True, cout=None, ksize=3):
     return out
 
 
+def conv_f16_dual_supported(cin, cout, ksize=3):
+    """ls3d_conv_f16_dual (fp32 maps, fp16 operands) has a shared-memory configuration for this shape."""
+    nb = ctypes.c_int64()
+    if cin % 8 or cout % 8 or cin > 256 or cout > 256:
+        return False
+    check(capi.lib().ls3d_conv_f16_dual_smem_bytes(cin, cout, ksize, ctypes.byref(nb)), "ls3d_conv_f16_dual_smem_bytes")
+    return nb.value <= 227 * 1024
+
+
+def conv_f16_split_supported(cin, cout, ksize=3, dual=True):
+    """Split (exact) weights [W_hi ; W_lo] fit the kernel for this shape (2 n_pad <= 256 columns, twice the weight bytes)."""
+    if cin % 8 or cout % 8 or cin > 256 or cout > 128:
+        return False
+    ok = ctypes.c_int32()
+    check(capi.lib().ls3d_conv_f16_split_supported(cin, cout, ksize, int(dual), ctypes.byref(ok)), "ls3d_conv_f16_split_supported")
+    return bool(ok.value)
+
+
+def pack_conv_f16_split(w_oihw):
+    """Like pack_conv_f16, split weights: fp16(w) and fp16(w - fp16(w)) stacked along N (ls3d_conv_f16_pack_split)."""
+    cout, cin, k = w_oihw.shape[:3]
+    w = w_oihw.detach().float().contiguous()
+    nb = ctypes.c_int64()
+    check(capi.lib().ls3d_conv_f16_packed_bytes(cin, cout, k, ctypes.byref(nb)), "ls3d_conv_f16_packed_bytes")
+    out = torch.empty(nb.value, dtype=torch.float16, device=w.device)            # twice the unsplit block
+    check(capi.lib().ls3d_conv_f16_pack_split(ptr(w), cin, cout, k, ptr(out), stream_ptr()), "ls3d_conv_f16_pack_split")
+    return out
+
+
+def conv_f16_dual(x16, w_packed, bias, res32=None, relu=True, cout=None, ksize=3, split=False, want32=True):
+    """fp32 residual stream: x16 [N, Cin, H, W] fp16 channels-last (operand copy of the input map), res32 fp32 channels-last or
+    None -> (out32, out16) = act(conv(x16) + bias + res32) as an fp32 map and its fp16 operand copy.  ``want32=False``: only the
+    operand copy is produced (out32 is None).  ``split``: w_packed holds split weights (pack_conv_f16_split)."""
+    N, cin, H, W = x16.shape
+    assert x16.dtype == torch.float16 and x16.is_contiguous(memory_format=torch.channels_last)
+    cout = cout if cout is not None else bias.shape[0]
+    if res32 is not None:
+        assert want32 and res32.dtype == torch.float32 and res32.shape == (N, cout, H, W) and \
+            res32.is_contiguous(memory_format=torch.channels_last)
+    out32 = torch.empty((N, cout, H, W), dtype=torch.float32, device=x16.device, memory_format=torch.channels_last) if want32 \
+        else None
+    out16 = torch.empty((N, cout, H, W), dtype=torch.float16, device=x16.device, memory_format=torch.channels_last)
+    check(capi.lib().ls3d_conv_f16_dual(ptr(x16), ptr(w_packed), ptr(bias), ptr(res32), ptr(out32), ptr(out16), N, H, W, cin,
+                                        cout, ksize, int(relu), int(split), stream_ptr()), "ls3d_conv_f16_dual")
+    return out32, out16
+
+
+def cast_f16(x):
+    """fp16 (RNE) copy of an fp32 tensor, same memory layout (ls3d_cast_f16)."""
+    assert x.dtype == torch.float32 and x.numel() % 4 == 0
+    assert x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty_like(x, dtype=torch.float16)
+    check(capi.lib().ls3d_cast_f16(ptr(x), ptr(out), x.numel(), stream_ptr()), "ls3d_cast_f16")
+    return out
+
+
+def upsample_sum_dual(terms, relu=True, bias=None):
+    """upsample_sum on fp32 terms that also writes the fp16 operand copy of the result: returns (out32, out16)."""
+    N, C = terms[0].shape[:2]
+    H = max(t.shape[2] for t in terms)
+    W = max(t.shape[3] for t in terms)
+    assert C % 4 == 0
+    ts = []
+    for t in terms:
+        assert t.dtype == torch.float32 and t.shape[0] == N and t.shape[1] == C
+        ts.append(t.contiguous(memory_format=torch.channels_last))
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=terms[0].device, memory_format=torch.channels_last)
+    out16 = torch.empty((N, C, H, W), dtype=torch.float16, device=terms[0].device, memory_format=torch.channels_last)
+    k = len(ts)
+    ptrs = (ctypes.c_void_p * k)(*[ptr(t) for t in ts])
+    hs = (ctypes.c_int32 * k)(*[t.shape[2] for t in ts])
+    ws = (ctypes.c_int32 * k)(*[t.shape[3] for t in ts])
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == C and bias.is_contiguous() and bias.device == out.device
+    check(capi.lib().ls3d_upsample_sum_dual(ptrs, hs, ws, k, N, H, W, C, int(relu), ptr(bias), ptr(out), ptr(out16),
+                                            stream_ptr()), "ls3d_upsample_sum_dual")
+    return out, out16
+
+
 def pack_conv3x3_f16(w_oihw):
     """[Cout_p, Cin_p, 3, 3] (BatchNorm folded, zero-padded channels, both multiples of 8) -> the packed fp16 weight block of
     ls3d_conv3x3_f16 (packed on the device in the kernel's K order)."""

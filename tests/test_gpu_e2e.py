@@ -91,6 +91,9 @@ def test_sdseg3d_forward_vs_oracle():
                                                                ("mseg3d_waymo.py", "WAYMO", None, False),
                                                                ("mseg3d_nuscenes.py", "NUSC", torch.float16, False),
                                                                ("mseg3d_nuscenes.py", "NUSC", torch.float16, True),
+                                                               ("mseg3d_nuscenes.py", "NUSC", "dual", False),
+                                                               ("mseg3d_nuscenes.py", "NUSC", "dual", True),
+                                                               ("mseg3d_waymo.py", "WAYMO", "dual", True),
                                                                ("mseg3d_waymo.py", "WAYMO", None, True)])
 def test_mseg3d_forward_vs_oracle(cfg_name, spec_name, image_dtype, u8):
     """BASELINE.json configs[2] (nuScenes: 17 classes, 6 cameras) and configs[3] (Waymo: 23 classes, 5 cameras, z range
@@ -110,7 +113,8 @@ def test_mseg3d_forward_vs_oracle(cfg_name, spec_name, image_dtype, u8):
     m.image_dtype = image_dtype          # fp16: camera branch on fp16 maps (own tcgen05 3x3 kernel); same logits gate
     if u8:      # bench.py's path: uint8 images uploaded and normalised on the device in the camera branch's storage type
         ex = pipeline.build_example(frames, spec["voxel_size"], spec["pc_range"], images_u8=ex_cpu["images_u8"],
-                                    img_mean=synth.IMG_MEAN, img_std=synth.IMG_STD, image_dtype=image_dtype or torch.float32,
+                                    img_mean=synth.IMG_MEAN, img_std=synth.IMG_STD,
+                                    image_dtype=image_dtype if isinstance(image_dtype, torch.dtype) else torch.float32,
                                     points_cuv=ex_cpu["points_cuv"])
     else:
         ex = pipeline.build_example(frames, spec["voxel_size"], spec["pc_range"], images=ex_cpu["images"],
@@ -129,7 +133,7 @@ def test_mseg3d_forward_vs_oracle(cfg_name, spec_name, image_dtype, u8):
     assert len(preds) == 2
 
 
-@pytest.mark.parametrize("image_dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("image_dtype", [torch.float32, torch.float16, "dual"])
 def test_mseg3d_full_size_parity_one_frame(image_dtype):
     """The BENCHMARKED configuration (32-beam ~30 k-point scan, 6 raw 900x1600 uint8 images resized to 640x960 on the
     device, GPU projection) through bench.py's own parity block, one frame: the gate the bench line carries
@@ -146,13 +150,13 @@ def test_mseg3d_full_size_parity_one_frame(image_dtype):
     cfg, model = bench.build_model(wl)
     model = model.to(DEV)
     batch = bench.make_batches(wl, spec, 1, 1, 0, n_image_sets=1)[0]
-    name = "fp32" if image_dtype == torch.float32 else "fp16cam"
+    name = {torch.float32: "fp32", torch.float16: "fp16cam", "dual": "dual"}[image_dtype]
     parity, _, _ = bench.parity_block(wl, spec, cfg, model, batch, 1, lambda b, dt: bench.gpu_forward(wl, spec, model, b, dt, DEV),
                                       [(name, image_dtype)])
     m = parity["modes"][name]
     assert m["coords_bit_exact"]
     assert m["points_cuv_cam_valid_mismatches"] <= 2 and m["points_cuv_max_abs_diff"] <= 2e-6
-    if image_dtype == torch.float32:
+    if image_dtype != torch.float16:
         assert m["resized_images_bit_exact"]
     assert m["rel_err"] <= 1e-3 and m["argmax_agreement"] >= 0.999, m
     assert parity["ok"]

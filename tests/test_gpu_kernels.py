@@ -319,6 +319,90 @@ def test_conv1x1_f16_vs_fp64(n, h, w, cin, cout, res, relu):
     assert err <= 6e-4, err
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,res,relu,k", [(2, 20, 30, 24, 24, True, True, 3), (1, 40, 60, 40, 40, False, True, 3),
+                                                       (3, 33, 17, 72, 72, True, True, 3), (1, 160, 240, 24, 24, True, True, 3),
+                                                       (2, 7, 129, 24, 40, False, False, 3), (1, 40, 60, 72, 24, True, False, 1),
+                                                       (1, 1, 1, 8, 8, True, True, 3)])
+def test_conv_f16_dual_vs_fp64(n, h, w, cin, cout, res, relu, k):
+    """fp32 residual-stream convolution: fp16 operand copy in, fp32 residual in, fp32 map + fp16 operand copy out.  Against an
+    fp64 convolution of the same fp16 operands the fp32 map differs by fp32 accumulation order only; the fp16 copy is its RNE
+    rounding bit for bit."""
+    import torch.nn.functional as F
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(n * 977 + h + k)
+    x = torch.randn(n, cin, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    z = torch.randn(n, cout, h, w, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) if res else None
+    if not ops.conv_f16_dual_supported(cin, cout, k):
+        pytest.skip("weights do not fit shared memory")
+    y32, y16 = ops.conv_f16_dual(x, ops.pack_conv_f16(wt), b, res32=z, relu=relu, cout=cout, ksize=k)
+    ref = F.conv2d(x.double(), wt.half().double(), b.double(), padding=k // 2)
+    if z is not None:
+        ref = ref + z.double()
+    if relu:
+        ref = ref.relu()
+    assert y32.dtype == torch.float32 and y32.is_contiguous(memory_format=torch.channels_last)
+    err = float((y32.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 2e-6, err
+    assert torch.equal(y16, y32.half())
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,res,relu,k", [(2, 20, 30, 24, 24, True, True, 3), (1, 40, 60, 40, 40, False, True, 3),
+                                                       (1, 160, 240, 24, 24, True, True, 3), (2, 7, 129, 24, 40, False, False, 3),
+                                                       (1, 40, 60, 72, 24, True, False, 1), (2, 33, 17, 64, 64, False, True, 1),
+                                                       (1, 24, 24, 144, 48, False, False, 1)])
+def test_conv_f16_dual_split_weights_vs_fp64(n, h, w, cin, cout, res, relu, k):
+    """Split weights [W_hi ; W_lo]: the fp32 weights enter exactly, so against an fp64 convolution of the fp16 ACTIVATIONS with
+    the UNROUNDED fp32 weights only fp32 accumulation error remains - and the operand-only variant (no fp32 map) is the RNE
+    rounding of the same result."""
+    import torch.nn.functional as F
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(n * 311 + h + k)
+    x = torch.randn(n, cin, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    z = torch.randn(n, cout, h, w, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) if res else None
+    assert ops.conv_f16_split_supported(cin, cout, k)
+    wp = ops.pack_conv_f16_split(wt)
+    y32, y16 = ops.conv_f16_dual(x, wp, b, res32=z, relu=relu, cout=cout, ksize=k, split=True)
+    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=k // 2)
+    if z is not None:
+        ref = ref + z.double()
+    if relu:
+        ref = ref.relu()
+    err = float((y32.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 2e-6, err
+    assert torch.equal(y16, y32.half())
+    # the plain (fp16-rounded weights) kernel is measurably further away: the split is doing something
+    p32, _ = ops.conv_f16_dual(x, ops.pack_conv_f16(wt), b, res32=z, relu=relu, cout=cout, ksize=k)
+    assert float((p32.double() - ref).abs().max() / ref.abs().max()) > 5 * err
+    if z is None:
+        n32, o16 = ops.conv_f16_dual(x, wp, b, relu=relu, cout=cout, ksize=k, split=True, want32=False)
+        assert n32 is None and torch.equal(o16, y16)
+
+
+def test_conv_f16_split_not_supported_shapes():
+    ops, _ = _ops()
+    assert not ops.conv_f16_split_supported(72, 72, 3)          # doubled weight block does not fit shared memory
+    assert not ops.conv_f16_split_supported(64, 256, 1)         # 2 n_pad > 256 accumulator columns
+    assert ops.conv_f16_split_supported(24, 24, 3) and ops.conv_f16_split_supported(40, 40, 3)
+
+
+def test_upsample_sum_dual_and_cast():
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(3)
+    C, sizes = 24, [(32, 48), (16, 24), (8, 12)]
+    terms = [torch.randn(2, C, h, w, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) for h, w in sizes]
+    bias = torch.randn(C, generator=g).to(DEV)
+    ref = ops.upsample_sum(terms, relu=True, bias=bias)
+    o32, o16 = ops.upsample_sum_dual(terms, relu=True, bias=bias)
+    assert torch.equal(o32, ref) and torch.equal(o16, ref.half())
+    x = torch.randn(3, 20, 9, 7, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    c = ops.cast_f16(x)
+    assert c.is_contiguous(memory_format=torch.channels_last) and torch.equal(c, x.half())
+
+
 @pytest.mark.parametrize("H,dh,L", [(4, 24, 34), (4, 24, 46), (2, 16, 5), (8, 32, 40)])
 def test_token_attention_vs_fp64(H, dh, L):
     """Class-token cross attention (context_module.py:320-376) vs a float64 softmax(q K^T) V, frames of uneven size with a
