@@ -233,6 +233,9 @@ int ls3d_upsample_sum_dual(const float* const* terms, const int32_t* term_h, con
                            void* out16, void* stream);   /* fp32 result + its fp16 operand copy in one pass */
 /* fp16 (round-to-nearest-even) copy of n fp32 values, n a multiple of 4: the tensor-core operand copy of an fp32 map */
 int ls3d_cast_f16(const float* in, void* out, int64_t n, void* stream);
+/* fp32 [n_pixels][3] (channels-last network input) -> fp16 [n_pixels][8] with channels 3..7 zero: operand copy of the image for
+ * the own stem convolution (hrnet.py:658-666), whose tensor-map copies need 16-byte pixel rows */
+int ls3d_pad3_f16(const float* in, int64_t n_pixels, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera input preparation: uint8 [n_pixels][3] (HWC images, any batch of them back to back) -> (x / 255 - mean[c]) / std[c]
@@ -300,6 +303,34 @@ int ls3d_conv_f16_dual(const void* in16, const void* w_packed, const float* bias
 int ls3d_conv_f16_dual_smem_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes);
 int ls3d_conv_f16_split_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t dual, int32_t* supported);
 int ls3d_conv_f16_pack_split(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream);
+
+/* General form of the same kernel: every convolution of the camera branch (HRNet stem / Bottlenecks / transitions / fuse layers,
+ * FCN head; reference hrnet.py:156-226,658-693, resnet_mmcv.py:20-225, fcn_mseg3d_head.py:150-163) is one or a few launches.
+ *   stride 2 (3x3, pad 1): the halo holds the four (row parity, column parity) phase planes of the input, each read through
+ *       its own tensor map over the same memory with doubled pixel strides; tap (dy, dx) = a shifted view of one plane.
+ *   channel slices: the launch convolves input channels [in_c_off, in_c_off + cin) of a tensor with in_c_total channels into
+ *       output channels [out_c_off, out_c_off + cout) of tensors with out_c_total channels.  Shapes whose weights do not fit
+ *       shared memory run as several launches over input slices that ACCUMULATE through the fp32 residual input
+ *       (res32 == out32 is allowed: each tile reads its residual before it is written); > 128 output channels with split
+ *       weights run as output slices.
+ *   H_in, W_in: input map size; the output is H_in x W_in (stride 1) or ceil(H_in / 2) x ceil(W_in / 2) (stride 2).
+ *   w_packed: ls3d_conv_f16_pack_ex of the [cout][cin][k][k] weight slice with the same (ksize, stride, w_split). */
+typedef struct ls3d_conv_args {
+  const void* in16;       /* fp16 operand copy of the input map, channels-last [n_img, H_in, W_in, in_c_total] */
+  const void* w_packed;
+  const float* bias;      /* [cout] fp32 or NULL */
+  const float* res32;     /* fp32 [n_img, H_out, W_out, out_c_total] or NULL */
+  float* out32;           /* fp32 output map or NULL (operand-only launch: out16 alone, no residual) */
+  void* out16;            /* fp16 operand copy of the output map */
+  int32_t in_c_total, in_c_off, cin;
+  int32_t out_c_total, out_c_off, cout;
+  int32_t n_img, H_in, W_in, ksize, stride, relu, w_split;
+} ls3d_conv_args;
+int ls3d_conv_f16_ex(const ls3d_conv_args* args, void* stream);
+int ls3d_conv_f16_ex_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t dual, int32_t split,
+                               int32_t* supported);
+int ls3d_conv_f16_pack_ex(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t split,
+                          void* packed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SF-Phase: class embedding aggregation and class-token memory path.

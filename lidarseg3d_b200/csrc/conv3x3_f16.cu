@@ -47,7 +47,11 @@ struct Args {
   int nb;                 // rows of the B operand = accumulator columns per tile: n_pad, or 2 n_pad with split weights
                           // ([W_hi ; W_lo] stacked along N: exact fp32 weights at the cost of a wider MMA, the epilogue adds
                           // the two halves)
-  int n_img, H, W, cin, cout, kcg, kc, n_mma, n_pad, relu, tiles_x, tiles_y, n_tiles, nbuf;
+  int n_img, H, W, cin, cout, kcg, kc, n_mma, n_pad, relu, tiles_x, tiles_y, n_tiles, nbuf;   // H, W: OUTPUT map size
+  int nphase;             // 1: stride 1; 4: stride 2 - the halo holds the four (row parity, column parity) phase planes of the
+                          // input, each loaded through its own tensor map (same memory, doubled pixel strides)
+  int kdata;              // nphase * kcg data chunks per halo buffer (chunk kdata = the all-zero chunk when kc > kdata)
+  int in_c_off, out_c_off;   // channel offsets of this launch's slices inside the input / output (and residual) tensors
   float inv_tiles_x, inv_tiles_per_img;
   // per MMA: low word of the A descriptor less the stage base = (offset of the lower K entry >> 4) | (LBO >> 4) << 16.
   // Lives in the kernel parameters so that the issue loop reads it with a warp-uniform constant load: descriptors fetched
@@ -77,16 +81,22 @@ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n) {
 // ntap = 9 (3x3) or 1 (1x1: the same kernel reading only the centre of the halo).
 // Entry c of the K list: tap = c / kcg, channel chunk = c % kcg; entries past ntap * kcg are the all-zero chunk (index kcg of the
 // halo buffer, never written by the copies).  Byte offset of its first row inside a halo buffer:
-__host__ __device__ __forceinline__ int k_entry_offset(int c, int kcg, int ntap) {
-  if (c >= ntap * kcg) return kcg * CH_STRIDE;
+// stride 2 (nphase = 4): tap row dy reads input row 2 oy + dy - 1 = phase plane (dy odd ? even rows : odd rows) at block row
+// oy - 1 (dy = 0) or oy (dy = 1, 2); the halo origin is block (ox0 - 1, oy0 - 1), so the in-halo offset is 0 or 1.  Columns alike.
+__host__ __device__ __forceinline__ int k_entry_offset(int c, int kcg, int ntap, int nphase = 1) {
+  if (c >= ntap * kcg) return nphase * kcg * CH_STRIDE;
   const int t = c / kcg, kc = c - t * kcg;
   const int tap = ntap == 1 ? 4 : t;                     // 1x1: the centre tap
-  return kc * CH_STRIDE + ((tap / 3) * HALO_W + (tap % 3)) * 16;
+  const int dy = tap / 3, dx = tap % 3;
+  if (nphase == 1) return kc * CH_STRIDE + (dy * HALO_W + dx) * 16;
+  const int by = dy == 0 ? 0 : 1, py = dy == 1 ? 0 : 1;
+  const int bx = dx == 0 ? 0 : 1, px = dx == 1 ? 0 : 1;
+  return ((py * 2 + px) * kcg + kc) * CH_STRIDE + (by * HALO_W + bx) * 16;
 }
 // MMA j multiplies K-list entries 2j and 2j+1; the one at the lower shared-memory offset is the first 8 of its 16 K values.
-__host__ __device__ __forceinline__ void mma_entries(int j, int kcg, int ntap, int& first, int& second) {
+__host__ __device__ __forceinline__ void mma_entries(int j, int kcg, int ntap, int nphase, int& first, int& second) {
   const int a = 2 * j, b = 2 * j + 1;
-  if (k_entry_offset(a, kcg, ntap) <= k_entry_offset(b, kcg, ntap)) {
+  if (k_entry_offset(a, kcg, ntap, nphase) <= k_entry_offset(b, kcg, ntap, nphase)) {
     first = a;
     second = b;
   } else {
@@ -117,6 +127,10 @@ __device__ __forceinline__ void prefetch_map(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
 
+struct InMaps {
+  CUtensorMap m[4];
+};
+
 struct TileXY {
   int img, ty, tx;
 };
@@ -145,7 +159,7 @@ __device__ __forceinline__ TileXY tile_coords(int tile, const Args& p) {
 }
 
 __global__ void __launch_bounds__(N_THREADS, 1)
-    conv3x3_f16_kernel(const Args p, const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_res,
+    conv3x3_f16_kernel(const Args p, const __grid_constant__ InMaps maps_in, const __grid_constant__ CUtensorMap map_res,
                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t w_bytes = (uint32_t)p.n_mma * 2u * p.nb * 16u;
@@ -173,10 +187,10 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     uint4* dst = reinterpret_cast<uint4*>(w_s);
     for (uint32_t i = tid; i < w_bytes / 16; i += N_THREADS) dst[i] = __ldg(src + i);
     for (int c = tid; c < p.n_pad; c += N_THREADS) bias_s[c] = (p.bias && c < p.cout) ? __ldg(p.bias + c) : 0.f;
-    if (p.kcg < p.kc) {
+    if (p.kdata < p.kc) {
       const int per = CH_STRIDE / 16;
       for (int i = tid; i < p.nbuf * per; i += N_THREADS)
-        reinterpret_cast<uint4*>(stage_s + (size_t)(i / per) * stage_bytes + (size_t)p.kcg * CH_STRIDE)[i % per] =
+        reinterpret_cast<uint4*>(stage_s + (size_t)(i / per) * stage_bytes + (size_t)p.kdata * CH_STRIDE)[i % per] =
             make_uint4(0, 0, 0, 0);
     }
   }
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   } else if (warp == PROD_WARP && lane == 0) {
-    prefetch_map(&map_in);
+    for (int ph = 0; ph < p.nphase; ++ph) prefetch_map(&maps_in.m[ph]);
     prefetch_map(&map_res);
     prefetch_map(&map_out);
     if (p.dual) prefetch_map(&map_out16);
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
   if (warp == PROD_WARP) {
     // =========================== producer (tensor-map copies) ===========================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)p.kcg * (HPIX * 16u) + (p.has_res ? (p.dual ? io32_bytes : io_bytes) : 0u);
+      const uint32_t tx_bytes = (uint32_t)p.kdata * (HPIX * 16u) + (p.has_res ? (p.dual ? io32_bytes : io_bytes) : 0u);
       int b = 0;
       uint32_t ph = 1;                                       // parity of the "previous" phase: passes on a fresh barrier
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -221,9 +235,11 @@ __global__ void __launch_bounds__(N_THREADS, 1)
         const uint32_t dst = stage0 + (uint32_t)b * stage_bytes;
         const uint32_t bar = full_bar0 + 8 * b;
         mbar_arrive_expect_tx(bar, tx_bytes);
-        for (int kc = 0; kc < p.kcg; ++kc)
-          tma_load_4d(dst + (uint32_t)kc * CH_STRIDE, &map_in, bar, kc * 8, t.tx * TW - 1, t.ty * TH - 1, t.img);
-        if (p.has_res) tma_load_4d(dst + halo_bytes, &map_res, bar, 0, t.tx * TW, t.ty * TH, t.img);
+        for (int ph = 0; ph < p.nphase; ++ph)
+          for (int kc = 0; kc < p.kcg; ++kc)
+            tma_load_4d(dst + (uint32_t)(ph * p.kcg + kc) * CH_STRIDE, &maps_in.m[ph], bar, p.in_c_off + kc * 8, t.tx * TW - 1,
+                        t.ty * TH - 1, t.img);
+        if (p.has_res) tma_load_4d(dst + halo_bytes, &map_res, bar, p.out_c_off, t.tx * TW, t.ty * TH, t.img);
         if (++b == p.nbuf) {
           b = 0;
           ph ^= 1u;
@@ -375,9 +391,10 @@ __global__ void __launch_bounds__(N_THREADS, 1)
       bar_sync_team(team);
       if (leader) {
         const TileXY t = tile_coords(tile, p);
-        tma_store_4d(&map_out, stage0 + (uint32_t)b * stage_bytes + halo_bytes, 0, t.tx * TW, t.ty * TH, t.img);
+        tma_store_4d(&map_out, stage0 + (uint32_t)b * stage_bytes + halo_bytes, p.out_c_off, t.tx * TW, t.ty * TH, t.img);
         if (p.dual)
-          tma_store_4d(&map_out16, stage0 + (uint32_t)b * stage_bytes + halo_bytes + io32_bytes, 0, t.tx * TW, t.ty * TH, t.img);
+          tma_store_4d(&map_out16, stage0 + (uint32_t)b * stage_bytes + halo_bytes + io32_bytes, p.out_c_off, t.tx * TW, t.ty * TH,
+                       t.img);
         bulk_commit();
         if (deep) {
           if (!first) {
@@ -406,15 +423,15 @@ __global__ void __launch_bounds__(N_THREADS, 1)
 
 // BatchNorm-folded fp32 weights [cout_p][cin_p][k][k] (k*k = ntap) -> fp16 [n_mma][2][n_pad][8] in the kernel's K-list order
 // split: [n_mma][2][2 n_pad][8], rows [0, n_pad) = fp16(w), rows [n_pad, 2 n_pad) = fp16(w - fp16(w)) (w_hi + w_lo = w to 2^-22)
-__global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int kcg, int ntap, int n_mma, int n_pad, int split,
-                            __half* __restrict__ out) {
+__global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int kcg, int ntap, int nphase, int n_mma, int n_pad,
+                            int split, __half* __restrict__ out) {
   const int nb = split ? 2 * n_pad : n_pad;
   const int total = n_mma * 2 * nb * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 7, row = (i >> 3) % nb, slot = ((i >> 3) / nb) & 1, j = (i >> 3) / nb / 2;
     const int n = row < n_pad ? row : row - n_pad;
     int e0, e1;
-    mma_entries(j, kcg, ntap, e0, e1);
+    mma_entries(j, kcg, ntap, nphase, e0, e1);
     const int c = slot ? e1 : e0;
     float v = 0.f;
     if (c < ntap * kcg && n < cout) {
@@ -427,12 +444,14 @@ __global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int 
 }
 
 struct Geom {
-  int kcg, kc, n_mma, n_pad;
+  int kcg, kc, n_mma, n_pad, nphase, kdata;
 };
-static Geom geom(int cin, int cout, int ntap) {
+static Geom geom(int cin, int cout, int ntap, int stride = 1) {
   Geom g;
   g.kcg = cin / 8;
-  g.kc = (g.kcg + 1) / 2 * 2;
+  g.nphase = stride == 2 ? 4 : 1;
+  g.kdata = g.nphase * g.kcg;
+  g.kc = g.kdata + ((ntap * g.kcg) & 1);          // an odd K list ends on the all-zero chunk
   g.n_mma = (ntap * g.kcg + 1) / 2;
   g.n_pad = (cout + 15) / 16 * 16;
   return g;
@@ -441,8 +460,6 @@ static size_t smem_for(const Geom& g, int cout, int nbuf, int dual = 0, int spli
   return (size_t)nbuf * ((size_t)g.kc * CH_STRIDE + 128 * (size_t)cout * (dual ? 6 : 2)) +
          (size_t)g.n_mma * 2 * g.n_pad * (split ? 2 : 1) * 16 + (size_t)g.n_pad * 4 + (2 * MAX_BUF + 8) * 8 + 16 + 128;
 }
-// split weights need 2 n_pad <= 256 accumulator columns per tile and twice the resident weight bytes
-static bool split_ok(const Geom& g, int cout, int dual) { return 2 * g.n_pad <= 256 && smem_for(g, cout, 2, dual, 1) <= 227 * 1024; }
 
 // ---- tensor maps (driver entry point fetched through the runtime: no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -459,15 +476,27 @@ static EncodeTiledFn encode_fn() {
   }
   return fn;
 }
-// [n_img, H, W, C] fp16 channels-last viewed as the 4-D tensor (C, W, H, n_img) with a (bc, bw, bh, 1) box
-static int make_map(CUtensorMap* m, const void* base, int C, int W, int H, int n_img, int bc, int bw, int bh, int es_bytes = 2) {
+// [n_img, H, W, C] channels-last viewed as the 4-D tensor (C, W, H, n_img) with a (bc, bw, bh, 1) box.  phase >= 0: the
+// (row parity py = phase >> 1, column parity px = phase & 1) plane of the map - the same memory with doubled pixel strides.
+static int make_map(CUtensorMap* m, const void* base, int C, int W, int H, int n_img, int bc, int bw, int bh, int es_bytes = 2,
+                    int phase = -1) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return LS3D_ERR_ARG;
-  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
-  const cuuint64_t strides[3] = {(cuuint64_t)C * es_bytes, (cuuint64_t)W * C * es_bytes, (cuuint64_t)H * W * C * es_bytes};
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es_bytes, (cuuint64_t)W * C * es_bytes, (cuuint64_t)H * W * C * es_bytes};
+  const char* b = (const char*)base;
+  if (phase >= 0) {
+    const int py = phase >> 1, px = phase & 1;
+    dims[1] = (cuuint64_t)((W - px + 1) / 2);
+    dims[2] = (cuuint64_t)((H - py + 1) / 2);
+    if (dims[1] == 0 || dims[2] == 0) return LS3D_ERR_ARG;      // W or H == 1: no odd plane (rejected by the caller)
+    strides[0] *= 2;
+    strides[1] *= 2;
+    b += ((size_t)py * W + px) * C * es_bytes;
+  }
   const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   const cuuint32_t es[4] = {1, 1, 1, 1};
-  const CUresult r = fn(m, es_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+  const CUresult r = fn(m, es_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<char*>(b), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? LS3D_OK : 1000 + (int)r;
@@ -477,68 +506,157 @@ static int make_map(CUtensorMap* m, const void* base, int C, int W, int H, int n
 }  // namespace ls3d
 
 static int ntap_of(int ksize) { return ksize == 3 ? 9 : ksize == 1 ? 1 : 0; }
+static bool shape_ok(int cin, int cout, int ksize, int stride) {
+  return cin > 0 && cout > 0 && !(cin & 7) && !(cout & 7) && ntap_of(ksize) && (stride == 1 || (stride == 2 && ksize == 3));
+}
 
 extern "C" int ls3d_conv_f16_smem_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes) {
   using namespace ls3d::c3;
-  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  if (!bytes || !shape_ok(cin, cout, ksize, 1)) return LS3D_ERR_ARG;
   *bytes = (int64_t)smem_for(geom(cin, cout, ntap_of(ksize)), cout, 2);
   return LS3D_OK;
 }
 
 extern "C" int ls3d_conv_f16_packed_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes) {
   using namespace ls3d::c3;
-  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  if (!bytes || !shape_ok(cin, cout, ksize, 1)) return LS3D_ERR_ARG;
   const Geom g = geom(cin, cout, ntap_of(ksize));
   *bytes = (int64_t)g.n_mma * 2 * g.n_pad * 16;
   return LS3D_OK;
 }
 
-static int pack_launch(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, int split, void* packed, void* stream) {
+static int pack_launch(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, int stride, int split, void* packed,
+                       void* stream) {
   using namespace ls3d::c3;
-  if (!w_oihw || !packed || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
-  const Geom g = geom(cin, cout, ntap_of(ksize));
+  if (!w_oihw || !packed || !shape_ok(cin, cout, ksize, stride)) return LS3D_ERR_ARG;
+  const Geom g = geom(cin, cout, ntap_of(ksize), stride);
   if (split && 2 * g.n_pad > 256) return LS3D_ERR_ARG;
   const int total = g.n_mma * 2 * g.n_pad * (split ? 2 : 1) * 8;
-  pack_kernel<<<ls3d_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, cout, cin, g.kcg, ntap_of(ksize), g.n_mma,
-                                                                        g.n_pad, split, (__half*)packed);
+  pack_kernel<<<ls3d_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, cout, cin, g.kcg, ntap_of(ksize), g.nphase,
+                                                                        g.n_mma, g.n_pad, split, (__half*)packed);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
 
 extern "C" int ls3d_conv_f16_pack(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream) {
-  return pack_launch(w_oihw, cin, cout, ksize, 0, packed, stream);
-}
-
-// split weights [W_hi ; W_lo] (twice ls3d_conv_f16_packed_bytes); *supported = 0 when the shape has no split configuration
-extern "C" int ls3d_conv_f16_split_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t dual, int32_t* supported) {
-  using namespace ls3d::c3;
-  if (!supported || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
-  *supported = split_ok(geom(cin, cout, ntap_of(ksize)), cout, dual) ? 1 : 0;
-  return LS3D_OK;
+  return pack_launch(w_oihw, cin, cout, ksize, 1, 0, packed, stream);
 }
 extern "C" int ls3d_conv_f16_pack_split(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, void* packed, void* stream) {
-  return pack_launch(w_oihw, cin, cout, ksize, 1, packed, stream);
+  return pack_launch(w_oihw, cin, cout, ksize, 1, 1, packed, stream);
+}
+// any (stride, split); packed holds ls3d_conv_f16_packed_bytes x (split ? 2 : 1)
+extern "C" int ls3d_conv_f16_pack_ex(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t split,
+                                     void* packed, void* stream) {
+  return pack_launch(w_oihw, cin, cout, ksize, stride, split ? 1 : 0, packed, stream);
 }
 
-static int conv_launch(const void* in, const void* w_packed, const float* bias, const void* res, void* out, void* out16, int dual,
-                       int split, int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream) {
+// does the kernel have a shared-memory / tensor-memory configuration for this launch shape?
+extern "C" int ls3d_conv_f16_ex_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t dual, int32_t split,
+                                          int32_t* supported) {
+  using namespace ls3d::c3;
+  if (!supported || !shape_ok(cin, cout, ksize, stride)) return LS3D_ERR_ARG;
+  const Geom g = geom(cin, cout, ntap_of(ksize), stride);
+  const int nb = split ? 2 * g.n_pad : g.n_pad;
+  *supported = (nb <= 256 && g.n_mma <= MAX_MMA && smem_for(g, cout, 2, dual, split) <= 227 * 1024) ? 1 : 0;
+  return LS3D_OK;
+}
+extern "C" int ls3d_conv_f16_split_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t dual, int32_t* supported) {
+  return ls3d_conv_f16_ex_supported(cin, cout, ksize, 1, dual, 1, supported);
+}
+
+extern "C" int ls3d_conv_f16_ex(const ls3d_conv_args* c, void* stream) {
   using namespace ls3d;
   using namespace ls3d::c3;
-  if (n_img <= 0 || H <= 0 || W <= 0) return LS3D_OK;
-  if (!in || !w_packed || !out || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
-  if (dual && !out16) return LS3D_ERR_ARG;
-  const int ntap = ntap_of(ksize);
-  if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)res) | ((uintptr_t)w_packed) | ((uintptr_t)out16)) & 15) return LS3D_ERR_ARG;
-  const Geom g = geom(cin, cout, ntap);
+  if (!c) return LS3D_ERR_ARG;
+  if (c->n_img <= 0 || c->H_in <= 0 || c->W_in <= 0) return LS3D_OK;
+  const int stride = c->stride ? c->stride : 1;
+  if (!c->in16 || !c->w_packed || !shape_ok(c->cin, c->cout, c->ksize, stride)) return LS3D_ERR_ARG;
+  const int dual = c->out32 != nullptr;
+  void* out = dual ? (void*)c->out32 : c->out16;          // operand-only launches write the fp16 map alone
+  if (!out || (dual && !c->out16) || (!dual && c->res32)) return LS3D_ERR_ARG;
+  const int in_ct = c->in_c_total ? c->in_c_total : c->cin, out_ct = c->out_c_total ? c->out_c_total : c->cout;
+  if ((in_ct & 7) || (out_ct & 7) || (c->in_c_off & 7) || (c->out_c_off & 7) || c->in_c_off < 0 || c->out_c_off < 0 ||
+      c->in_c_off + c->cin > in_ct || c->out_c_off + c->cout > out_ct)
+    return LS3D_ERR_ARG;
+  if ((((uintptr_t)c->in16) | ((uintptr_t)c->out32) | ((uintptr_t)c->res32) | ((uintptr_t)c->w_packed) | ((uintptr_t)c->out16)) & 15)
+    return LS3D_ERR_ARG;
+  const int ntap = ntap_of(c->ksize), split = c->w_split ? 1 : 0;
+  const int H = stride == 2 ? (c->H_in + 1) / 2 : c->H_in, W = stride == 2 ? (c->W_in + 1) / 2 : c->W_in;   // output size
+  if (stride == 2 && (c->H_in < 2 || c->W_in < 2)) return LS3D_ERR_ARG;
+  const Geom g = geom(c->cin, c->cout, ntap, stride);
   Args a;
-  a.w = (const __half*)w_packed; a.bias = bias; a.has_res = res != nullptr; a.dual = dual;
-  a.n_img = n_img; a.H = H; a.W = W; a.cin = cin; a.cout = cout; a.relu = relu;
-  a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad;
+  a.w = (const __half*)c->w_packed; a.bias = c->bias; a.has_res = c->res32 != nullptr; a.dual = dual;
+  a.n_img = c->n_img; a.H = H; a.W = W; a.cin = c->cin; a.cout = c->cout; a.relu = c->relu;
+  a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad; a.nphase = g.nphase; a.kdata = g.kdata;
+  a.in_c_off = c->in_c_off; a.out_c_off = c->out_c_off;
   a.nb = split ? 2 * g.n_pad : g.n_pad;
   if (a.nb > 256 || g.n_mma > MAX_MMA) return LS3D_ERR_ARG;
   for (int j = 0; j < g.n_mma; ++j) {
     int e0, e1;
-    mma_entries(j, g.kcg, ntap, e0, e1);
+    mma_entries(j, g.kcg, ntap, g.nphase, e0, e1);
+    const int o0 = k_entry_offset(e0, g.kcg, ntap, g.nphase), o1 = k_entry_offset(e1, g.kcg, ntap, g.nphase);
+    a.a_lo[j] = ((uint32_t)o0 >> 4) | (((uint32_t)(o1 - o0) >> 4) << 16);
+  }
+  a.tiles_x = ls3d_div_up(W, TW);
+  a.tiles_y = ls3d_div_up(H, TH);
+  const long long nt = (long long)c->n_img * a.tiles_x * a.tiles_y;
+  if (nt >= (1LL << 22)) return LS3D_ERR_ARG;
+  a.n_tiles = (int)nt;
+  a.inv_tiles_x = 1.0f / (float)a.tiles_x;
+  a.inv_tiles_per_img = 1.0f / (float)(a.tiles_x * a.tiles_y);
+  a.nbuf = MAX_BUF;
+  while (a.nbuf > 2 && smem_for(g, c->cout, a.nbuf, dual, split) > 227 * 1024) --a.nbuf;
+  const size_t smem = smem_for(g, c->cout, a.nbuf, dual, split);
+  if (smem > 227 * 1024) return LS3D_ERR_ARG;           // weights do not fit in shared memory: slice the channels / library conv
+  const int num_sms = ls3d_num_sms();
+  static bool optin[64] = {false};
+  cudaError_t eo = ls3d_optin_smem(conv3x3_f16_kernel, optin);
+  if (eo != cudaSuccess) return (int)eo;
+  InMaps m_in;
+  CUtensorMap m_res, m_out, m_out16;
+  const int es = dual ? 4 : 2;
+  int rc;
+  for (int ph = 0; ph < 4; ++ph) {
+    rc = make_map(&m_in.m[ph], c->in16, in_ct, c->W_in, c->H_in, c->n_img, 8, HALO_W, HALO_H, 2,
+                  stride == 2 ? ph : -1);
+    if (rc) return rc;
+    if (stride != 2 && ph == 0) {
+      m_in.m[1] = m_in.m[2] = m_in.m[3] = m_in.m[0];
+      break;
+    }
+  }
+  rc = make_map(&m_out, out, out_ct, W, H, c->n_img, c->cout, TW, TH, es);
+  if (rc) return rc;
+  rc = make_map(&m_res, c->res32 ? (const void*)c->res32 : out, out_ct, W, H, c->n_img, c->cout, TW, TH, es);
+  if (rc) return rc;
+  rc = make_map(&m_out16, dual ? c->out16 : out, out_ct, W, H, c->n_img, c->cout, TW, TH, 2);
+  if (rc) return rc;
+  const int grid = a.n_tiles < num_sms ? a.n_tiles : num_sms;
+  conv3x3_f16_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(a, m_in, m_res, m_out, m_out16);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}
+
+// fp16 maps (round-1 entry point): fp16 residual / output
+extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img,
+                             int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream) {
+  using namespace ls3d;
+  using namespace ls3d::c3;
+  if (n_img <= 0 || H <= 0 || W <= 0) return LS3D_OK;
+  if (!in || !w_packed || !out || !shape_ok(cin, cout, ksize, 1)) return LS3D_ERR_ARG;
+  if ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)res) | ((uintptr_t)w_packed)) & 15) return LS3D_ERR_ARG;
+  const int ntap = ntap_of(ksize);
+  const Geom g = geom(cin, cout, ntap);
+  Args a;
+  a.w = (const __half*)w_packed; a.bias = bias; a.has_res = res != nullptr; a.dual = 0;
+  a.n_img = n_img; a.H = H; a.W = W; a.cin = cin; a.cout = cout; a.relu = relu;
+  a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad; a.nphase = 1; a.kdata = g.kdata;
+  a.in_c_off = a.out_c_off = 0;
+  a.nb = g.n_pad;
+  if (a.nb > 256 || g.n_mma > MAX_MMA) return LS3D_ERR_ARG;
+  for (int j = 0; j < g.n_mma; ++j) {
+    int e0, e1;
+    mma_entries(j, g.kcg, ntap, 1, e0, e1);
     const int o0 = k_entry_offset(e0, g.kcg, ntap), o1 = k_entry_offset(e1, g.kcg, ntap);
     a.a_lo[j] = ((uint32_t)o0 >> 4) | (((uint32_t)(o1 - o0) >> 4) << 16);
   }
@@ -550,51 +668,43 @@ static int conv_launch(const void* in, const void* w_packed, const float* bias, 
   a.inv_tiles_x = 1.0f / (float)a.tiles_x;
   a.inv_tiles_per_img = 1.0f / (float)(a.tiles_x * a.tiles_y);
   a.nbuf = MAX_BUF;
-  while (a.nbuf > 2 && smem_for(g, cout, a.nbuf, dual, split) > 227 * 1024) --a.nbuf;
-  const size_t smem = smem_for(g, cout, a.nbuf, dual, split);
-  if (smem > 227 * 1024) return LS3D_ERR_ARG;           // weights do not fit in shared memory: caller uses the library conv
+  while (a.nbuf > 2 && smem_for(g, cout, a.nbuf, 0, 0) > 227 * 1024) --a.nbuf;
+  const size_t smem = smem_for(g, cout, a.nbuf, 0, 0);
+  if (smem > 227 * 1024) return LS3D_ERR_ARG;
   const int num_sms = ls3d_num_sms();
   static bool optin[64] = {false};
   cudaError_t eo = ls3d_optin_smem(conv3x3_f16_kernel, optin);
   if (eo != cudaSuccess) return (int)eo;
-  CUtensorMap m_in, m_res, m_out, m_out16;
-  const int es = dual ? 4 : 2;
-  int rc = make_map(&m_in, in, cin, W, H, n_img, 8, HALO_W, HALO_H);
+  InMaps m_in;
+  CUtensorMap m_res, m_out;
+  int rc = make_map(&m_in.m[0], in, cin, W, H, n_img, 8, HALO_W, HALO_H);
   if (rc) return rc;
-  rc = make_map(&m_out, out, cout, W, H, n_img, cout, TW, TH, es);
+  m_in.m[1] = m_in.m[2] = m_in.m[3] = m_in.m[0];
+  rc = make_map(&m_out, out, cout, W, H, n_img, cout, TW, TH, 2);
   if (rc) return rc;
-  rc = make_map(&m_res, res ? res : out, cout, W, H, n_img, cout, TW, TH, es);
-  if (rc) return rc;
-  rc = make_map(&m_out16, dual ? out16 : out, cout, W, H, n_img, cout, TW, TH, 2);
+  rc = make_map(&m_res, res ? res : out, cout, W, H, n_img, cout, TW, TH, 2);
   if (rc) return rc;
   const int grid = a.n_tiles < num_sms ? a.n_tiles : num_sms;
-  conv3x3_f16_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(a, m_in, m_res, m_out, m_out16);
+  conv3x3_f16_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(a, m_in, m_res, m_out, m_out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
 
-extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img,
-                             int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream) {
-  return conv_launch(in, w_packed, bias, res, out, nullptr, 0, 0, n_img, H, W, cin, cout, ksize, relu, stream);
-}
-
-// fp32 feature maps with fp16 tensor-core operands: `in` is the fp16 operand copy of the input map, `res` / `out` are fp32
-// maps (the residual stream never leaves fp32), `out16` receives the fp16 operand copy of the result for the next convolution.
-// out32 == NULL: operand-only result (out16 alone is written; res32 must be NULL) - a map that only feeds the next convolution.
-// w_split: w_packed comes from ls3d_conv_f16_pack_split (exact fp32 weights as fp16 hi + lo).
+// fp32 feature maps with fp16 tensor-core operands (see include/ls3d.h); thin wrapper over ls3d_conv_f16_ex
 extern "C" int ls3d_conv_f16_dual(const void* in16, const void* w_packed, const float* bias, const float* res32, float* out32,
                                   void* out16, int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize,
                                   int32_t relu, int32_t w_split, void* stream) {
-  if (!out32) {
-    if (res32 || !out16) return LS3D_ERR_ARG;
-    return conv_launch(in16, w_packed, bias, nullptr, out16, nullptr, 0, w_split ? 1 : 0, n_img, H, W, cin, cout, ksize, relu, stream);
-  }
-  return conv_launch(in16, w_packed, bias, res32, out32, out16, 1, w_split ? 1 : 0, n_img, H, W, cin, cout, ksize, relu, stream);
+  ls3d_conv_args c = {};
+  c.in16 = in16; c.in_c_total = cin; c.in_c_off = 0; c.cin = cin;
+  c.w_packed = w_packed; c.bias = bias; c.res32 = res32; c.out32 = out32; c.out16 = out16;
+  c.out_c_total = cout; c.out_c_off = 0; c.cout = cout;
+  c.n_img = n_img; c.H_in = H; c.W_in = W; c.ksize = ksize; c.stride = 1; c.relu = relu; c.w_split = w_split;
+  return ls3d_conv_f16_ex(&c, stream);
 }
 
 extern "C" int ls3d_conv_f16_dual_smem_bytes(int32_t cin, int32_t cout, int32_t ksize, int64_t* bytes) {
   using namespace ls3d::c3;
-  if (!bytes || cin <= 0 || cout <= 0 || (cin & 7) || (cout & 7) || !ntap_of(ksize)) return LS3D_ERR_ARG;
+  if (!bytes || !shape_ok(cin, cout, ksize, 1)) return LS3D_ERR_ARG;
   *bytes = (int64_t)smem_for(geom(cin, cout, ntap_of(ksize)), cout, 2, 1);
   return LS3D_OK;
 }

@@ -224,3 +224,26 @@ extern "C" int ls3d_cast_f16(const float* in, void* out, int64_t n, void* stream
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
+
+// fp32 [npix][3] (channels-last 3-channel images) -> fp16 [npix][8], channels 3..7 zero
+namespace ls3d {
+__global__ void __launch_bounds__(256) pad3_f16_kernel(const float* __restrict__ in, uint4* __restrict__ out, long long npix) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < npix; e += (long long)gridDim.x * blockDim.x) {
+    const float a = __ldg(in + 3 * e), b = __ldg(in + 3 * e + 1), c = __ldg(in + 3 * e + 2);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(a, b);
+    *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(c, 0.f);
+    out[e] = o;
+  }
+}
+}  // namespace ls3d
+
+extern "C" int ls3d_pad3_f16(const float* in, int64_t n_pixels, void* out, void* stream) {
+  if (n_pixels <= 0) return LS3D_OK;
+  if (!in || !out || (((uintptr_t)out) & 15)) return LS3D_ERR_ARG;
+  const long long blocks = (n_pixels + 255) / 256;
+  const int grid = (int)(blocks < 148LL * 32 ? blocks : 148LL * 32);
+  ls3d::pad3_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, (uint4*)out, n_pixels);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}

@@ -116,6 +116,7 @@ class SegMSeg3DNet(_SegBase):
         self.img_backbone.keep_channel_padding = True      # the image head consumes zero-padded channel maps directly
         dual = isinstance(self.image_dtype, str) and self.image_dtype == "dual"
         self.img_backbone.dual_maps = dual
+        self.img_backbone.keep_dual_maps = dual               # the image head consumes the operand copies as well
         if self.image_dtype is not None and not dual:
             images = images.to(self.image_dtype)
         img_data = dict(inputs=self.img_backbone(images), batch_size=batch_size)

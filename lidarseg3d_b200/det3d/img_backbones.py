@@ -155,6 +155,16 @@ def _own_conv_ok(conv, x):
 
 
 def conv_deferred_bias(conv, bn, x, dual=False):
+    if isinstance(x, DualMap):
+        if own_dual_ok(conv, bn, x.shape[1]):
+            plan = conv_plan(conv, bn, x.shape[1])
+            o32, _ = plan.run(x.f16, relu=False, want32=True, use_bias=False)
+            return o32, plan.bias
+        x = x.f32
+    return _conv_deferred_bias(conv, bn, x, dual)
+
+
+def _conv_deferred_bias(conv, bn, x, dual=False):
     """conv -> BatchNorm (folded) WITHOUT the shift: returns (conv(x, w_folded), shift fp32 [Cout_p]).  For the linear terms
     of a branch fusion: the caller sums the shifts of all terms and ls3d_upsample_sum adds them once (a library convolution
     with a bias and no activation would run a separate elementwise add over every output map)."""
@@ -168,64 +178,128 @@ def conv_deferred_bias(conv, bn, x, dual=False):
 
 
 DUAL_EXACT_WEIGHTS = os.environ.get("LS3D_DUAL_EXACT_WEIGHTS", "1") == "1"
+DUAL_OWN_ALL = os.environ.get("LS3D_DUAL_OWN_ALL", "1") == "1"     # 0: only 3x3 stride-1 convs on the own kernel (development A/B)
 
 
-def folded_packed_dual(conv, bn, x_channels):
-    """BN-folded weights of a 3x3 / 1x1 stride-1 convolution packed for ls3d_conv_f16_dual.  Returns (mode, w, w_lo, bias,
-    cout_p): mode "split" = one launch on split weights [W_hi ; W_lo]; "hilo" = the shape has no split configuration (the
-    doubled weight block does not fit shared memory): two launches, W_hi then W_lo accumulated through the fp32 residual
-    input; "plain" = fp16-rounded weights (DUAL_EXACT_WEIGHTS off); None = not served by the own kernel."""
-    ver = _versions(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
-    store = conv.__dict__.setdefault("_ls3d_fold3", {})
+class ConvPlan:
+    """One BN-folded convolution (3x3 stride 1 / 2, or 1x1) as launches of ls3d_conv_f16_ex (csrc/conv3x3_f16.cu).
+
+    The weights [cout_p, cin_p, k, k] are cut into output-channel slices (<= 128 channels: the split-weight accumulator holds
+    2 n_pad <= 256 columns) and input-channel slices (so that the resident weight block and two stages fit shared memory);
+    launches over the input slices of one output slice accumulate through the fp32 residual input.  With ``split`` the fp32
+    weights enter exactly (fp16 hi + lo)."""
+
+    def __init__(self, w, bias, ksize, stride, split):
+        from .. import ops
+        cout_p, cin_p = w.shape[:2]
+        self.cout_p, self.cin_p, self.k, self.stride, self.split = cout_p, cin_p, ksize, stride, split
+        self.bias = None if bias is None else bias.float().contiguous()
+        best = None
+        for n_out in (1, 2, 3, 4, 6, 8):
+            cs = ((cout_p + n_out - 1) // n_out + 7) // 8 * 8
+            if split and cs > 128:
+                continue
+            for n_in in (1, 2, 3, 4, 6, 8, 12, 16, 32):
+                ci = ((cin_p + n_in - 1) // n_in + 7) // 8 * 8
+                if ops.conv_ex_supported(ci, cs, ksize, stride, dual=True, split=split):
+                    cand = (n_in * n_out, n_out, cs, ci)
+                    best = cand if best is None or cand < best else best
+                    break
+        self.ok = best is not None
+        if not self.ok:
+            return
+        _, _, cs, ci = best
+        self.launches = []          # (out_off, cout, [(in_off, cin, packed)])
+        for o0 in range(0, cout_p, cs):
+            co = min(cs, cout_p - o0)
+            ins = []
+            for i0 in range(0, cin_p, ci):
+                cn = min(ci, cin_p - i0)
+                ins.append((i0, cn, ops.pack_conv_ex(w[o0:o0 + co, i0:i0 + cn].contiguous(), stride, split)))
+            self.launches.append((o0, co, ins))
+        self.n_launch = sum(len(l[2]) for l in self.launches)
+
+    def run(self, x16, res32=None, relu=True, want32=True, use_bias=True):
+        """x16 [N, cin_p, H, W] fp16 channels-last -> (out32 or None, out16)."""
+        from .. import ops
+        N, C, H, W = x16.shape
+        assert C == self.cin_p and x16.dtype == torch.float16 and x16.is_contiguous(memory_format=torch.channels_last)
+        Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if self.stride == 2 else (H, W)
+        multi = any(len(l[2]) > 1 for l in self.launches)
+        need32 = want32 or multi or res32 is not None
+        out16 = torch.empty((N, self.cout_p, Ho, Wo), dtype=torch.float16, device=x16.device, memory_format=torch.channels_last)
+        out32 = torch.empty((N, self.cout_p, Ho, Wo), dtype=torch.float32, device=x16.device,
+                            memory_format=torch.channels_last) if need32 else None
+        for o0, co, ins in self.launches:
+            for i, (i0, cn, wp) in enumerate(ins):
+                first, last = i == 0, i == len(ins) - 1
+                b = self.bias[o0:o0 + co] if (first and use_bias and self.bias is not None) else None
+                r = res32 if first else out32
+                ops.conv_ex(x16, wp, b, cin=cn, in_off=i0, cout=co, out_off=o0, out32=out32, out16=out16, res32=r,
+                            ksize=self.k, stride=self.stride, relu=relu and last, split=self.split)
+        return (out32 if want32 or res32 is not None else None), out16
+
+
+def _plannable(conv):
+    k, st = conv.kernel_size, conv.stride
+    if conv.groups != 1 or conv.dilation != (1, 1) or k[0] != k[1] or st[0] != st[1]:
+        return False
+    if k == (3, 3) and conv.padding == (1, 1) and st in ((1, 1), (2, 2)):
+        return True
+    return k == (1, 1) and conv.padding == (0, 0) and st == (1, 1)
+
+
+def conv_plan(conv, bn, x_channels):
+    """The cached ConvPlan of conv (+ folded eval BatchNorm ``bn``, may be None: the conv's own bias) for an input map with
+    ``x_channels`` (zero-padded) channels; None when the own kernel does not serve the shape."""
+    ts = (conv.weight, conv.bias) if bn is None else (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    ver = _versions(*ts)
+    store = conv.__dict__.setdefault("_ls3d_plan", {})
     if store.get("ver") != ver:
         store.clear()
         store["ver"] = ver
-    key = ("dualpk", x_channels, PAD_CHANNELS, DUAL_EXACT_WEIGHTS)
-    ent = store.get(key)
-    if ent is None:
-        from .. import ops
-        k = conv.kernel_size[0]
-        cout_p = _pad_to(conv.out_channels, torch.float16)
-        if not ops.conv_f16_dual_supported(x_channels, cout_p, k):
-            ent = (None, None, None, None, cout_p)
-        else:
+    key = (x_channels, DUAL_EXACT_WEIGHTS)
+    if key not in store:
+        plan = None
+        if _plannable(conv) and x_channels % 8 == 0 and x_channels >= conv.in_channels:
             with torch.no_grad():
-                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-                w = (conv.weight * scale.view(-1, 1, 1, 1)).float()
-                b = (bn.bias - bn.running_mean * scale).float()
+                k = conv.kernel_size[0]
+                cout_p = _pad_to(conv.out_channels, torch.float16)
+                if bn is None:
+                    w = conv.weight.float()
+                    b = conv.bias.float() if conv.bias is not None else torch.zeros(conv.out_channels, device=w.device)
+                else:
+                    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                    w = (conv.weight * scale.view(-1, 1, 1, 1)).float()
+                    b = (bn.bias - bn.running_mean * scale).float()
                 wp = w.new_zeros(cout_p, x_channels, k, k)
                 wp[:conv.out_channels, :conv.in_channels] = w
                 bp = b.new_zeros(cout_p)
                 bp[:conv.out_channels] = b
-                bp = bp.contiguous()
-                if not DUAL_EXACT_WEIGHTS:
-                    ent = ("plain", ops.pack_conv_f16(wp), None, bp, cout_p)
-                elif ops.conv_f16_split_supported(x_channels, cout_p, k, dual=True):
-                    ent = ("split", ops.pack_conv_f16_split(wp), None, bp, cout_p)
-                else:
-                    hi = wp.half().float()
-                    ent = ("hilo", ops.pack_conv_f16(hi), ops.pack_conv_f16(wp - hi), bp, cout_p)
-        store[key] = ent
-    return ent
+                plan = ConvPlan(wp, bp, k, conv.stride[0], DUAL_EXACT_WEIGHTS)
+                if not plan.ok:
+                    plan = None
+        store[key] = plan
+    return store[key]
+
+
+def own_dual_ok(conv, bn, channels):
+    """Will _cbr_dual run ``conv`` on the own kernel (so that its input may be an operand-only map)?"""
+    if not FUSED_CONV3X3:
+        return False
+    if not DUAL_OWN_ALL and not (conv.kernel_size == (3, 3) and conv.stride == (1, 1)):
+        return False
+    return conv_plan(conv, bn, channels) is not None
 
 
 def _cbr_dual(conv, bn, x, relu, z, want):
-    """cbr on DualMaps (fp32 maps, fp16 tensor-core operands).  want: "f16" = the result only feeds an own convolution (no fp32
-    map is written), "both" = fp32 map + operand copy, "f32" = fp32 map (operand copy on demand)."""
-    from .. import ops
+    """cbr on DualMaps (fp32 maps, fp16 tensor-core operands).  want: "f16" = the result only feeds own convolutions (no fp32
+    map is written), "both" / "f32" = fp32 map (+ operand copy)."""
     C = x.shape[1]
-    if (FUSED_CONV3X3 and _is_plain(conv) and C % 8 == 0 and
-            (conv.kernel_size == (3, 3) or x.shape[0] * x.shape[2] * x.shape[3] >= OWN_1X1_DUAL_MIN_PIXELS)):
-        k = conv.kernel_size[0]
-        mode, wp, wlo, bp, cout_p = folded_packed_dual(conv, bn, C)
-        if mode is not None and (z is None or z.shape[1] == cout_p):
-            z32 = None if z is None else z.f32
-            if mode == "hilo":
-                t32, _ = ops.conv_f16_dual(x.f16, wp, bp, res32=z32, relu=False, cout=cout_p, ksize=k)
-                o32, o16 = ops.conv_f16_dual(x.f16, wlo, None, res32=t32, relu=relu, cout=cout_p, ksize=k)
-            else:
-                o32, o16 = ops.conv_f16_dual(x.f16, wp, bp, res32=z32, relu=relu, cout=cout_p, ksize=k, split=mode == "split",
-                                             want32=not (want == "f16" and z is None))
+    if own_dual_ok(conv, bn, C):
+        plan = conv_plan(conv, bn, C)
+        if z is None or z.shape[1] == plan.cout_p:
+            o32, o16 = plan.run(x.f16, res32=None if z is None else z.f32, relu=relu, want32=want != "f16")
             return DualMap(o32, o16)
     w, b = folded(conv, bn, C, torch.float32, pad_dtype=torch.float16)
     xf, zf = x.f32, (None if z is None else z.f32)
@@ -237,13 +311,6 @@ def _cbr_dual(conv, bn, x, relu, z, want):
     if zf is not None:
         y = y + zf
     return DualMap(torch.relu_(y) if relu else y)
-
-
-def own_dual_ok(conv, channels):
-    """Will _cbr_dual run ``conv`` on the own kernel (so that its input may be an operand-only map)?"""
-    from .. import ops
-    return (FUSED_CONV3X3 and _is_plain(conv) and conv.kernel_size == (3, 3) and channels % 8 == 0
-            and ops.conv_f16_dual_supported(channels, _pad_to(conv.out_channels, torch.float16), 3))
 
 
 def cbr(conv, bn, x, relu, z=None, want="both"):
@@ -288,7 +355,7 @@ class BasicBlock(nn.Module):
     def forward(self, x):
         idt = x if self.downsample is None else cbr(self.downsample[0], self.downsample[1], x, False)
         want = "both"
-        if isinstance(x, DualMap) and own_dual_ok(self.conv2, _pad_to(self.conv1.out_channels, torch.float16)):
+        if isinstance(x, DualMap) and own_dual_ok(self.conv2, self.bn2, _pad_to(self.conv1.out_channels, torch.float16)):
             want = "f16"                                          # conv1's result is only ever conv2's operand
         out = cbr(self.conv1, self.bn1, x, True, want=want)
         return cbr(self.conv2, self.bn2, out, True, z=idt)
@@ -310,8 +377,15 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         idt = x if self.downsample is None else cbr(self.downsample[0], self.downsample[1], x, False)
-        out = cbr(self.conv1, self.bn1, x, True)
-        out = cbr(self.conv2, self.bn2, out, True)
+        w1 = w2 = "both"
+        if isinstance(x, DualMap):              # conv1 / conv2 results are operands of the next convolution only
+            c1 = _pad_to(self.conv1.out_channels, torch.float16)
+            if own_dual_ok(self.conv2, self.bn2, c1):
+                w1 = "f16"
+            if own_dual_ok(self.conv3, self.bn3, _pad_to(self.conv2.out_channels, torch.float16)):
+                w2 = "f16"
+        out = cbr(self.conv1, self.bn1, x, True, want=w1)
+        out = cbr(self.conv2, self.bn2, out, True, want=w2)
         return cbr(self.conv3, self.bn3, out, True, z=idt)
 
 
@@ -414,13 +488,11 @@ def _forward_fused(self, x):
     outs = []
     cache = self.__dict__.setdefault("_ls3d_fuse_bias", {})
     dual = isinstance(x[0], DualMap)
-    if dual:                                  # the linear fusion terms are fp32 maps; library 1x1 / stride-2 convs read them
-        x = [t.f32 for t in x]
     for i in range(len(self.fuse_layers)):
         terms, shifts = [], []
         for j in range(self.num_branches):
             if i == j:
-                terms.append(x[j])
+                terms.append(x[j].f32 if dual else x[j])
             elif j > i:
                 fl = self.fuse_layers[i][j]
                 t, b = conv_deferred_bias(fl[0], fl[1], x[j], dual)
@@ -430,7 +502,7 @@ def _forward_fused(self, x):
                 t = x[j]
                 for seq in self.fuse_layers[i][j]:
                     if len(seq) == 3:
-                        t = cbr(seq[0], seq[1], DualMap(t), True).f32 if dual else cbr(seq[0], seq[1], t, True)
+                        t = cbr(seq[0], seq[1], t, True, want="f16")      # feeds the next stride-2 convolution only
                     else:
                         t, b = conv_deferred_bias(seq[0], seq[1], t, dual)
                         shifts.append(b)
@@ -540,11 +612,20 @@ class HRNet(nn.Module):
                     p.requires_grad = False
 
     def forward(self, x):
-        x = cbr(self.conv1, self.bn1, x, True)
-        x = cbr(self.conv2, self.bn2, x, True)
         dual = getattr(self, "dual_maps", False) and x.is_cuda and not self.training and x.dtype == torch.float32
-        if dual:
-            x = DualMap(x)
+        if dual and x.shape[1] == 3 and x.is_contiguous(memory_format=torch.channels_last) and own_dual_ok(self.conv1, self.bn1, 8):
+            from .. import ops
+            x = DualMap(None, ops.pad3_f16(x))               # operand copy of the image, 8-channel pixel rows
+            x = cbr(self.conv1, self.bn1, x, True, want="f16" if own_dual_ok(self.conv2, self.bn2, 64) else "both")
+            l0 = self.layer1[0]                               # its conv1 and downsample conv are the only readers of the stem map
+            only_ops = (l0.downsample is not None and own_dual_ok(l0.conv1, l0.bn1, 64)
+                        and own_dual_ok(l0.downsample[0], l0.downsample[1], 64))
+            x = cbr(self.conv2, self.bn2, x, True, want="f16" if only_ops else "both")
+        else:
+            x = cbr(self.conv1, self.bn1, x, True)
+            x = cbr(self.conv2, self.bn2, x, True)
+            if dual:
+                x = DualMap(x)
         x = self.layer1(x)
         ys = [x]
         for st in (2, 3, 4):
@@ -562,8 +643,10 @@ class HRNet(nn.Module):
                 else:
                     xs.append(ys[i])
             ys = getattr(self, f"stage{st}")(xs)
-        if dual:
+        if dual and not getattr(self, "keep_dual_maps", False):
             ys = [y.f32 for y in ys]
+        if dual and getattr(self, "keep_dual_maps", False):
+            return ys
         if not getattr(self, "keep_channel_padding", False):
             true_c = [c * self.blocks_dict[self.extra["stage4"]["block"]].expansion for c in self.extra["stage4"]["num_channels"]]
             ys = [y if y.shape[1] == c else y[:, :c] for y, c in zip(ys, true_c)]

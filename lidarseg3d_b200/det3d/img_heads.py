@@ -6,7 +6,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
-from .img_backbones import _bn, cbr, folded
+from .img_backbones import ConvPlan, DualMap, _bn, _pad_to, _versions, cbr, conv_plan, folded
+from . import img_backbones as _ib
 from .registry import IMG_HEADS
 
 
@@ -126,10 +127,68 @@ class FCNMSeg3DHead(nn.Module):
             y = y + F.interpolate(t, size=(H, W), mode="bilinear", align_corners=self.align_corners)
         return torch.relu_(y)
 
+    def _forward_dual(self, batch_dict):
+        """fp32 maps with fp16 operand copies (DualMap inputs): every convolution of the head on ls3d_conv_f16_ex with exact
+        weights - per-branch 1x1 convolutions at native resolution, resize + sum + folded-BN shift + ReLU in one pass
+        (ls3d_upsample_sum_dual), the remaining 1x1 ConvModules, conv_seg (17 -> 24 zero-padded class channels)."""
+        xs = [batch_dict["inputs"][i] for i in self.in_index]
+        cm = self.convs[0]
+        ver = _versions(cm.conv.weight, cm.bn.weight, cm.bn.bias, cm.bn.running_mean, cm.bn.running_var)
+        key = (tuple(x.shape[1] for x in xs), ver, _ib.DUAL_EXACT_WEIGHTS)
+        ent = self.__dict__.get("_ls3d_dual_branch")
+        if ent is None or ent[0] != key:
+            with torch.no_grad():
+                bn = cm.bn
+                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                w = (cm.conv.weight * scale.view(-1, 1, 1, 1)).float()
+                b = (bn.bias - bn.running_mean * scale).float()
+                cout_p = _pad_to(w.shape[0], torch.float16)
+                plans, c0 = [], 0
+                for x, c in zip(xs, self._branch_channels):
+                    wb = w.new_zeros(cout_p, x.shape[1], 1, 1)
+                    wb[:w.shape[0], :c] = w[:, c0:c0 + c]
+                    plans.append(ConvPlan(wb, None, 1, 1, _ib.DUAL_EXACT_WEIGHTS))
+                    c0 += c
+                bp = b.new_zeros(cout_p)
+                bp[:w.shape[0]] = b
+            ent = self.__dict__["_ls3d_dual_branch"] = (key, plans, bp.contiguous())
+        _, plans, bias = ent
+        if not all(pl.ok for pl in plans):
+            return None
+        terms = [pl.run(x.f16, relu=False, want32=True, use_bias=False)[0] for pl, x in zip(plans, xs)]
+        feats = DualMap(*ops.upsample_sum_dual(terms, relu=True, bias=bias))
+        for m in list(self.convs)[1:]:
+            feats = m(feats)
+        seg = conv_plan(self.conv_seg, None, feats.shape[1])
+        if seg is None:
+            return None
+        logits_p, _ = seg.run(feats.f16, relu=False, want32=True)            # [N, 24, h, w]: classes zero-padded to 8k channels
+        f32 = feats.f32
+        n, Cp, h, w_ = f32.shape
+        rows = (n // batch_dict["batch_size"]) * h * w_
+        off = torch.arange(0, batch_dict["batch_size"] + 1, dtype=torch.int32, device=f32.device) * rows
+        emb = ops.class_embed(logits_p.permute(0, 2, 3, 1).reshape(-1, logits_p.shape[1]), f32.permute(0, 2, 3, 1).reshape(-1, Cp),
+                              off, batch_dict["batch_size"], rows, ncls=self.num_classes, C=self.channels)
+        logits = logits_p[:, :self.num_classes]
+        if Cp != self.channels:
+            f32 = f32[:, :self.channels].contiguous(memory_format=torch.channels_last)
+        self.forward_ret_dict["image_logits"] = logits
+        batch_dict["image_logits"] = logits
+        batch_dict["image_features"] = f32
+        batch_dict["camera_semantic_embeddings"] = emb
+        return batch_dict
+
     def forward(self, batch_dict, return_loss=True, **kwargs):
         if return_loss:
             raise NotImplementedError("lidarseg3d_b200 image head: inference path only (return_loss=False)")
         inputs = batch_dict["inputs"]
+        if isinstance(inputs[0], DualMap):
+            if (self.input_transform == "resize_concat" and self.num_convs > 0 and self.kernel_size == 1 and not self.training
+                    and self.convs[0].with_norm and not self.concat_input and not self.align_corners and len(self.in_index) <= 4):
+                out = self._forward_dual(batch_dict)
+                if out is not None:
+                    return out
+            inputs = batch_dict["inputs"] = [x.f32 for x in inputs]
         fast = (self.input_transform == "resize_concat" and self.num_convs > 0 and self.kernel_size == 1 and inputs[0].is_cuda
                 and not self.training and self.convs[0].with_norm and not self.concat_input)
         if fast:

@@ -408,6 +408,53 @@ def conv_f16_dual(x16, w_packed, bias, res32=None, relu=True, cout=None, ksize=3
     return out32, out16
 
 
+def conv_ex_supported(cin, cout, ksize, stride, dual=True, split=True):
+    """ls3d_conv_f16_ex has a shared / tensor-memory configuration for a (cin -> cout) launch of this kind."""
+    if cin % 8 or cout % 8 or cin <= 0 or cout <= 0:
+        return False
+    ok = ctypes.c_int32()
+    check(capi.lib().ls3d_conv_f16_ex_supported(cin, cout, ksize, stride, int(dual), int(split), ctypes.byref(ok)),
+          "ls3d_conv_f16_ex_supported")
+    return bool(ok.value)
+
+
+def pack_conv_ex(w_oihw, stride=1, split=True):
+    """[Cout, Cin, k, k] fp32 (both multiples of 8) -> packed block of ls3d_conv_f16_ex for this (stride, split)."""
+    cout, cin, k = w_oihw.shape[:3]
+    w = w_oihw.detach().float().contiguous()
+    nb = ctypes.c_int64()
+    check(capi.lib().ls3d_conv_f16_packed_bytes(cin, cout, k, ctypes.byref(nb)), "ls3d_conv_f16_packed_bytes")
+    out = torch.empty(nb.value // 2 * (2 if split else 1), dtype=torch.float16, device=w.device)
+    check(capi.lib().ls3d_conv_f16_pack_ex(ptr(w), cin, cout, k, stride, int(split), ptr(out), stream_ptr()),
+          "ls3d_conv_f16_pack_ex")
+    return out
+
+
+def conv_ex(x16, w_packed, bias, *, cin, in_off, cout, out_off, out32, out16, res32=None, ksize=3, stride=1, relu=False,
+            split=True):
+    """One ls3d_conv_f16_ex launch: input channels [in_off, in_off + cin) of the fp16 channels-last map ``x16`` -> output channels
+    [out_off, out_off + cout) of ``out32`` (fp32, may be None: operand-only) / ``out16`` (fp16), both preallocated channels-last;
+    ``res32`` (may alias out32) is added before the ReLU."""
+    N, ct, H, W = x16.shape
+    a = capi.ConvArgs()
+    a.in16, a.w_packed, a.bias = ptr(x16), ptr(w_packed), ptr(bias)
+    a.res32, a.out32, a.out16 = ptr(res32), ptr(out32), ptr(out16)
+    a.in_c_total, a.in_c_off, a.cin = ct, in_off, cin
+    a.out_c_total, a.out_c_off, a.cout = out16.shape[1], out_off, cout
+    a.n_img, a.H_in, a.W_in, a.ksize, a.stride, a.relu, a.w_split = N, H, W, ksize, stride, int(relu), int(split)
+    check(capi.lib().ls3d_conv_f16_ex(ctypes.byref(a), stream_ptr()), "ls3d_conv_f16_ex")
+
+
+def pad3_f16(x):
+    """fp32 channels-last image batch [N, 3, H, W] -> fp16 [N, 8, H, W] channels-last, channels 3..7 zero: the operand copy of
+    the network input for the own stem convolution (16-byte pixel rows for the tensor-map copies)."""
+    N, C, H, W = x.shape
+    assert C == 3 and x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((N, 8, H, W), dtype=torch.float16, device=x.device, memory_format=torch.channels_last)
+    check(capi.lib().ls3d_pad3_f16(ptr(x), N * H * W, ptr(out), stream_ptr()), "ls3d_pad3_f16")
+    return out
+
+
 def cast_f16(x):
     """fp16 (RNE) copy of an fp32 tensor, same memory layout (ls3d_cast_f16)."""
     assert x.dtype == torch.float32 and x.numel() % 4 == 0

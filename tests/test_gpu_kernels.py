@@ -382,6 +382,55 @@ def test_conv_f16_dual_split_weights_vs_fp64(n, h, w, cin, cout, res, relu, k):
         assert n32 is None and torch.equal(o16, y16)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,k,stride,res,relu", [
+    (2, 32, 48, 8, 64, 3, 2, False, True),          # stem conv1: 3 (-> 8 padded) -> 64, stride 2
+    (1, 40, 60, 64, 64, 3, 2, False, True),         # stem conv2
+    (2, 20, 30, 24, 40, 3, 2, False, False),        # fuse-layer downsample
+    (1, 17, 23, 24, 24, 3, 2, False, True),         # odd sizes: the last output row / column reads the zero padding
+    (1, 16, 24, 256, 40, 3, 2, False, True),        # transition from the 256-channel stage: input slices
+    (1, 40, 60, 72, 72, 3, 1, True, True),          # 72 channels: the split weight block needs input slices
+    (2, 20, 30, 144, 144, 3, 1, True, True),        # 144 channels: output AND input slices
+    (1, 40, 60, 64, 256, 1, 1, True, True),         # Bottleneck conv3: two 128-channel output slices
+    (1, 40, 60, 256, 64, 1, 1, False, True),        # Bottleneck conv1 of the later blocks
+    (1, 24, 36, 144, 48, 1, 1, False, False),       # FCN head branch 1x1
+    (3, 9, 7, 48, 24, 1, 1, False, False)])         # conv_seg (17 -> 24 padded classes)
+def test_conv_plan_vs_fp64(n, h, w, cin, cout, k, stride, res, relu):
+    """ls3d_conv_f16_ex through the launch planner of the camera branch (stride 2 via phase planes, channel slices accumulated
+    through the fp32 residual input, split exact weights) against an fp64 convolution of the fp16 activations with the
+    UNROUNDED weights."""
+    import torch.nn.functional as F
+    from lidarseg3d_b200.det3d.img_backbones import ConvPlan
+    g = torch.Generator().manual_seed(n * 53 + h + cin + cout)
+    x = torch.randn(n, cin, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
+    z = torch.randn(n, cout, ho, wo, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) if res else None
+    plan = ConvPlan(wt, b, k, stride, True)
+    assert plan.ok
+    y32, y16 = plan.run(x, res32=z, relu=relu)
+    ref = F.conv2d(x.double(), wt.double(), b.double(), stride=stride, padding=k // 2)
+    if z is not None:
+        ref = ref + z.double()
+    if relu:
+        ref = ref.relu()
+    assert y32.shape == ref.shape
+    err = float((y32.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 3e-6, (err, plan.n_launch)
+    assert torch.equal(y16, y32.half())
+    if z is None and plan.n_launch == len(plan.launches):             # single input slice: operand-only variant
+        n32, o16 = plan.run(x, relu=relu, want32=False)
+        assert n32 is None and torch.equal(o16, y16)
+
+
+def test_pad3_f16():
+    ops, _ = _ops()
+    x = torch.randn(2, 3, 10, 14).to(DEV).contiguous(memory_format=torch.channels_last)
+    y = ops.pad3_f16(x)
+    assert y.shape == (2, 8, 10, 14) and y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y[:, :3], x.half()) and float(y[:, 3:].abs().max()) == 0.0
+
+
 def test_conv_f16_split_not_supported_shapes():
     ops, _ = _ops()
     assert not ops.conv_f16_split_supported(72, 72, 3)          # doubled weight block does not fit shared memory
