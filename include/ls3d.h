@@ -236,6 +236,8 @@ int ls3d_cast_f16(const float* in, void* out, int64_t n, void* stream);
 /* fp32 [n_pixels][3] (channels-last network input) -> fp16 [n_pixels][8] with channels 3..7 zero: operand copy of the image for
  * the own stem convolution (hrnet.py:658-666), whose tensor-map copies need 16-byte pixel rows */
 int ls3d_pad3_f16(const float* in, int64_t n_pixels, void* out, void* stream);
+/* fp32 copy of n fp16 values (n a multiple of 4) */
+int ls3d_cast_f32(const void* in, float* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera input preparation: uint8 [n_pixels][3] (HWC images, any batch of them back to back) -> (x / 255 - mean[c]) / std[c]
@@ -325,6 +327,7 @@ typedef struct ls3d_conv_args {
   int32_t in_c_total, in_c_off, cin;
   int32_t out_c_total, out_c_off, cout;
   int32_t n_img, H_in, W_in, ksize, stride, relu, w_split;
+  const void* res16;      /* fp16 residual [n_img, H_out, W_out, out_c_total] for operand-only launches (out32 == NULL): fp16 maps */
 } ls3d_conv_args;
 int ls3d_conv_f16_ex(const ls3d_conv_args* args, void* stream);
 int ls3d_conv_f16_ex_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t dual, int32_t split,

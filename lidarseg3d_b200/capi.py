@@ -75,7 +75,7 @@ class ConvArgs(ctypes.Structure):
     _fields_ = [("in16", c_void_p), ("w_packed", c_void_p), ("bias", c_void_p), ("res32", c_void_p), ("out32", c_void_p),
                 ("out16", c_void_p), ("in_c_total", c_int), ("in_c_off", c_int), ("cin", c_int), ("out_c_total", c_int),
                 ("out_c_off", c_int), ("cout", c_int), ("n_img", c_int), ("H_in", c_int), ("W_in", c_int), ("ksize", c_int),
-                ("stride", c_int), ("relu", c_int), ("w_split", c_int)]
+                ("stride", c_int), ("relu", c_int), ("w_split", c_int), ("res16", c_void_p)]
 
 
 P, I, L = c_void_p, c_int, ctypes.c_int64
@@ -117,6 +117,7 @@ _SIGNATURES = {
     "ls3d_conv_f16_ex_supported": ([I, I, I, I, I, I, ctypes.POINTER(ctypes.c_int32)], ctypes.c_int),
     "ls3d_conv_f16_pack_ex": ([P, I, I, I, I, I, P, P], ctypes.c_int),
     "ls3d_pad3_f16": ([P, L, P, P], ctypes.c_int),
+    "ls3d_cast_f32": ([P, P, L, P], ctypes.c_int),
     "ls3d_conv_f16_dual_smem_bytes": ([I, I, I, PL], ctypes.c_int),
     "ls3d_upsample_sum_dual": ([P, P, P, I, I, I, I, I, I, P, P, P, P], ctypes.c_int),
     "ls3d_cast_f16": ([P, P, L, P], ctypes.c_int),
@@ -157,7 +158,7 @@ KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_tile_plan_build": 1, "ls3d_voxe
                     "ls3d_rulebook_gather": 1, "ls3d_rulebook_scatter": 1, "ls3d_three_nn_grid": 2, "ls3d_three_nn": 1,
                     "ls3d_three_interpolate": 1, "ls3d_sample_image_features": 1, "ls3d_project_points": 1, "ls3d_project_points_global": 1,
                     "ls3d_resize_images_u8": 1, "ls3d_upsample_sum": 1, "ls3d_upsample_sum_f16": 1,
-                    "ls3d_conv3x3_f16": 1, "ls3d_conv3x3_f16_pack": 1, "ls3d_conv_f16": 1, "ls3d_conv_f16_dual": 1, "ls3d_upsample_sum_dual": 1, "ls3d_cast_f16": 1, "ls3d_conv_f16_pack": 1, "ls3d_conv_f16_pack_split": 1, "ls3d_conv_f16_ex": 1, "ls3d_conv_f16_pack_ex": 1, "ls3d_pad3_f16": 1, "ls3d_normalize_images_u8": 1, "ls3d_token_attention": 1, "ls3d_class_embed": 4,
+                    "ls3d_conv3x3_f16": 1, "ls3d_conv3x3_f16_pack": 1, "ls3d_conv_f16": 1, "ls3d_conv_f16_dual": 1, "ls3d_upsample_sum_dual": 1, "ls3d_cast_f16": 1, "ls3d_conv_f16_pack": 1, "ls3d_conv_f16_pack_split": 1, "ls3d_conv_f16_ex": 1, "ls3d_conv_f16_pack_ex": 1, "ls3d_pad3_f16": 1, "ls3d_cast_f32": 1, "ls3d_normalize_images_u8": 1, "ls3d_token_attention": 1, "ls3d_class_embed": 4,
                     "ls3d_class_tokens": 1}
 
 

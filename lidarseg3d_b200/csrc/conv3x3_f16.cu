@@ -33,7 +33,9 @@ namespace c3 {
 constexpr int TW = 8, TH = 16;              // output tile: 8 wide x 16 tall
 constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
 constexpr int HPIX = HALO_W * HALO_H;       // 180 halo pixels
-constexpr int CH_STRIDE = 2944;             // bytes between channel chunks of a halo buffer (180 * 16 rounded up to 128)
+constexpr int CH_STRIDE = 2944;             // bytes between channel chunks of a 3x3 halo buffer (180 * 16 rounded up to 128)
+constexpr int CH_STRIDE_1X1 = 2048;         // 1x1: the staged box is the 128-pixel tile itself
+__host__ __device__ __forceinline__ int ch_stride_of(int ntap) { return ntap == 1 ? CH_STRIDE_1X1 : CH_STRIDE; }
 constexpr int PROD_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 2, N_EPI_WARPS = 8;   // two epilogue teams of 4 warps alternate tiles
 constexpr int N_THREADS = (EPI_WARP0 + N_EPI_WARPS) * 32;
 constexpr int MAX_BUF = 8;
@@ -52,6 +54,8 @@ struct Args {
                           // input, each loaded through its own tensor map (same memory, doubled pixel strides)
   int kdata;              // nphase * kcg data chunks per halo buffer (chunk kdata = the all-zero chunk when kc > kdata)
   int in_c_off, out_c_off;   // channel offsets of this launch's slices inside the input / output (and residual) tensors
+  int ch_stride;             // bytes between the channel chunks of a staged box
+  int halo_w, halo_pix, org; // staged input box: (TW + 2) x (TH + 2) from (-1, -1) for 3x3; exactly the TW x TH tile for 1x1
   float inv_tiles_x, inv_tiles_per_img;
   // per MMA: low word of the A descriptor less the stage base = (offset of the lower K entry >> 4) | (LBO >> 4) << 16.
   // Lives in the kernel parameters so that the issue loop reads it with a warp-uniform constant load: descriptors fetched
@@ -84,9 +88,10 @@ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n) {
 // stride 2 (nphase = 4): tap row dy reads input row 2 oy + dy - 1 = phase plane (dy odd ? even rows : odd rows) at block row
 // oy - 1 (dy = 0) or oy (dy = 1, 2); the halo origin is block (ox0 - 1, oy0 - 1), so the in-halo offset is 0 or 1.  Columns alike.
 __host__ __device__ __forceinline__ int k_entry_offset(int c, int kcg, int ntap, int nphase = 1) {
-  if (c >= ntap * kcg) return nphase * kcg * CH_STRIDE;
+  if (c >= ntap * kcg) return nphase * kcg * ch_stride_of(ntap);
   const int t = c / kcg, kc = c - t * kcg;
-  const int tap = ntap == 1 ? 4 : t;                     // 1x1: the centre tap
+  if (ntap == 1) return kc * CH_STRIDE_1X1;              // 1x1: the staged box is the tile itself
+  const int tap = t;
   const int dy = tap / 3, dx = tap % 3;
   if (nphase == 1) return kc * CH_STRIDE + (dy * HALO_W + dx) * 16;
   const int by = dy == 0 ? 0 : 1, py = dy == 1 ? 0 : 1;
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t w_bytes = (uint32_t)p.n_mma * 2u * p.nb * 16u;
-  const uint32_t halo_bytes = (uint32_t)p.kc * CH_STRIDE;
+  const uint32_t halo_bytes = (uint32_t)p.kc * (uint32_t)p.ch_stride;
   const uint32_t io32_bytes = p.dual ? 128u * p.cout * 4u : 0u;      // dual: fp32 residual / output tile, then the fp16 copy
   const uint32_t io_bytes = io32_bytes + 128u * p.cout * 2u;
   const uint32_t stage_bytes = halo_bytes + io_bytes;                 // both multiples of 128
@@ -188,9 +193,9 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     for (uint32_t i = tid; i < w_bytes / 16; i += N_THREADS) dst[i] = __ldg(src + i);
     for (int c = tid; c < p.n_pad; c += N_THREADS) bias_s[c] = (p.bias && c < p.cout) ? __ldg(p.bias + c) : 0.f;
     if (p.kdata < p.kc) {
-      const int per = CH_STRIDE / 16;
+      const int per = p.ch_stride / 16;
       for (int i = tid; i < p.nbuf * per; i += N_THREADS)
-        reinterpret_cast<uint4*>(stage_s + (size_t)(i / per) * stage_bytes + (size_t)p.kdata * CH_STRIDE)[i % per] =
+        reinterpret_cast<uint4*>(stage_s + (size_t)(i / per) * stage_bytes + (size_t)p.kdata * p.ch_stride)[i % per] =
             make_uint4(0, 0, 0, 0);
     }
   }
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
   if (warp == PROD_WARP) {
     // =========================== producer (tensor-map copies) ===========================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)p.kdata * (HPIX * 16u) + (p.has_res ? (p.dual ? io32_bytes : io_bytes) : 0u);
+      const uint32_t tx_bytes = (uint32_t)p.kdata * ((uint32_t)p.halo_pix * 16u) + (p.has_res ? (p.dual ? io32_bytes : io_bytes) : 0u);
       int b = 0;
       uint32_t ph = 1;                                       // parity of the "previous" phase: passes on a fresh barrier
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -237,8 +242,8 @@ __global__ void __launch_bounds__(N_THREADS, 1)
         mbar_arrive_expect_tx(bar, tx_bytes);
         for (int ph = 0; ph < p.nphase; ++ph)
           for (int kc = 0; kc < p.kcg; ++kc)
-            tma_load_4d(dst + (uint32_t)(ph * p.kcg + kc) * CH_STRIDE, &maps_in.m[ph], bar, p.in_c_off + kc * 8, t.tx * TW - 1,
-                        t.ty * TH - 1, t.img);
+            tma_load_4d(dst + (uint32_t)((ph * p.kcg + kc) * p.ch_stride), &maps_in.m[ph], bar, p.in_c_off + kc * 8, t.tx * TW - p.org,
+                        t.ty * TH - p.org, t.img);
         if (p.has_res) tma_load_4d(dst + halo_bytes, &map_res, bar, p.out_c_off, t.tx * TW, t.ty * TH, t.img);
         if (++b == p.nbuf) {
           b = 0;
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     // =========================== MMA issuer ===========================
     const uint32_t idesc = make_idesc_f16((uint32_t)p.nb);
     const uint32_t tbase = bcast0(tmem_base);
-    const uint32_t a_hi = ((HALO_W * 16u) >> 4) | (1u << 14);       // SBO (8-row group pitch) | descriptor version
+    const uint32_t a_hi = (((uint32_t)p.halo_w * 16u) >> 4) | (1u << 14);   // SBO (8-row group pitch) | descriptor version
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
     const uint32_t b_lo0 = (smem_u32(w_s) >> 4) | ((((uint32_t)p.nb * 16u) >> 4) << 16);
     const uint32_t b_step = 2u * (uint32_t)p.nb;                    // one MMA's weights: [2][nb][16 B]
@@ -444,7 +449,7 @@ __global__ void pack_kernel(const float* __restrict__ w, int cout, int cin, int 
 }
 
 struct Geom {
-  int kcg, kc, n_mma, n_pad, nphase, kdata;
+  int kcg, kc, n_mma, n_pad, nphase, kdata, ch_stride;
 };
 static Geom geom(int cin, int cout, int ntap, int stride = 1) {
   Geom g;
@@ -454,10 +459,11 @@ static Geom geom(int cin, int cout, int ntap, int stride = 1) {
   g.kc = g.kdata + ((ntap * g.kcg) & 1);          // an odd K list ends on the all-zero chunk
   g.n_mma = (ntap * g.kcg + 1) / 2;
   g.n_pad = (cout + 15) / 16 * 16;
+  g.ch_stride = ch_stride_of(ntap);
   return g;
 }
 static size_t smem_for(const Geom& g, int cout, int nbuf, int dual = 0, int split = 0) {
-  return (size_t)nbuf * ((size_t)g.kc * CH_STRIDE + 128 * (size_t)cout * (dual ? 6 : 2)) +
+  return (size_t)nbuf * ((size_t)g.kc * g.ch_stride + 128 * (size_t)cout * (dual ? 6 : 2)) +
          (size_t)g.n_mma * 2 * g.n_pad * (split ? 2 : 1) * 16 + (size_t)g.n_pad * 4 + (2 * MAX_BUF + 8) * 8 + 16 + 128;
 }
 
@@ -573,22 +579,25 @@ extern "C" int ls3d_conv_f16_ex(const ls3d_conv_args* c, void* stream) {
   if (!c->in16 || !c->w_packed || !shape_ok(c->cin, c->cout, c->ksize, stride)) return LS3D_ERR_ARG;
   const int dual = c->out32 != nullptr;
   void* out = dual ? (void*)c->out32 : c->out16;          // operand-only launches write the fp16 map alone
-  if (!out || (dual && !c->out16) || (!dual && c->res32)) return LS3D_ERR_ARG;
+  if (!out || (dual && !c->out16) || (!dual && c->res32) || (dual && c->res16)) return LS3D_ERR_ARG;
+  const void* res = dual ? (const void*)c->res32 : c->res16;
   const int in_ct = c->in_c_total ? c->in_c_total : c->cin, out_ct = c->out_c_total ? c->out_c_total : c->cout;
   if ((in_ct & 7) || (out_ct & 7) || (c->in_c_off & 7) || (c->out_c_off & 7) || c->in_c_off < 0 || c->out_c_off < 0 ||
       c->in_c_off + c->cin > in_ct || c->out_c_off + c->cout > out_ct)
     return LS3D_ERR_ARG;
-  if ((((uintptr_t)c->in16) | ((uintptr_t)c->out32) | ((uintptr_t)c->res32) | ((uintptr_t)c->w_packed) | ((uintptr_t)c->out16)) & 15)
+  if ((((uintptr_t)c->in16) | ((uintptr_t)c->out32) | ((uintptr_t)res) | ((uintptr_t)c->w_packed) | ((uintptr_t)c->out16)) & 15)
     return LS3D_ERR_ARG;
   const int ntap = ntap_of(c->ksize), split = c->w_split ? 1 : 0;
   const int H = stride == 2 ? (c->H_in + 1) / 2 : c->H_in, W = stride == 2 ? (c->W_in + 1) / 2 : c->W_in;   // output size
   if (stride == 2 && (c->H_in < 2 || c->W_in < 2)) return LS3D_ERR_ARG;
   const Geom g = geom(c->cin, c->cout, ntap, stride);
   Args a;
-  a.w = (const __half*)c->w_packed; a.bias = c->bias; a.has_res = c->res32 != nullptr; a.dual = dual;
+  a.w = (const __half*)c->w_packed; a.bias = c->bias; a.has_res = res != nullptr; a.dual = dual;
   a.n_img = c->n_img; a.H = H; a.W = W; a.cin = c->cin; a.cout = c->cout; a.relu = c->relu;
   a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad; a.nphase = g.nphase; a.kdata = g.kdata;
   a.in_c_off = c->in_c_off; a.out_c_off = c->out_c_off;
+  const int bw = ntap == 1 ? TW : HALO_W, bh = ntap == 1 ? TH : HALO_H;
+  a.halo_w = bw; a.halo_pix = bw * bh; a.org = ntap == 1 ? 0 : 1; a.ch_stride = g.ch_stride;
   a.nb = split ? 2 * g.n_pad : g.n_pad;
   if (a.nb > 256 || g.n_mma > MAX_MMA) return LS3D_ERR_ARG;
   for (int j = 0; j < g.n_mma; ++j) {
@@ -617,8 +626,7 @@ extern "C" int ls3d_conv_f16_ex(const ls3d_conv_args* c, void* stream) {
   const int es = dual ? 4 : 2;
   int rc;
   for (int ph = 0; ph < 4; ++ph) {
-    rc = make_map(&m_in.m[ph], c->in16, in_ct, c->W_in, c->H_in, c->n_img, 8, HALO_W, HALO_H, 2,
-                  stride == 2 ? ph : -1);
+    rc = make_map(&m_in.m[ph], c->in16, in_ct, c->W_in, c->H_in, c->n_img, 8, bw, bh, 2, stride == 2 ? ph : -1);
     if (rc) return rc;
     if (stride != 2 && ph == 0) {
       m_in.m[1] = m_in.m[2] = m_in.m[3] = m_in.m[0];
@@ -627,7 +635,7 @@ extern "C" int ls3d_conv_f16_ex(const ls3d_conv_args* c, void* stream) {
   }
   rc = make_map(&m_out, out, out_ct, W, H, c->n_img, c->cout, TW, TH, es);
   if (rc) return rc;
-  rc = make_map(&m_res, c->res32 ? (const void*)c->res32 : out, out_ct, W, H, c->n_img, c->cout, TW, TH, es);
+  rc = make_map(&m_res, res ? res : out, out_ct, W, H, c->n_img, c->cout, TW, TH, es);
   if (rc) return rc;
   rc = make_map(&m_out16, dual ? c->out16 : out, out_ct, W, H, c->n_img, c->cout, TW, TH, 2);
   if (rc) return rc;
@@ -652,6 +660,8 @@ extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* 
   a.n_img = n_img; a.H = H; a.W = W; a.cin = cin; a.cout = cout; a.relu = relu;
   a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad; a.nphase = 1; a.kdata = g.kdata;
   a.in_c_off = a.out_c_off = 0;
+  const int bw = ntap == 1 ? TW : HALO_W, bh = ntap == 1 ? TH : HALO_H;
+  a.halo_w = bw; a.halo_pix = bw * bh; a.org = ntap == 1 ? 0 : 1; a.ch_stride = g.ch_stride;
   a.nb = g.n_pad;
   if (a.nb > 256 || g.n_mma > MAX_MMA) return LS3D_ERR_ARG;
   for (int j = 0; j < g.n_mma; ++j) {
@@ -677,7 +687,7 @@ extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* 
   if (eo != cudaSuccess) return (int)eo;
   InMaps m_in;
   CUtensorMap m_res, m_out;
-  int rc = make_map(&m_in.m[0], in, cin, W, H, n_img, 8, HALO_W, HALO_H);
+  int rc = make_map(&m_in.m[0], in, cin, W, H, n_img, 8, bw, bh);
   if (rc) return rc;
   m_in.m[1] = m_in.m[2] = m_in.m[3] = m_in.m[0];
   rc = make_map(&m_out, out, cout, W, H, n_img, cout, TW, TH, 2);

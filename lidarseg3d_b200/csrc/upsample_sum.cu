@@ -247,3 +247,25 @@ extern "C" int ls3d_pad3_f16(const float* in, int64_t n_pixels, void* out, void*
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }
+
+namespace ls3d {
+__global__ void __launch_bounds__(256) cast_f32_kernel(const uint2* __restrict__ in, float4* __restrict__ out, long long n4) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const uint2 v = __ldg(in + e);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    out[e] = make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+}  // namespace ls3d
+
+extern "C" int ls3d_cast_f32(const void* in, float* out, int64_t n, void* stream) {
+  if (n <= 0) return LS3D_OK;
+  if (!in || !out || (n & 3) || (((uintptr_t)in) & 7) || (((uintptr_t)out) & 15)) return LS3D_ERR_ARG;
+  const long long n4 = n / 4;
+  const long long blocks = (n4 + 255) / 256;
+  const int grid = (int)(blocks < 148LL * 32 ? blocks : 148LL * 32);
+  ls3d::cast_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint2*)in, (float4*)out, n4);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}

@@ -157,7 +157,7 @@ def _own_conv_ok(conv, x):
 def conv_deferred_bias(conv, bn, x, dual=False):
     if isinstance(x, DualMap):
         if own_dual_ok(conv, bn, x.shape[1]):
-            plan = conv_plan(conv, bn, x.shape[1])
+            plan = conv_plan(conv, bn, x.shape[1], pixels=x.shape[0] * x.shape[2] * x.shape[3])
             o32, _ = plan.run(x.f16, relu=False, want32=True, use_bias=False)
             return o32, plan.bias
         x = x.f32
@@ -165,6 +165,12 @@ def conv_deferred_bias(conv, bn, x, dual=False):
 
 
 def _conv_deferred_bias(conv, bn, x, dual=False):
+    if (F16_OWN_ALL and x.is_cuda and x.dtype == torch.float16 and x.shape[1] % 8 == 0 and not bn.training
+            and x.is_contiguous(memory_format=torch.channels_last)):
+        y = _cbr_f16_plan(conv, bn, x, False, None, use_bias=False)
+        if y is not None:
+            plan = conv_plan(conv, bn, x.shape[1], fp32out=False) or conv_plan(conv, bn, x.shape[1], fp32out=True)
+            return y, plan.bias                                  # (the folded shift is the same vector in every plan)
     """conv -> BatchNorm (folded) WITHOUT the shift: returns (conv(x, w_folded), shift fp32 [Cout_p]).  For the linear terms
     of a branch fusion: the caller sums the shifts of all terms and ls3d_upsample_sum adds them once (a library convolution
     with a bias and no activation would run a separate elementwise add over every output map)."""
@@ -184,60 +190,93 @@ DUAL_OWN_ALL = os.environ.get("LS3D_DUAL_OWN_ALL", "1") == "1"     # 0: only 3x3
 class ConvPlan:
     """One BN-folded convolution (3x3 stride 1 / 2, or 1x1) as launches of ls3d_conv_f16_ex (csrc/conv3x3_f16.cu).
 
-    The weights [cout_p, cin_p, k, k] are cut into output-channel slices (<= 128 channels: the split-weight accumulator holds
-    2 n_pad <= 256 columns) and input-channel slices (so that the resident weight block and two stages fit shared memory);
-    launches over the input slices of one output slice accumulate through the fp32 residual input.  With ``split`` the fp32
-    weights enter exactly (fp16 hi + lo)."""
+    ``fp32out`` plans write an fp32 map + its fp16 operand copy (dual launches) and may cut the INPUT channels into slices whose
+    launches accumulate through the fp32 residual input; operand-only plans (fp16 output, fp16 residual) are single-slice.
+    Output channels are cut into slices when the accumulator (split weights: 2 n_pad <= 256 columns) or the staged output tile
+    demands it.  With ``exact`` the fp32 weights enter exactly: split weights [W_hi ; W_lo] in one launch where the doubled
+    weight block fits shared memory, else W_hi and W_lo as two accumulating launches ("hilo") when that needs fewer launches
+    than slicing."""
 
-    def __init__(self, w, bias, ksize, stride, split):
+    LAUNCH_US = 8.0          # cost model: fixed cost of a launch (prologue: resident weights, barriers, tensor memory)
+    BYTES_PER_US = 4.5e6     # and sustained HBM bytes per microsecond
+
+    @staticmethod
+    def _cost(pixels, stride, cin_p, cout_p, ci, cs, hilo, fp32out, has_res):
+        """Estimated microseconds of the launch list: per output slice every input-slice launch reads its input channels,
+        re-reads the fp32 partial sums of the previous launch and writes the output slice again."""
+        p_out = pixels / (4 if stride == 2 else 1)
+        n_o, n_i = (cout_p + cs - 1) // cs, (cin_p + ci - 1) // ci
+        per_in = n_i * (2 if hilo else 1)
+        byts = n_o * per_in * pixels * ci * 2
+        byts += n_o * per_in * p_out * cs * (6 if fp32out else 2)
+        byts += n_o * (per_in - 1 + (1 if has_res else 0)) * p_out * cs * (4 if fp32out else 2)
+        return n_o * per_in * ConvPlan.LAUNCH_US + byts / ConvPlan.BYTES_PER_US
+
+    def __init__(self, w, bias, ksize, stride, exact=True, fp32out=True, pixels=100000):
         from .. import ops
         cout_p, cin_p = w.shape[:2]
-        self.cout_p, self.cin_p, self.k, self.stride, self.split = cout_p, cin_p, ksize, stride, split
+        self.cout_p, self.cin_p, self.k, self.stride, self.exact, self.fp32out = cout_p, cin_p, ksize, stride, exact, fp32out
         self.bias = None if bias is None else bias.float().contiguous()
         best = None
-        for n_out in (1, 2, 3, 4, 6, 8):
-            cs = ((cout_p + n_out - 1) // n_out + 7) // 8 * 8
-            if split and cs > 128:
-                continue
-            for n_in in (1, 2, 3, 4, 6, 8, 12, 16, 32):
-                ci = ((cin_p + n_in - 1) // n_in + 7) // 8 * 8
-                if ops.conv_ex_supported(ci, cs, ksize, stride, dual=True, split=split):
-                    cand = (n_in * n_out, n_out, cs, ci)
-                    best = cand if best is None or cand < best else best
-                    break
+        for hilo in ((False, True) if (exact and fp32out) else (False,)):
+            split = exact and not hilo
+            for n_out in (1, 2, 3, 4, 6, 8):
+                cs = ((cout_p + n_out - 1) // n_out + 7) // 8 * 8
+                if split and cs > 128:
+                    continue
+                for n_in in ((1, 2, 3, 4, 6, 8, 12, 16, 32) if fp32out else (1,)):
+                    ci = ((cin_p + n_in - 1) // n_in + 7) // 8 * 8
+                    if ops.conv_ex_supported(ci, cs, ksize, stride, dual=fp32out, split=split):
+                        cand = (self._cost(pixels, stride, cin_p, cout_p, ci, cs, hilo, fp32out, True), hilo, cs, ci)
+                        best = cand if best is None or cand < best else best
+                        break
         self.ok = best is not None
         if not self.ok:
             return
-        _, _, cs, ci = best
+        self.est_us, self.hilo, cs, ci = best
+        self.split = exact and not self.hilo
         self.launches = []          # (out_off, cout, [(in_off, cin, packed)])
         for o0 in range(0, cout_p, cs):
             co = min(cs, cout_p - o0)
             ins = []
             for i0 in range(0, cin_p, ci):
                 cn = min(ci, cin_p - i0)
-                ins.append((i0, cn, ops.pack_conv_ex(w[o0:o0 + co, i0:i0 + cn].contiguous(), stride, split)))
+                ws = w[o0:o0 + co, i0:i0 + cn].contiguous()
+                if self.hilo:
+                    hi = ws.half().float()
+                    ins.append((i0, cn, ops.pack_conv_ex(hi, stride, False)))
+                    ins.append((i0, cn, ops.pack_conv_ex(ws - hi, stride, False)))
+                else:
+                    ins.append((i0, cn, ops.pack_conv_ex(ws, stride, self.split)))
             self.launches.append((o0, co, ins))
         self.n_launch = sum(len(l[2]) for l in self.launches)
+        self.multi = any(len(l[2]) > 1 for l in self.launches)
 
-    def run(self, x16, res32=None, relu=True, want32=True, use_bias=True):
-        """x16 [N, cin_p, H, W] fp16 channels-last -> (out32 or None, out16)."""
+    def run(self, x16, res=None, relu=True, want32=True, use_bias=True):
+        """x16 [N, cin_p, H, W] fp16 channels-last -> (out32 or None, out16).  ``res``: fp32 map for fp32out plans, fp16 map for
+        operand-only plans."""
         from .. import ops
         N, C, H, W = x16.shape
         assert C == self.cin_p and x16.dtype == torch.float16 and x16.is_contiguous(memory_format=torch.channels_last)
         Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if self.stride == 2 else (H, W)
-        multi = any(len(l[2]) > 1 for l in self.launches)
-        need32 = want32 or multi or res32 is not None
         out16 = torch.empty((N, self.cout_p, Ho, Wo), dtype=torch.float16, device=x16.device, memory_format=torch.channels_last)
-        out32 = torch.empty((N, self.cout_p, Ho, Wo), dtype=torch.float32, device=x16.device,
-                            memory_format=torch.channels_last) if need32 else None
+        if not self.fp32out:
+            assert res is None or res.dtype == torch.float16
+            for o0, co, ins in self.launches:
+                (i0, cn, wp), = ins
+                ops.conv_ex(x16, wp, self.bias[o0:o0 + co] if (use_bias and self.bias is not None) else None, cin=cn, in_off=i0,
+                            cout=co, out_off=o0, out32=None, out16=out16, res16=res, ksize=self.k, stride=self.stride, relu=relu,
+                            split=self.split)
+            return None, out16
+        assert res is None or res.dtype == torch.float32
+        out32 = torch.empty((N, self.cout_p, Ho, Wo), dtype=torch.float32, device=x16.device, memory_format=torch.channels_last)
         for o0, co, ins in self.launches:
             for i, (i0, cn, wp) in enumerate(ins):
                 first, last = i == 0, i == len(ins) - 1
                 b = self.bias[o0:o0 + co] if (first and use_bias and self.bias is not None) else None
-                r = res32 if first else out32
-                ops.conv_ex(x16, wp, b, cin=cn, in_off=i0, cout=co, out_off=o0, out32=out32, out16=out16, res32=r,
-                            ksize=self.k, stride=self.stride, relu=relu and last, split=self.split)
-        return (out32 if want32 or res32 is not None else None), out16
+                ops.conv_ex(x16, wp, b, cin=cn, in_off=i0, cout=co, out_off=o0, out32=out32, out16=out16,
+                            res32=res if first else out32, ksize=self.k, stride=self.stride, relu=relu and last, split=self.split)
+        return out32, out16
 
 
 def _plannable(conv):
@@ -249,7 +288,7 @@ def _plannable(conv):
     return k == (1, 1) and conv.padding == (0, 0) and st == (1, 1)
 
 
-def conv_plan(conv, bn, x_channels):
+def conv_plan(conv, bn, x_channels, fp32out=True, pixels=100000):
     """The cached ConvPlan of conv (+ folded eval BatchNorm ``bn``, may be None: the conv's own bias) for an input map with
     ``x_channels`` (zero-padded) channels; None when the own kernel does not serve the shape."""
     ts = (conv.weight, conv.bias) if bn is None else (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
@@ -258,7 +297,7 @@ def conv_plan(conv, bn, x_channels):
     if store.get("ver") != ver:
         store.clear()
         store["ver"] = ver
-    key = (x_channels, DUAL_EXACT_WEIGHTS)
+    key = (x_channels, DUAL_EXACT_WEIGHTS, fp32out, int(pixels).bit_length())
     if key not in store:
         plan = None
         if _plannable(conv) and x_channels % 8 == 0 and x_channels >= conv.in_channels:
@@ -276,7 +315,7 @@ def conv_plan(conv, bn, x_channels):
                 wp[:conv.out_channels, :conv.in_channels] = w
                 bp = b.new_zeros(cout_p)
                 bp[:conv.out_channels] = b
-                plan = ConvPlan(wp, bp, k, conv.stride[0], DUAL_EXACT_WEIGHTS)
+                plan = ConvPlan(wp, bp, k, conv.stride[0], DUAL_EXACT_WEIGHTS, fp32out, pixels)
                 if not plan.ok:
                     plan = None
         store[key] = plan
@@ -297,9 +336,14 @@ def _cbr_dual(conv, bn, x, relu, z, want):
     map is written), "both" / "f32" = fp32 map (+ operand copy)."""
     C = x.shape[1]
     if own_dual_ok(conv, bn, C):
-        plan = conv_plan(conv, bn, C)
+        pix = x.shape[0] * x.shape[2] * x.shape[3]
+        plan = conv_plan(conv, bn, C, pixels=pix)
+        if want == "f16" and z is None:
+            op = conv_plan(conv, bn, C, fp32out=False, pixels=pix)       # operand-only: no fp32 map is written
+            if op is not None and op.est_us <= plan.est_us:
+                return DualMap(None, op.run(x.f16, relu=relu)[1])
         if z is None or z.shape[1] == plan.cout_p:
-            o32, o16 = plan.run(x.f16, res32=None if z is None else z.f32, relu=relu, want32=want != "f16")
+            o32, o16 = plan.run(x.f16, res=None if z is None else z.f32, relu=relu)
             return DualMap(o32, o16)
     w, b = folded(conv, bn, C, torch.float32, pad_dtype=torch.float16)
     xf, zf = x.f32, (None if z is None else z.f32)
@@ -313,6 +357,29 @@ def _cbr_dual(conv, bn, x, relu, z, want):
     return DualMap(torch.relu_(y) if relu else y)
 
 
+F16_OWN_ALL = os.environ.get("LS3D_F16_OWN_ALL", "1") == "1"     # fp16 maps: every convolution on the own kernel, exact weights
+
+
+def _cbr_f16_plan(conv, bn, x, relu, z, use_bias=True):
+    """fp16 maps: conv (+ folded BN) (+ z) (+ ReLU) on ls3d_conv_f16_ex with exact weights; None when not served."""
+    from .. import ops
+    C = x.shape[1]
+    if not FUSED_CONV3X3:
+        return None
+    pix = x.shape[0] * x.shape[2] * x.shape[3]
+    plan = conv_plan(conv, bn, C, fp32out=False, pixels=pix)
+    alt = conv_plan(conv, bn, C, fp32out=True, pixels=pix)    # sliced shapes accumulate in an fp32 temporary
+    if plan is not None and (alt is None or plan.est_us <= alt.est_us):
+        if z is not None and (z.shape[1] != plan.cout_p or not z.is_contiguous(memory_format=torch.channels_last)):
+            return None
+        return plan.run(x, res=z, relu=relu, use_bias=use_bias)[1]
+    plan = alt
+    if plan is None or (z is not None and z.shape[1] != plan.cout_p):
+        return None
+    z32 = None if z is None else ops.cast_f32(z.contiguous(memory_format=torch.channels_last))
+    return plan.run(x, res=z32, relu=relu, use_bias=use_bias)[1]
+
+
 def cbr(conv, bn, x, relu, z=None, want="both"):
     """conv -> BatchNorm -> (+z) -> (ReLU).  Training / CPU: plain modules.  Eval on CUDA: BN folded into the conv weights
     (cached, refreshed when a parameter changes); fp16 3x3 / 1x1 stride-1 convs run on the hand-written tensor-core kernel, the rest
@@ -324,6 +391,10 @@ def cbr(conv, bn, x, relu, z=None, want="both"):
         if z is not None:
             y = y + z
         return torch.relu(y) if relu else y
+    if F16_OWN_ALL and x.dtype == torch.float16 and x.shape[1] % 8 == 0 and x.is_contiguous(memory_format=torch.channels_last):
+        y = _cbr_f16_plan(conv, bn, x, relu, z)
+        if y is not None:
+            return y
     if _own_conv_ok(conv, x):
         wp, bp, cout_p = folded_packed(conv, bn, x.shape[1])
         if wp is not None and (z is None or (z.shape[1] == cout_p and z.is_contiguous(memory_format=torch.channels_last))):
@@ -622,6 +693,9 @@ class HRNet(nn.Module):
                         and own_dual_ok(l0.downsample[0], l0.downsample[1], 64))
             x = cbr(self.conv2, self.bn2, x, True, want="f16" if only_ops else "both")
         else:
+            if (F16_OWN_ALL and x.is_cuda and not self.training and x.dtype == torch.float16 and x.shape[1] == 3
+                    and conv_plan(self.conv1, self.bn1, 8, fp32out=False) is not None):
+                x = F.pad(x, (0, 0, 0, 0, 0, 5)).contiguous(memory_format=torch.channels_last)   # 16-byte pixel rows
             x = cbr(self.conv1, self.bn1, x, True)
             x = cbr(self.conv2, self.bn2, x, True)
             if dual:

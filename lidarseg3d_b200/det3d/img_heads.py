@@ -127,15 +127,16 @@ class FCNMSeg3DHead(nn.Module):
             y = y + F.interpolate(t, size=(H, W), mode="bilinear", align_corners=self.align_corners)
         return torch.relu_(y)
 
-    def _forward_dual(self, batch_dict):
-        """fp32 maps with fp16 operand copies (DualMap inputs): every convolution of the head on ls3d_conv_f16_ex with exact
-        weights - per-branch 1x1 convolutions at native resolution, resize + sum + folded-BN shift + ReLU in one pass
-        (ls3d_upsample_sum_dual), the remaining 1x1 ConvModules, conv_seg (17 -> 24 zero-padded class channels)."""
+    def _forward_plans(self, batch_dict, half):
+        """Every convolution of the head on ls3d_conv_f16_ex with exact weights: per-branch 1x1 convolutions at native
+        resolution, resize + sum + folded-BN shift + ReLU in one pass (ls3d_upsample_sum*), the remaining 1x1 ConvModules,
+        conv_seg (17 -> 24 zero-padded class channels).  ``half``: fp16 maps; else DualMaps (fp32 maps + fp16 operand copies)."""
         xs = [batch_dict["inputs"][i] for i in self.in_index]
         cm = self.convs[0]
         ver = _versions(cm.conv.weight, cm.bn.weight, cm.bn.bias, cm.bn.running_mean, cm.bn.running_var)
-        key = (tuple(x.shape[1] for x in xs), ver, _ib.DUAL_EXACT_WEIGHTS)
-        ent = self.__dict__.get("_ls3d_dual_branch")
+        key = (tuple(x.shape[1] for x in xs), ver, _ib.DUAL_EXACT_WEIGHTS, half)
+        store = self.__dict__.setdefault("_ls3d_plan_branch", {})
+        ent = store.get(half)
         if ent is None or ent[0] != key:
             with torch.no_grad():
                 bn = cm.bn
@@ -147,34 +148,44 @@ class FCNMSeg3DHead(nn.Module):
                 for x, c in zip(xs, self._branch_channels):
                     wb = w.new_zeros(cout_p, x.shape[1], 1, 1)
                     wb[:w.shape[0], :c] = w[:, c0:c0 + c]
-                    plans.append(ConvPlan(wb, None, 1, 1, _ib.DUAL_EXACT_WEIGHTS))
+                    plans.append(ConvPlan(wb, None, 1, 1, _ib.DUAL_EXACT_WEIGHTS, not half,
+                                          pixels=x.shape[0] * x.shape[2] * x.shape[3]))
                     c0 += c
                 bp = b.new_zeros(cout_p)
                 bp[:w.shape[0]] = b
-            ent = self.__dict__["_ls3d_dual_branch"] = (key, plans, bp.contiguous())
+            ent = store[half] = (key, plans, bp.contiguous())
         _, plans, bias = ent
         if not all(pl.ok for pl in plans):
             return None
-        terms = [pl.run(x.f16, relu=False, want32=True, use_bias=False)[0] for pl, x in zip(plans, xs)]
-        feats = DualMap(*ops.upsample_sum_dual(terms, relu=True, bias=bias))
+        if half:
+            terms = [pl.run(x.contiguous(memory_format=torch.channels_last), relu=False, use_bias=False)[1] for pl, x in zip(plans, xs)]
+            feats = ops.upsample_sum(terms, relu=True, bias=bias)
+        else:
+            terms = [pl.run(x.f16, relu=False, use_bias=False)[0] for pl, x in zip(plans, xs)]
+            feats = DualMap(*ops.upsample_sum_dual(terms, relu=True, bias=bias))
         for m in list(self.convs)[1:]:
             feats = m(feats)
-        seg = conv_plan(self.conv_seg, None, feats.shape[1])
+        seg = conv_plan(self.conv_seg, None, feats.shape[1], fp32out=not half,
+                        pixels=feats.shape[0] * feats.shape[2] * feats.shape[3])
         if seg is None:
             return None
-        logits_p, _ = seg.run(feats.f16, relu=False, want32=True)            # [N, 24, h, w]: classes zero-padded to 8k channels
-        f32 = feats.f32
-        n, Cp, h, w_ = f32.shape
+        if half:
+            logits_p = seg.run(feats, relu=False)[1]                 # [N, 24, h, w]: classes zero-padded to 8k channels
+            fmap = feats
+        else:
+            logits_p = seg.run(feats.f16, relu=False)[0]
+            fmap = feats.f32
+        n, Cp, h, w_ = fmap.shape
         rows = (n // batch_dict["batch_size"]) * h * w_
-        off = torch.arange(0, batch_dict["batch_size"] + 1, dtype=torch.int32, device=f32.device) * rows
-        emb = ops.class_embed(logits_p.permute(0, 2, 3, 1).reshape(-1, logits_p.shape[1]), f32.permute(0, 2, 3, 1).reshape(-1, Cp),
+        off = torch.arange(0, batch_dict["batch_size"] + 1, dtype=torch.int32, device=fmap.device) * rows
+        emb = ops.class_embed(logits_p.permute(0, 2, 3, 1).reshape(-1, logits_p.shape[1]), fmap.permute(0, 2, 3, 1).reshape(-1, Cp),
                               off, batch_dict["batch_size"], rows, ncls=self.num_classes, C=self.channels)
         logits = logits_p[:, :self.num_classes]
         if Cp != self.channels:
-            f32 = f32[:, :self.channels].contiguous(memory_format=torch.channels_last)
+            fmap = fmap[:, :self.channels].contiguous(memory_format=torch.channels_last)
         self.forward_ret_dict["image_logits"] = logits
         batch_dict["image_logits"] = logits
-        batch_dict["image_features"] = f32
+        batch_dict["image_features"] = fmap
         batch_dict["camera_semantic_embeddings"] = emb
         return batch_dict
 
@@ -182,13 +193,19 @@ class FCNMSeg3DHead(nn.Module):
         if return_loss:
             raise NotImplementedError("lidarseg3d_b200 image head: inference path only (return_loss=False)")
         inputs = batch_dict["inputs"]
+        plannable = (self.input_transform == "resize_concat" and self.num_convs > 0 and self.kernel_size == 1 and not self.training
+                     and self.convs[0].with_norm and not self.concat_input and not self.align_corners and len(self.in_index) <= 4)
         if isinstance(inputs[0], DualMap):
-            if (self.input_transform == "resize_concat" and self.num_convs > 0 and self.kernel_size == 1 and not self.training
-                    and self.convs[0].with_norm and not self.concat_input and not self.align_corners and len(self.in_index) <= 4):
-                out = self._forward_dual(batch_dict)
+            if plannable:
+                out = self._forward_plans(batch_dict, half=False)
                 if out is not None:
                     return out
             inputs = batch_dict["inputs"] = [x.f32 for x in inputs]
+        elif (plannable and _ib.F16_OWN_ALL and inputs[0].is_cuda and inputs[0].dtype == torch.float16
+              and all(x.shape[1] % 8 == 0 for x in inputs)):
+            out = self._forward_plans(batch_dict, half=True)
+            if out is not None:
+                return out
         fast = (self.input_transform == "resize_concat" and self.num_convs > 0 and self.kernel_size == 1 and inputs[0].is_cuda
                 and not self.training and self.convs[0].with_norm and not self.concat_input)
         if fast:

@@ -430,18 +430,30 @@ def pack_conv_ex(w_oihw, stride=1, split=True):
     return out
 
 
-def conv_ex(x16, w_packed, bias, *, cin, in_off, cout, out_off, out32, out16, res32=None, ksize=3, stride=1, relu=False,
-            split=True):
+CONV_PROFILE = None      # development: list -> (CUDA events, shape) per ls3d_conv_f16_ex launch (scripts/prof_camera.py)
+
+
+def conv_ex(x16, w_packed, bias, *, cin, in_off, cout, out_off, out32, out16, res32=None, res16=None, ksize=3, stride=1,
+            relu=False, split=True):
     """One ls3d_conv_f16_ex launch: input channels [in_off, in_off + cin) of the fp16 channels-last map ``x16`` -> output channels
     [out_off, out_off + cout) of ``out32`` (fp32, may be None: operand-only) / ``out16`` (fp16), both preallocated channels-last;
     ``res32`` (may alias out32) is added before the ReLU."""
     N, ct, H, W = x16.shape
     a = capi.ConvArgs()
     a.in16, a.w_packed, a.bias = ptr(x16), ptr(w_packed), ptr(bias)
-    a.res32, a.out32, a.out16 = ptr(res32), ptr(out32), ptr(out16)
+    a.res32, a.out32, a.out16, a.res16 = ptr(res32), ptr(out32), ptr(out16), ptr(res16)
     a.in_c_total, a.in_c_off, a.cin = ct, in_off, cin
     a.out_c_total, a.out_c_off, a.cout = out16.shape[1], out_off, cout
     a.n_img, a.H_in, a.W_in, a.ksize, a.stride, a.relu, a.w_split = N, H, W, ksize, stride, int(relu), int(split)
+    if CONV_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(capi.lib().ls3d_conv_f16_ex(ctypes.byref(a), stream_ptr()), "ls3d_conv_f16_ex")
+        e1.record()
+        CONV_PROFILE.append(dict(e0=e0, e1=e1, n=N, h=H, w=W, cin=cin, cout=cout, k=ksize, stride=stride,
+                                 res=res32 is not None or res16 is not None,
+                                 out32=out32 is not None, in_total=ct, out_total=out16.shape[1]))
+        return
     check(capi.lib().ls3d_conv_f16_ex(ctypes.byref(a), stream_ptr()), "ls3d_conv_f16_ex")
 
 
@@ -452,6 +464,15 @@ def pad3_f16(x):
     assert C == 3 and x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last)
     out = torch.empty((N, 8, H, W), dtype=torch.float16, device=x.device, memory_format=torch.channels_last)
     check(capi.lib().ls3d_pad3_f16(ptr(x), N * H * W, ptr(out), stream_ptr()), "ls3d_pad3_f16")
+    return out
+
+
+def cast_f32(x):
+    """fp32 copy of an fp16 tensor, same memory layout (ls3d_cast_f32)."""
+    assert x.dtype == torch.float16 and x.numel() % 4 == 0
+    assert x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty_like(x, dtype=torch.float32)
+    check(capi.lib().ls3d_cast_f32(ptr(x), ptr(out), x.numel(), stream_ptr()), "ls3d_cast_f32")
     return out
 
 

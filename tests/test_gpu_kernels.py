@@ -406,9 +406,9 @@ def test_conv_plan_vs_fp64(n, h, w, cin, cout, k, stride, res, relu):
     b = torch.randn(cout, generator=g).to(DEV)
     ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
     z = torch.randn(n, cout, ho, wo, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) if res else None
-    plan = ConvPlan(wt, b, k, stride, True)
+    plan = ConvPlan(wt, b, k, stride, True, True)
     assert plan.ok
-    y32, y16 = plan.run(x, res32=z, relu=relu)
+    y32, y16 = plan.run(x, res=z, relu=relu)
     ref = F.conv2d(x.double(), wt.double(), b.double(), stride=stride, padding=k // 2)
     if z is not None:
         ref = ref + z.double()
@@ -418,9 +418,17 @@ def test_conv_plan_vs_fp64(n, h, w, cin, cout, k, stride, res, relu):
     err = float((y32.double() - ref).abs().max() / ref.abs().max())
     assert err <= 3e-6, (err, plan.n_launch)
     assert torch.equal(y16, y32.half())
-    if z is None and plan.n_launch == len(plan.launches):             # single input slice: operand-only variant
-        n32, o16 = plan.run(x, relu=relu, want32=False)
-        assert n32 is None and torch.equal(o16, y16)
+    op = ConvPlan(wt, b, k, stride, True, False)                      # operand-only plan (fp16 output, fp16 residual)
+    if op.ok:
+        z16 = None if z is None else z.half()
+        n32, o16 = op.run(x, res=z16, relu=relu)
+        ref16 = F.conv2d(x.double(), wt.double(), b.double(), stride=stride, padding=k // 2)
+        if z16 is not None:
+            ref16 = ref16 + z16.double()
+        if relu:
+            ref16 = ref16.relu()
+        assert n32 is None
+        assert float((o16.double() - ref16).abs().max() / ref16.abs().max()) <= 6e-4
 
 
 def test_pad3_f16():
