@@ -330,6 +330,16 @@ typedef struct ls3d_conv_args {
   const void* res16;      /* fp16 residual [n_img, H_out, W_out, out_c_total] for operand-only launches (out32 == NULL): fp16 maps */
 } ls3d_conv_args;
 int ls3d_conv_f16_ex(const ls3d_conv_args* args, void* stream);
+/* The launches of a sliced convolution as PASSES of one launch (a CTA owns the same tiles in every pass, so accumulation through
+ * the fp32 output map stays inside the CTA): args->cin / cout = the uniform slice sizes (slices may overlap: the overlapping
+ * weights of the later slice are zero / the overlapping outputs are recomputed), args->bias = bias of the WHOLE output tensor.
+ *   flags: 1 add bias[out_c_off ...], 2 add the external residual (res32 / res16), 4 add the output map itself (what the
+ *          previous pass left: needs out32), 8 ReLU.  At most 24 passes. */
+typedef struct ls3d_conv_pass {
+  const void* w_packed;
+  int32_t in_c_off, out_c_off, flags;
+} ls3d_conv_pass;
+int ls3d_conv_f16_multi(const ls3d_conv_args* args, const ls3d_conv_pass* passes, int32_t n_pass, void* stream);
 int ls3d_conv_f16_ex_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t dual, int32_t split,
                                int32_t* supported);
 int ls3d_conv_f16_pack_ex(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t split,

@@ -78,6 +78,11 @@ class ConvArgs(ctypes.Structure):
                 ("stride", c_int), ("relu", c_int), ("w_split", c_int), ("res16", c_void_p)]
 
 
+class ConvPass(ctypes.Structure):
+    """ls3d_conv_pass (include/ls3d.h)."""
+    _fields_ = [("w_packed", c_void_p), ("in_c_off", c_int), ("out_c_off", c_int), ("flags", c_int)]
+
+
 P, I, L = c_void_p, c_int, ctypes.c_int64
 PL = ctypes.POINTER(ctypes.c_int64)
 # name -> (argtypes, restype): one row per prototype of include/ls3d.h
@@ -114,6 +119,7 @@ _SIGNATURES = {
     "ls3d_conv_f16_split_supported": ([I, I, I, I, ctypes.POINTER(ctypes.c_int32)], ctypes.c_int),
     "ls3d_conv_f16_pack_split": ([P, I, I, I, P, P], ctypes.c_int),
     "ls3d_conv_f16_ex": ([ctypes.POINTER(ConvArgs), P], ctypes.c_int),
+    "ls3d_conv_f16_multi": ([ctypes.POINTER(ConvArgs), ctypes.POINTER(ConvPass), I, P], ctypes.c_int),
     "ls3d_conv_f16_ex_supported": ([I, I, I, I, I, I, ctypes.POINTER(ctypes.c_int32)], ctypes.c_int),
     "ls3d_conv_f16_pack_ex": ([P, I, I, I, I, I, P, P], ctypes.c_int),
     "ls3d_pad3_f16": ([P, L, P, P], ctypes.c_int),
@@ -158,7 +164,7 @@ KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_tile_plan_build": 1, "ls3d_voxe
                     "ls3d_rulebook_gather": 1, "ls3d_rulebook_scatter": 1, "ls3d_three_nn_grid": 2, "ls3d_three_nn": 1,
                     "ls3d_three_interpolate": 1, "ls3d_sample_image_features": 1, "ls3d_project_points": 1, "ls3d_project_points_global": 1,
                     "ls3d_resize_images_u8": 1, "ls3d_upsample_sum": 1, "ls3d_upsample_sum_f16": 1,
-                    "ls3d_conv3x3_f16": 1, "ls3d_conv3x3_f16_pack": 1, "ls3d_conv_f16": 1, "ls3d_conv_f16_dual": 1, "ls3d_upsample_sum_dual": 1, "ls3d_cast_f16": 1, "ls3d_conv_f16_pack": 1, "ls3d_conv_f16_pack_split": 1, "ls3d_conv_f16_ex": 1, "ls3d_conv_f16_pack_ex": 1, "ls3d_pad3_f16": 1, "ls3d_cast_f32": 1, "ls3d_normalize_images_u8": 1, "ls3d_token_attention": 1, "ls3d_class_embed": 4,
+                    "ls3d_conv3x3_f16": 1, "ls3d_conv3x3_f16_pack": 1, "ls3d_conv_f16": 1, "ls3d_conv_f16_dual": 1, "ls3d_upsample_sum_dual": 1, "ls3d_cast_f16": 1, "ls3d_conv_f16_pack": 1, "ls3d_conv_f16_pack_split": 1, "ls3d_conv_f16_ex": 1, "ls3d_conv_f16_multi": 1, "ls3d_conv_f16_pack_ex": 1, "ls3d_pad3_f16": 1, "ls3d_cast_f32": 1, "ls3d_normalize_images_u8": 1, "ls3d_token_attention": 1, "ls3d_class_embed": 4,
                     "ls3d_class_tokens": 1}
 
 

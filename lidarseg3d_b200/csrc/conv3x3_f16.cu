@@ -41,10 +41,21 @@ constexpr int N_THREADS = (EPI_WARP0 + N_EPI_WARPS) * 32;
 constexpr int MAX_BUF = 8;
 constexpr int MAX_MMA = 144;                 // ceil(9 * 32 / 2): cin <= 256
 
+constexpr int MAX_PASS = 24;
+constexpr int PASS_BIAS = 1, PASS_RES_EXT = 2, PASS_RES_OUT = 4, PASS_RELU = 8;
+
 struct Args {
-  const __half* w;        // packed weights, see pack kernel
-  const float* bias;      // [cout] fp32 or NULL
-  int has_res;
+  const __half* w;        // packed weights, see pack kernel (pass 0; pass i: pass_w[i])
+  const float* bias;      // fp32 bias of the whole output tensor (indexed from out_c_off) or NULL
+  int has_res;            // single-pass launches: residual present (multi-pass: per-pass flags)
+  // A launch may run several PASSES over the same tiles: each pass has its own resident weight block, input-channel and
+  // output-channel slice; passes over the input slices of one output slice accumulate through the fp32 output map (a CTA
+  // always owns the same tiles, so pass i + 1 reads what the same CTA wrote in pass i).  One launch per convolution instead
+  // of one per slice: no launch / tail / tensor-memory set-up cost between the slices.
+  int n_pass, use_table;
+  const __half* pass_w[MAX_PASS];
+  short pass_in_off[MAX_PASS], pass_out_off[MAX_PASS];
+  unsigned char pass_flags[MAX_PASS];
   int dual;               // 1: fp32 residual / output maps + an fp16 operand copy of the output (see ls3d_conv_f16_dual)
   int nb;                 // rows of the B operand = accumulator columns per tile: n_pad, or 2 n_pad with split weights
                           // ([W_hi ; W_lo] stacked along N: exact fp32 weights at the cost of a wider MMA, the epilogue adds
@@ -186,18 +197,12 @@ __global__ void __launch_bounds__(N_THREADS, 1)
   const int nacc = p.nb <= 128 ? 4 : 2;                        // accumulators in tensor memory (nacc * nb <= 512 columns)
   const uint32_t lo_col = p.nb > p.n_pad ? (uint32_t)p.n_pad : 0u;   // split weights: column offset of the W_lo partial sums
 
-  // ---- one-time staging: weights (resident), bias, the all-zero K chunk of every halo buffer
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.w);
-    uint4* dst = reinterpret_cast<uint4*>(w_s);
-    for (uint32_t i = tid; i < w_bytes / 16; i += N_THREADS) dst[i] = __ldg(src + i);
-    for (int c = tid; c < p.n_pad; c += N_THREADS) bias_s[c] = (p.bias && c < p.cout) ? __ldg(p.bias + c) : 0.f;
-    if (p.kdata < p.kc) {
-      const int per = p.ch_stride / 16;
-      for (int i = tid; i < p.nbuf * per; i += N_THREADS)
-        reinterpret_cast<uint4*>(stage_s + (size_t)(i / per) * stage_bytes + (size_t)p.kdata * p.ch_stride)[i % per] =
-            make_uint4(0, 0, 0, 0);
-    }
+  // ---- one-time staging: the all-zero K chunk of every halo buffer (weights / bias: per pass, below)
+  if (p.kdata < p.kc) {
+    const int per = p.ch_stride / 16;
+    for (int i = tid; i < p.nbuf * per; i += N_THREADS)
+      reinterpret_cast<uint4*>(stage_s + (size_t)(i / per) * stage_bytes + (size_t)p.kdata * p.ch_stride)[i % per] =
+          make_uint4(0, 0, 0, 0);
   }
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(nacc * p.nb)) tmem_cols <<= 1;
@@ -221,19 +226,51 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     prefetch_map(&map_out);
     if (p.dual) prefetch_map(&map_out16);
   }
-  fence_proxy_async_smem();          // the staged weights / zero chunk are read by the tensor core (async proxy)
+  fence_proxy_async_smem();          // the zero chunk is read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t stage0 = smem_u32(stage_s);
 
+  // pipeline state of each role, carried across the passes
+  int st_b = 0, st_it = 0;                    // producer / MMA: ring slot, tile counter
+  uint32_t st_ph = warp == PROD_WARP ? 1u : 0u;
+  const int e_team = (warp - EPI_WARP0) >> 2;
+  int e_b = 0, e_bprev = 0, e_it = 0;         // epilogue team state
+  uint32_t e_ph = 0;
+  bool e_first = true;
+  if (warp >= EPI_WARP0) {
+    e_b = e_team % p.nbuf;
+    e_it = e_team;
+    e_ph = (uint32_t)(e_team / p.nbuf) & 1u;
+  }
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA per pass
+
+  for (int pass = 0; pass < p.n_pass; ++pass) {
+  const int pflags = p.use_table ? (int)p.pass_flags[pass] : (PASS_BIAS | (p.has_res ? PASS_RES_EXT : 0) | (p.relu ? PASS_RELU : 0));
+  const int in_c_off = p.use_table ? (int)p.pass_in_off[pass] : p.in_c_off;
+  const int out_c_off = p.use_table ? (int)p.pass_out_off[pass] : p.out_c_off;
+  const bool has_res = (pflags & (PASS_RES_EXT | PASS_RES_OUT)) != 0;
+  const bool relu = (pflags & PASS_RELU) != 0;
+  {
+    // this pass's weights (resident) and bias; the previous pass's MMAs and stores are complete (barrier at the loop end)
+    const uint4* src = reinterpret_cast<const uint4*>(p.use_table ? p.pass_w[pass] : p.w);
+    uint4* dst = reinterpret_cast<uint4*>(w_s);
+    for (uint32_t i = tid; i < w_bytes / 16; i += N_THREADS) dst[i] = __ldg(src + i);
+    for (int c = tid; c < p.n_pad; c += N_THREADS)
+      bias_s[c] = (p.bias && (pflags & PASS_BIAS) && c < p.cout) ? __ldg(p.bias + (p.use_table ? out_c_off : 0) + c) : 0.f;
+    fence_proxy_async_smem();
+    __syncthreads();
+  }
+
   if (warp == PROD_WARP) {
     // =========================== producer (tensor-map copies) ===========================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)p.kdata * ((uint32_t)p.halo_pix * 16u) + (p.has_res ? (p.dual ? io32_bytes : io_bytes) : 0u);
-      int b = 0;
-      uint32_t ph = 1;                                       // parity of the "previous" phase: passes on a fresh barrier
+      if (pass > 0) asm volatile("fence.proxy.async;" ::: "memory");
+      const uint32_t tx_bytes = (uint32_t)p.kdata * ((uint32_t)p.halo_pix * 16u) + (has_res ? (p.dual ? io32_bytes : io_bytes) : 0u);
+      int b = st_b;
+      uint32_t ph = st_ph;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         mbar_wait(empty_bar0 + 8 * b, ph);
         const TileXY t = tile_coords(tile, p);
@@ -242,14 +279,17 @@ __global__ void __launch_bounds__(N_THREADS, 1)
         mbar_arrive_expect_tx(bar, tx_bytes);
         for (int ph = 0; ph < p.nphase; ++ph)
           for (int kc = 0; kc < p.kcg; ++kc)
-            tma_load_4d(dst + (uint32_t)((ph * p.kcg + kc) * p.ch_stride), &maps_in.m[ph], bar, p.in_c_off + kc * 8, t.tx * TW - p.org,
+            tma_load_4d(dst + (uint32_t)((ph * p.kcg + kc) * p.ch_stride), &maps_in.m[ph], bar, in_c_off + kc * 8, t.tx * TW - p.org,
                         t.ty * TH - p.org, t.img);
-        if (p.has_res) tma_load_4d(dst + halo_bytes, &map_res, bar, p.out_c_off, t.tx * TW, t.ty * TH, t.img);
+        if (has_res)
+          tma_load_4d(dst + halo_bytes, (pflags & PASS_RES_OUT) ? &map_out : &map_res, bar, out_c_off, t.tx * TW, t.ty * TH, t.img);
         if (++b == p.nbuf) {
           b = 0;
           ph ^= 1u;
         }
       }
+      st_b = b;
+      st_ph = ph;
     }
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
@@ -259,8 +299,8 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
     const uint32_t b_lo0 = (smem_u32(w_s) >> 4) | ((((uint32_t)p.nb * 16u) >> 4) << 16);
     const uint32_t b_step = 2u * (uint32_t)p.nb;                    // one MMA's weights: [2][nb][16 B]
-    int b = 0, it = 0;
-    uint32_t ph = 0;
+    int b = st_b, it = st_it;
+    uint32_t ph = st_ph;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int ab = it & (nacc - 1);
       mbar_wait(full_bar0 + 8 * b, ph);
@@ -285,6 +325,9 @@ __global__ void __launch_bounds__(N_THREADS, 1)
         ph ^= 1u;
       }
     }
+    st_b = b;
+    st_it = it;
+    st_ph = ph;
   } else {
     // =========================== epilogue ===========================
     const int ew = warp - EPI_WARP0;
@@ -294,14 +337,17 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     const bool leader = ((ew & 3) == 0 && lane == 0);
     const int n_groups = p.n_pad >> 4;
     const bool deep = p.nbuf >= 4;                // a stage may stay occupied until this team's next tile
-    int b = team % p.nbuf, b_prev = 0, it = team;
-    uint32_t ph = (uint32_t)(team / p.nbuf) & 1u;
-    bool first = true;
-    for (int tile = blockIdx.x + team * gridDim.x; tile < p.n_tiles; tile += 2 * gridDim.x, it += 2) {
+    // this team takes the CTA's tiles whose running index (over all passes) has its parity
+    int b = e_b, b_prev = e_bprev, it = e_it;
+    uint32_t ph = e_ph;
+    bool first = e_first;
+    const int it_begin = pass * my_tiles, it_end = it_begin + my_tiles;
+    for (; it < it_end; it += 2) {
+      const int tile = blockIdx.x + (it - it_begin) * gridDim.x;
       uint8_t* io = stage_s + (size_t)b * stage_bytes + halo_bytes + (size_t)m * p.cout * 2;
       const int ab = it & (nacc - 1);
       const uint32_t trow = tmem_base + (uint32_t)(ab * p.nb) + ((uint32_t)(q * 32) << 16);
-      if (p.has_res) mbar_wait(full_bar0 + 8 * b, ph);
+      if (has_res) mbar_wait(full_bar0 + 8 * b, ph);
       mbar_wait(accf_bar0 + 8 * ab, (uint32_t)(it / nacc) & 1u);
       tc_fence_after();
       if (p.dual) {
@@ -316,7 +362,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
           float4 rr[4];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
-            rr[q4] = (p.has_res && c0 + 4 * q4 < p.cout) ? *reinterpret_cast<const float4*>(io32 + c0 + 4 * q4)
+            rr[q4] = (has_res && c0 + 4 * q4 < p.cout) ? *reinterpret_cast<const float4*>(io32 + c0 + 4 * q4)
                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
           tmem_ld_wait();
           if (lo_col) {
@@ -336,7 +382,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
               v[4 * q4 + 2] = __uint_as_float(raw[8 * g8 + 4 * q4 + 2]) + bb.z + r4.z;
               v[4 * q4 + 3] = __uint_as_float(raw[8 * g8 + 4 * q4 + 3]) + bb.w + r4.w;
             }
-            if (p.relu) {
+            if (relu) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
             }
@@ -356,7 +402,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
         tmem_ld16(trow + c0, raw);
         if (lo_col) tmem_ld16(trow + lo_col + c0, raw2);
         uint4 rz[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (p.has_res) {
+        if (has_res) {
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8)
             if (c0 + 8 * g8 < p.cout) rz[g8] = *reinterpret_cast<const uint4*>(io + (c0 + 8 * g8) * 2);
@@ -380,7 +426,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
             const float2 rr = __half22float2(r2[e]);
             float v0 = __uint_as_float(raw[8 * g8 + 2 * e]) + bb[2 * e] + rr.x;
             float v1 = __uint_as_float(raw[8 * g8 + 2 * e + 1]) + bb[2 * e + 1] + rr.y;
-            if (p.relu) {
+            if (relu) {
               v0 = fmaxf(v0, 0.f);
               v1 = fmaxf(v1, 0.f);
             }
@@ -396,9 +442,9 @@ __global__ void __launch_bounds__(N_THREADS, 1)
       bar_sync_team(team);
       if (leader) {
         const TileXY t = tile_coords(tile, p);
-        tma_store_4d(&map_out, stage0 + (uint32_t)b * stage_bytes + halo_bytes, p.out_c_off, t.tx * TW, t.ty * TH, t.img);
+        tma_store_4d(&map_out, stage0 + (uint32_t)b * stage_bytes + halo_bytes, out_c_off, t.tx * TW, t.ty * TH, t.img);
         if (p.dual)
-          tma_store_4d(&map_out16, stage0 + (uint32_t)b * stage_bytes + halo_bytes + io32_bytes, p.out_c_off, t.tx * TW, t.ty * TH,
+          tma_store_4d(&map_out16, stage0 + (uint32_t)b * stage_bytes + halo_bytes + io32_bytes, out_c_off, t.tx * TW, t.ty * TH,
                        t.img);
         bulk_commit();
         if (deep) {
@@ -419,12 +465,26 @@ __global__ void __launch_bounds__(N_THREADS, 1)
         ph ^= 1u;
       }
     }
-    if (leader) bulk_wait_all();
+    if (leader) {
+      // the pass's last store of this team has drained its stage and is visible before the next pass re-reads / re-stages
+      bulk_wait_all();
+      if (deep && !first) mbar_arrive(empty_bar0 + 8 * b_prev);
+    }
+    first = true;                                 // the deferred stage release above closed this pass
+    e_b = b;
+    e_bprev = b_prev;
+    e_it = it;
+    e_ph = ph;
+    e_first = first;
   }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                                // end of the pass: every MMA consumed, every store complete
+  tc_fence_after();
+  }  // pass loop
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
 }
+
+
 
 // BatchNorm-folded fp32 weights [cout_p][cin_p][k][k] (k*k = ntap) -> fp16 [n_mma][2][n_pad][8] in the kernel's K-list order
 // split: [n_mma][2][2 n_pad][8], rows [0, n_pad) = fp16(w), rows [n_pad, 2 n_pad) = fp16(w - fp16(w)) (w_hi + w_lo = w to 2^-22)
@@ -570,21 +630,25 @@ extern "C" int ls3d_conv_f16_split_supported(int32_t cin, int32_t cout, int32_t 
   return ls3d_conv_f16_ex_supported(cin, cout, ksize, 1, dual, 1, supported);
 }
 
-extern "C" int ls3d_conv_f16_ex(const ls3d_conv_args* c, void* stream) {
+static int conv_ex_launch(const ls3d_conv_args* c, const ls3d_conv_pass* passes, int n_pass, void* stream) {
   using namespace ls3d;
   using namespace ls3d::c3;
-  if (!c) return LS3D_ERR_ARG;
+  if (!c || n_pass < 1 || n_pass > MAX_PASS || (n_pass > 1 && !passes)) return LS3D_ERR_ARG;
   if (c->n_img <= 0 || c->H_in <= 0 || c->W_in <= 0) return LS3D_OK;
   const int stride = c->stride ? c->stride : 1;
-  if (!c->in16 || !c->w_packed || !shape_ok(c->cin, c->cout, c->ksize, stride)) return LS3D_ERR_ARG;
+  if (!c->in16 || (!passes && !c->w_packed) || !shape_ok(c->cin, c->cout, c->ksize, stride)) return LS3D_ERR_ARG;
   const int dual = c->out32 != nullptr;
   void* out = dual ? (void*)c->out32 : c->out16;          // operand-only launches write the fp16 map alone
   if (!out || (dual && !c->out16) || (!dual && c->res32) || (dual && c->res16)) return LS3D_ERR_ARG;
   const void* res = dual ? (const void*)c->res32 : c->res16;
   const int in_ct = c->in_c_total ? c->in_c_total : c->cin, out_ct = c->out_c_total ? c->out_c_total : c->cout;
-  if ((in_ct & 7) || (out_ct & 7) || (c->in_c_off & 7) || (c->out_c_off & 7) || c->in_c_off < 0 || c->out_c_off < 0 ||
-      c->in_c_off + c->cin > in_ct || c->out_c_off + c->cout > out_ct)
-    return LS3D_ERR_ARG;
+  if ((in_ct & 7) || (out_ct & 7)) return LS3D_ERR_ARG;
+  for (int i = 0; i < n_pass; ++i) {
+    const int io = passes ? passes[i].in_c_off : c->in_c_off, oo = passes ? passes[i].out_c_off : c->out_c_off;
+    if ((io & 7) || (oo & 7) || io < 0 || oo < 0 || io + c->cin > in_ct || oo + c->cout > out_ct) return LS3D_ERR_ARG;
+    if (passes && (!passes[i].w_packed || (((uintptr_t)passes[i].w_packed) & 15))) return LS3D_ERR_ARG;
+    if (passes && (passes[i].flags & 4) && !dual) return LS3D_ERR_ARG;         // accumulation needs the fp32 output map
+  }
   if ((((uintptr_t)c->in16) | ((uintptr_t)c->out32) | ((uintptr_t)res) | ((uintptr_t)c->w_packed) | ((uintptr_t)c->out16)) & 15)
     return LS3D_ERR_ARG;
   const int ntap = ntap_of(c->ksize), split = c->w_split ? 1 : 0;
@@ -592,8 +656,21 @@ extern "C" int ls3d_conv_f16_ex(const ls3d_conv_args* c, void* stream) {
   if (stride == 2 && (c->H_in < 2 || c->W_in < 2)) return LS3D_ERR_ARG;
   const Geom g = geom(c->cin, c->cout, ntap, stride);
   Args a;
-  a.w = (const __half*)c->w_packed; a.bias = c->bias; a.has_res = res != nullptr; a.dual = dual;
+  a.w = (const __half*)(passes ? passes[0].w_packed : c->w_packed); a.bias = c->bias; a.has_res = res != nullptr; a.dual = dual;
   a.n_img = c->n_img; a.H = H; a.W = W; a.cin = c->cin; a.cout = c->cout; a.relu = c->relu;
+  a.n_pass = passes ? n_pass : 1;
+  a.use_table = passes ? 1 : 0;
+  if (passes) {
+    // a single-entry pass list still goes through the table (flags), so force the multi-pass decode with n_pass >= 2 semantics
+    for (int i = 0; i < n_pass; ++i) {
+      a.pass_w[i] = (const __half*)passes[i].w_packed;
+      a.pass_in_off[i] = (short)passes[i].in_c_off;
+      a.pass_out_off[i] = (short)passes[i].out_c_off;
+      int f = passes[i].flags & 15;
+      if ((f & 2) && !res) f &= ~2;
+      a.pass_flags[i] = (unsigned char)f;
+    }
+  }
   a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad; a.nphase = g.nphase; a.kdata = g.kdata;
   a.in_c_off = c->in_c_off; a.out_c_off = c->out_c_off;
   const int bw = ntap == 1 ? TW : HALO_W, bh = ntap == 1 ? TH : HALO_H;
@@ -645,6 +722,15 @@ extern "C" int ls3d_conv_f16_ex(const ls3d_conv_args* c, void* stream) {
   return LS3D_OK;
 }
 
+extern "C" int ls3d_conv_f16_ex(const ls3d_conv_args* c, void* stream) { return conv_ex_launch(c, nullptr, 1, stream); }
+
+// several passes (weight block, input / output channel slice, flags) over the same tiles in ONE launch; args->cin / cout are the
+// uniform slice sizes, args->bias the bias of the whole output tensor, args->in_c_off / out_c_off / relu / w_packed are unused
+extern "C" int ls3d_conv_f16_multi(const ls3d_conv_args* c, const ls3d_conv_pass* passes, int32_t n_pass, void* stream) {
+  if (!passes) return LS3D_ERR_ARG;
+  return conv_ex_launch(c, passes, n_pass, stream);
+}
+
 // fp16 maps (round-1 entry point): fp16 residual / output
 extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* bias, const void* res, void* out, int32_t n_img,
                              int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t ksize, int32_t relu, void* stream) {
@@ -660,6 +746,8 @@ extern "C" int ls3d_conv_f16(const void* in, const void* w_packed, const float* 
   a.n_img = n_img; a.H = H; a.W = W; a.cin = cin; a.cout = cout; a.relu = relu;
   a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad; a.nphase = 1; a.kdata = g.kdata;
   a.in_c_off = a.out_c_off = 0;
+  a.n_pass = 1;
+  a.use_table = 0;
   const int bw = ntap == 1 ? TW : HALO_W, bh = ntap == 1 ? TH : HALO_H;
   a.halo_w = bw; a.halo_pix = bw * bh; a.org = ntap == 1 ? 0 : 1; a.ch_stride = g.ch_stride;
   a.nb = g.n_pad;

@@ -235,47 +235,68 @@ class ConvPlan:
             return
         self.est_us, self.hilo, cs, ci = best
         self.split = exact and not self.hilo
-        self.launches = []          # (out_off, cout, [(in_off, cin, packed)])
-        for o0 in range(0, cout_p, cs):
-            co = min(cs, cout_p - o0)
-            ins = []
-            for i0 in range(0, cin_p, ci):
-                cn = min(ci, cin_p - i0)
-                ws = w[o0:o0 + co, i0:i0 + cn].contiguous()
+        self.cs, self.ci = cs, ci
+        # uniform slices: the last slice of a dimension is shifted back so that it ends with the tensor; input channels it
+        # shares with the previous slice get zero weights, output channels it shares are simply computed twice
+        self.passes = []            # (packed weights, in_off, out_off, first-of-out-slice, last-of-out-slice)
+        n_o, n_i = (cout_p + cs - 1) // cs, (cin_p + ci - 1) // ci
+        for o in range(n_o):
+            o0 = min(o * cs, cout_p - cs)
+            row = []
+            for i in range(n_i):
+                i0 = min(i * ci, cin_p - ci)
+                ws = w[o0:o0 + cs, i0:i0 + ci].clone()
+                if i0 < i * ci:
+                    ws[:, :i * ci - i0] = 0
                 if self.hilo:
                     hi = ws.half().float()
-                    ins.append((i0, cn, ops.pack_conv_ex(hi, stride, False)))
-                    ins.append((i0, cn, ops.pack_conv_ex(ws - hi, stride, False)))
+                    row.append((ops.pack_conv_ex(hi, stride, False), i0, o0))
+                    row.append((ops.pack_conv_ex(ws - hi, stride, False), i0, o0))
                 else:
-                    ins.append((i0, cn, ops.pack_conv_ex(ws, stride, self.split)))
-            self.launches.append((o0, co, ins))
-        self.n_launch = sum(len(l[2]) for l in self.launches)
-        self.multi = any(len(l[2]) > 1 for l in self.launches)
+                    row.append((ops.pack_conv_ex(ws, stride, self.split), i0, o0))
+            for j, (wp, i0, oo) in enumerate(row):
+                self.passes.append((wp, i0, oo, j == 0, j == len(row) - 1))
+        self.n_launch = len(self.passes)
+        self.multi = n_i * (2 if self.hilo else 1) > 1
+        self._tables = {}
+
+    def _table(self, has_res, relu, use_bias):
+        from .. import capi
+        key = (has_res, relu, use_bias)
+        t = self._tables.get(key)
+        if t is None:
+            arr = (capi.ConvPass * len(self.passes))()
+            for k, (wp, i0, o0, first, last) in enumerate(self.passes):
+                f = 0
+                if first:
+                    f |= (1 if use_bias and self.bias is not None else 0) | (2 if has_res else 0)
+                else:
+                    f |= 4
+                if last and relu:
+                    f |= 8
+                arr[k].w_packed, arr[k].in_c_off, arr[k].out_c_off, arr[k].flags = wp.data_ptr(), i0, o0, f
+            t = self._tables[key] = arr
+        return t
 
     def run(self, x16, res=None, relu=True, want32=True, use_bias=True):
-        """x16 [N, cin_p, H, W] fp16 channels-last -> (out32 or None, out16).  ``res``: fp32 map for fp32out plans, fp16 map for
-        operand-only plans."""
+        """x16 [N, cin_p, H, W] fp16 channels-last -> (out32 or None, out16): ONE launch, the slices are its passes.  ``res``:
+        fp32 map for fp32out plans, fp16 map for operand-only plans."""
         from .. import ops
         N, C, H, W = x16.shape
         assert C == self.cin_p and x16.dtype == torch.float16 and x16.is_contiguous(memory_format=torch.channels_last)
         Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if self.stride == 2 else (H, W)
         out16 = torch.empty((N, self.cout_p, Ho, Wo), dtype=torch.float16, device=x16.device, memory_format=torch.channels_last)
-        if not self.fp32out:
+        out32 = None
+        if self.fp32out:
+            assert res is None or res.dtype == torch.float32
+            out32 = torch.empty((N, self.cout_p, Ho, Wo), dtype=torch.float32, device=x16.device,
+                                memory_format=torch.channels_last)
+        else:
             assert res is None or res.dtype == torch.float16
-            for o0, co, ins in self.launches:
-                (i0, cn, wp), = ins
-                ops.conv_ex(x16, wp, self.bias[o0:o0 + co] if (use_bias and self.bias is not None) else None, cin=cn, in_off=i0,
-                            cout=co, out_off=o0, out32=None, out16=out16, res16=res, ksize=self.k, stride=self.stride, relu=relu,
-                            split=self.split)
-            return None, out16
-        assert res is None or res.dtype == torch.float32
-        out32 = torch.empty((N, self.cout_p, Ho, Wo), dtype=torch.float32, device=x16.device, memory_format=torch.channels_last)
-        for o0, co, ins in self.launches:
-            for i, (i0, cn, wp) in enumerate(ins):
-                first, last = i == 0, i == len(ins) - 1
-                b = self.bias[o0:o0 + co] if (first and use_bias and self.bias is not None) else None
-                ops.conv_ex(x16, wp, b, cin=cn, in_off=i0, cout=co, out_off=o0, out32=out32, out16=out16,
-                            res32=res if first else out32, ksize=self.k, stride=self.stride, relu=relu and last, split=self.split)
+        tab = self._table(res is not None, bool(relu), bool(use_bias))
+        ops.conv_multi(x16, tab, len(self.passes), self.bias if use_bias else None, cin=self.ci, cout=self.cs, out32=out32,
+                       out16=out16, res32=res if self.fp32out else None, res16=None if self.fp32out else res, ksize=self.k,
+                       stride=self.stride, split=self.split)
         return out32, out16
 
 

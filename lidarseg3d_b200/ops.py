@@ -457,6 +457,26 @@ def conv_ex(x16, w_packed, bias, *, cin, in_off, cout, out_off, out32, out16, re
     check(capi.lib().ls3d_conv_f16_ex(ctypes.byref(a), stream_ptr()), "ls3d_conv_f16_ex")
 
 
+def conv_multi(x16, passes, n_pass, bias, *, cin, cout, out32, out16, res32=None, res16=None, ksize=3, stride=1, split=True):
+    """One ls3d_conv_f16_multi launch: ``passes`` = ctypes array of capi.ConvPass (weight block, channel offsets, flags)."""
+    N, ct, H, W = x16.shape
+    a = capi.ConvArgs()
+    a.in16, a.bias = ptr(x16), ptr(bias)
+    a.res32, a.out32, a.out16, a.res16 = ptr(res32), ptr(out32), ptr(out16), ptr(res16)
+    a.in_c_total, a.cin, a.out_c_total, a.cout = ct, cin, out16.shape[1], cout
+    a.n_img, a.H_in, a.W_in, a.ksize, a.stride, a.w_split = N, H, W, ksize, stride, int(split)
+    if CONV_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(capi.lib().ls3d_conv_f16_multi(ctypes.byref(a), passes, n_pass, stream_ptr()), "ls3d_conv_f16_multi")
+        e1.record()
+        CONV_PROFILE.append(dict(e0=e0, e1=e1, n=N, h=H, w=W, cin=ct, cout=out16.shape[1], k=ksize, stride=stride,
+                                 res=res32 is not None or res16 is not None, out32=out32 is not None, in_total=ct,
+                                 out_total=out16.shape[1], passes=n_pass))
+        return
+    check(capi.lib().ls3d_conv_f16_multi(ctypes.byref(a), passes, n_pass, stream_ptr()), "ls3d_conv_f16_multi")
+
+
 def pad3_f16(x):
     """fp32 channels-last image batch [N, 3, H, W] -> fp16 [N, 8, H, W] channels-last, channels 3..7 zero: the operand copy of
     the network input for the own stem convolution (16-byte pixel rows for the tensor-map copies)."""
