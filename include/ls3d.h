@@ -197,6 +197,27 @@ int ls3d_token_attention(const float* q, int32_t ld_q, int32_t n, const float* k
                          int32_t ld_out, int32_t round_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SF-Phase: the whole POINT stream of the TransformerDecoder in one persistent launch (csrc/sffm_decoder.cu).
+ * replaces: TransformerDecoder.forward layer loop + norm_tgt (det3d/models/point_heads/context_module.py:147-171),
+ *           TransformerDecoderLayer.forward_post, point side (context_module.py:211-250),
+ *           SparsePointCorssAttention.forward (context_module.py:320-376) - i.e. per layer q_proj, the class-token cross
+ *           attention, out_proj + residual + norm2, linear1 + ReLU, linear2 + residual + norm3.
+ *   tgt_in [n, ld_in] fp32 = input_proj_point output; out [n, ld_out] fp32 (after norm_tgt when final_norm != 0)
+ *   w   : per layer the bf16x3 weight images (the gather-GEMM's packed layout, see ls3d_gemm_args.w, precise = 2) of
+ *         q_proj (3 chunks), out_proj (3), linear1 (3 chunks of 192 rows x 128 B), linear2 (6), concatenated in that order;
+ *         ls3d_sffm_decoder_weight_bytes gives the total size
+ *   vec : per layer 864 floats [q bias 96 | out bias 96 | norm2 gamma 96, beta 96 | linear1 bias 192 | linear2 bias 96 |
+ *         norm3 gamma 96, beta 96], then norm_tgt gamma 96, beta 96
+ *   k, v [n_layer][n_frames][n_head][n_tok][d_model / n_head] from ls3d_class_tokens; frame_off[n_frames] first row per frame
+ *   supported: d_model 96, d_ffn 192, n_head 4, n_layer <= 8, n_tok <= 64 (the shipped MSeg3D configs); else LS3D_ERR_ARG
+ * ------------------------------------------------------------------------------------------------ */
+int ls3d_sffm_decoder_weight_bytes(int32_t n_layer, int64_t* w_bytes, int64_t* vec_floats);
+int ls3d_sffm_decoder(const float* tgt_in, int32_t ld_in, int32_t n, const void* w, const float* vec, const float* k,
+                      const float* v, const int32_t* frame_off, int32_t n_frames, int32_t n_tok, int32_t n_layer,
+                      int32_t n_head, int32_t d_model, int32_t d_ffn, int32_t final_norm, float attn_scale, float ln_eps,
+                      float* out, int32_t ld_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Point -> camera projection (on the CPU, in the data loader, in the reference).
  * replaces: nuScenes branch of LoadPointCloudFromFile (det3d/datasets/pipelines/loading.py:373-416, view_points :67-103)
  *           + rescale / normalisation of SegImagePreprocess (det3d/datasets/pipelines/segpreprocess.py:544-565,654-671).

@@ -107,6 +107,8 @@ _SIGNATURES = {
     "ls3d_project_points": ([P, I, I, I, P, P, I, I, I, I, I, P, P], ctypes.c_int),
     "ls3d_project_points_global": ([P, I, I, I, P, P, P, I, I, I, I, I, P, P], ctypes.c_int),
     "ls3d_resize_images_u8": ([P, I, I, I, I, I, P, P, P, I, P], ctypes.c_int),
+    "ls3d_sffm_decoder_weight_bytes": ([I, PL, PL], ctypes.c_int),
+    "ls3d_sffm_decoder": ([P, I, I, P, P, P, P, P, I, I, I, I, I, I, I, ctypes.c_float, ctypes.c_float, P, I, P], ctypes.c_int),
     "ls3d_token_attention": ([P, I, I, P, P, P, I, I, I, I, ctypes.c_float, P, I, I, P], ctypes.c_int),
     "ls3d_upsample_sum": ([P, P, P, I, I, I, I, I, I, P, P, P], ctypes.c_int),
     "ls3d_normalize_images_u8": ([P, L, P, P, P, I, P], ctypes.c_int),
@@ -164,7 +166,7 @@ KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_tile_plan_build": 1, "ls3d_voxe
                     "ls3d_rulebook_gather": 1, "ls3d_rulebook_scatter": 1, "ls3d_three_nn_grid": 2, "ls3d_three_nn": 1,
                     "ls3d_three_interpolate": 1, "ls3d_sample_image_features": 1, "ls3d_project_points": 1, "ls3d_project_points_global": 1,
                     "ls3d_resize_images_u8": 1, "ls3d_upsample_sum": 1, "ls3d_upsample_sum_f16": 1,
-                    "ls3d_conv3x3_f16": 1, "ls3d_conv3x3_f16_pack": 1, "ls3d_conv_f16": 1, "ls3d_conv_f16_dual": 1, "ls3d_upsample_sum_dual": 1, "ls3d_cast_f16": 1, "ls3d_conv_f16_pack": 1, "ls3d_conv_f16_pack_split": 1, "ls3d_conv_f16_ex": 1, "ls3d_conv_f16_multi": 1, "ls3d_conv_f16_pack_ex": 1, "ls3d_pad3_f16": 1, "ls3d_cast_f32": 1, "ls3d_normalize_images_u8": 1, "ls3d_token_attention": 1, "ls3d_class_embed": 4,
+                    "ls3d_conv3x3_f16": 1, "ls3d_conv3x3_f16_pack": 1, "ls3d_conv_f16": 1, "ls3d_conv_f16_dual": 1, "ls3d_upsample_sum_dual": 1, "ls3d_cast_f16": 1, "ls3d_conv_f16_pack": 1, "ls3d_conv_f16_pack_split": 1, "ls3d_conv_f16_ex": 1, "ls3d_conv_f16_multi": 1, "ls3d_conv_f16_pack_ex": 1, "ls3d_pad3_f16": 1, "ls3d_cast_f32": 1, "ls3d_normalize_images_u8": 1, "ls3d_token_attention": 1, "ls3d_sffm_decoder": 1, "ls3d_class_embed": 4,
                     "ls3d_class_tokens": 1}
 
 

@@ -69,18 +69,19 @@ __global__ void ce_max_kernel(const T* __restrict__ logits, int ld_l, int ncls, 
 }
 
 // pass 2: partial sums  part[b][chunk][cls][C+1] = sum_r e * [feat | 1]   (probs^T @ [feats | 1] before normalisation)
-// Register-tiled outer product: a thread owns a 6-class x 4-channel block of the [ncls, C+1] result for one slice of the
-// rows, so each staged row costs it 6 scalar + 1 float4 shared-memory reads for 24 FMAs; slices are summed at the end.
-constexpr int CE_TR = 32;                       // rows staged per step
-constexpr int CE_CG = 6, CE_HG = 4;             // classes / channels per thread
-constexpr int CE_SE_LD = (CE_MAXCLS + CE_CG - 1) / CE_CG * CE_CG;          // 36
-constexpr int CE_SF_LD = (CE_MAXC + 1 + CE_HG - 1) / CE_HG * CE_HG;        // 68
-constexpr int CE_RED = 6144;                    // floats of cross-slice reduction space
-template <typename T>
-__global__ void __launch_bounds__(256) ce_partial_kernel(const T* __restrict__ logits, int ld_l, int ncls,
-                                                         const T* __restrict__ feats, int ld_f, int C,
-                                                         const int* __restrict__ seg_off, const float* __restrict__ cmax,
-                                                         float* __restrict__ part, int nchunk) {
+// Streaming layout: a warp owns rows chunk_start + warp, + 8, ... in groups of CE_GR; lane l owns channels l, l + 32 (, l + 64)
+// of [feats | 1] for ALL classes (NCLS4 * 4 x NCH accumulators in registers).  Per group the lanes load the feature rows
+// (coalesced, all CE_GR rows in flight), compute the group's e = exp(logit - max) values once into a per-warp shared-memory
+// strip and read them back as broadcast float4: per row 2-3 global loads, NCLS4 LDS.128 and ncls * NCH FMAs per lane and no
+// block-wide synchronisation inside the row loop.  Cross-warp sum in a fixed order (deterministic).
+constexpr int CE_GR = 8;                        // rows per warp step
+constexpr int CE_WARPS = 8;
+template <typename T, int NCLS4, int NCH>
+__global__ void __launch_bounds__(CE_WARPS * 32) ce_partial_kernel(const T* __restrict__ logits, int ld_l, int ncls,
+                                                                   const T* __restrict__ feats, int ld_f, int C,
+                                                                   const int* __restrict__ seg_off, const float* __restrict__ cmax,
+                                                                   float* __restrict__ part, int nchunk) {
+  constexpr int NC = NCLS4 * 4;
   const int b = blockIdx.y;
   const int r0 = seg_off[b], r1 = seg_off[b + 1];
   const int start = r0 + blockIdx.x * CE_ROWS;
@@ -91,82 +92,97 @@ __global__ void __launch_bounds__(256) ce_partial_kernel(const T* __restrict__ l
     return;
   }
   const int end = min(start + CE_ROWS, r1);
-  __shared__ __align__(16) float se[CE_TR][CE_SE_LD];
-  __shared__ __align__(16) float sf[CE_TR][CE_SF_LD];
-  __shared__ float red[CE_RED];
-  __shared__ float smx[CE_MAXCLS];
-  const int n_cg = (ncls + CE_CG - 1) / CE_CG, n_hg = (C + 1 + CE_HG - 1) / CE_HG;
-  const int per_slice = n_cg * n_hg;                       // threads per row slice (<= 6 * 17 = 102)
-  int n_slices = blockDim.x / per_slice;
-  while (n_slices * per_slice * CE_CG * CE_HG > CE_RED) --n_slices;
-  const int slice = threadIdx.x / per_slice, t = threadIdx.x % per_slice;
-  const bool active = slice < n_slices;
-  const int cg = t / n_hg, hg = t % n_hg;
-  float acc[CE_CG][CE_HG];
+  __shared__ __align__(16) float se[CE_WARPS][CE_GR * NC];
+  __shared__ float red[CE_WARPS][NC * NCH * 32 + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[NC][NCH];
 #pragma unroll
-  for (int i = 0; i < CE_CG; ++i)
+  for (int c = 0; c < NC; ++c)
 #pragma unroll
-    for (int j = 0; j < CE_HG; ++j) acc[i][j] = 0.f;
-  // zero the padding once (classes >= ncls, channels > C): they are multiplied but never stored
-  for (int q = threadIdx.x; q < CE_TR * CE_SE_LD; q += blockDim.x) (&se[0][0])[q] = 0.f;
-  for (int q = threadIdx.x; q < CE_TR * CE_SF_LD; q += blockDim.x) (&sf[0][0])[q] = 0.f;
-  if (threadIdx.x < ncls) smx[threadIdx.x] = __ldg(cmax + b * ncls + threadIdx.x);
-  __syncthreads();
-  for (int t0 = start; t0 < end; t0 += CE_TR) {
-    const int nr = min(CE_TR, end - t0);
-    for (int q = threadIdx.x; q < CE_TR * ncls; q += blockDim.x) {
-      const int r = q / ncls, c = q % ncls;
-      se[r][c] = r < nr ? __expf(ce_ld(logits + (size_t)(t0 + r) * ld_l + c) - smx[c]) : 0.f;
+    for (int j = 0; j < NCH; ++j) acc[c][j] = 0.f;
+  // this lane's share of a group's e strip: entries lane + 32 i -> (row idx / NC, class idx % NC)
+  constexpr int EPL = (CE_GR * NC + 31) / 32;
+  float mxv[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int c = (lane + 32 * i) % NC;
+    mxv[i] = c < ncls ? __ldg(cmax + b * ncls + c) : 0.f;
+  }
+  float* sew = se[warp];
+  for (int g0 = start + warp * CE_GR; g0 < end; g0 += CE_WARPS * CE_GR) {
+    float f[CE_GR][NCH];
+#pragma unroll
+    for (int rr = 0; rr < CE_GR; ++rr) {
+      const int r = g0 + rr;
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int ch = lane + 32 * j;
+        f[rr][j] = (r < end) ? (ch < C ? ce_ld(feats + (size_t)r * ld_f + ch) : (ch == C ? 1.f : 0.f)) : 0.f;
+      }
     }
-    for (int q = threadIdx.x; q < CE_TR * (C + 1); q += blockDim.x) {
-      const int r = q / (C + 1), c = q % (C + 1);
-      sf[r][c] = r < nr ? (c < C ? ce_ld(feats + (size_t)(t0 + r) * ld_f + c) : 1.f) : 0.f;
+    float ev[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int idx = lane + 32 * i, rr = idx / NC, c = idx % NC, r = g0 + rr;
+      ev[i] = (idx < CE_GR * NC && c < ncls && r < end) ? __expf(ce_ld(logits + (size_t)r * ld_l + c) - mxv[i]) : 0.f;
     }
-    __syncthreads();
-    if (active) {
-      for (int r = slice; r < CE_TR; r += n_slices) {
-        const float4 f = *reinterpret_cast<const float4*>(&sf[r][hg * CE_HG]);
-        const float fv[CE_HG] = {f.x, f.y, f.z, f.w};
+    __syncwarp();                                   // the previous group's strip has been read by every lane
 #pragma unroll
-        for (int i = 0; i < CE_CG; ++i) {
-          const float e = se[r][cg * CE_CG + i];
+    for (int i = 0; i < EPL; ++i)
+      if (lane + 32 * i < CE_GR * NC) sew[lane + 32 * i] = ev[i];
+    __syncwarp();
 #pragma unroll
-          for (int j = 0; j < CE_HG; ++j) acc[i][j] = fmaf(e, fv[j], acc[i][j]);
+    for (int rr = 0; rr < CE_GR; ++rr) {
+#pragma unroll
+      for (int c4 = 0; c4 < NCLS4; ++c4) {
+        const float4 e = *reinterpret_cast<const float4*>(sew + rr * NC + c4 * 4);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          acc[c4 * 4 + 0][j] = fmaf(e.x, f[rr][j], acc[c4 * 4 + 0][j]);
+          acc[c4 * 4 + 1][j] = fmaf(e.y, f[rr][j], acc[c4 * 4 + 1][j]);
+          acc[c4 * 4 + 2][j] = fmaf(e.z, f[rr][j], acc[c4 * 4 + 2][j]);
+          acc[c4 * 4 + 3][j] = fmaf(e.w, f[rr][j], acc[c4 * 4 + 3][j]);
         }
       }
     }
-    __syncthreads();
   }
-  // cross-slice sum (fixed order: deterministic)
-  if (active) {
+  // cross-warp sum (fixed order: deterministic)
 #pragma unroll
-    for (int i = 0; i < CE_CG; ++i)
+  for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int j = 0; j < CE_HG; ++j) red[(slice * per_slice + t) * (CE_CG * CE_HG) + i * CE_HG + j] = acc[i][j];
-  }
+    for (int j = 0; j < NCH; ++j) red[warp][(c * NCH + j) * 32 + lane] = acc[c][j];
   __syncthreads();
   for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
     const int cls = a / (C + 1), ch = a % (C + 1);
-    const int tt = (cls / CE_CG) * n_hg + ch / CE_HG, k = (cls % CE_CG) * CE_HG + ch % CE_HG;
+    const int slot = (cls * NCH + (ch >> 5)) * 32 + (ch & 31);
     float v = 0.f;
-    for (int sl = 0; sl < n_slices; ++sl) v += red[(sl * per_slice + tt) * (CE_CG * CE_HG) + k];
+#pragma unroll
+    for (int w = 0; w < CE_WARPS; ++w) v += red[w][slot];
     dst[a] = v;
   }
 }
 
-// pass 3: emb[b][cls][c] = sum_chunks num / sum_chunks den
+// pass 3: emb[b][cls][c] = sum_chunks num / sum_chunks den.  grid = (ncls, frames), thread = channel (C + 1 <= 128):
+// a chunk's [C + 1] strip is one coalesced read; sequential over the chunks in a fixed order (deterministic).
 __global__ void ce_final_kernel(const float* __restrict__ part, int nchunk, int ncls, int C, float* __restrict__ emb) {
-  const int b = blockIdx.x;
-  for (int a = threadIdx.x; a < ncls * C; a += blockDim.x) {
-    const int cls = a / C, c = a % C;
-    float num = 0.f, den = 0.f;
-    for (int k = 0; k < nchunk; ++k) {
-      const float* src = part + ((size_t)b * nchunk + k) * ncls * (C + 1) + cls * (C + 1);
-      num += src[c];
-      den += src[C];
+  const int cls = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+  __shared__ float s_den;
+  float num = 0.f;
+  if (c <= C) {
+    const float* src = part + (size_t)b * nchunk * ncls * (C + 1) + (size_t)cls * (C + 1) + c;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= nchunk; k += 4) {                  // four independent loads in flight, summed in chunk order
+      const float v0 = src[(size_t)(k + 0) * ncls * (C + 1)], v1 = src[(size_t)(k + 1) * ncls * (C + 1)];
+      const float v2 = src[(size_t)(k + 2) * ncls * (C + 1)], v3 = src[(size_t)(k + 3) * ncls * (C + 1)];
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
     }
-    emb[((size_t)b * ncls + cls) * C + c] = num / den;
+    for (; k < nchunk; ++k) a0 += src[(size_t)k * ncls * (C + 1)];
+    num = (a0 + a1) + (a2 + a3);
   }
+  if (c == C) s_den = num;
+  __syncthreads();
+  if (c < C) emb[((size_t)b * ncls + cls) * C + c] = num / s_den;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -370,16 +386,27 @@ extern "C" int ls3d_class_embed(const void* logits, int32_t ld_l, int32_t ncls, 
   float* part = cmax + (size_t)n_frames * ncls;
   fill_f32_kernel<<<1, 256, 0, st>>>(cmax, n_frames * ncls, -INFINITY);
   dim3 grid(nchunk, n_frames);
+  const int ncls4 = (ncls + 3) / 4, nch = (C + 1 + 31) / 32;
+#define LS3D_CE_PARTIAL(T, A, B)                                                                                      \
+  ce_partial_kernel<T, A, B><<<grid, CE_WARPS * 32, 0, st>>>((const T*)logits, ld_l, ncls, (const T*)feats, ld_f, C, seg_off, \
+                                                             cmax, part, nchunk)
+#define LS3D_CE_DISPATCH(T)                                                        \
+  do {                                                                             \
+    if (ncls4 <= 5 && nch <= 2) LS3D_CE_PARTIAL(T, 5, 2);                          \
+    else if (ncls4 <= 5) LS3D_CE_PARTIAL(T, 5, 3);                                 \
+    else if (nch <= 2) LS3D_CE_PARTIAL(T, 8, 2);                                   \
+    else LS3D_CE_PARTIAL(T, 8, 3);                                                 \
+  } while (0)
   if (in_fp16) {
     ce_max_kernel<__half><<<grid, 256, 0, st>>>((const __half*)logits, ld_l, ncls, seg_off, cmax);
-    ce_partial_kernel<__half><<<grid, 256, 0, st>>>((const __half*)logits, ld_l, ncls, (const __half*)feats, ld_f, C, seg_off,
-                                                   cmax, part, nchunk);
+    LS3D_CE_DISPATCH(__half);
   } else {
     ce_max_kernel<float><<<grid, 256, 0, st>>>((const float*)logits, ld_l, ncls, seg_off, cmax);
-    ce_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)logits, ld_l, ncls, (const float*)feats, ld_f, C, seg_off,
-                                                  cmax, part, nchunk);
+    LS3D_CE_DISPATCH(float);
   }
-  ce_final_kernel<<<n_frames, 256, 0, st>>>(part, nchunk, ncls, C, emb);
+#undef LS3D_CE_DISPATCH
+#undef LS3D_CE_PARTIAL
+  ce_final_kernel<<<dim3(ncls, n_frames), 128, 0, st>>>(part, nchunk, ncls, C, emb);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }

@@ -8,6 +8,7 @@ containers only; the forward runs on the C-ABI kernels: devoxelization (grid 3-N
 sampling, class-embedding aggregation, class-token memory path, and the tcgen05 gather-GEMM for every Linear with
 BatchNorm / ReLU / residual / LayerNorm / cross-attention fused into its epilogue.
 """
+import os
 from functools import partial
 
 import torch
@@ -60,6 +61,25 @@ def _run_mlp(x, packed):
     for i, (pw, s, b, relu) in enumerate(packed):
         x = gemm.run(x, pw, scale=s, shift=b, relu=relu, round_out=i + 1 < len(packed))
     return x
+
+
+# SF-Phase decoder of the point stream as one launch (csrc/sffm_decoder.cu) where the kernel serves the configuration
+# (d_model 96, ffn 192, 4 heads: every shipped MSeg3D config); False = one launch per Linear / attention (development A/B)
+FUSED_DECODER = os.environ.get("LS3D_FUSED_DECODER", "1") == "1"
+
+
+def _pack_decoder(sf, layers, norm_tgt):
+    """Weight image + vector block of ls3d_sffm_decoder (layout: include/ls3d.h) or None when the shape is not served."""
+    ffn = sf.decoder.layers[0].linear1.out_features if len(sf.decoder.layers) else 0
+    if sf.d_model != 96 or sf.nhead != 4 or ffn != 192 or not 1 <= len(layers) <= 8 or gemm.PRECISE != 2:
+        return None
+    w, vec = [], []
+    for ly in layers:
+        for key in ("q", "o", "l1", "l2"):
+            w.append(ly[key][0].data.reshape(-1).view(torch.uint8))
+        vec += [ly["q"][1], ly["o"][1], ly["n2"][0], ly["n2"][1], ly["l1"][1], ly["l2"][1], ly["n3"][0], ly["n3"][1]]
+    vec += [norm_tgt[0], norm_tgt[1]]
+    return dict(w=torch.cat(w).contiguous(), vec=torch.cat([t.reshape(-1).float() for t in vec]).contiguous(), ffn=ffn)
 
 
 def devoxelize(batch_dict, points, voxel_features, voxel_size, pc_range, batch_size):
@@ -276,6 +296,7 @@ class PointSegMSeg3DHead(Prepared):
             layers.append(dict(q=linear_pack(ca.q_proj), o=linear_pack(ca.out_proj), l1=linear_pack(ly.linear1),
                                l2=linear_pack(ly.linear2), n2=ln(ly.norm2), n3=ln(ly.norm3)))
         return dict(
+            decoder=_pack_decoder(sf, layers, ln(sf.decoder.norm_tgt)),
             voxel_cls=_pack_convcls(self.voxel_cls_layers),
             gffm_lidar=linear_bn_pack(self.gffm_lidar[0], self.gffm_lidar[1]),
             gffm_camera=linear_bn_pack(self.gffm_camera[0], self.gffm_camera[1]),
@@ -330,7 +351,11 @@ class PointSegMSeg3DHead(Prepared):
         K, V = ops.class_tokens(cam_emb, lidar_emb, P["token_params"], nl, sf.nhead, sf.d_model)
         tgt = gemm.run(geo, P["proj_point"][0], shift=P["proj_point"][1])
         dh = sf.d_model // sf.nhead
-        for i, ly in enumerate(P["layers"]):
+        dec = P["decoder"] if FUSED_DECODER else None
+        if dec is not None:
+            # all decoder layers of the point stream + norm_tgt in one persistent launch (csrc/sffm_decoder.cu)
+            tgt = ops.sffm_decoder(tgt, dec["w"], dec["vec"], K, V, point_off, dh ** -0.5, nl, sf.nhead, dec["ffn"])
+        for i, ly in enumerate(P["layers"] if dec is None else ()):
             q = gemm.run(tgt, ly["q"][0], shift=ly["q"][1])
             att = ops.token_attention(q, K[i], V[i], point_off, dh ** -0.5)
             tgt = gemm.run(att, ly["o"][0], shift=ly["o"][1], res=tgt, res_mode=1, ln=(ly["n2"],))

@@ -278,6 +278,19 @@ def token_attention(q, k, v, frame_off, scale, round_out=False):
     return out
 
 
+def sffm_decoder(tgt, w_image, vec, k, v, frame_off, scale, n_layer, n_head, d_ffn, final_norm=True, ln_eps=1e-5):
+    """The point stream of the SF-Phase TransformerDecoder (all layers + norm_tgt) in one launch (csrc/sffm_decoder.cu).
+    tgt [N, E] fp32; w_image uint8 / vec fp32 from det3d.point_heads (layout: include/ls3d.h); k, v [n_layer, F, H, L, dh]."""
+    n, E = tgt.shape
+    nl, F_, H, L, dh = k.shape
+    assert nl == n_layer and H == n_head and H * dh == E and tgt.dtype == torch.float32 and tgt.stride(1) == 1
+    out = _f32(tgt.device, n, E)
+    check(capi.lib().ls3d_sffm_decoder(ptr(tgt), tgt.stride(0), n, ptr(w_image), ptr(vec), ptr(k), ptr(v), ptr(frame_off), F_, L,
+                                       n_layer, n_head, E, d_ffn, int(final_norm), float(scale), float(ln_eps), ptr(out),
+                                       out.stride(0), stream_ptr()), "ls3d_sffm_decoder")
+    return out
+
+
 def normalize_images_u8(images_u8, mean, std, dtype=torch.float32):
     """uint8 [..., H, W, 3] (HWC images as the loader decodes them) -> (x / 255 - mean) / std as [..., 3, H, W] ``dtype`` maps in
     channels-last memory (the tensor is a permuted view of the pixel-major result, so no transpose is ever materialised).

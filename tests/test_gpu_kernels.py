@@ -539,3 +539,55 @@ def test_mseg3d_head_vs_reference_golden(ref_modules):
     rel = float((out - ref).abs().max() / ref.abs().max())
     agree = float((out.argmax(1) == ref.argmax(1)).float().mean())
     assert rel <= 1e-4 and agree >= 0.999, (rel, agree)          # compensated GEMM chain vs the reference module's fp32 output
+
+
+@pytest.mark.parametrize("n,nl,L", [(1000, 2, 34), (129, 1, 34), (40000, 6, 34), (777, 3, 46)])
+def test_sffm_decoder_fused_vs_fp64(n, nl, L):
+    """ls3d_sffm_decoder (all layers of the point stream in one launch; context_module.py:147-171,211-250,320-376) vs a float64
+    restatement of forward_post, frames of uneven size with a frame boundary inside a 128-point tile."""
+    ops, gemm = _ops()
+    from lidarseg3d_b200.det3d.common import linear_pack
+    from lidarseg3d_b200.det3d.point_heads import _pack_decoder
+    E, H, dh, FFN, Fr = 96, 4, 24, 192, 3
+    torch.manual_seed(11 + n)
+    lin = lambda i, o: torch.nn.Linear(i, o)
+    mods = [dict(q=lin(E, E), o=lin(E, E), l1=lin(E, FFN), l2=lin(FFN, E), n2=torch.nn.LayerNorm(E), n3=torch.nn.LayerNorm(E))
+            for _ in range(nl)]
+    norm_tgt = torch.nn.LayerNorm(E)
+    for md in mods + [dict(n=norm_tgt)]:
+        for k, v in md.items():
+            if isinstance(v, torch.nn.LayerNorm):
+                torch.nn.init.normal_(v.weight, 1.0, 0.2)
+                torch.nn.init.normal_(v.bias, 0.0, 0.2)
+            v.to(DEV)
+    ln = lambda m: (m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous())
+    layers = [dict(q=linear_pack(md["q"]), o=linear_pack(md["o"]), l1=linear_pack(md["l1"]), l2=linear_pack(md["l2"]),
+                   n2=ln(md["n2"]), n3=ln(md["n3"])) for md in mods]
+
+    class SF:
+        d_model, nhead = E, H
+        class decoder:
+            layers = [type("L", (), dict(linear1=md["l1"]))() for md in mods]
+    dec = _pack_decoder(SF, layers, ln(norm_tgt))
+    assert dec is not None
+    g = torch.Generator().manual_seed(5)
+    tgt = torch.randn(n, E, generator=g).to(DEV)
+    K = torch.randn(nl, Fr, H, L, dh, generator=g).to(DEV)
+    V = torch.randn(nl, Fr, H, L, dh, generator=g).to(DEV)
+    fo = torch.tensor([0, int(n * 0.3) + 1, int(n * 0.65) + 3, n], dtype=torch.int32, device=DEV)
+    out = ops.sffm_decoder(tgt, dec["w"], dec["vec"], K, V, fo, dh ** -0.5, nl, H, FFN)
+    fid = torch.bucketize(torch.arange(n, device=DEV), fo[1:Fr].long(), right=True)
+    x = tgt.double()
+    F = torch.nn.functional
+    for i, md in enumerate(mods):
+        d = {k: v.double() for k, v in md.items()}
+        q = d["q"](x).view(n, H, dh)
+        s = torch.einsum("mhd,mhld->mhl", q, K[i].double()[fid]) * dh ** -0.5
+        att = torch.einsum("mhl,mhld->mhd", s.softmax(-1), V[i].double()[fid]).reshape(n, E)
+        x = d["n2"](x + d["o"](att))
+        x = d["n3"](x + d["l2"](F.relu(d["l1"](x))))
+        for v in md.values():
+            v.float()
+    ref = norm_tgt.double()(x)
+    err = float((out.double() - ref).abs().max())
+    assert err <= 2e-4, err
