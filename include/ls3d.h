@@ -160,6 +160,8 @@ int ls3d_rulebook_scatter(const void* out_words, int32_t B, int32_t oD, int32_t 
  *   points [n, ld_p] fp32 rows (frame, x, y, z, ...); words/perm = level-1 bitmap of the voxel grid;
  *   idx are GLOBAL voxel rows (reference: per-frame rows; subtract voxel_off[frame] to compare);
  *   dist2 = squared distances (reference three_nn returns sqrt of these).
+ *   workspace: todo int32[2 n] + todo_count int32[2] (work lists of the points handed from the per-thread box search to the
+ *   warp-cooperative box search and from there to the exact brute-force pass).
  * ------------------------------------------------------------------------------------------------ */
 /* Reference-signature twin: any point sets, b batches of n unknown / m known points [b, n|m, 3]; dist2 [b, n, 3] squared
  * distances, idx [b, n, 3] per-batch rows - exactly what three_nn_wrapper_fast(b, n, m, unknown, known, dist2, idx) fills

@@ -63,15 +63,37 @@ __device__ __forceinline__ int frame_of_point(const int* off, int nf, int i) {
   return f;
 }
 
-__global__ void three_nn_grid_kernel(const float* __restrict__ pts, int ld_p, NNParams p, float* __restrict__ dist2_out,
-                                     int* __restrict__ idx_out, int* __restrict__ todo, int* __restrict__ todo_count) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n) return;
-  const int f = frame_of_point(p.point_off, p.n_frames, i);
-  const float ux = pts[(size_t)i * ld_p + 1], uy = pts[(size_t)i * ld_p + 2], uz = pts[(size_t)i * ld_p + 3];
+// Box of "radius" r around cell c: the per-axis half-widths are scaled so that the box is roughly a metric cube (a z cell is
+// twice as tall as it is wide in the shipped configs, so it needs half as many z layers for the same lower bound):
+// ra[a] = ceil(r * min(vs) / vs[a]).  Any box shape is exact - termination only uses the true distance to the first cells
+// outside the scanned box.
+struct Box {
+  int ra[3];
+};
+__device__ __forceinline__ Box make_box(const NNParams& p, int r) {
+  const float vmin = fminf(p.vs[0], fminf(p.vs[1], p.vs[2]));
+  Box b;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) b.ra[a] = max(1, (int)ceilf((float)r * vmin / p.vs[a] - 1e-4f));
+  return b;
+}
+// lower bound of the distance from u to any centre outside the box (INFINITY: the box covers the whole frame grid)
+__device__ __forceinline__ float box_bound(const NNParams& p, const int* c, const float* u, const Box& bx) {
   const int G[3] = {p.W, p.H, p.D};
-  const float u[3] = {ux, uy, uz};
-  int c[3];
+  float bound = INFINITY;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int lo_i = c[a] - bx.ra[a] - 1, hi_i = c[a] + bx.ra[a] + 1;
+    if (lo_i >= 0) bound = fminf(bound, u[a] - centre(lo_i, p.vs[a], p.lo[a]));
+    if (hi_i <= G[a] - 1) bound = fminf(bound, centre(hi_i, p.vs[a], p.lo[a]) - u[a]);
+  }
+  return bound;
+}
+__device__ __forceinline__ bool box_done(float bound, float d3) {
+  return bound == INFINITY || (bound > 0.f && d3 < bound * bound * 0.9999f);
+}
+__device__ __forceinline__ void point_cell(const NNParams& p, const float* u, int* c) {
+  const int G[3] = {p.W, p.H, p.D};
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     float t = floorf((u[a] - p.lo[a]) / p.vs[a]);
@@ -79,57 +101,64 @@ __global__ void three_nn_grid_kernel(const float* __restrict__ pts, int ld_p, NN
     if (!(t == t)) t = 0.f;
     c[a] = (int)t;
   }
+}
+// one bitmap row (fixed z, y; x in [x0, x1]) of frame f into `best`; cells with |x - cx| <= skip_x are skipped when the row
+// itself lies inside the previously scanned box (inner_row)
+__device__ __forceinline__ void scan_row(const NNParams& p, int f, int z, int y, int x0, int x1, bool inner_row, int cx,
+                                         int skip_x, float ux, float uy, float uz, Top3& best) {
+  const float cz = centre(z, p.vs[2], p.lo[2]);
+  const float cy = centre(y, p.vs[1], p.lo[1]);
+  const long long base = (((long long)f * p.D + z) * p.H + y) * p.W;
+  const long long w0 = (base + x0) >> 5, w1 = (base + x1) >> 5;
+  for (long long wi = w0; wi <= w1; ++wi) {
+    const uint2 w = __ldg(&p.words[wi]);
+    unsigned bits = w.x;
+    if (!bits) continue;
+    const long long cell0 = wi << 5;
+    const long long lo_c = base + x0, hi_c = base + x1;
+    if (cell0 < lo_c) bits &= ~0u << (int)(lo_c - cell0);
+    if (cell0 + 31 > hi_c) bits &= ~0u >> (int)(cell0 + 31 - hi_c);
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int x = (int)(cell0 + b - base);
+      if (inner_row && abs(x - cx) <= skip_x) continue;  // visited with the previous box
+      const float dd = dist2(ux, uy, uz, centre(x, p.vs[0], p.lo[0]), cy, cz);
+      if (dd <= best.d[2]) {
+        const int rank = (int)w.y + __popc(w.x & ((1u << b) - 1u));
+        best.push(dd, __ldg(&p.perm[rank]));
+      }
+    }
+  }
+}
+
+// pass 1: one thread per point, boxes of radius 2 and 4 (most points of a LiDAR sweep resolve here)
+__global__ void three_nn_grid_kernel(const float* __restrict__ pts, int ld_p, NNParams p, float* __restrict__ dist2_out,
+                                     int* __restrict__ idx_out, int* __restrict__ todo, int* __restrict__ todo_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const int f = frame_of_point(p.point_off, p.n_frames, i);
+  const float ux = pts[(size_t)i * ld_p + 1], uy = pts[(size_t)i * ld_p + 2], uz = pts[(size_t)i * ld_p + 3];
+  const float u[3] = {ux, uy, uz};
+  int c[3];
+  point_cell(p, u, c);
   Top3 best;
   best.init();
   bool done = false;
-  int rprev = -1;
-  const int radii[4] = {2, 4, 8, 16};
-  for (int ri = 0; ri < 4 && !done; ++ri) {
-    const int r = radii[ri];
-    const int z0 = max(c[2] - r, 0), z1 = min(c[2] + r, p.D - 1);
-    const int y0 = max(c[1] - r, 0), y1 = min(c[1] + r, p.H - 1);
-    const int x0 = max(c[0] - r, 0), x1 = min(c[0] + r, p.W - 1);
-    for (int z = z0; z <= z1; ++z) {
-      const float cz = centre(z, p.vs[2], p.lo[2]);
+  Box prev;
+  prev.ra[0] = prev.ra[1] = prev.ra[2] = -1;
+  for (int r = 2; r <= 4 && !done; r <<= 1) {
+    const Box bx = make_box(p, r);
+    const int z0 = max(c[2] - bx.ra[2], 0), z1 = min(c[2] + bx.ra[2], p.D - 1);
+    const int y0 = max(c[1] - bx.ra[1], 0), y1 = min(c[1] + bx.ra[1], p.H - 1);
+    const int x0 = max(c[0] - bx.ra[0], 0), x1 = min(c[0] + bx.ra[0], p.W - 1);
+    for (int z = z0; z <= z1; ++z)
       for (int y = y0; y <= y1; ++y) {
-        const float cy = centre(y, p.vs[1], p.lo[1]);
-        const bool inner_row = (rprev >= 0) && (abs(z - c[2]) <= rprev) && (abs(y - c[1]) <= rprev);
-        const long long base = (((long long)f * p.D + z) * p.H + y) * p.W;
-        const long long w0 = (base + x0) >> 5, w1 = (base + x1) >> 5;
-        for (long long wi = w0; wi <= w1; ++wi) {
-          const uint2 w = __ldg(&p.words[wi]);
-          unsigned bits = w.x;
-          if (!bits) continue;
-          // restrict to [x0, x1] of this row
-          const long long cell0 = wi << 5;
-          const long long lo_c = base + x0, hi_c = base + x1;
-          if (cell0 < lo_c) bits &= ~0u << (int)(lo_c - cell0);
-          if (cell0 + 31 > hi_c) bits &= ~0u >> (int)(cell0 + 31 - hi_c);
-          while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int x = (int)(cell0 + b - base);
-            if (inner_row && abs(x - c[0]) <= rprev) continue;  // visited with the previous radius
-            const float dd = dist2(ux, uy, uz, centre(x, p.vs[0], p.lo[0]), cy, cz);
-            if (dd <= best.d[2]) {
-              const int rank = (int)w.y + __popc(w.x & ((1u << b) - 1u));
-              best.push(dd, __ldg(&p.perm[rank]));
-            }
-          }
-        }
+        const bool inner_row = (prev.ra[0] >= 0) && (abs(z - c[2]) <= prev.ra[2]) && (abs(y - c[1]) <= prev.ra[1]);
+        scan_row(p, f, z, y, x0, x1, inner_row, c[0], prev.ra[0], ux, uy, uz, best);
       }
-    }
-    rprev = r;
-    // lower bound of the distance to any centre outside the scanned box
-    float bound = INFINITY;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int lo_i = c[a] - r - 1, hi_i = c[a] + r + 1;
-      if (lo_i >= 0) bound = fminf(bound, u[a] - centre(lo_i, p.vs[a], p.lo[a]));
-      if (hi_i <= G[a] - 1) bound = fminf(bound, centre(hi_i, p.vs[a], p.lo[a]) - u[a]);
-    }
-    if (bound == INFINITY) done = true;  // box covered the whole frame grid
-    else if (bound > 0.f && best.d[2] < bound * bound * 0.9999f) done = true;
+    prev = bx;
+    done = box_done(box_bound(p, c, u, bx), best.d[2]);
   }
   if (!done) {
     todo[atomicAdd(todo_count, 1)] = i;
@@ -139,6 +168,61 @@ __global__ void three_nn_grid_kernel(const float* __restrict__ pts, int ld_p, NN
   for (int k = 0; k < 3; ++k) {
     dist2_out[(size_t)i * 3 + k] = best.d[k];
     idx_out[(size_t)i * 3 + k] = best.i[k];
+  }
+}
+
+// pass 2: one WARP per unresolved point, boxes of radius 8, 16, 32 rescanned from scratch with the rows dealt to the lanes;
+// the lanes' candidate lists are merged with (d, row)-ordered pushes, which makes the result independent of the order
+// (== the sequential strict-'<' scan).  Points that still do not converge are compacted into todo2 for the brute-force pass.
+__global__ void three_nn_grid_warp_kernel(const float* __restrict__ pts, int ld_p, NNParams p, const int* __restrict__ todo,
+                                          const int* __restrict__ todo_count, float* __restrict__ dist2_out,
+                                          int* __restrict__ idx_out, int* __restrict__ todo2, int* __restrict__ todo2_count) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int cnt = *todo_count;
+  for (int t = wid; t < cnt; t += nw) {
+    const int i = todo[t];
+    const int f = frame_of_point(p.point_off, p.n_frames, i);
+    const float ux = pts[(size_t)i * ld_p + 1], uy = pts[(size_t)i * ld_p + 2], uz = pts[(size_t)i * ld_p + 3];
+    const float u[3] = {ux, uy, uz};
+    int c[3];
+    point_cell(p, u, c);
+    bool done = false;
+    Top3 best;
+    for (int r = 8; r <= 32 && !done; r <<= 1) {
+      const Box bx = make_box(p, r);
+      const int z0 = max(c[2] - bx.ra[2], 0), z1 = min(c[2] + bx.ra[2], p.D - 1);
+      const int y0 = max(c[1] - bx.ra[1], 0), y1 = min(c[1] + bx.ra[1], p.H - 1);
+      const int x0 = max(c[0] - bx.ra[0], 0), x1 = min(c[0] + bx.ra[0], p.W - 1);
+      const int ny = y1 - y0 + 1, nrows = (z1 - z0 + 1) * ny;
+      best.init();
+      for (int q = lane; q < nrows; q += 32) scan_row(p, f, z0 + q / ny, y0 + q % ny, x0, x1, false, 0, 0, ux, uy, uz, best);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        float od[3];
+        int oi[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          od[k] = __shfl_xor_sync(0xffffffffu, best.d[k], o);
+          oi[k] = __shfl_xor_sync(0xffffffffu, best.i[k], o);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (od[k] != INFINITY && od[k] <= best.d[2]) best.push(od[k], oi[k]);
+      }
+      done = box_done(box_bound(p, c, u, bx), best.d[2]);
+    }
+    if (lane == 0) {
+      if (done) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          dist2_out[(size_t)i * 3 + k] = best.d[k];
+          idx_out[(size_t)i * 3 + k] = best.i[k];
+        }
+      } else {
+        todo2[atomicAdd(todo2_count, 1)] = i;
+      }
+    }
   }
 }
 
@@ -281,9 +365,12 @@ extern "C" int ls3d_three_nn_grid(const float* points, int32_t ld_p, int32_t n, 
   p.words = (const uint2*)words; p.perm = perm; p.B = B; p.D = D; p.H = H; p.W = W;
   for (int a = 0; a < 3; ++a) { p.vs[a] = voxel_size_xyz[a]; p.lo[a] = range_min_xyz[a]; }
   p.n = n; p.n_frames = B; p.point_off = point_off; p.voxel_off = voxel_off;
-  cudaMemsetAsync(todo_count, 0, sizeof(int), st);
+  // todo_count[0]: points left by pass 1 (list todo[0, n)), todo_count[1]: points left by pass 2 (list todo[n, 2n))
+  cudaMemsetAsync(todo_count, 0, 2 * sizeof(int), st);
   three_nn_grid_kernel<<<ls3d_div_up(n, 128), 128, 0, st>>>(points, ld_p, p, dist2, idx, todo, todo_count);
-  three_nn_brute_kernel<<<592, 256, 0, st>>>(points, ld_p, p, voxel_coords, todo, todo_count, dist2, idx);
+  three_nn_grid_warp_kernel<<<4 * ls3d_num_sms(), 256, 0, st>>>(points, ld_p, p, todo, todo_count, dist2, idx, todo + n,
+                                                                todo_count + 1);
+  three_nn_brute_kernel<<<592, 256, 0, st>>>(points, ld_p, p, voxel_coords, todo + n, todo_count + 1, dist2, idx);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }

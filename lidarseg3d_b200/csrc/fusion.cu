@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(CE_WARPS * 32) ce_partial_kernel(const T* __re
   }
   const int end = min(start + CE_ROWS, r1);
   __shared__ __align__(16) float se[CE_WARPS][CE_GR * NC];
-  __shared__ float red[CE_WARPS][NC * NCH * 32 + 1];
+  __shared__ float red[CE_WARPS][NCH * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[NC][NCH];
 #pragma unroll
@@ -146,19 +146,20 @@ __global__ void __launch_bounds__(CE_WARPS * 32) ce_partial_kernel(const T* __re
       }
     }
   }
-  // cross-warp sum (fixed order: deterministic)
+  // cross-warp sum, one class at a time (fixed order: deterministic)
 #pragma unroll
-  for (int c = 0; c < NC; ++c)
+  for (int c = 0; c < NC; ++c) {
+    if (c >= ncls) break;
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) red[warp][(c * NCH + j) * 32 + lane] = acc[c][j];
-  __syncthreads();
-  for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
-    const int cls = a / (C + 1), ch = a % (C + 1);
-    const int slot = (cls * NCH + (ch >> 5)) * 32 + (ch & 31);
-    float v = 0.f;
+    for (int j = 0; j < NCH; ++j) red[warp][j * 32 + lane] = acc[c][j];
+    __syncthreads();
+    if (threadIdx.x <= C) {
+      float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < CE_WARPS; ++w) v += red[w][slot];
-    dst[a] = v;
+      for (int w = 0; w < CE_WARPS; ++w) v += red[w][threadIdx.x];
+      dst[c * (C + 1) + threadIdx.x] = v;
+    }
+    __syncthreads();
   }
 }
 
@@ -207,10 +208,19 @@ __device__ __forceinline__ void tokens_matvec(const float* __restrict__ Wt, cons
     const float b = bias[e];
 #pragma unroll
     for (int l = 0; l < MAXL; ++l) acc[l] = b;
+    // the next step's 8 weights are in flight while this step's L x 8 FMAs run (the loop is otherwise a chain of exposed
+    // L2 / DRAM latencies: one CTA per frame has nothing else to switch to)
+    float wn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wn[i] = __ldg(Wt + (size_t)i * nout + e);
     for (int c0 = 0; c0 < nin; c0 += 8) {
       float w[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = __ldg(Wt + (size_t)(c0 + i) * nout + e);
+      for (int i = 0; i < 8; ++i) w[i] = wn[i];
+      if (c0 + 8 < nin) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wn[i] = __ldg(Wt + (size_t)(c0 + 8 + i) * nout + e);
+      }
 #pragma unroll
       for (int l = 0; l < MAXL; ++l) {
         if (l < L) {
@@ -227,6 +237,11 @@ __device__ __forceinline__ void tokens_matvec(const float* __restrict__ Wt, cons
     for (int l = 0; l < MAXL; ++l)
       if (l < L) store(l, e, acc[l]);
   }
+}
+
+// L2 prefetch of a parameter block (one 128-byte line per thread and step)
+__device__ __forceinline__ void prefetch_l2(const float* p, int nfloats) {
+  for (int i = threadIdx.x * 32; i < nfloats; i += blockDim.x * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i));
 }
 
 __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restrict__ emb1, int C1,
@@ -254,6 +269,8 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
   const float* b2 = P2t + C2 * E;
   const float* lp = b2 + E;
   const int layer_sz = E * 3 * E + 3 * E + E * E + E + E + E + E * E + E + E * E + E;
+  // every CTA walks the whole parameter block once: ask L2 for all of it up front
+  prefetch_l2(params, (C1 + C2 + 2) * E + n_layer * layer_sz);
   // ---- input projections
   // stage the two embedding sets in shared memory (att is free here), then column-owner projections
   float* e1s = &att[0][0];                       // [ncls][C1]
@@ -333,10 +350,17 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
         const float bb = which ? bv[e] : bk[e];
 #pragma unroll
         for (int l = 0; l < CT_MAXL; ++l) acc[l] = bb;
+        float wn[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wn[i] = __ldg(Wt + i * E + e);
         for (int c0 = 0; c0 < E; c0 += 8) {
           float w[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) w[i] = __ldg(Wt + (c0 + i) * E + e);
+          for (int i = 0; i < 8; ++i) w[i] = wn[i];
+          if (c0 + 8 < E) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wn[i] = __ldg(Wt + (c0 + 8 + i) * E + e);
+          }
 #pragma unroll
           for (int l = 0; l < CT_MAXL; ++l) {
             if (l < L) {

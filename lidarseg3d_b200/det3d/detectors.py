@@ -80,6 +80,9 @@ class SegMSeg3DNet(_SegBase):
     # arithmetic stay fp32) whose convolutions read an fp16 OPERAND COPY written by the producing kernel: the products see the
     # same 11-bit significand as the TF32 tensor-core convolutions of the stock reference path, on the own tcgen05 kernels.
     image_dtype = None
+    # measurement aid (bench.py roofline pass): join the camera stream BEFORE the LiDAR branch starts, so that per-launch CUDA
+    # events on the main stream time each kernel alone instead of time-sliced against the concurrent camera kernels
+    serialize_branches = False
 
     # ---- the captured camera-branch graphs hold pointers to BN-folded / packed weight tensors: drop them whenever the
     # parameters, their device / dtype or the train / eval mode can have changed (same events as common.Prepared)
@@ -167,6 +170,8 @@ class SegMSeg3DNet(_SegBase):
             else:
                 feats, img_logits, cam_emb = self._image_branch(images, batch_size)
             _, c, ho, wo = feats.shape
+            if side is not None and self.serialize_branches:
+                torch.cuda.current_stream().wait_stream(side)
             data = self._lidar_branch(example)
             data["points_cuv"] = example["points_cuv"]
             data["metadata"] = example.get("metadata", None)

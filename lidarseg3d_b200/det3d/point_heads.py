@@ -329,6 +329,24 @@ class PointSegMSeg3DHead(Prepared):
         join = batch_dict.pop("_ls3d_join_images", None)
         if join is not None:
             join()
+        # SF-Phase memory path first: the class-token kernel (one CTA per frame, all layers) depends on the two embedding sets
+        # only, so it runs on a side stream underneath the full-GPU sampling / GFFM launches below
+        cam_emb = batch_dict["camera_semantic_embeddings"]
+        if cam_emb.dim() == 4:                                              # reference layout [B, C, ncls, 1]
+            cam_emb = cam_emb.squeeze(-1).permute(0, 2, 1).contiguous()
+        sf = self.sffm
+        nl = len(P["layers"])
+        main = torch.cuda.current_stream()
+        tok = self.__dict__.get("_tok_stream")
+        if tok is None or tok.device != cam_emb.device:
+            tok = self.__dict__["_tok_stream"] = torch.cuda.Stream(device=cam_emb.device)
+        tok.wait_stream(main)
+        with torch.cuda.stream(tok):
+            K, V = ops.class_tokens(cam_emb, lidar_emb, P["token_params"], nl, sf.nhead, sf.d_model)
+        for t in (cam_emb, lidar_emb):
+            t.record_stream(tok)
+        for t in (K, V):
+            t.record_stream(main)
         # image feature maps -> point camera features; invalid rows zeroed by the row mask.  The reference evaluates the
         # pseudo-camera (mimic) MLP on valid points only and pads the others with zeros, so at inference the completed
         # camera feature of an out-of-image point is exactly zero (point_seg_mseg3d_head.py:305-334).
@@ -342,14 +360,8 @@ class PointSegMSeg3DHead(Prepared):
         ccam = gemm.run(fc0, pw, scale=s, shift=b, relu=True, row_mask=cuv)
         pw, s, b = P["gffm_lc"]
         geo = gemm.run(fl, pw, x1=ccam, scale=s, shift=b, relu=True)
-        # SF-Phase
-        cam_emb = batch_dict["camera_semantic_embeddings"]
-        if cam_emb.dim() == 4:                                              # reference layout [B, C, ncls, 1]
-            cam_emb = cam_emb.squeeze(-1).permute(0, 2, 1).contiguous()
-        sf = self.sffm
-        nl = len(P["layers"])
-        K, V = ops.class_tokens(cam_emb, lidar_emb, P["token_params"], nl, sf.nhead, sf.d_model)
         tgt = gemm.run(geo, P["proj_point"][0], shift=P["proj_point"][1])
+        main.wait_stream(tok)
         dh = sf.d_model // sf.nhead
         dec = P["decoder"] if FUSED_DECODER else None
         if dec is not None:

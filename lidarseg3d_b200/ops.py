@@ -182,7 +182,7 @@ def three_nn_grid(points, grid, voxel_size, range_min, point_off, voxel_off, vox
     n = points.shape[0]
     dev = points.device
     d2, idx = _f32(dev, n, 3), _i32(dev, n, 3)
-    todo, cnt = _i32(dev, max(n, 1)), _i32(dev, 1)
+    todo, cnt = _i32(dev, 2 * max(n, 1)), _i32(dev, 2)          # two work lists + counters (pass 1 -> 2 -> brute force)
     check(capi.lib().ls3d_three_nn_grid(ptr(points), points.stride(0), n, ptr(grid.words), ptr(grid.perm), grid.B,
                                         grid.D, grid.H, grid.W, host_f32(voxel_size), host_f32(range_min),
                                         ptr(point_off), ptr(voxel_off), ptr(voxel_coords), ptr(todo), ptr(cnt),
