@@ -15,8 +15,11 @@
 //     order, by a loader thread that runs ahead of the MMA issuer;
 //   * the class-token K / V of the tile's frame and layer (2 x 13 KB) are double-buffered in shared memory; rows of another
 //     frame (a tile straddling a frame boundary) read theirs from global memory;
-//   * 4 row warps (thread = point = TMEM lane): bias, the 34-token cross attention on the CUDA cores (fp32), residual,
-//     exact two-pass LayerNorm in registers, ReLU, operand split; 1 MMA-issue warp; 1 loader warp.
+//   * 16 row warps: warp w serves the 32 points of TMEM lane quarter w & 3 and column group (= attention head) w >> 2,
+//     i.e. 24 of the 96 channels (48 of the 192 FFN channels) of each of its points: bias, the 34-token cross attention of
+//     its head on the CUDA cores (fp32), residual, exact two-pass LayerNorm (row sums exchanged through shared memory between
+//     the four warps of a point), ReLU, operand split; 1 MMA-issue warp; 1 loader warp.  (Four warps per scheduler: a single
+//     row warp per scheduler left every shared-memory / tensor-memory / FMA latency exposed - 1.3 ms per launch against 0.x.)
 // Arithmetic is the unfused path's: x_hi.W_hi + x_hi.W_lo + x_lo.W_hi bf16 products with fp32 accumulation (~2^-17 per
 // product), fp32 softmax / LayerNorm.
 #include "common.cuh"
@@ -26,7 +29,7 @@ namespace ls3d {
 namespace dec {
 
 constexpr int E = 96, FF = 192, DH = 24, NH = 4, TILE = 128;
-constexpr int ROW_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, N_THREADS = 6 * 32;
+constexpr int ROW_WARPS = 16, MMA_WARP = 16, LOAD_WARP = 17, N_THREADS = 18 * 32;   // row warp w: TMEM lane quarter w & 3, column group w >> 2
 constexpr int RING = 5, SLOT_BYTES = 24576;
 constexpr int CH_E = E * 2 * 64;        // stacked chunk: [W_hi ; W_lo] rows of 64 bytes (32 bf16), SWIZZLE_64B
 constexpr int CH_F = FF * 128;          // wide chunk: rows [hi 32 | lo 32] of 128 bytes, SWIZZLE_128B
@@ -77,23 +80,6 @@ __device__ __forceinline__ void split16(const float* x, uint32_t* hi, uint32_t* 
     hi[j] = h;
     lo[j] = pack_bf16x2(x[2 * j] - __uint_as_float(h << 16), x[2 * j + 1] - __uint_as_float(h & 0xFFFF0000u));
   }
-}
-
-// exact two-pass LayerNorm of the E values a thread holds
-__device__ __forceinline__ void layer_norm(float* v, const float* g, const float* b, float eps) {
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < E; ++j) s += v[j];
-  const float m = s / (float)E;
-  float s2 = 0.f;
-#pragma unroll
-  for (int j = 0; j < E; ++j) {
-    const float d = v[j] - m;
-    s2 = fmaf(d, d, s2);
-  }
-  const float rstd = rsqrtf(s2 / (float)E + eps);
-#pragma unroll
-  for (int j = 0; j < E; ++j) v[j] = (v[j] - m) * rstd * g[j] + b[j];
 }
 
 // softmax(q . K^T * scale) V over L tokens of one head; K / V rows of DH floats (shared or global memory)
@@ -158,7 +144,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) sffm_decoder_kernel(const Args p
   uint8_t* ring_s = smem;                                       // [RING][SLOT_BYTES]
   float* kv_s = reinterpret_cast<float*>(ring_s + RING * SLOT_BYTES);     // [2][K | V]
   float* vec_s = kv_s + 2 * 2 * kv_floats;                      // [n_layer][VEC_LAYER] + [2][E]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(((uintptr_t)(vec_s + p.n_layer * VEC_LAYER + 2 * E) + 7) & ~(uintptr_t)7);
+  float* red_s = vec_s + p.n_layer * VEC_LAYER + 2 * E;        // [2][4][TILE] LayerNorm partial sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(((uintptr_t)(red_s + 2 * 4 * TILE) + 7) & ~(uintptr_t)7);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RING + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -195,43 +182,89 @@ __global__ void __launch_bounds__(N_THREADS, 1) sffm_decoder_kernel(const Args p
 
   if (warp < ROW_WARPS) {
     // =========================== row warps ===========================
-    const int row = warp * 32 + lane;
-    const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int q = warp & 3, h = warp >> 2;                      // TMEM lane quarter; column group = attention head
+    const int row = q * 32 + lane;
+    const int cg = h * DH;                                      // first of this thread's 24 channels
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_acc = tl + COL_ACC, t_a = tl + COL_A, t_tgt = tl + COL_TGT;
+    float* red_a = red_s + h * TILE + row;                      // [4][TILE]: this thread's slot; the row's four are TILE apart
+    float* red_b = red_a + 4 * TILE;
     uint32_t acc_ph = 0;
     uint32_t g = 0;                                             // (tile, layer) counter: K / V buffer g & 1
+    auto bar_rows = [] { asm volatile("bar.sync 1, 512;" ::: "memory"); };
 
-    // tgt -> TMEM (fp32) and the A operand slots (bf16 hi / lo); then publish
-    auto publish_tgt = [&](const float* v) {
+    // 24 channels -> the A operand slots (bf16 hi / lo): three 8-channel groups; group g8 of the row -> chunk g8 / 4,
+    // 4 TMEM columns at 4 (g8 % 4) (+ 16 for the lo half)
+    auto store_a24 = [&](const float* x) {
 #pragma unroll
-      for (int pn = 0; pn < E / 16; ++pn) {
-        uint32_t raw[16], hi[8], lo[8];
+      for (int gq = 0; gq < 3; ++gq) {
+        uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) raw[j] = __float_as_uint(v[16 * pn + j]);
-        tmem_st16(t_tgt + 16 * pn, raw);
-        split16(v + 16 * pn, hi, lo);
-        const uint32_t col = (uint32_t)(32 * (pn >> 1) + 8 * (pn & 1));
-        tmem_st8(t_a + col, hi);
-        tmem_st8(t_a + col + 16, lo);
+        for (int j = 0; j < 4; ++j) {
+          const float x0 = x[8 * gq + 2 * j], x1 = x[8 * gq + 2 * j + 1];
+          const uint32_t hh = pack_bf16x2(x0, x1);
+          hi[j] = hh;
+          lo[j] = pack_bf16x2(x0 - __uint_as_float(hh << 16), x1 - __uint_as_float(hh & 0xFFFF0000u));
+        }
+        const int g8 = 3 * h + gq;
+        const uint32_t col = (uint32_t)(32 * (g8 >> 2) + 4 * (g8 & 3));
+        tmem_st4(t_a + col, hi);
+        tmem_st4(t_a + col + 16, lo);
       }
+    };
+    auto publish = [&] {
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(aready);
     };
-    // v = acc (two stacked halves) + bias + tgt
-    auto residual_row = [&](float* v, const float* bias) {
+    // tgt -> TMEM (fp32) and the A operand slots; then publish
+    auto publish_tgt = [&](const float* v) {
 #pragma unroll
-      for (int pn = 0; pn < E / 16; ++pn) {
-        uint32_t a[16], b[16], t[16];
-        tmem_ld16(t_acc + 16 * pn, a);
-        tmem_ld16(t_acc + E + 16 * pn, b);
-        tmem_ld16(t_tgt + 16 * pn, t);
-        tmem_ld_wait();
+      for (int gq = 0; gq < 3; ++gq) {
+        uint32_t raw[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[16 * pn + j] = (__uint_as_float(a[j]) + __uint_as_float(b[j])) + bias[16 * pn + j] + __uint_as_float(t[j]);
+        for (int j = 0; j < 8; ++j) raw[j] = __float_as_uint(v[8 * gq + j]);
+        tmem_st8(t_tgt + cg + 8 * gq, raw);
       }
+      store_a24(v);
+      publish();
+    };
+    // v = acc (two stacked halves) + bias + tgt for this thread's 24 channels
+    auto residual_row = [&](float* v, const float* bias) {
+      uint32_t a[24], b[24], t[24];
+#pragma unroll
+      for (int gq = 0; gq < 3; ++gq) {
+        tmem_ld8(t_acc + cg + 8 * gq, a + 8 * gq);
+        tmem_ld8(t_acc + E + cg + 8 * gq, b + 8 * gq);
+        tmem_ld8(t_tgt + cg + 8 * gq, t + 8 * gq);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < DH; ++j)
+        v[j] = (__uint_as_float(a[j]) + __uint_as_float(b[j])) + bias[cg + j] + __uint_as_float(t[j]);
+    };
+    // exact two-pass LayerNorm over the row's 96 channels held by four threads (fixed summation order)
+    auto layer_norm = [&](float* v, const float* gm, const float* bt) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) s += v[j];
+      *red_a = s;
+      bar_rows();
+      const float* ra = red_s + row;
+      const float m = ((ra[0] + ra[TILE]) + (ra[2 * TILE] + ra[3 * TILE])) / (float)E;
+      float s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < DH; ++j) {
+        const float d = v[j] - m;
+        s2 = fmaf(d, d, s2);
+      }
+      *red_b = s2;
+      bar_rows();
+      const float* rb = ra + 4 * TILE;
+      const float rstd = rsqrtf(((rb[0] + rb[TILE]) + (rb[2 * TILE] + rb[3 * TILE])) / (float)E + p.eps);
+#pragma unroll
+      for (int j = 0; j < DH; ++j) v[j] = (v[j] - m) * rstd * gm[cg + j] + bt[cg + j];
     };
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -239,11 +272,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) sffm_decoder_kernel(const Args p
       const bool live = r < p.n;
       const int f0 = frame_of(p.frame_off, p.n_frames, tile * TILE);
       const int f = live ? frame_of(p.frame_off, p.n_frames, r) : f0;
-      float v[E];
+      float v[DH];
       {
-        const float* src = p.in + (size_t)r * p.ld_in;
+        const float* src = p.in + (size_t)r * p.ld_in + cg;
 #pragma unroll
-        for (int c = 0; c < E / 4; ++c) {
+        for (int c = 0; c < DH / 4; ++c) {
           const float4 t = live ? ldg_f4(src + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
           v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
         }
@@ -251,7 +284,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) sffm_decoder_kernel(const Args p
       publish_tgt(v);
       for (int l = 0; l < p.n_layer; ++l, ++g) {
         const float* vl = vec_s + l * VEC_LAYER;
-        // ---------------- q projection -> cross attention over the class tokens -> A operand
+        // ---------------- q projection -> cross attention of head h over the class tokens -> A operand
         mbar_wait(accfull, acc_ph);
         acc_ph ^= 1u;
         tc_fence_after();
@@ -259,59 +292,42 @@ __global__ void __launch_bounds__(N_THREADS, 1) sffm_decoder_kernel(const Args p
         mbar_wait(kvfull0 + 8 * kb, (g >> 1) & 1u);
         const float* ks = kv_s + kb * 2 * kv_floats;
         const float* vs = ks + kv_floats;
-        const bool own = f == f0;
-        const size_t goff = ((size_t)l * p.n_frames + f) * kv_floats;
-#pragma unroll 1
-        for (int h = 0; h < NH; ++h) {
+        {
           uint32_t a[24], b[24];
-          tmem_ld8(t_acc + h * DH, a);
-          tmem_ld8(t_acc + h * DH + 8, a + 8);
-          tmem_ld8(t_acc + h * DH + 16, a + 16);
-          tmem_ld8(t_acc + E + h * DH, b);
-          tmem_ld8(t_acc + E + h * DH + 8, b + 8);
-          tmem_ld8(t_acc + E + h * DH + 16, b + 16);
-          tmem_ld_wait();
-          float q[DH], o[DH];
-#pragma unroll
-          for (int d = 0; d < DH; ++d) q[d] = (__uint_as_float(a[d]) + __uint_as_float(b[d])) + vl[V_BQ + h * DH + d];
-          if (own) attend(q, ks + h * p.n_tok * DH, vs + h * p.n_tok * DH, p.n_tok, p.scale, o);
-          else attend(q, p.k + goff + h * p.n_tok * DH, p.v + goff + h * p.n_tok * DH, p.n_tok, p.scale, o);
-          // 24 channels = three 8-channel groups; group g8 of the row -> chunk g8 / 4, 4 TMEM columns at 4 (g8 % 4)
 #pragma unroll
           for (int gq = 0; gq < 3; ++gq) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x0 = o[8 * gq + 2 * j], x1 = o[8 * gq + 2 * j + 1];
-              const uint32_t hh = pack_bf16x2(x0, x1);
-              hi[j] = hh;
-              lo[j] = pack_bf16x2(x0 - __uint_as_float(hh << 16), x1 - __uint_as_float(hh & 0xFFFF0000u));
-            }
-            const int g8 = 3 * h + gq;
-            const uint32_t col = (uint32_t)(32 * (g8 >> 2) + 4 * (g8 & 3));
-            tmem_st4(t_a + col, hi);
-            tmem_st4(t_a + col + 16, lo);
+            tmem_ld8(t_acc + cg + 8 * gq, a + 8 * gq);
+            tmem_ld8(t_acc + E + cg + 8 * gq, b + 8 * gq);
           }
+          tmem_ld_wait();
+          float qv[DH], o[DH];
+#pragma unroll
+          for (int d = 0; d < DH; ++d) qv[d] = (__uint_as_float(a[d]) + __uint_as_float(b[d])) + vl[V_BQ + cg + d];
+          if (f == f0) {
+            attend(qv, ks + h * p.n_tok * DH, vs + h * p.n_tok * DH, p.n_tok, p.scale, o);
+          } else {
+            const size_t goff = ((size_t)l * p.n_frames + f) * kv_floats + (size_t)h * p.n_tok * DH;
+            attend(qv, p.k + goff, p.v + goff, p.n_tok, p.scale, o);
+          }
+          store_a24(o);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(kvempty0 + 8 * kb);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(aready);
+        publish();
         // ---------------- out projection + residual + norm2
         mbar_wait(accfull, acc_ph);
         acc_ph ^= 1u;
         tc_fence_after();
         residual_row(v, vl + V_BO);
-        layer_norm(v, vl + V_G2, vl + V_B2, p.eps);
+        layer_norm(v, vl + V_G2, vl + V_B2);
         publish_tgt(v);
-        // ---------------- linear1 + ReLU -> A operand (6 chunks)
+        // ---------------- linear1 + ReLU -> A operand (this warp: FFN channels [48 h, 48 h + 48) = panels 3 h .. 3 h + 2)
         mbar_wait(accfull, acc_ph);
         acc_ph ^= 1u;
         tc_fence_after();
 #pragma unroll
-        for (int pn = 0; pn < FF / 16; ++pn) {
+        for (int i = 0; i < 3; ++i) {
+          const int pn = 3 * h + i;
           uint32_t a[16], hi[8], lo[8];
           tmem_ld16(t_acc + 16 * pn, a);
           tmem_ld_wait();
@@ -323,23 +339,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) sffm_decoder_kernel(const Args p
           tmem_st8(t_a + col, hi);
           tmem_st8(t_a + col + 16, lo);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(aready);
+        publish();
         // ---------------- linear2 + residual + norm3
         mbar_wait(accfull, acc_ph);
         acc_ph ^= 1u;
         tc_fence_after();
         residual_row(v, vl + V_BF2);
-        layer_norm(v, vl + V_G3, vl + V_B3, p.eps);
+        layer_norm(v, vl + V_G3, vl + V_B3);
         if (l + 1 < p.n_layer) publish_tgt(v);
       }
-      if (p.final_norm) layer_norm(v, vec_s + p.n_layer * VEC_LAYER, vec_s + p.n_layer * VEC_LAYER + E, p.eps);
+      if (p.final_norm) layer_norm(v, vec_s + p.n_layer * VEC_LAYER, vec_s + p.n_layer * VEC_LAYER + E);
       if (live) {
-        float* dst = p.out + (size_t)r * p.ld_out;
+        float* dst = p.out + (size_t)r * p.ld_out + cg;
 #pragma unroll
-        for (int c = 0; c < E / 4; ++c)
+        for (int c = 0; c < DH / 4; ++c)
           *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
     }
@@ -438,7 +451,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) sffm_decoder_kernel(const Args p
 static size_t smem_bytes_for(int n_layer, int n_tok) {
   size_t b = 1024 + (size_t)RING * SLOT_BYTES;
   b += (size_t)2 * 2 * NH * n_tok * DH * 4;
-  b += (size_t)(n_layer * VEC_LAYER + 2 * E) * 4 + 8;
+  b += (size_t)(n_layer * VEC_LAYER + 2 * E + 2 * 4 * TILE) * 4 + 8;
   b += (2 * RING + 6) * 8 + 16;
   return b;
 }

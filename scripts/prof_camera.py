@@ -31,10 +31,14 @@ with torch.no_grad():
     torch.cuda.synchronize()
     ops.CONV_PROFILE = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if os.environ.get("LS3D_PROFILE_RANGE") == "1":           # ncu --profile-from-start off: this forward only
+        torch.cuda.profiler.start()
     e0.record()
     model._image_branch(images, 3)
     e1.record()
     torch.cuda.synchronize()
+    if os.environ.get("LS3D_PROFILE_RANGE") == "1":
+        torch.cuda.profiler.stop()
 prof, ops.CONV_PROFILE = ops.CONV_PROFILE, None
 peak = 6541.8e9
 agg = collections.OrderedDict()
