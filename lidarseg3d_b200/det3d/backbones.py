@@ -20,7 +20,7 @@ from .registry import BACKBONES
 class SparseConvWeight(nn.Module):
     """Holds ``weight [kz,ky,kx,Cin,Cout]`` (spconv 1.x layout, bias=False everywhere in UNetSCN3D)."""
 
-    def __init__(self, in_channels, out_channels, kernel_size):
+    def __init__(self, in_channels, out_channels, kernel_size, bias=False):
         super().__init__()
         ks = tuple(kernel_size) if isinstance(kernel_size, (tuple, list)) else (kernel_size,) * 3
         self.kernel_size = ks
@@ -29,6 +29,10 @@ class SparseConvWeight(nn.Module):
         # spconv reset_parameters: kaiming_uniform(a=sqrt(5)) with fan_in = Cin * prod(k)
         bound = 1.0 / math.sqrt(in_channels * ks[0] * ks[1] * ks[2])
         nn.init.uniform_(self.weight, -bound, bound)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-bound, bound))
+        else:
+            self.register_parameter("bias", None)
 
     def packed(self):
         w = self.weight.detach()
@@ -230,3 +234,95 @@ class UNetSCN3D(Prepared):
         batch_dict["_ls3d_levels"] = levels
         batch_dict["_ls3d_rulebooks"] = dict(down=down, up=up)
         return batch_dict
+
+
+class SparseBasicBlockBias(nn.Module):
+    """SparseBasicBlock of scn.py:37-81: like the UNet's, but its two SubM convolutions carry a bias (scn.py:56)."""
+
+    def __init__(self, planes, norm_fn):
+        super().__init__()
+        self.conv1 = SparseConvWeight(planes, planes, 3, bias=True)
+        self.bn1 = norm_fn(planes)
+        self.conv2 = SparseConvWeight(planes, planes, 3, bias=True)
+        self.bn2 = norm_fn(planes)
+
+
+@BACKBONES.register_module
+class SpMiddleResNetFHD(Prepared):
+    """Reference det3d/models/backbones/scn.py:84-177 (the sparse ResNet encoder of the detection configs): same constructor,
+    state-dict names and ``forward(voxel_features, coors, batch_size, input_shape) -> (dense [N, C*D, H, W], multi_scale)``
+    contract, on the bitmap rulebooks + tcgen05 gather-GEMM (conv bias and eval BatchNorm folded into the epilogue)."""
+
+    def __init__(self, num_input_features=128, norm_cfg=None, name="SpMiddleResNetFHD", **kwargs):
+        super().__init__()
+        self.name = name
+        norm_cfg = norm_cfg or dict(type="BN1d", eps=1e-3, momentum=0.01)
+        if norm_cfg.get("type", "BN1d") != "BN1d":
+            raise NotImplementedError("SpMiddleResNetFHD: BN1d norm layers only (scn.py default)")
+        norm_fn = partial(nn.BatchNorm1d, eps=norm_cfg.get("eps", 1e-3), momentum=norm_cfg.get("momentum", 0.01))
+        self.conv_input = nn.Sequential(SparseConvWeight(num_input_features, 16, 3), norm_fn(16), nn.ReLU())
+        self.conv1 = nn.Sequential(SparseBasicBlockBias(16, norm_fn), SparseBasicBlockBias(16, norm_fn))
+
+        def stage(cin, cout):
+            return nn.Sequential(SparseConvWeight(cin, cout, 3), norm_fn(cout), nn.ReLU(), SparseBasicBlockBias(cout, norm_fn),
+                                 SparseBasicBlockBias(cout, norm_fn))
+
+        self.conv2, self.conv3, self.conv4 = stage(16, 32), stage(32, 64), stage(64, 128)
+        self.extra_conv = nn.Sequential(SparseConvWeight(128, 128, (3, 1, 1)), norm_fn(128), nn.ReLU())
+        self.down_geom = {2: ((3, 3, 3), (2, 2, 2), (1, 1, 1)), 3: ((3, 3, 3), (2, 2, 2), (1, 1, 1)),
+                          4: ((3, 3, 3), (2, 2, 2), (0, 1, 1))}
+
+    def _prepare(self):
+        def cbr(conv, bn):
+            s, b = fold_bn(bn)
+            if conv.bias is not None:
+                b = b + conv.bias.detach().float() * s
+            return (conv.packed(), s, b.contiguous())
+
+        def blk(m):
+            return (cbr(m.conv1, m.bn1), cbr(m.conv2, m.bn2))
+
+        P = {"conv_input": cbr(self.conv_input[0], self.conv_input[1]), "conv1": [blk(m) for m in self.conv1],
+             "extra": cbr(self.extra_conv[0], self.extra_conv[1])}
+        for lv in (2, 3, 4):
+            seq = getattr(self, f"conv{lv}")
+            P[f"conv{lv}"] = (cbr(seq[0], seq[1]), [blk(seq[3]), blk(seq[4])])
+        return P
+
+    def forward(self, voxel_features, coors, batch_size, input_shape):
+        if self.training:
+            raise NotImplementedError("lidarseg3d_b200 SpMiddleResNetFHD: inference path only (model.eval())")
+        P = self.prep()
+        conv, block = UNetSCN3D._conv, UNetSCN3D._block
+        B = batch_size
+        shape1 = tuple(int(v) for v in (np.array(input_shape[::-1]) + [1, 0, 0]))            # scn.py:149
+        coords1 = coors.int().contiguous()
+        lv1 = SparseLevel(coords1, B, shape1, ops.grid_from_coords(coords1, B, shape1, need_perm=True))
+        levels, down = {1: lv1}, {}
+        for lv in (2, 3, 4):
+            ks, st, pd = self.down_geom[lv]
+            prev = levels[lv - 1]
+            grid, oc = ops.grid_strided(prev.coords, B, prev.shape, ks, st, pd)
+            levels[lv] = SparseLevel(oc, B, grid.shape, grid)
+            down[lv] = ops.rulebook_gather(prev.grid, oc, ks, st, pd)
+        l4 = levels[4]
+        g5, c5 = ops.grid_strided(l4.coords, B, l4.shape, (3, 1, 1), (2, 1, 1), (0, 0, 0))
+        nb5 = ops.rulebook_gather(l4.grid, c5, (3, 1, 1), (2, 1, 1), (0, 0, 0))
+        x = conv(pad_cols(voxel_features.float()), P["conv_input"], lv1.subm_table())
+        for pk in P["conv1"]:
+            x = block(self, x, pk, lv1.subm_table())
+        feats = {1: x}
+        for lv in (2, 3, 4):
+            cbr, blocks = P[f"conv{lv}"]
+            y = conv(feats[lv - 1], cbr, down[lv])
+            for pk in blocks:
+                y = block(self, y, pk, levels[lv].subm_table())
+            feats[lv] = y
+        y = conv(feats[4], P["extra"], nb5)
+        D, H, W = g5.shape
+        dense = torch.zeros(B, D, H, W, y.shape[1], dtype=y.dtype, device=y.device)           # SparseConvTensor.dense()
+        ci = c5.long()
+        dense[ci[:, 0], ci[:, 1], ci[:, 2], ci[:, 3]] = y
+        ret = dense.permute(0, 4, 1, 2, 3).contiguous().view(B, y.shape[1] * D, H, W)         # scn.py:165-168
+        ms = {f"conv{lv}": SparseTensorView(feats[lv], levels[lv].coords, levels[lv].shape, B) for lv in (1, 2, 3, 4)}
+        return ret, ms

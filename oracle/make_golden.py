@@ -464,6 +464,14 @@ def gen_backbones():
                 encoded_shape=list(bd["encoded_spconv_tensor"].spatial_shape),
                 multi_scale={k: dict(features=v.features, indices=v.indices, shape=list(v.spatial_shape)) for k, v in ms.items()},
                 keys=sorted(net.state_dict().keys()))
+        # ---- SpMiddleResNetFHD (scn.py:84-177): the reference's own forward on the shim
+        net = R["scn"].SpMiddleResNetFHD(num_input_features=13).eval()
+        net.load_state_dict(unet_fill(net.state_dict()))
+        dense, ms = net(vf.clone(), ex["coordinates"], 2, ex["shape"][0])
+        fx["spmiddle"] = dict(voxel_features=vf, coordinates=ex["coordinates"], input_shape=ex["shape"][0], dense=dense,
+                              multi_scale={k: dict(features=v.features, indices=v.indices, shape=list(v.spatial_shape))
+                                           for k, v in ms.items()},
+                              keys=sorted(net.state_dict().keys()))
         # ---- SegNet (SDSeg3D SemanticKITTI model section of the reference config, small range)
         cfg = Config.fromfile(os.path.join(REF, "configs/semantickitti/SDSeg3D/semkitti_transVFE_unetscn3d_batchloss_e10.py"))
         mc = cfg.model
@@ -529,8 +537,8 @@ def gen_backbones():
         fx["tta"] = dict(points=pts_tta, out_logits=log_tta, point_sem_labels=exT["point_sem_labels"], ntta=ntta,
                          ret=[dict(metadata=r["metadata"], pred=r["pred_point_sem_labels"], gt=r["point_sem_labels"]) for r in rt])
     torch.save(fx, os.path.join(OUT, "ref_backbones.pt"))
-    print("backbones:", {k: (tuple(v["conv_point_features"].shape) if "conv_point_features" in v else
-                             tuple(v["out_logits"].shape)) for k, v in fx.items()})
+    print("backbones:", {k: tuple(v[next(n for n in ("conv_point_features", "out_logits", "dense") if n in v)].shape)
+                         for k, v in fx.items()})
 
 
 

@@ -104,6 +104,43 @@ class _Sp:
         self.features, self.indices, self.shape = features, indices, tuple(shape)
 
 
+def sp_middle_resnet_fhd(sd, p, voxel_features, coors, batch_size, input_shape_xyz):
+    """SpMiddleResNetFHD.forward (det3d/models/backbones/scn.py:146-177): conv_input (SubM, key res0) -> 2 residual blocks ->
+    three times [SparseConv3d k3 s2 (padding 1 / 1 / [0,1,1]) + 2 residual blocks] -> extra_conv k(3,1,1) s(2,1,1) -> dense
+    [N, C*D, H, W].  SparseBasicBlock (scn.py:37-81): its two SubM convs carry a BIAS (bias = norm_cfg is not None, :56), the
+    sequence entries are (conv, BN, ReLU, block, block) so the blocks sit at indices 3 and 4.  Returns (dense, levels)."""
+    EPS = 1e-3                                                                      # scn.py:50,96
+    shape1 = tuple(int(v) for v in (np.array(input_shape_xyz[::-1]) + [1, 0, 0]))   # scn.py:149
+    idx = coors.numpy().astype(np.int32)
+
+    def block(x, q, nbr):
+        out = osp.sparse_conv(x, sd[q + ".conv1.weight"], nbr) + sd[q + ".conv1.bias"]
+        out = torch.relu(_bn(sd, q + ".bn1", out, EPS))
+        out = osp.sparse_conv(out, sd[q + ".conv2.weight"], nbr) + sd[q + ".conv2.bias"]
+        return torch.relu(_bn(sd, q + ".bn2", out, EPS) + x)
+
+    n1 = osp.subm_rulebook(idx, shape1, 3)
+    x = torch.relu(_bn(sd, p + "conv_input.1", osp.sparse_conv(voxel_features, sd[p + "conv_input.0.weight"], n1), EPS))
+    x = block(block(x, p + "conv1.0", n1), p + "conv1.1", n1)
+    levels = {"conv1": _Sp(x, idx, shape1)}
+    cur = levels["conv1"]
+    for lv, pad in ((2, (1, 1, 1)), (3, (1, 1, 1)), (4, (0, 1, 1))):                # scn.py:110-140
+        oidx, oshape, nb = osp.strided_rulebook(cur.indices, cur.shape, 3, 2, pad)
+        y = torch.relu(_bn(sd, f"{p}conv{lv}.1", osp.sparse_conv(cur.features, sd[f"{p}conv{lv}.0.weight"], nb), EPS))
+        ns = osp.subm_rulebook(oidx, oshape, 3)
+        y = block(block(y, f"{p}conv{lv}.3", ns), f"{p}conv{lv}.4", ns)
+        cur = _Sp(y, oidx, oshape)
+        levels[f"conv{lv}"] = cur
+    oidx, oshape, nb = osp.strided_rulebook(cur.indices, cur.shape, (3, 1, 1), (2, 1, 1), (0, 0, 0))
+    y = torch.relu(_bn(sd, p + "extra_conv.1", osp.sparse_conv(cur.features, sd[p + "extra_conv.0.weight"], nb), EPS))
+    D, H, W = oshape
+    dense = torch.zeros(batch_size, D, H, W, y.shape[1])
+    oi = torch.as_tensor(oidx).long()
+    dense[oi[:, 0], oi[:, 1], oi[:, 2], oi[:, 3]] = y
+    dense = dense.permute(0, 4, 1, 2, 3).contiguous()                               # SparseConvTensor.dense(): [N, C, D, H, W]
+    return dense.view(batch_size, y.shape[1] * D, H, W), levels
+
+
 def unet_scn3d(sd, p, voxel_features, voxel_coords, input_shape_xyz, voxel_size, pc_range,
                with_conv_out=True, last_pad=0, return_levels=False, backend=None):
     """UNetSCN3D.forward (det3d/models/backbones/scn_unet.py:189-249) with spconv semantics from oracle.sparse.

@@ -99,3 +99,20 @@ def test_tta_merge_vs_reference_predict(fx):
         assert torch.equal(a["point_sem_labels"], b["gt"])
     with pytest.raises(AssertionError):
         _predict(g["out_logits"], ex, dict(tta_flag=True, num_tta_tranforms=3))
+
+
+def test_spmiddle_resnet_vs_reference_forward(fx):
+    """SpMiddleResNetFHD (det3d/models/backbones/scn.py:84-177): oracle restatement vs the reference's own forward on the
+    spconv shim; the product module carries the reference's state-dict key set."""
+    from lidarseg3d_b200.det3d.backbones import SpMiddleResNetFHD
+    g = fx["spmiddle"]
+    net = SpMiddleResNetFHD(num_input_features=13)
+    sd = _sd_for(g["keys"], net)
+    dense, levels = on.sp_middle_resnet_fhd(sd, "", g["voxel_features"], g["coordinates"], 2, list(g["input_shape"]))
+    ref = g["dense"]
+    assert list(dense.shape) == list(ref.shape) and float(ref.abs().max()) > 1e-2
+    assert float((dense - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    for k, r in g["multi_scale"].items():
+        assert np.array_equal(np.asarray(levels[k].indices), r["indices"].numpy()), k
+        assert list(levels[k].shape) == r["shape"], k
+        assert float((levels[k].features - r["features"]).abs().max()) <= 2e-5 * float(r["features"].abs().max()), k
