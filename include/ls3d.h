@@ -19,7 +19,7 @@ extern "C" {
 #define LS3D_EPI_ATTN 1
 
 /* ------------------------------------------------------------------------------------------------
- * Gather-GEMM (tcgen05, TF32 in / fp32 accumulate) with fused epilogue.
+ * Gather-GEMM (tcgen05, error-compensated bf16x3 products by default / fp32 accumulate) with fused epilogue.
  *   out[j, :cout] = epi( sum_{k<koff} in[nbr[k][j], :] . W[k]^T )
  * replaces: spconv `indice_conv` as called by det3d/models/backbones/scn_unet.py:15-20,39-46,89-160
  *           (SubMConv3d / SparseConv3d / SparseInverseConv3d + BatchNorm1d + ReLU + residual,
@@ -35,9 +35,10 @@ typedef struct ls3d_gemm_args {
   const int32_t* nbr; /* [koff][m_out] input row per (offset, output row), -1 = none; NULL =   */
                       /* identity (dense Linear, requires koff == 1)                           */
   int32_t koff, m_out;
-  const float* w;     /* precise=0: [koff][n_pad][cin_pad] (K-major) tf32-rounded, zero padded;  */
+  const float* w;     /* precise=2: ls3d_gemm_pack_bf16x3 image (below);                          */
+                      /* precise=0: [koff][n_pad][cin_pad] (K-major) tf32-rounded, zero padded;  */
                       /* precise=1: [koff][2][n_pad][cin_pad] = {trunc_tf32(W), W - trunc_tf32(W)} */
-  int32_t cin_pad;    /* multiple of 8, >= c0 + c1                                             */
+  int32_t cin_pad;    /* multiple of 8 (16 with precise=2), >= c0 + c1                         */
   int32_t n_pad;      /* multiple of 16 in [16, 256]                                           */
   int32_t cout;       /* valid output columns (<= n_pad)                                       */
   int32_t epi;        /* LS3D_EPI_LINEAR | LS3D_EPI_ATTN                                       */
@@ -79,6 +80,17 @@ typedef struct ls3d_gemm_args {
 } ls3d_gemm_args;
 
 int ls3d_gather_gemm(const ls3d_gemm_args* args, void* stream);
+
+/* Weight image of the default engine (precise = 2): from fp32 w_kio [koff][cin][cout] on the device (the spconv weight
+ * [kz, ky, kx, Cin, Cout] with the offsets flattened; an nn.Linear weight is its transpose with koff = 1) to one block of
+ * n_pad * 128 bytes per (offset, 32-channel chunk), the swizzled shared-memory image of a tcgen05 K-major B tile:
+ *   n_pad <= 96: 2 n_pad rows of 64 bytes, rows [0, n_pad) = bf16 hi of W[n, 32c .. 32c+31], rows [n_pad, 2 n_pad) = bf16 lo,
+ *                16-byte unit u of row r holds logical unit u ^ ((r >> 1) & 3)   (SWIZZLE_64B);
+ *   n_pad  > 96: n_pad rows of 128 bytes [hi (32 ch) | lo (32 ch)], unit u of row r holds logical unit u ^ (r & 7);
+ *   hi = bf16_rn(w), lo = bf16_rn(w - hi); cin_pad = cin rounded up to 16, n_pad = cout rounded up to 16 (returned).
+ * The same chunks are what ls3d_sffm_decoder streams. */
+int ls3d_gemm_packed_bytes(int32_t koff, int32_t cin, int32_t cout, int64_t* bytes, int32_t* cin_pad, int32_t* n_pad);
+int ls3d_gemm_pack_bf16x3(const float* w_kio, int32_t koff, int32_t cin, int32_t cout, void* out, void* stream);
 
 /* Tile plan of a rulebook table nbr[koff][m_out] (see ls3d_gemm_args.plan_*): per 128-row output tile the sorted list of
  * distinct input rows (in `pool`), the uint16 position table local[tile][k][128] and a 32-int header {n_pass, per pass:

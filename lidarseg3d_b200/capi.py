@@ -87,6 +87,8 @@ P, I, L = c_void_p, c_int, ctypes.c_int64
 PL = ctypes.POINTER(ctypes.c_int64)
 # name -> (argtypes, restype): one row per prototype of include/ls3d.h
 _SIGNATURES = {
+    "ls3d_gemm_packed_bytes": ([I, I, I, PL, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)], ctypes.c_int),
+    "ls3d_gemm_pack_bf16x3": ([P, I, I, I, P, P], ctypes.c_int),
     "ls3d_tile_plan_bytes": ([I, I, PL, PL, PL], ctypes.c_int),
     "ls3d_tile_plan_build": ([P, I, I, P, P, P, P, P], ctypes.c_int),
     "ls3d_voxelize_workspace_bytes": ([L, I, I, PL], ctypes.c_int),
@@ -161,7 +163,7 @@ def stream_ptr():
 
 # C-ABI calls since the last COUNTERS.clear(), and the (lower-bound) number of kernels each call launches
 COUNTERS = {}
-KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_tile_plan_build": 1, "ls3d_voxelize": 8, "ls3d_vfe_descriptor": 1, "ls3d_vfe_token_attn": 1,
+KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_gemm_pack_bf16x3": 1, "ls3d_tile_plan_build": 1, "ls3d_voxelize": 8, "ls3d_vfe_descriptor": 1, "ls3d_vfe_token_attn": 1,
                     "ls3d_vfe_token_max": 1, "ls3d_grid_build": 4, "ls3d_grid_build_strided": 4, "ls3d_grid_enumerate": 1,
                     "ls3d_rulebook_gather": 1, "ls3d_rulebook_scatter": 1, "ls3d_three_nn_grid": 3, "ls3d_three_nn": 1,
                     "ls3d_three_interpolate": 1, "ls3d_sample_image_features": 1, "ls3d_project_points": 1, "ls3d_project_points_global": 1,

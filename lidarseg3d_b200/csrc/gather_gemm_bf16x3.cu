@@ -18,6 +18,8 @@
 //   warps 4-11  splitters : two groups of four (one thread per tile row = TMEM lane), alternate steps
 //   warps 12-15 epilogue  : gemm_epilogue.cuh
 //   warp  16    MMA issuer, warp 17 W loader (one elected thread each), warp 18 rulebook scout (one tile ahead)
+#include <cuda_bf16.h>
+
 #include "gemm_epilogue.cuh"
 
 namespace ls3d {
@@ -433,6 +435,66 @@ static size_t smem_bytes_for(int rs, int ws, int n_pad, int koff) {
 }
 
 }  // namespace bf16x3
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight image of the bf16x3 engines (ls3d_gemm_args.w with precise = 2; also the chunks ls3d_sffm_decoder streams).
+// One block of n_pad * 128 bytes per (offset, 32-channel chunk), stored as the swizzled shared-memory image so that a single
+// cp.async.bulk lands a ready tcgen05 K-major B tile:
+//   n_pad <= 96 ("stacked"): 2 n_pad rows of 64 bytes; rows [0, n) = bf16 hi of W[n, 32c .. 32c+31], rows [n, 2n) = bf16 lo;
+//                SWIZZLE_64B: the 16-byte unit u of row r holds logical unit u ^ ((r >> 1) & 3);
+//   n_pad  > 96 : n_pad rows of 128 bytes = [hi (32) | lo (32)]; SWIZZLE_128B: unit u of row r holds logical unit u ^ (r & 7).
+// hi = bf16_rn(w), lo = bf16_rn(w - hi).
+__global__ void pack_bf16x3_kernel(const float* __restrict__ w_kio, int koff, int cin, int cout, int n_pad, int nchunk,
+                                   __nv_bfloat16* __restrict__ out) {
+  const bool stacked = n_pad <= 96;
+  const int rows = stacked ? 2 * n_pad : n_pad, units = stacked ? 4 : 8;
+  const long long total = (long long)koff * nchunk * rows * units * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 7);
+    long long t = i >> 3;
+    const int u = (int)(t % units);
+    t /= units;
+    const int r = (int)(t % rows);
+    t /= rows;
+    const int c = (int)(t % nchunk), k = (int)(t / nchunk);
+    const int lu = stacked ? (u ^ ((r >> 1) & 3)) : (u ^ (r & 7));
+    const bool lo = stacked ? (r >= n_pad) : (lu >= 4);
+    const int n = stacked ? (r >= n_pad ? r - n_pad : r) : r;
+    const int ch = 32 * c + 8 * (lu & 3) + e;
+    float v = 0.f;
+    if (n < cout && ch < cin) v = w_kio[((size_t)k * cin + ch) * cout + n];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = lo ? __float2bfloat16_rn(v - __bfloat162float(h)) : h;
+  }
+}
+
+}  // namespace ls3d (reopened below)
+
+extern "C" int ls3d_gemm_packed_bytes(int32_t koff, int32_t cin, int32_t cout, int64_t* bytes, int32_t* cin_pad, int32_t* n_pad) {
+  if (!bytes || koff < 1 || cin < 1 || cout < 1 || cout > 256) return LS3D_ERR_ARG;
+  const int cp = (cin + 15) / 16 * 16, np = (cout + 15) / 16 * 16;
+  *bytes = (int64_t)koff * ((cp + 31) / 32) * np * 128;
+  if (cin_pad) *cin_pad = cp;
+  if (n_pad) *n_pad = np;
+  return LS3D_OK;
+}
+
+// w_kio: fp32 [koff][cin][cout] (spconv weight [kz, ky, kx, Cin, Cout] flattened over the offsets; an nn.Linear weight is its
+// transpose with koff = 1) on the device; out: ls3d_gemm_packed_bytes bytes, 16-byte aligned
+extern "C" int ls3d_gemm_pack_bf16x3(const float* w_kio, int32_t koff, int32_t cin, int32_t cout, void* out, void* stream) {
+  int64_t bytes;
+  int32_t cp, np;
+  if (!w_kio || !out || (((uintptr_t)out) & 15) || ls3d_gemm_packed_bytes(koff, cin, cout, &bytes, &cp, &np)) return LS3D_ERR_ARG;
+  const long long total = bytes / 2;
+  const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  ls3d::pack_bf16x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_kio, koff, cin, cout, np, (cp + 31) / 32,
+                                                                  (__nv_bfloat16*)out);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}
+
+namespace ls3d {
+
 }  // namespace ls3d
 
 #ifdef LS3D_PROF

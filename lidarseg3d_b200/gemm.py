@@ -55,7 +55,7 @@ class PackedWeight:
         self.n_pad = pad_to(cout, 16)
         wt = w_kio.float().permute(0, 2, 1)
         if self.precise == 2:
-            buf = self._pack_bf16x3(wt)
+            buf = self._pack_bf16x3_device(w_kio) if w_kio.is_cuda else self._pack_bf16x3(wt)
         elif self.precise:
             buf = torch.zeros(koff, 2, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
             hi = trunc_tf32(wt)
@@ -65,6 +65,20 @@ class PackedWeight:
             buf = torch.zeros(koff, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
             buf[:, :cout, :cin] = round_tf32(wt)
         self.data = buf.contiguous()
+
+    def _pack_bf16x3_device(self, w_kio):
+        """ls3d_gemm_pack_bf16x3 (the C-ABI packer, csrc/gather_gemm_bf16x3.cu): the layout documented in include/ls3d.h."""
+        import ctypes
+        koff, cin, cout = w_kio.shape
+        nbytes, cp, npd = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int32()
+        capi.check(capi.lib().ls3d_gemm_packed_bytes(koff, cin, cout, ctypes.byref(nbytes), ctypes.byref(cp), ctypes.byref(npd)),
+                   "ls3d_gemm_packed_bytes")
+        assert cp.value == self.cin_pad and npd.value == self.n_pad
+        buf = torch.empty(nbytes.value // 2, dtype=torch.bfloat16, device=w_kio.device)
+        w = w_kio.detach().float().contiguous()
+        capi.check(capi.lib().ls3d_gemm_pack_bf16x3(capi.ptr(w), koff, cin, cout, capi.ptr(buf), capi.stream_ptr()),
+                   "ls3d_gemm_pack_bf16x3")
+        return buf
 
     def _pack_bf16x3(self, wt):
         """One contiguous block of n_pad * 128 bytes per (offset, 32-channel chunk), stored as the swizzled shared-memory

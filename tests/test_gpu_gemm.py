@@ -312,3 +312,16 @@ def test_multi_pass_convolution():
     nbr = _random_table(g, 27, m_out, rows_in, 0.7)
     out = gemm.run(x.to(DEV), gemm.PackedWeight(w.to(DEV)), nbr=nbr.to(DEV))
     _close(out, _ref_from_table(x, w, nbr))
+
+
+@pytest.mark.parametrize("koff,cin,cout", [(27, 13, 32), (1, 96, 96), (1, 96, 192), (1, 192, 96), (27, 128, 128), (3, 64, 17),
+                                           (27, 256, 128)])
+def test_pack_bf16x3_c_abi_matches_layout_restatement(koff, cin, cout):
+    """ls3d_gemm_pack_bf16x3 (the C-ABI weight packer a reference-side binding calls) writes bit for bit the image the
+    documented layout (gemm.PackedWeight._pack_bf16x3, tensor ops) describes - stacked SWIZZLE_64B and wide SWIZZLE_128B."""
+    from lidarseg3d_b200 import gemm
+    w = torch.randn(koff, cin, cout, generator=torch.Generator().manual_seed(koff * 1000 + cin + cout)).to(DEV)
+    pw = gemm.PackedWeight(w)
+    ref = pw._pack_bf16x3(w.float().permute(0, 2, 1))
+    assert pw.data.numel() == ref.numel()
+    assert torch.equal(pw.data.view(torch.int16).reshape(-1), ref.view(torch.int16).reshape(-1))
