@@ -174,6 +174,100 @@ __device__ __forceinline__ TileXY tile_coords(int tile, const Args& p) {
   return {img, ty, tx};
 }
 
+// Epilogue arithmetic of one output tile for thread m (= tile pixel = accumulator row): TMEM accumulator (+ the W_lo partial
+// sums at column lo_col) + bias + residual (read from the staged io tile) -> ReLU -> io tile in place (dual: fp32 tile + fp16
+// operand copy behind it; else fp16 tile).  `tile_io` = start of the stage's io area.
+__device__ __forceinline__ void epilogue_rows(const Args& p, uint8_t* tile_io, uint32_t io32_bytes, int m, uint32_t trow,
+                                              uint32_t lo_col, bool has_res, bool relu, const float* bias_s) {
+  const int n_groups = p.n_pad >> 4;
+  uint8_t* io = tile_io + (size_t)m * p.cout * 2;
+  if (p.dual) {
+    // fp32 residual stream: acc + bias + residual (fp32, read from the stage) -> ReLU -> fp32 in place + fp16 operand copy
+    float* io32 = reinterpret_cast<float*>(tile_io) + (size_t)m * p.cout;
+    __half* io16 = reinterpret_cast<__half*>(tile_io + io32_bytes) + (size_t)m * p.cout;
+    for (int g = 0; g < n_groups; ++g) {
+      const int c0 = g * 16;
+      uint32_t raw[16], raw2[16];
+      tmem_ld16(trow + c0, raw);
+      if (lo_col) tmem_ld16(trow + lo_col + c0, raw2);
+      float4 rr[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4)
+        rr[q4] = (has_res && c0 + 4 * q4 < p.cout) ? *reinterpret_cast<const float4*>(io32 + c0 + 4 * q4)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      tmem_ld_wait();
+      if (lo_col) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(__uint_as_float(raw[e]) + __uint_as_float(raw2[e]));
+      }
+#pragma unroll
+      for (int g8 = 0; g8 < 2; ++g8) {
+        if (c0 + 8 * g8 >= p.cout) continue;
+        float v[8];
+#pragma unroll
+        for (int q4 = 0; q4 < 2; ++q4) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8 + 4 * q4);
+          const float4 r4 = rr[2 * g8 + q4];
+          v[4 * q4 + 0] = __uint_as_float(raw[8 * g8 + 4 * q4 + 0]) + bb.x + r4.x;
+          v[4 * q4 + 1] = __uint_as_float(raw[8 * g8 + 4 * q4 + 1]) + bb.y + r4.y;
+          v[4 * q4 + 2] = __uint_as_float(raw[8 * g8 + 4 * q4 + 2]) + bb.z + r4.z;
+          v[4 * q4 + 3] = __uint_as_float(raw[8 * g8 + 4 * q4 + 3]) + bb.w + r4.w;
+        }
+        if (relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        *reinterpret_cast<float4*>(io32 + c0 + 8 * g8) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(io32 + c0 + 8 * g8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        uint4 o;
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        *reinterpret_cast<uint4*>(io16 + c0 + 8 * g8) = o;
+      }
+    }
+  } else
+  for (int g = 0; g < n_groups; ++g) {
+    const int c0 = g * 16;
+    uint32_t raw[16], raw2[16];
+    tmem_ld16(trow + c0, raw);
+    if (lo_col) tmem_ld16(trow + lo_col + c0, raw2);
+    uint4 rz[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (has_res) {
+#pragma unroll
+      for (int g8 = 0; g8 < 2; ++g8)
+        if (c0 + 8 * g8 < p.cout) rz[g8] = *reinterpret_cast<const uint4*>(io + (c0 + 8 * g8) * 2);
+    }
+    tmem_ld_wait();
+    if (lo_col) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(__uint_as_float(raw[e]) + __uint_as_float(raw2[e]));
+    }
+#pragma unroll
+    for (int g8 = 0; g8 < 2; ++g8) {
+      if (c0 + 8 * g8 >= p.cout) continue;
+      const __half2* r2 = reinterpret_cast<const __half2*>(&rz[g8]);
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8 + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint4 o;
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 rr = __half22float2(r2[e]);
+        float v0 = __uint_as_float(raw[8 * g8 + 2 * e]) + bb[2 * e] + rr.x;
+        float v1 = __uint_as_float(raw[8 * g8 + 2 * e + 1]) + bb[2 * e + 1] + rr.y;
+        if (relu) {
+          v0 = fmaxf(v0, 0.f);
+          v1 = fmaxf(v1, 0.f);
+        }
+        o2[e] = __floats2half2_rn(v0, v1);
+      }
+      *reinterpret_cast<uint4*>(io + (c0 + 8 * g8) * 2) = o;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(N_THREADS, 1)
     conv3x3_f16_kernel(const Args p, const __grid_constant__ InMaps maps_in, const __grid_constant__ CUtensorMap map_res,
                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16) {
@@ -335,7 +429,6 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     const int team = ew >> 2;                     // team 0: even tiles of this CTA (accumulator 0), team 1: odd tiles
     const int m = q * 32 + lane;                  // tile pixel = accumulator row
     const bool leader = ((ew & 3) == 0 && lane == 0);
-    const int n_groups = p.n_pad >> 4;
     const bool deep = p.nbuf >= 4;                // a stage may stay occupied until this team's next tile
     // this team takes the CTA's tiles whose running index (over all passes) has its parity
     int b = e_b, b_prev = e_bprev, it = e_it;
@@ -344,97 +437,12 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     const int it_begin = pass * my_tiles, it_end = it_begin + my_tiles;
     for (; it < it_end; it += 2) {
       const int tile = blockIdx.x + (it - it_begin) * gridDim.x;
-      uint8_t* io = stage_s + (size_t)b * stage_bytes + halo_bytes + (size_t)m * p.cout * 2;
       const int ab = it & (nacc - 1);
       const uint32_t trow = tmem_base + (uint32_t)(ab * p.nb) + ((uint32_t)(q * 32) << 16);
       if (has_res) mbar_wait(full_bar0 + 8 * b, ph);
       mbar_wait(accf_bar0 + 8 * ab, (uint32_t)(it / nacc) & 1u);
       tc_fence_after();
-      if (p.dual) {
-        // fp32 residual stream: acc + bias + residual (fp32, read from the stage) -> ReLU -> fp32 in place + fp16 operand copy
-        float* io32 = reinterpret_cast<float*>(stage_s + (size_t)b * stage_bytes + halo_bytes) + (size_t)m * p.cout;
-        __half* io16 = reinterpret_cast<__half*>(stage_s + (size_t)b * stage_bytes + halo_bytes + io32_bytes) + (size_t)m * p.cout;
-        for (int g = 0; g < n_groups; ++g) {
-          const int c0 = g * 16;
-          uint32_t raw[16], raw2[16];
-          tmem_ld16(trow + c0, raw);
-          if (lo_col) tmem_ld16(trow + lo_col + c0, raw2);
-          float4 rr[4];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            rr[q4] = (has_res && c0 + 4 * q4 < p.cout) ? *reinterpret_cast<const float4*>(io32 + c0 + 4 * q4)
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-          tmem_ld_wait();
-          if (lo_col) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(__uint_as_float(raw[e]) + __uint_as_float(raw2[e]));
-          }
-#pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
-            if (c0 + 8 * g8 >= p.cout) continue;
-            float v[8];
-#pragma unroll
-            for (int q4 = 0; q4 < 2; ++q4) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8 + 4 * q4);
-              const float4 r4 = rr[2 * g8 + q4];
-              v[4 * q4 + 0] = __uint_as_float(raw[8 * g8 + 4 * q4 + 0]) + bb.x + r4.x;
-              v[4 * q4 + 1] = __uint_as_float(raw[8 * g8 + 4 * q4 + 1]) + bb.y + r4.y;
-              v[4 * q4 + 2] = __uint_as_float(raw[8 * g8 + 4 * q4 + 2]) + bb.z + r4.z;
-              v[4 * q4 + 3] = __uint_as_float(raw[8 * g8 + 4 * q4 + 3]) + bb.w + r4.w;
-            }
-            if (relu) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-            }
-            *reinterpret_cast<float4*>(io32 + c0 + 8 * g8) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(io32 + c0 + 8 * g8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            uint4 o;
-            __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-            *reinterpret_cast<uint4*>(io16 + c0 + 8 * g8) = o;
-          }
-        }
-      } else
-      for (int g = 0; g < n_groups; ++g) {
-        const int c0 = g * 16;
-        uint32_t raw[16], raw2[16];
-        tmem_ld16(trow + c0, raw);
-        if (lo_col) tmem_ld16(trow + lo_col + c0, raw2);
-        uint4 rz[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (has_res) {
-#pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8)
-            if (c0 + 8 * g8 < p.cout) rz[g8] = *reinterpret_cast<const uint4*>(io + (c0 + 8 * g8) * 2);
-        }
-        tmem_ld_wait();
-        if (lo_col) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(__uint_as_float(raw[e]) + __uint_as_float(raw2[e]));
-        }
-#pragma unroll
-        for (int g8 = 0; g8 < 2; ++g8) {
-          if (c0 + 8 * g8 >= p.cout) continue;
-          const __half2* r2 = reinterpret_cast<const __half2*>(&rz[g8]);
-          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8);
-          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8 + 4);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          uint4 o;
-          __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 rr = __half22float2(r2[e]);
-            float v0 = __uint_as_float(raw[8 * g8 + 2 * e]) + bb[2 * e] + rr.x;
-            float v1 = __uint_as_float(raw[8 * g8 + 2 * e + 1]) + bb[2 * e + 1] + rr.y;
-            if (relu) {
-              v0 = fmaxf(v0, 0.f);
-              v1 = fmaxf(v1, 0.f);
-            }
-            o2[e] = __floats2half2_rn(v0, v1);
-          }
-          *reinterpret_cast<uint4*>(io + (c0 + 8 * g8) * 2) = o;
-        }
-      }
+      epilogue_rows(p, stage_s + (size_t)b * stage_bytes + halo_bytes, io32_bytes, m, trow, lo_col, has_res, relu, bias_s);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce_bar0 + 8 * ab);
@@ -485,6 +493,277 @@ __global__ void __launch_bounds__(N_THREADS, 1)
 }
 
 
+
+// Epilogue of one tile pixel WITHOUT a staged io tile (K-block kernel: the maps of its convolutions are small, so the shared
+// memory goes to staged halos and the weight ring instead): the pixel's residual row is fetched from global memory before the
+// accumulator is awaited (whole row in registers), results go out with 16-byte global stores.
+constexpr int DIRECT_MAX_C = 80;
+struct DirectRes {
+  float4 v[DIRECT_MAX_C / 4];
+};
+__device__ __forceinline__ void direct_prefetch(const Args& p, DirectRes& r, const void* res, size_t pix, int ct, int c_off,
+                                                bool live) {
+  if (p.dual) {
+    const float* src = reinterpret_cast<const float*>(res) + pix * ct + c_off;
+#pragma unroll
+    for (int i = 0; i < DIRECT_MAX_C / 4; ++i)
+      r.v[i] = (live && 4 * i < p.cout) ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    const __half* src = reinterpret_cast<const __half*>(res) + pix * ct + c_off;
+#pragma unroll
+    for (int i = 0; i < DIRECT_MAX_C / 8; ++i) {
+      uint4 t = (live && 8 * i < p.cout) ? __ldg(reinterpret_cast<const uint4*>(src) + i) : make_uint4(0, 0, 0, 0);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&t);
+      const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]), d = __half22float2(h2[3]);
+      r.v[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+      r.v[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+    }
+  }
+}
+__device__ __forceinline__ void epilogue_rows_direct(const Args& p, const DirectRes& r, bool has_res, float* out32, __half* out16,
+                                                     size_t pix, int ct, int c_off, bool live, uint32_t trow, uint32_t lo_col,
+                                                     bool relu, const float* bias_s) {
+  const int n_groups = p.n_pad >> 4;
+  float* o32 = out32 ? out32 + pix * ct + c_off : nullptr;
+  __half* o16 = out16 + pix * ct + c_off;
+#pragma unroll
+  for (int g = 0; g < DIRECT_MAX_C / 16; ++g) {
+    if (g >= n_groups) break;
+    const int c0 = g * 16;
+    uint32_t raw[16], raw2[16];
+    tmem_ld16(trow + c0, raw);
+    if (lo_col) tmem_ld16(trow + lo_col + c0, raw2);
+    tmem_ld_wait();
+    if (lo_col) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) raw[e] = __float_as_uint(__uint_as_float(raw[e]) + __uint_as_float(raw2[e]));
+    }
+#pragma unroll
+    for (int g8 = 0; g8 < 2; ++g8) {
+      if (c0 + 8 * g8 >= p.cout) continue;
+      float v[8];
+#pragma unroll
+      for (int q4 = 0; q4 < 2; ++q4) {
+        const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + 8 * g8 + 4 * q4);
+        const float4 r4 = has_res ? r.v[4 * g + 2 * g8 + q4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * q4 + 0] = __uint_as_float(raw[8 * g8 + 4 * q4 + 0]) + bb.x + r4.x;
+        v[4 * q4 + 1] = __uint_as_float(raw[8 * g8 + 4 * q4 + 1]) + bb.y + r4.y;
+        v[4 * q4 + 2] = __uint_as_float(raw[8 * g8 + 4 * q4 + 2]) + bb.z + r4.z;
+        v[4 * q4 + 3] = __uint_as_float(raw[8 * g8 + 4 * q4 + 3]) + bb.w + r4.w;
+      }
+      if (relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+      }
+      if (live) {
+        if (o32) {
+          *reinterpret_cast<float4*>(o32 + c0 + 8 * g8) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o32 + c0 + 8 * g8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        uint4 o;
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        *reinterpret_cast<uint4*>(o16 + c0 + 8 * g8) = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K-block variant for the WEIGHT-HEAVY, PIXEL-LIGHT convolutions (the 72- and 144-channel HRNet branches at 40x60 / 20x30:
+// 85-340 output tiles against 190-750 KB of split weights).  The resident-weight kernel above has to cut such a convolution
+// into 3-12 output / input channel slices that each fit shared memory, and every slice pays the tensor core's per-MMA
+// A-operand fetch again at a small N.  Here the weights are NOT resident: a work item is (group of T tiles, output slice);
+// the T halos of the group stay staged in shared memory with T accumulators in tensor memory, and the slice's weight image
+// streams ONCE per item through a two-slot ring (cp.async.bulk of G consecutive MMAs' B tiles, which the packed layout
+// already stores contiguously) while the MMA warp walks block-outer / tile-inner: every MMA runs at the slice's full N and
+// a weight byte is fetched once per T tiles.  3x3 stride 1 only; epilogue = epilogue_rows (same arithmetic, same outputs).
+constexpr int KB_WSLOTS = 3;               // weight ring depth: bytes in flight from L2 while the MMAs of a block run
+struct KbArgs {
+  int T;                      // tiles per group = stages = accumulators (T * nb <= 512 TMEM columns)
+  int n_groups;               // ceil(n_tiles / T)
+  int n_os;                   // output slices (work item = group * n_os + slice)
+  int g_mma;                  // MMAs per weight block
+  int n_blocks;               // ceil(n_mma / g_mma)
+  uint32_t wslot_bytes;       // g_mma * 2 * nb * 16
+  const void* res;            // residual map (fp32 in dual launches, else fp16) or NULL; out32 (dual) / out16 maps; their
+  float* out32;               //   channel count out_ct
+  __half* out16;
+  int out_ct;
+  const __half* os_w[8];      // per output slice: packed weights, output channel offset, flags (PASS_*)
+  short os_out_off[8];
+  unsigned char os_flags[8];
+};
+
+__global__ void __launch_bounds__(N_THREADS, 1)
+    conv3x3_kb_kernel(const Args p, const KbArgs kb, const __grid_constant__ InMaps maps_in, const __grid_constant__ CUtensorMap map_res,
+                      const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_out16) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t stage_bytes = (uint32_t)p.kc * (uint32_t)p.ch_stride;       // a stage is the halo alone (direct epilogue)
+  uint8_t* stage_s = smem;                                             // [T][halo]
+  uint8_t* w_s = stage_s + (size_t)kb.T * stage_bytes;                 // [KB_WSLOTS][wslot_bytes]
+  float* bias_s = (float*)(w_s + KB_WSLOTS * (size_t)kb.wslot_bytes);  // [n_os][n_pad]
+  uint64_t* bars = (uint64_t*)(bias_s + kb.n_os * p.n_pad);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4 * MAX_BUF + 2 * KB_WSLOTS);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t full_bar0 = smem_u32(bars);                   // halo of stage t landed   [T]
+  const uint32_t empty_bar0 = smem_u32(bars + MAX_BUF);        // stage t free: the item's MMAs retired [T] (tcgen05.commit)
+  const uint32_t accf_bar0 = smem_u32(bars + 2 * MAX_BUF);     // accumulator t complete [T]
+  const uint32_t acce_bar0 = smem_u32(bars + 3 * MAX_BUF);     // accumulator t drained  [T] (4 epilogue warps)
+  const uint32_t wfull_bar0 = smem_u32(bars + 4 * MAX_BUF);    // weight slot landed   [KB_WSLOTS]
+  const uint32_t wempty_bar0 = smem_u32(bars + 4 * MAX_BUF + KB_WSLOTS);   // weight slot consumed (tcgen05.commit)
+  const uint32_t lo_col = p.nb > p.n_pad ? (uint32_t)p.n_pad : 0u;
+
+  if (p.kdata < p.kc) {
+    const int per = p.ch_stride / 16;
+    for (int i = tid; i < kb.T * per; i += N_THREADS)
+      reinterpret_cast<uint4*>(stage_s + (size_t)(i / per) * stage_bytes + (size_t)p.kdata * p.ch_stride)[i % per] =
+          make_uint4(0, 0, 0, 0);
+  }
+  for (int i = tid; i < kb.n_os * p.n_pad; i += N_THREADS) {
+    const int os = i / p.n_pad, c = i % p.n_pad;
+    bias_s[i] = (p.bias && (kb.os_flags[os] & PASS_BIAS) && c < p.cout) ? __ldg(p.bias + kb.os_out_off[os] + c) : 0.f;
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(kb.T * p.nb)) tmem_cols <<= 1;
+  if (warp == MMA_WARP) {
+    if (lane == 0) {
+      for (int s = 0; s < MAX_BUF; ++s) {
+        mbar_init(full_bar0 + 8 * s, 1);
+        mbar_init(empty_bar0 + 8 * s, 1);
+        mbar_init(accf_bar0 + 8 * s, 1);
+        mbar_init(acce_bar0 + 8 * s, 4);
+      }
+      for (int s = 0; s < KB_WSLOTS; ++s) {
+        mbar_init(wfull_bar0 + 8 * s, 1);
+        mbar_init(wempty_bar0 + 8 * s, 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  } else if (warp == PROD_WARP && lane == 0) {
+    prefetch_map(&maps_in.m[0]);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t stage0 = smem_u32(stage_s);
+  const int n_items = kb.n_groups * kb.n_os;
+
+  if (warp == PROD_WARP) {
+    // =========================== producer: halos (+ residual tiles) of the item, then its weight blocks ===========================
+    if (lane == 0) {
+      uint32_t it = 0, wc = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int group = item / kb.n_os, os = item - group * kb.n_os;
+        const uint32_t tx_bytes = (uint32_t)p.kdata * ((uint32_t)p.halo_pix * 16u);
+        for (int t = 0; t < kb.T; ++t) {
+          const int tile = group * kb.T + t;
+          if (tile >= p.n_tiles) break;
+          mbar_wait(empty_bar0 + 8 * t, (it & 1u) ^ 1u);
+          const TileXY xy = tile_coords(tile, p);
+          const uint32_t dst = stage0 + (uint32_t)t * stage_bytes;
+          const uint32_t bar = full_bar0 + 8 * t;
+          mbar_arrive_expect_tx(bar, tx_bytes);
+          for (int kc = 0; kc < p.kcg; ++kc)
+            tma_load_4d(dst + (uint32_t)(kc * p.ch_stride), &maps_in.m[0], bar, p.in_c_off + kc * 8, xy.tx * TW - p.org,
+                        xy.ty * TH - p.org, xy.img);
+        }
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(kb.os_w[os]);
+        for (int b = 0; b < kb.n_blocks; ++b, ++wc) {
+          const int slot = wc % KB_WSLOTS;
+          const int nm = min(kb.g_mma, p.n_mma - b * kb.g_mma);
+          const uint32_t bytes = (uint32_t)nm * 2u * (uint32_t)p.nb * 16u;
+          mbar_wait(wempty_bar0 + 8 * slot, ((wc / KB_WSLOTS) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(wfull_bar0 + 8 * slot, bytes);
+          bulk_g2s(smem_u32(w_s) + (uint32_t)slot * kb.wslot_bytes, wsrc + (size_t)b * kb.wslot_bytes, bytes, wfull_bar0 + 8 * slot);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // =========================== MMA issuer: block-outer / tile-inner ===========================
+    const uint32_t idesc = make_idesc_f16((uint32_t)p.nb);
+    const uint32_t tbase = bcast0(tmem_base);
+    const uint32_t a_hi = (((uint32_t)p.halo_w * 16u) >> 4) | (1u << 14);
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t b_step = 2u * (uint32_t)p.nb;
+    uint32_t it = 0, wc = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int group = item / kb.n_os;
+      const int nt = min(kb.T, p.n_tiles - group * kb.T);
+      for (int b = 0; b < kb.n_blocks; ++b, ++wc) {
+        const int slot = wc % KB_WSLOTS;
+        const int j0 = b * kb.g_mma, nm = min(kb.g_mma, p.n_mma - j0);
+        mbar_wait(wfull_bar0 + 8 * slot, (wc / KB_WSLOTS) & 1u);
+        const uint32_t b_lo0 = ((smem_u32(w_s) + (uint32_t)slot * kb.wslot_bytes) >> 4) | ((((uint32_t)p.nb * 16u) >> 4) << 16);
+        for (int t = 0; t < nt; ++t) {
+          if (b == 0) {
+            mbar_wait(full_bar0 + 8 * t, it & 1u);
+            mbar_wait(acce_bar0 + 8 * t, (it & 1u) ^ 1u);
+          }
+          tc_fence_after();
+          const uint32_t tacc = tbase + (uint32_t)(t * p.nb);
+          const uint32_t a_base = (stage0 + (uint32_t)t * stage_bytes) >> 4;
+          if (elect_one()) {
+            for (int j = 0; j < nm; ++j) {
+              const uint64_t adesc = ((uint64_t)a_hi << 32) | (uint64_t)(p.a_lo[j0 + j] + a_base);
+              const uint64_t bdesc = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)j * b_step);
+              umma_bf16_ss(tacc, adesc, bdesc, idesc, (b > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          umma_commit(wempty_bar0 + 8 * slot);
+          if (b == kb.n_blocks - 1)
+            for (int t = 0; t < nt; ++t) {
+              umma_commit(empty_bar0 + 8 * t);
+              umma_commit(accf_bar0 + 8 * t);
+            }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== epilogue: team (t & 1) takes tile t of every item ===========================
+    const int ew = warp - EPI_WARP0;
+    const int q = warp & 3;
+    const int team = ew >> 2;
+    const int m = q * 32 + lane;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int group = item / kb.n_os, os = item - group * kb.n_os;
+      const int flags = kb.os_flags[os], out_c_off = kb.os_out_off[os];
+      const bool has_res = (flags & PASS_RES_EXT) != 0, relu = (flags & PASS_RELU) != 0;
+      const int nt = min(kb.T, p.n_tiles - group * kb.T);
+      for (int t = team; t < nt; t += 2) {
+        const int tile = group * kb.T + t;
+        const uint32_t trow = tmem_base + (uint32_t)(t * p.nb) + ((uint32_t)(q * 32) << 16);
+        const TileXY xy = tile_coords(tile, p);
+        const int x = xy.tx * TW + (m & (TW - 1)), y = xy.ty * TH + (m >> 3);
+        const bool live = x < p.W && y < p.H;
+        const size_t pix = ((size_t)xy.img * p.H + (live ? y : 0)) * p.W + (live ? x : 0);
+        DirectRes rr;
+        if (has_res) direct_prefetch(p, rr, kb.res, pix, kb.out_ct, out_c_off, live);      // in flight while the MMAs finish
+        mbar_wait(accf_bar0 + 8 * t, it & 1u);
+        tc_fence_after();
+        epilogue_rows_direct(p, rr, has_res, kb.out32, kb.out16, pix, kb.out_ct, out_c_off, live, trow, lo_col, relu,
+                             bias_s + os * p.n_pad);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acce_bar0 + 8 * t);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
+}
 
 // BatchNorm-folded fp32 weights [cout_p][cin_p][k][k] (k*k = ntap) -> fp16 [n_mma][2][n_pad][8] in the kernel's K-list order
 // split: [n_mma][2][2 n_pad][8], rows [0, n_pad) = fp16(w), rows [n_pad, 2 n_pad) = fp16(w - fp16(w)) (w_hi + w_lo = w to 2^-22)
@@ -718,6 +997,126 @@ static int conv_ex_launch(const ls3d_conv_args* c, const ls3d_conv_pass* passes,
   if (rc) return rc;
   const int grid = a.n_tiles < num_sms ? a.n_tiles : num_sms;
   conv3x3_f16_kernel<<<grid, N_THREADS, smem, (cudaStream_t)stream>>>(a, m_in, m_res, m_out, m_out16);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}
+
+// ---- K-block (streamed-weight) variant: configuration for a launch shape, or T = 0 when it does not apply
+struct KbCfg {
+  int T, g_mma, n_blocks;
+  size_t smem;
+};
+static KbCfg kb_config(int cin, int cout, int dual, int split, long long n_tiles, int num_sms) {
+  using namespace ls3d::c3;
+  KbCfg k = {0, 0, 0, 0};
+  const Geom g = geom(cin, cout, 9, 1);
+  const int nb = split ? 2 * g.n_pad : g.n_pad;
+  if (nb > 256 || g.n_mma > MAX_MMA) return k;
+  (void)dual;
+  if (cout > DIRECT_MAX_C) return k;
+  const size_t stage = (size_t)g.kc * g.ch_stride;                 // halo only: the K-block kernel's epilogue goes straight to global memory
+  const size_t fixed = (size_t)8 * g.n_pad * 4 + (4 * MAX_BUF + 2 * KB_WSLOTS) * 8 + 16 + 128;
+  const size_t per_mma = (size_t)2 * nb * 16;
+  int T = (int)((n_tiles + num_sms - 1) / num_sms);
+  if (T > 512 / nb) T = 512 / nb;
+  if (T > 4) T = 4;
+  for (; T >= 1; --T) {
+    const size_t left = 227 * 1024 - fixed;
+    if ((size_t)T * stage + KB_WSLOTS * 2 * per_mma > left) continue;
+    int gm = (int)((left - (size_t)T * stage) / (KB_WSLOTS * per_mma));
+    if (gm > g.n_mma) gm = g.n_mma;
+    if (gm < 2) continue;
+    k.T = T;
+    k.g_mma = gm;
+    k.n_blocks = (g.n_mma + gm - 1) / gm;
+    k.smem = (size_t)T * stage + KB_WSLOTS * (size_t)gm * per_mma + fixed;
+    return k;
+  }
+  return k;
+}
+
+extern "C" int ls3d_conv_f16_kb_supported(int32_t cin, int32_t cout, int32_t dual, int32_t split, int64_t n_pixels,
+                                          int32_t* supported) {
+  if (!supported || !shape_ok(cin, cout, 3, 1)) return LS3D_ERR_ARG;
+  const KbCfg k = kb_config(cin, cout, dual, split, (n_pixels + 127) / 128, ls3d_num_sms() > 0 ? ls3d_num_sms() : 148);
+  *supported = k.T > 0 ? 1 : 0;
+  return LS3D_OK;
+}
+
+// 3x3 / stride 1 convolution with STREAMED weights (conv3x3_kb_kernel): args as ls3d_conv_f16_multi, every pass = one output
+// channel slice over ALL input channels (pass.in_c_off must be 0, no accumulating passes); args->cout = slice size.
+extern "C" int ls3d_conv_f16_kb(const ls3d_conv_args* c, const ls3d_conv_pass* passes, int32_t n_os, void* stream) {
+  using namespace ls3d;
+  using namespace ls3d::c3;
+  if (!c || !passes || n_os < 1 || n_os > 8) return LS3D_ERR_ARG;
+  if (c->n_img <= 0 || c->H_in <= 0 || c->W_in <= 0) return LS3D_OK;
+  if (!c->in16 || c->ksize != 3 || (c->stride != 0 && c->stride != 1) || !shape_ok(c->cin, c->cout, 3, 1)) return LS3D_ERR_ARG;
+  const int dual = c->out32 != nullptr;
+  void* out = dual ? (void*)c->out32 : c->out16;
+  if (!out || (dual && !c->out16) || (!dual && c->res32) || (dual && c->res16)) return LS3D_ERR_ARG;
+  const void* res = dual ? (const void*)c->res32 : c->res16;
+  const int in_ct = c->in_c_total ? c->in_c_total : c->cin, out_ct = c->out_c_total ? c->out_c_total : c->cout;
+  if ((in_ct & 7) || (out_ct & 7) || in_ct != c->cin) return LS3D_ERR_ARG;
+  if ((((uintptr_t)c->in16) | ((uintptr_t)c->out32) | ((uintptr_t)res) | ((uintptr_t)c->out16)) & 15) return LS3D_ERR_ARG;
+  const int split = c->w_split ? 1 : 0, H = c->H_in, W = c->W_in;
+  const Geom g = geom(c->cin, c->cout, 9, 1);
+  Args a = {};
+  KbArgs kb = {};
+  for (int i = 0; i < n_os; ++i) {
+    if (!passes[i].w_packed || (((uintptr_t)passes[i].w_packed) & 15) || passes[i].in_c_off != 0 || (passes[i].out_c_off & 7) ||
+        passes[i].out_c_off < 0 || passes[i].out_c_off + c->cout > out_ct || (passes[i].flags & 4))
+      return LS3D_ERR_ARG;
+    kb.os_w[i] = (const __half*)passes[i].w_packed;
+    kb.os_out_off[i] = (short)passes[i].out_c_off;
+    int f = passes[i].flags & 15;
+    if ((f & 2) && !res) f &= ~2;
+    kb.os_flags[i] = (unsigned char)f;
+  }
+  a.bias = c->bias; a.dual = dual; a.n_img = c->n_img; a.H = H; a.W = W; a.cin = c->cin; a.cout = c->cout;
+  a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad; a.nphase = 1; a.kdata = g.kdata;
+  a.in_c_off = 0; a.out_c_off = 0; a.n_pass = 1; a.use_table = 0;
+  a.halo_w = HALO_W; a.halo_pix = HALO_W * HALO_H; a.org = 1; a.ch_stride = g.ch_stride;
+  a.nb = split ? 2 * g.n_pad : g.n_pad;
+  if (a.nb > 256 || g.n_mma > MAX_MMA) return LS3D_ERR_ARG;
+  for (int j = 0; j < g.n_mma; ++j) {
+    int e0, e1;
+    mma_entries(j, g.kcg, 9, 1, e0, e1);
+    const int o0 = k_entry_offset(e0, g.kcg, 9, 1), o1 = k_entry_offset(e1, g.kcg, 9, 1);
+    a.a_lo[j] = ((uint32_t)o0 >> 4) | (((uint32_t)(o1 - o0) >> 4) << 16);
+  }
+  a.tiles_x = ls3d_div_up(W, TW);
+  a.tiles_y = ls3d_div_up(H, TH);
+  const long long nt = (long long)c->n_img * a.tiles_x * a.tiles_y;
+  if (nt >= (1LL << 22)) return LS3D_ERR_ARG;
+  a.n_tiles = (int)nt;
+  a.inv_tiles_x = 1.0f / (float)a.tiles_x;
+  a.inv_tiles_per_img = 1.0f / (float)(a.tiles_x * a.tiles_y);
+  const int num_sms = ls3d_num_sms();
+  const KbCfg k = kb_config(c->cin, c->cout, dual, split, nt, num_sms);
+  if (k.T < 1) return LS3D_ERR_ARG;
+  a.nbuf = k.T;
+  kb.T = k.T; kb.g_mma = k.g_mma; kb.n_blocks = k.n_blocks; kb.n_os = n_os;
+  kb.n_groups = (int)((nt + k.T - 1) / k.T);
+  kb.wslot_bytes = (uint32_t)k.g_mma * 2u * (uint32_t)a.nb * 16u;
+  kb.res = res; kb.out32 = dual ? c->out32 : nullptr; kb.out16 = (__half*)(dual ? c->out16 : out); kb.out_ct = out_ct;
+  static bool optin[64] = {false};
+  cudaError_t eo = ls3d_optin_smem(conv3x3_kb_kernel, optin);
+  if (eo != cudaSuccess) return (int)eo;
+  InMaps m_in;
+  CUtensorMap m_res, m_out, m_out16;
+  const int es = dual ? 4 : 2;
+  int rc = make_map(&m_in.m[0], c->in16, in_ct, W, H, c->n_img, 8, HALO_W, HALO_H, 2, -1);
+  if (rc) return rc;
+  m_in.m[1] = m_in.m[2] = m_in.m[3] = m_in.m[0];
+  rc = make_map(&m_out, out, out_ct, W, H, c->n_img, c->cout, TW, TH, es);
+  if (rc) return rc;
+  rc = make_map(&m_res, res ? res : out, out_ct, W, H, c->n_img, c->cout, TW, TH, es);
+  if (rc) return rc;
+  rc = make_map(&m_out16, dual ? c->out16 : out, out_ct, W, H, c->n_img, c->cout, TW, TH, 2);
+  if (rc) return rc;
+  const int n_items = kb.n_groups * n_os;
+  const int grid = n_items < num_sms ? n_items : num_sms;
+  conv3x3_kb_kernel<<<grid, N_THREADS, k.smem, (cudaStream_t)stream>>>(a, kb, m_in, m_res, m_out, m_out16);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }

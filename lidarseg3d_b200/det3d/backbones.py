@@ -293,7 +293,11 @@ class SpMiddleResNetFHD(Prepared):
         if self.training:
             raise NotImplementedError("lidarseg3d_b200 SpMiddleResNetFHD: inference path only (model.eval())")
         P = self.prep()
-        conv, block = UNetSCN3D._conv, UNetSCN3D._block
+        conv = UNetSCN3D._conv
+
+        def block(_, x, pk, nbr):                     # relu(bn2(conv2(relu(bn1(conv1 x)))) + x), scn.py:63-81
+            return conv(conv(x, pk[0], nbr), pk[1], nbr, res=x, res_mode=1)
+
         B = batch_size
         shape1 = tuple(int(v) for v in (np.array(input_shape[::-1]) + [1, 0, 0]))            # scn.py:149
         coords1 = coors.int().contiguous()

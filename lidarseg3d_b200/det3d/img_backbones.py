@@ -187,6 +187,14 @@ DUAL_EXACT_WEIGHTS = os.environ.get("LS3D_DUAL_EXACT_WEIGHTS", "1") == "1"
 DUAL_OWN_ALL = os.environ.get("LS3D_DUAL_OWN_ALL", "1") == "1"     # 0: only 3x3 stride-1 convs on the own kernel (development A/B)
 
 
+# streamed-weight kernel (ls3d_conv_f16_kb) for the weight-heavy, pixel-light 3x3 / stride-1 convolutions: at least this many
+# (padded) input channels and few enough output tiles (<= ~4 per SM) that streaming the weights once per tile group is cheaper
+# than slicing the convolution into resident-weight passes
+USE_KB = os.environ.get("LS3D_CONV_KB", "1") == "1"
+KB_MIN_CIN = 64
+KB_MAX_PIXELS = 80000
+
+
 class ConvPlan:
     """One BN-folded convolution (3x3 stride 1 / 2, or 1x1) as launches of ls3d_conv_f16_ex (csrc/conv3x3_f16.cu).
 
@@ -217,6 +225,20 @@ class ConvPlan:
         cout_p, cin_p = w.shape[:2]
         self.cout_p, self.cin_p, self.k, self.stride, self.exact, self.fp32out = cout_p, cin_p, ksize, stride, exact, fp32out
         self.bias = None if bias is None else bias.float().contiguous()
+        self.kb = False
+        # weight-heavy 3x3 / stride-1 convolutions (the 72- / 144-channel branches): streamed-weight kernel, whole input
+        # channel range per launch, output slices only where the accumulator (2 n_pad <= 256 columns) demands it
+        if USE_KB and exact and ksize == 3 and stride == 1 and cin_p >= KB_MIN_CIN and pixels <= KB_MAX_PIXELS:
+            for n_out in (1, 2, 3, 4):
+                cs = ((cout_p + n_out - 1) // n_out + 7) // 8 * 8
+                if 2 * ((cs + 15) // 16 * 16) <= 256 and ops.conv_kb_supported(cin_p, cs, fp32out, True, pixels):
+                    self.kb, self.ok, self.hilo, self.split, self.cs, self.ci = True, True, False, True, cs, cin_p
+                    self.passes = []
+                    for o in range((cout_p + cs - 1) // cs):
+                        o0 = min(o * cs, cout_p - cs)
+                        self.passes.append((ops.pack_conv_ex(w[o0:o0 + cs].clone(), 1, True), 0, o0, True, True))
+                    self.n_launch, self.multi, self._tables, self.est_us = 1, False, {}, 0.0
+                    return
         best = None
         for hilo in ((False, True) if (exact and fp32out) else (False,)):
             split = exact and not hilo
@@ -294,6 +316,10 @@ class ConvPlan:
         else:
             assert res is None or res.dtype == torch.float16
         tab = self._table(res is not None, bool(relu), bool(use_bias))
+        if self.kb:
+            ops.conv_kb(x16, tab, len(self.passes), self.bias if use_bias else None, cout=self.cs, out32=out32, out16=out16,
+                        res32=res if self.fp32out else None, res16=None if self.fp32out else res, split=True)
+            return out32, out16
         ops.conv_multi(x16, tab, len(self.passes), self.bias if use_bias else None, cin=self.ci, cout=self.cs, out32=out32,
                        out16=out16, res32=res if self.fp32out else None, res16=None if self.fp32out else res, ksize=self.k,
                        stride=self.stride, split=self.split)

@@ -490,6 +490,36 @@ def conv_multi(x16, passes, n_pass, bias, *, cin, cout, out32, out16, res32=None
     check(capi.lib().ls3d_conv_f16_multi(ctypes.byref(a), passes, n_pass, stream_ptr()), "ls3d_conv_f16_multi")
 
 
+def conv_kb_supported(cin, cout, dual, split, pixels):
+    """ls3d_conv_f16_kb (streamed weights) has a configuration for a 3x3 / stride-1 (cin -> cout slice) launch over ``pixels``."""
+    if cin % 8 or cout % 8 or cin <= 0 or cout <= 0:
+        return False
+    ok = ctypes.c_int32()
+    check(capi.lib().ls3d_conv_f16_kb_supported(cin, cout, int(dual), int(split), int(pixels), ctypes.byref(ok)),
+          "ls3d_conv_f16_kb_supported")
+    return bool(ok.value)
+
+
+def conv_kb(x16, passes, n_slices, bias, *, cout, out32, out16, res32=None, res16=None, split=True):
+    """One ls3d_conv_f16_kb launch: ``passes`` = ctypes array of capi.ConvPass, one per output channel slice of ``cout``."""
+    N, ct, H, W = x16.shape
+    a = capi.ConvArgs()
+    a.in16, a.bias = ptr(x16), ptr(bias)
+    a.res32, a.out32, a.out16, a.res16 = ptr(res32), ptr(out32), ptr(out16), ptr(res16)
+    a.in_c_total, a.cin, a.out_c_total, a.cout = ct, ct, out16.shape[1], cout
+    a.n_img, a.H_in, a.W_in, a.ksize, a.stride, a.w_split = N, H, W, 3, 1, int(split)
+    e0 = e1 = None
+    if CONV_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(capi.lib().ls3d_conv_f16_kb(ctypes.byref(a), passes, n_slices, stream_ptr()), "ls3d_conv_f16_kb")
+    if CONV_PROFILE is not None:
+        e1.record()
+        CONV_PROFILE.append(dict(e0=e0, e1=e1, n=N, h=H, w=W, cin=ct, cout=out16.shape[1], k=3, stride=1,
+                                 res=res32 is not None or res16 is not None, out32=out32 is not None, in_total=ct,
+                                 out_total=out16.shape[1], passes=n_slices, kb=True))
+
+
 def pad3_f16(x):
     """fp32 channels-last image batch [N, 3, H, W] -> fp16 [N, 8, H, W] channels-last, channels 3..7 zero: the operand copy of
     the network input for the own stem convolution (16-byte pixel rows for the tensor-map copies)."""

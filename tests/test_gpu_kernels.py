@@ -611,3 +611,43 @@ def test_spmiddle_resnet_vs_reference_golden(golden_dir):
         assert torch.equal(ms[k].indices.cpu().int(), r["indices"].int()), k
         assert ms[k].spatial_shape == r["shape"], k
         assert float((ms[k].features.cpu() - r["features"]).abs().max()) <= 1e-4 * float(r["features"].abs().max()), k
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,res,relu", [
+    (18, 40, 60, 72, 72, True, True),       # the bench's 1/4-resolution branch: 432 tiles, two staged tiles per group
+    (9, 40, 52, 72, 72, True, False),       # 189 tiles: the last group is partial
+    (18, 20, 30, 144, 144, True, True),     # 1/8-resolution branch: two 72-channel output slices, one tile per item
+    (2, 20, 30, 144, 144, False, True),
+    (1, 17, 23, 72, 72, False, False)])     # partial tiles in both directions
+def test_conv_kb_streamed_weights_vs_fp64(n, h, w, cin, cout, res, relu):
+    """ls3d_conv_f16_kb (streamed weights, group of staged tiles, block-outer / tile-inner MMA order) through the planner against
+    an fp64 convolution; fp32-map plan (dual) and operand-only plan."""
+    import torch.nn.functional as F
+    from lidarseg3d_b200.det3d.img_backbones import ConvPlan
+    g = torch.Generator().manual_seed(n * 31 + h + cin)
+    x = torch.randn(n, cin, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    z = torch.randn(n, cout, h, w, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) if res else None
+    plan = ConvPlan(wt, b, 3, 1, True, True, pixels=n * h * w)
+    assert plan.ok and plan.kb
+    y32, y16 = plan.run(x, res=z, relu=relu)
+    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1)
+    if z is not None:
+        ref = ref + z.double()
+    if relu:
+        ref = ref.relu()
+    err = float((y32.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 3e-6, err
+    assert torch.equal(y16, y32.half())
+    op = ConvPlan(wt, b, 3, 1, True, False, pixels=n * h * w)
+    assert op.ok and op.kb
+    z16 = None if z is None else z.half()
+    n32, o16 = op.run(x, res=z16, relu=relu)
+    ref16 = F.conv2d(x.double(), wt.double(), b.double(), padding=1)
+    if z16 is not None:
+        ref16 = ref16 + z16.double()
+    if relu:
+        ref16 = ref16.relu()
+    assert n32 is None
+    assert float((o16.double() - ref16).abs().max() / ref16.abs().max()) <= 6e-4
