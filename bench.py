@@ -245,6 +245,17 @@ def run_sweep(args):
         if need > 150e9:
             skipped.append(dict(occupancy=occ, channels=C, reason="N*(Cin+Cout)*4 + rulebook > 150 GB"))
             continue
+        try:
+            _sweep_combo(args, rank, dev, G, shape, occ, C, n, peak, rows, gemm, ops)
+        except (RuntimeError, torch.OutOfMemoryError) as e:
+            skipped.append(dict(occupancy=occ, channels=C, reason=repr(e)[:160]))
+            torch.cuda.empty_cache()
+    clocks = sampler.stop()
+    return _sweep_report(args, rank, world, dev, rows, skipped, clocks, peak, gemm)
+
+
+def _sweep_combo(args, rank, dev, G, shape, occ, C, n, peak, rows, gemm, ops):
+    if True:
         g = torch.Generator(device=dev).manual_seed(1234 + rank)
         cells = torch.unique(torch.randint(0, G ** 3, (int(n * 1.06),), device=dev, generator=g, dtype=torch.int64))
         cells = cells[torch.randperm(cells.numel(), device=dev, generator=g)[:n]].sort().values
@@ -293,7 +304,10 @@ def run_sweep(args):
                          ms=ms2, gbs=b2 / ms2 / 1e6, tflops=2.0 * pairs2 * C * C / ms2 / 1e9, frac=b2 / ms2 / 1e6 / peak))
         del feats, w, pw, nbr, nb2, out, out2, grid, og, oc, coords
         torch.cuda.empty_cache()
-    clocks = sampler.stop()
+
+
+def _sweep_report(args, rank, world, dev, rows, skipped, clocks, peak, gemm):
+    import torch.distributed as dist
     head = [r for r in rows if r["op"] == "SubM3"]
     agg = float(np.mean([r["gbs"] for r in head])) if head else 0.0
     if world > 1:
@@ -313,7 +327,7 @@ def run_sweep(args):
                               clocks=clocks, gpu_launches=len(rows) * (args.steps + 3),
                               roofline=None if best is None else dict(bound="hbm", achieved=best["gbs"], peak=peak, unit="GB/s",
                                                                      frac=best["frac"], traffic=None,
-                                                                     kernel=f"gather_gemm_kernel SubM3 occ={best['occupancy']} C={best['channels']}"),
+                                                                     kernel=f"{gemm.ENGINE_NAME} SubM3 occ={best['occupancy']} C={best['channels']}"),
                               sweep=rows, skipped=skipped, cpu_baseline=None,
                               e2e=dict(value=agg, unit="GB/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0,
                                        note="kernel sweep: operands are generated on the device; no host path exists for this config"))))

@@ -375,13 +375,16 @@ typedef struct ls3d_conv_pass {
   int32_t in_c_off, out_c_off, flags;
 } ls3d_conv_pass;
 int ls3d_conv_f16_multi(const ls3d_conv_args* args, const ls3d_conv_pass* passes, int32_t n_pass, void* stream);
-/* Streamed-weight variant for the weight-heavy, pixel-light 3x3 / stride-1 convolutions (HRNet's 72- and 144-channel branches):
+/* Streamed-weight variant for the weight-heavy, pixel-light 3x3 convolutions, stride 1 or 2 (HRNet's 72- and 144-channel branches
+ * and the stride-2 fuse convolutions that feed them):
  * every pass = one OUTPUT channel slice over all input channels (in_c_off = 0, flags without 4); a work item is (group of up to
  * 4 output tiles, slice): the group's halos stay staged, the slice's packed weights (ls3d_conv_f16_pack_ex image, unchanged)
- * stream once per item through a shared-memory ring and every MMA runs at the slice's full N.  args->cout = slice size,
- * at most 8 slices.  ls3d_conv_f16_kb_supported: is there a shared / tensor-memory configuration for this shape? */
+ * stream once per item through a shared-memory ring and every MMA runs at the slice's full N.  args->cout = slice size
+ * (<= 128), at most 8 slices.  Its epilogue reads the residual and writes the maps straight from / to global memory (no staged
+ * output tile), which also makes it the kernel of the wide 1x1 convolutions (Bottleneck conv3, 64 -> 256: 128-channel slices).  ls3d_conv_f16_kb_supported: is there a shared / tensor-memory configuration for this shape? */
 int ls3d_conv_f16_kb(const ls3d_conv_args* args, const ls3d_conv_pass* passes, int32_t n_slices, void* stream);
-int ls3d_conv_f16_kb_supported(int32_t cin, int32_t cout, int32_t dual, int32_t split, int64_t n_pixels, int32_t* supported);
+int ls3d_conv_f16_kb_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t dual, int32_t split,
+                               int64_t n_out_pixels, int32_t* supported);
 int ls3d_conv_f16_ex_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t dual, int32_t split,
                                int32_t* supported);
 int ls3d_conv_f16_pack_ex(const float* w_oihw, int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t split,

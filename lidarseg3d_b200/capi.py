@@ -125,7 +125,7 @@ _SIGNATURES = {
     "ls3d_conv_f16_ex": ([ctypes.POINTER(ConvArgs), P], ctypes.c_int),
     "ls3d_conv_f16_multi": ([ctypes.POINTER(ConvArgs), ctypes.POINTER(ConvPass), I, P], ctypes.c_int),
     "ls3d_conv_f16_kb": ([ctypes.POINTER(ConvArgs), ctypes.POINTER(ConvPass), I, P], ctypes.c_int),
-    "ls3d_conv_f16_kb_supported": ([I, I, I, I, L, ctypes.POINTER(ctypes.c_int32)], ctypes.c_int),
+    "ls3d_conv_f16_kb_supported": ([I, I, I, I, I, I, L, ctypes.POINTER(ctypes.c_int32)], ctypes.c_int),
     "ls3d_conv_f16_ex_supported": ([I, I, I, I, I, I, ctypes.POINTER(ctypes.c_int32)], ctypes.c_int),
     "ls3d_conv_f16_pack_ex": ([P, I, I, I, I, I, P, P], ctypes.c_int),
     "ls3d_pad3_f16": ([P, L, P, P], ctypes.c_int),

@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
 // Epilogue of one tile pixel WITHOUT a staged io tile (K-block kernel: the maps of its convolutions are small, so the shared
 // memory goes to staged halos and the weight ring instead): the pixel's residual row is fetched from global memory before the
 // accumulator is awaited (whole row in registers), results go out with 16-byte global stores.
-constexpr int DIRECT_MAX_C = 80;
+constexpr int DIRECT_MAX_C = 128;
 struct DirectRes {
   float4 v[DIRECT_MAX_C / 4];
 };
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(N_THREADS, 1)
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   } else if (warp == PROD_WARP && lane == 0) {
-    prefetch_map(&maps_in.m[0]);
+    for (int ph = 0; ph < p.nphase; ++ph) prefetch_map(&maps_in.m[ph]);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -670,9 +670,10 @@ __global__ void __launch_bounds__(N_THREADS, 1)
           const uint32_t dst = stage0 + (uint32_t)t * stage_bytes;
           const uint32_t bar = full_bar0 + 8 * t;
           mbar_arrive_expect_tx(bar, tx_bytes);
-          for (int kc = 0; kc < p.kcg; ++kc)
-            tma_load_4d(dst + (uint32_t)(kc * p.ch_stride), &maps_in.m[0], bar, p.in_c_off + kc * 8, xy.tx * TW - p.org,
-                        xy.ty * TH - p.org, xy.img);
+          for (int ph = 0; ph < p.nphase; ++ph)
+            for (int kc = 0; kc < p.kcg; ++kc)
+              tma_load_4d(dst + (uint32_t)((ph * p.kcg + kc) * p.ch_stride), &maps_in.m[ph], bar, p.in_c_off + kc * 8,
+                          xy.tx * TW - p.org, xy.ty * TH - p.org, xy.img);
         }
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(kb.os_w[os]);
         for (int b = 0; b < kb.n_blocks; ++b, ++wc) {
@@ -1006,10 +1007,10 @@ struct KbCfg {
   int T, g_mma, n_blocks;
   size_t smem;
 };
-static KbCfg kb_config(int cin, int cout, int dual, int split, long long n_tiles, int num_sms) {
+static KbCfg kb_config(int cin, int cout, int dual, int split, long long n_tiles, int num_sms, int stride = 1, int ntap = 9) {
   using namespace ls3d::c3;
   KbCfg k = {0, 0, 0, 0};
-  const Geom g = geom(cin, cout, 9, 1);
+  const Geom g = geom(cin, cout, ntap, stride);
   const int nb = split ? 2 * g.n_pad : g.n_pad;
   if (nb > 256 || g.n_mma > MAX_MMA) return k;
   (void)dual;
@@ -1035,10 +1036,11 @@ static KbCfg kb_config(int cin, int cout, int dual, int split, long long n_tiles
   return k;
 }
 
-extern "C" int ls3d_conv_f16_kb_supported(int32_t cin, int32_t cout, int32_t dual, int32_t split, int64_t n_pixels,
-                                          int32_t* supported) {
-  if (!supported || !shape_ok(cin, cout, 3, 1)) return LS3D_ERR_ARG;
-  const KbCfg k = kb_config(cin, cout, dual, split, (n_pixels + 127) / 128, ls3d_num_sms() > 0 ? ls3d_num_sms() : 148);
+extern "C" int ls3d_conv_f16_kb_supported(int32_t cin, int32_t cout, int32_t ksize, int32_t stride, int32_t dual, int32_t split,
+                                          int64_t n_out_pixels, int32_t* supported) {
+  if (!supported || (stride != 1 && stride != 2) || !shape_ok(cin, cout, ksize, stride)) return LS3D_ERR_ARG;
+  const KbCfg k = kb_config(cin, cout, dual, split, (n_out_pixels + 127) / 128, ls3d_num_sms() > 0 ? ls3d_num_sms() : 148, stride,
+                            ntap_of(ksize));
   *supported = k.T > 0 ? 1 : 0;
   return LS3D_OK;
 }
@@ -1050,7 +1052,10 @@ extern "C" int ls3d_conv_f16_kb(const ls3d_conv_args* c, const ls3d_conv_pass* p
   using namespace ls3d::c3;
   if (!c || !passes || n_os < 1 || n_os > 8) return LS3D_ERR_ARG;
   if (c->n_img <= 0 || c->H_in <= 0 || c->W_in <= 0) return LS3D_OK;
-  if (!c->in16 || c->ksize != 3 || (c->stride != 0 && c->stride != 1) || !shape_ok(c->cin, c->cout, 3, 1)) return LS3D_ERR_ARG;
+  const int stride = c->stride ? c->stride : 1;
+  if (!c->in16 || (stride != 1 && stride != 2) || !shape_ok(c->cin, c->cout, c->ksize, stride)) return LS3D_ERR_ARG;
+  const int ntap = ntap_of(c->ksize);
+  if (stride == 2 && (c->H_in < 2 || c->W_in < 2)) return LS3D_ERR_ARG;
   const int dual = c->out32 != nullptr;
   void* out = dual ? (void*)c->out32 : c->out16;
   if (!out || (dual && !c->out16) || (!dual && c->res32) || (dual && c->res16)) return LS3D_ERR_ARG;
@@ -1058,8 +1063,9 @@ extern "C" int ls3d_conv_f16_kb(const ls3d_conv_args* c, const ls3d_conv_pass* p
   const int in_ct = c->in_c_total ? c->in_c_total : c->cin, out_ct = c->out_c_total ? c->out_c_total : c->cout;
   if ((in_ct & 7) || (out_ct & 7) || in_ct != c->cin) return LS3D_ERR_ARG;
   if ((((uintptr_t)c->in16) | ((uintptr_t)c->out32) | ((uintptr_t)res) | ((uintptr_t)c->out16)) & 15) return LS3D_ERR_ARG;
-  const int split = c->w_split ? 1 : 0, H = c->H_in, W = c->W_in;
-  const Geom g = geom(c->cin, c->cout, 9, 1);
+  const int split = c->w_split ? 1 : 0;
+  const int H = stride == 2 ? (c->H_in + 1) / 2 : c->H_in, W = stride == 2 ? (c->W_in + 1) / 2 : c->W_in;   // output size
+  const Geom g = geom(c->cin, c->cout, ntap, stride);
   Args a = {};
   KbArgs kb = {};
   for (int i = 0; i < n_os; ++i) {
@@ -1073,15 +1079,16 @@ extern "C" int ls3d_conv_f16_kb(const ls3d_conv_args* c, const ls3d_conv_pass* p
     kb.os_flags[i] = (unsigned char)f;
   }
   a.bias = c->bias; a.dual = dual; a.n_img = c->n_img; a.H = H; a.W = W; a.cin = c->cin; a.cout = c->cout;
-  a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad; a.nphase = 1; a.kdata = g.kdata;
+  a.kcg = g.kcg; a.kc = g.kc; a.n_mma = g.n_mma; a.n_pad = g.n_pad; a.nphase = g.nphase; a.kdata = g.kdata;
   a.in_c_off = 0; a.out_c_off = 0; a.n_pass = 1; a.use_table = 0;
-  a.halo_w = HALO_W; a.halo_pix = HALO_W * HALO_H; a.org = 1; a.ch_stride = g.ch_stride;
+  const int bw = ntap == 1 ? TW : HALO_W, bh = ntap == 1 ? TH : HALO_H;
+  a.halo_w = bw; a.halo_pix = bw * bh; a.org = ntap == 1 ? 0 : 1; a.ch_stride = g.ch_stride;
   a.nb = split ? 2 * g.n_pad : g.n_pad;
   if (a.nb > 256 || g.n_mma > MAX_MMA) return LS3D_ERR_ARG;
   for (int j = 0; j < g.n_mma; ++j) {
     int e0, e1;
-    mma_entries(j, g.kcg, 9, 1, e0, e1);
-    const int o0 = k_entry_offset(e0, g.kcg, 9, 1), o1 = k_entry_offset(e1, g.kcg, 9, 1);
+    mma_entries(j, g.kcg, ntap, g.nphase, e0, e1);
+    const int o0 = k_entry_offset(e0, g.kcg, ntap, g.nphase), o1 = k_entry_offset(e1, g.kcg, ntap, g.nphase);
     a.a_lo[j] = ((uint32_t)o0 >> 4) | (((uint32_t)(o1 - o0) >> 4) << 16);
   }
   a.tiles_x = ls3d_div_up(W, TW);
@@ -1092,7 +1099,7 @@ extern "C" int ls3d_conv_f16_kb(const ls3d_conv_args* c, const ls3d_conv_pass* p
   a.inv_tiles_x = 1.0f / (float)a.tiles_x;
   a.inv_tiles_per_img = 1.0f / (float)(a.tiles_x * a.tiles_y);
   const int num_sms = ls3d_num_sms();
-  const KbCfg k = kb_config(c->cin, c->cout, dual, split, nt, num_sms);
+  const KbCfg k = kb_config(c->cin, c->cout, dual, split, nt, num_sms, stride, ntap);
   if (k.T < 1) return LS3D_ERR_ARG;
   a.nbuf = k.T;
   kb.T = k.T; kb.g_mma = k.g_mma; kb.n_blocks = k.n_blocks; kb.n_os = n_os;
@@ -1105,15 +1112,17 @@ extern "C" int ls3d_conv_f16_kb(const ls3d_conv_args* c, const ls3d_conv_pass* p
   InMaps m_in;
   CUtensorMap m_res, m_out, m_out16;
   const int es = dual ? 4 : 2;
-  int rc = make_map(&m_in.m[0], c->in16, in_ct, W, H, c->n_img, 8, HALO_W, HALO_H, 2, -1);
-  if (rc) return rc;
-  m_in.m[1] = m_in.m[2] = m_in.m[3] = m_in.m[0];
-  rc = make_map(&m_out, out, out_ct, W, H, c->n_img, c->cout, TW, TH, es);
-  if (rc) return rc;
-  rc = make_map(&m_res, res ? res : out, out_ct, W, H, c->n_img, c->cout, TW, TH, es);
-  if (rc) return rc;
-  rc = make_map(&m_out16, dual ? c->out16 : out, out_ct, W, H, c->n_img, c->cout, TW, TH, 2);
-  if (rc) return rc;
+  int rc = 0;
+  for (int ph = 0; ph < 4; ++ph) {
+    rc = make_map(&m_in.m[ph], c->in16, in_ct, c->W_in, c->H_in, c->n_img, 8, bw, bh, 2, stride == 2 ? ph : -1);
+    if (rc) return rc;
+    if (stride != 2 && ph == 0) {
+      m_in.m[1] = m_in.m[2] = m_in.m[3] = m_in.m[0];
+      break;
+    }
+  }
+  (void)es;
+  m_res = m_out = m_out16 = m_in.m[0];          // the K-block kernel's epilogue addresses the output maps directly
   const int n_items = kb.n_groups * n_os;
   const int grid = n_items < num_sms ? n_items : num_sms;
   conv3x3_kb_kernel<<<grid, N_THREADS, k.smem, (cudaStream_t)stream>>>(a, kb, m_in, m_res, m_out, m_out16);

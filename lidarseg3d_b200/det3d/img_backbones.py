@@ -192,7 +192,9 @@ DUAL_OWN_ALL = os.environ.get("LS3D_DUAL_OWN_ALL", "1") == "1"     # 0: only 3x3
 # than slicing the convolution into resident-weight passes
 USE_KB = os.environ.get("LS3D_CONV_KB", "1") == "1"
 KB_MIN_CIN = 64
+KB_MIN_S2_WEIGHT = 24 * 72           # stride-2 fuse convolutions into the 72- / 144-channel branches
 KB_MAX_PIXELS = 80000
+KB_MIN_1X1_COUT = 128
 
 
 class ConvPlan:
@@ -228,15 +230,21 @@ class ConvPlan:
         self.kb = False
         # weight-heavy 3x3 / stride-1 convolutions (the 72- / 144-channel branches): streamed-weight kernel, whole input
         # channel range per launch, output slices only where the accumulator (2 n_pad <= 256 columns) demands it
-        if USE_KB and exact and ksize == 3 and stride == 1 and cin_p >= KB_MIN_CIN and pixels <= KB_MAX_PIXELS:
+        out_pixels = pixels // (4 if stride == 2 else 1)
+        heavy = cin_p >= KB_MIN_CIN if stride == 1 else cin_p * cout_p >= KB_MIN_S2_WEIGHT
+        use_kb = USE_KB and exact and ksize == 3 and heavy and out_pixels <= KB_MAX_PIXELS
+        # wide 1x1 convolutions writing an fp32 map (Bottleneck conv3 / downsample, 64 -> 256): the same kernel for its direct
+        # epilogue - no staged output tile, so 128-channel slices fit where the resident-weight kernel needs three 88-channel passes
+        use_kb = use_kb or (USE_KB and exact and ksize == 1 and stride == 1 and fp32out and cout_p >= KB_MIN_1X1_COUT)
+        if use_kb:
             for n_out in (1, 2, 3, 4):
                 cs = ((cout_p + n_out - 1) // n_out + 7) // 8 * 8
-                if 2 * ((cs + 15) // 16 * 16) <= 256 and ops.conv_kb_supported(cin_p, cs, fp32out, True, pixels):
+                if cs <= 128 and ops.conv_kb_supported(cin_p, cs, ksize, stride, fp32out, True, out_pixels):
                     self.kb, self.ok, self.hilo, self.split, self.cs, self.ci = True, True, False, True, cs, cin_p
                     self.passes = []
                     for o in range((cout_p + cs - 1) // cs):
                         o0 = min(o * cs, cout_p - cs)
-                        self.passes.append((ops.pack_conv_ex(w[o0:o0 + cs].clone(), 1, True), 0, o0, True, True))
+                        self.passes.append((ops.pack_conv_ex(w[o0:o0 + cs].clone(), stride, True), 0, o0, True, True))
                     self.n_launch, self.multi, self._tables, self.est_us = 1, False, {}, 0.0
                     return
         best = None
@@ -318,7 +326,8 @@ class ConvPlan:
         tab = self._table(res is not None, bool(relu), bool(use_bias))
         if self.kb:
             ops.conv_kb(x16, tab, len(self.passes), self.bias if use_bias else None, cout=self.cs, out32=out32, out16=out16,
-                        res32=res if self.fp32out else None, res16=None if self.fp32out else res, split=True)
+                        res32=res if self.fp32out else None, res16=None if self.fp32out else res, split=True, stride=self.stride,
+                        ksize=self.k)
             return out32, out16
         ops.conv_multi(x16, tab, len(self.passes), self.bias if use_bias else None, cin=self.ci, cout=self.cs, out32=out32,
                        out16=out16, res32=res if self.fp32out else None, res16=None if self.fp32out else res, ksize=self.k,

@@ -490,24 +490,24 @@ def conv_multi(x16, passes, n_pass, bias, *, cin, cout, out32, out16, res32=None
     check(capi.lib().ls3d_conv_f16_multi(ctypes.byref(a), passes, n_pass, stream_ptr()), "ls3d_conv_f16_multi")
 
 
-def conv_kb_supported(cin, cout, dual, split, pixels):
-    """ls3d_conv_f16_kb (streamed weights) has a configuration for a 3x3 / stride-1 (cin -> cout slice) launch over ``pixels``."""
+def conv_kb_supported(cin, cout, ksize, stride, dual, split, out_pixels):
+    """ls3d_conv_f16_kb (streamed weights) has a configuration for a 3x3 (cin -> cout slice) launch with ``out_pixels`` outputs."""
     if cin % 8 or cout % 8 or cin <= 0 or cout <= 0:
         return False
     ok = ctypes.c_int32()
-    check(capi.lib().ls3d_conv_f16_kb_supported(cin, cout, int(dual), int(split), int(pixels), ctypes.byref(ok)),
+    check(capi.lib().ls3d_conv_f16_kb_supported(cin, cout, ksize, stride, int(dual), int(split), int(out_pixels), ctypes.byref(ok)),
           "ls3d_conv_f16_kb_supported")
     return bool(ok.value)
 
 
-def conv_kb(x16, passes, n_slices, bias, *, cout, out32, out16, res32=None, res16=None, split=True):
+def conv_kb(x16, passes, n_slices, bias, *, cout, out32, out16, res32=None, res16=None, split=True, stride=1, ksize=3):
     """One ls3d_conv_f16_kb launch: ``passes`` = ctypes array of capi.ConvPass, one per output channel slice of ``cout``."""
     N, ct, H, W = x16.shape
     a = capi.ConvArgs()
     a.in16, a.bias = ptr(x16), ptr(bias)
     a.res32, a.out32, a.out16, a.res16 = ptr(res32), ptr(out32), ptr(out16), ptr(res16)
     a.in_c_total, a.cin, a.out_c_total, a.cout = ct, ct, out16.shape[1], cout
-    a.n_img, a.H_in, a.W_in, a.ksize, a.stride, a.w_split = N, H, W, 3, 1, int(split)
+    a.n_img, a.H_in, a.W_in, a.ksize, a.stride, a.w_split = N, H, W, ksize, stride, int(split)
     e0 = e1 = None
     if CONV_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -515,7 +515,7 @@ def conv_kb(x16, passes, n_slices, bias, *, cout, out32, out16, res32=None, res1
     check(capi.lib().ls3d_conv_f16_kb(ctypes.byref(a), passes, n_slices, stream_ptr()), "ls3d_conv_f16_kb")
     if CONV_PROFILE is not None:
         e1.record()
-        CONV_PROFILE.append(dict(e0=e0, e1=e1, n=N, h=H, w=W, cin=ct, cout=out16.shape[1], k=3, stride=1,
+        CONV_PROFILE.append(dict(e0=e0, e1=e1, n=N, h=H, w=W, cin=ct, cout=out16.shape[1], k=ksize, stride=stride,
                                  res=res32 is not None or res16 is not None, out32=out32 is not None, in_total=ct,
                                  out_total=out16.shape[1], passes=n_slices, kb=True))
 

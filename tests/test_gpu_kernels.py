@@ -613,13 +613,16 @@ def test_spmiddle_resnet_vs_reference_golden(golden_dir):
         assert float((ms[k].features.cpu() - r["features"]).abs().max()) <= 1e-4 * float(r["features"].abs().max()), k
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout,res,relu", [
-    (18, 40, 60, 72, 72, True, True),       # the bench's 1/4-resolution branch: 432 tiles, two staged tiles per group
-    (9, 40, 52, 72, 72, True, False),       # 189 tiles: the last group is partial
-    (18, 20, 30, 144, 144, True, True),     # 1/8-resolution branch: two 72-channel output slices, one tile per item
-    (2, 20, 30, 144, 144, False, True),
-    (1, 17, 23, 72, 72, False, False)])     # partial tiles in both directions
-def test_conv_kb_streamed_weights_vs_fp64(n, h, w, cin, cout, res, relu):
+@pytest.mark.parametrize("n,h,w,cin,cout,res,relu,stride", [
+    (18, 40, 60, 72, 72, True, True, 1),       # the bench's 1/4-resolution branch: 432 tiles, three staged tiles per group
+    (9, 40, 52, 72, 72, True, False, 1),       # 189 tiles: the last group is partial
+    (18, 20, 30, 144, 144, True, True, 1),     # 1/8-resolution branch: two 72-channel output slices, one tile per item
+    (2, 20, 30, 144, 144, False, True, 1),
+    (1, 17, 23, 72, 72, False, False, 1),      # partial tiles in both directions
+    (18, 80, 120, 40, 72, False, False, 2),    # stride-2 fuse convolutions into the 72- / 144-channel branches (phase planes)
+    (18, 40, 60, 72, 144, False, True, 2),
+    (3, 41, 59, 24, 72, True, True, 2)])       # odd input size: the last output row / column reads the zero padding
+def test_conv_kb_streamed_weights_vs_fp64(n, h, w, cin, cout, res, relu, stride):
     """ls3d_conv_f16_kb (streamed weights, group of staged tiles, block-outer / tile-inner MMA order) through the planner against
     an fp64 convolution; fp32-map plan (dual) and operand-only plan."""
     import torch.nn.functional as F
@@ -628,11 +631,12 @@ def test_conv_kb_streamed_weights_vs_fp64(n, h, w, cin, cout, res, relu):
     x = torch.randn(n, cin, h, w, generator=g).half().to(DEV).contiguous(memory_format=torch.channels_last)
     wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(DEV)
     b = torch.randn(cout, generator=g).to(DEV)
-    z = torch.randn(n, cout, h, w, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) if res else None
-    plan = ConvPlan(wt, b, 3, 1, True, True, pixels=n * h * w)
+    ho, wo = ((h + 1) // 2, (w + 1) // 2) if stride == 2 else (h, w)
+    z = torch.randn(n, cout, ho, wo, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) if res else None
+    plan = ConvPlan(wt, b, 3, stride, True, True, pixels=n * h * w)
     assert plan.ok and plan.kb
     y32, y16 = plan.run(x, res=z, relu=relu)
-    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1)
+    ref = F.conv2d(x.double(), wt.double(), b.double(), stride=stride, padding=1)
     if z is not None:
         ref = ref + z.double()
     if relu:
@@ -640,11 +644,11 @@ def test_conv_kb_streamed_weights_vs_fp64(n, h, w, cin, cout, res, relu):
     err = float((y32.double() - ref).abs().max() / ref.abs().max())
     assert err <= 3e-6, err
     assert torch.equal(y16, y32.half())
-    op = ConvPlan(wt, b, 3, 1, True, False, pixels=n * h * w)
+    op = ConvPlan(wt, b, 3, stride, True, False, pixels=n * h * w)
     assert op.ok and op.kb
     z16 = None if z is None else z.half()
     n32, o16 = op.run(x, res=z16, relu=relu)
-    ref16 = F.conv2d(x.double(), wt.double(), b.double(), padding=1)
+    ref16 = F.conv2d(x.double(), wt.double(), b.double(), stride=stride, padding=1)
     if z16 is not None:
         ref16 = ref16 + z16.double()
     if relu:
