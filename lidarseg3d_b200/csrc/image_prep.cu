@@ -93,14 +93,12 @@ __device__ __forceinline__ Tap linear_tap(int d, double scale, int src, bool cla
 template <int KIND>   // 0: normalised fp32, 1: normalised fp16, 2: resized uint8
 __global__ void resize_u8_kernel(const uint8_t* __restrict__ in, int n_img, int in_h, int in_w, int out_h, int out_w,
                                  double scale_x, double scale_y, Norm3 p, void* __restrict__ out) {
-  const long long total = (long long)n_img * out_h * out_w;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int dx = (int)(i % out_w);
-    const long long r = i / out_w;
-    const int dy = (int)(r % out_h);
-    const int img = (int)(r / out_h);
+  // grid = (column blocks, output rows, images): no 64-bit index division per pixel, the row tap is block-uniform
+  const int dy = blockIdx.y, img = blockIdx.z;
+  const Tap ty = linear_tap(dy, scale_y, in_h, false);
+  for (int dx = blockIdx.x * blockDim.x + threadIdx.x; dx < out_w; dx += gridDim.x * blockDim.x) {
+    const size_t i = ((size_t)img * out_h + dy) * out_w + dx;
     const Tap tx = linear_tap(dx, scale_x, in_w, true);
-    const Tap ty = linear_tap(dy, scale_y, in_h, false);
     const uint8_t* r0 = in + ((size_t)img * in_h + ty.s0) * in_w * 3;
     const uint8_t* r1 = in + ((size_t)img * in_h + ty.s1) * in_w * 3;
     uint32_t v[3];
@@ -140,13 +138,12 @@ extern "C" int ls3d_resize_images_u8(const uint8_t* in, int32_t n_img, int32_t i
   }
   if (out_kind != 2 && (!mean3 || !std3)) return LS3D_ERR_ARG;
   const double sx = (double)in_w / (double)out_w, sy = (double)in_h / (double)out_h;
-  const long long total = (long long)n_img * out_h * out_w;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (out_h > 65535 || n_img > 65535) return LS3D_ERR_ARG;
+  const dim3 blocks((unsigned)((out_w + 255) / 256), (unsigned)out_h, (unsigned)n_img);
   cudaStream_t st = (cudaStream_t)stream;
-  if (out_kind == 0) resize_u8_kernel<0><<<(int)blocks, 256, 0, st>>>(in, n_img, in_h, in_w, out_h, out_w, sx, sy, p, out);
-  else if (out_kind == 1) resize_u8_kernel<1><<<(int)blocks, 256, 0, st>>>(in, n_img, in_h, in_w, out_h, out_w, sx, sy, p, out);
-  else resize_u8_kernel<2><<<(int)blocks, 256, 0, st>>>(in, n_img, in_h, in_w, out_h, out_w, sx, sy, p, out);
+  if (out_kind == 0) resize_u8_kernel<0><<<blocks, 256, 0, st>>>(in, n_img, in_h, in_w, out_h, out_w, sx, sy, p, out);
+  else if (out_kind == 1) resize_u8_kernel<1><<<blocks, 256, 0, st>>>(in, n_img, in_h, in_w, out_h, out_w, sx, sy, p, out);
+  else resize_u8_kernel<2><<<blocks, 256, 0, st>>>(in, n_img, in_h, in_w, out_h, out_w, sx, sy, p, out);
   LS3D_LAUNCH_CHECK();
   return LS3D_OK;
 }

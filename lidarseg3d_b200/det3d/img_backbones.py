@@ -195,6 +195,7 @@ KB_MIN_CIN = 64
 KB_MIN_S2_WEIGHT = 24 * 72           # stride-2 fuse convolutions into the 72- / 144-channel branches
 KB_MAX_PIXELS = 80000
 KB_MIN_1X1_COUT = 128
+KB_1X1 = os.environ.get("LS3D_CONV_KB_1X1", "0") == "1"
 
 
 class ConvPlan:
@@ -233,9 +234,10 @@ class ConvPlan:
         out_pixels = pixels // (4 if stride == 2 else 1)
         heavy = cin_p >= KB_MIN_CIN if stride == 1 else cin_p * cout_p >= KB_MIN_S2_WEIGHT
         use_kb = USE_KB and exact and ksize == 3 and heavy and out_pixels <= KB_MAX_PIXELS
-        # wide 1x1 convolutions writing an fp32 map (Bottleneck conv3 / downsample, 64 -> 256): the same kernel for its direct
-        # epilogue - no staged output tile, so 128-channel slices fit where the resident-weight kernel needs three 88-channel passes
-        use_kb = use_kb or (USE_KB and exact and ksize == 1 and stride == 1 and fp32out and cout_p >= KB_MIN_1X1_COUT)
+        # (the kernel also serves 1x1 convolutions - 128-channel slices of Bottleneck conv3, 64 -> 256, fit thanks to its direct
+        # epilogue - but at 160x240 its per-thread global stores lose to the staged TMA stores: measured 645 us against 554 us
+        # for the three 88-channel passes of the resident-weight kernel, so the route stays off)
+        use_kb = use_kb or (KB_1X1 and USE_KB and exact and ksize == 1 and stride == 1 and fp32out and cout_p >= KB_MIN_1X1_COUT)
         if use_kb:
             for n_out in (1, 2, 3, 4):
                 cs = ((cout_p + n_out - 1) // n_out + 7) // 8 * 8
