@@ -15,6 +15,7 @@ logits within 1e-3 relative and >= 99.9 % argmax agreement, bit-exact voxel coor
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -24,6 +25,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rotating batches of different point counts make the caching allocator re-carve its segments now and then (a cudaFree +
+# cudaMalloc pair = one 35-200 ms outlier step in an otherwise 17.6 ms series): growable segments avoid it
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -69,16 +73,55 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------ helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line: the same fields).
+    In-process NVML (nvidia_ml_py) polled from a thread: a freshly spawned `nvidia-smi -lms` initialises NVML inside the timed
+    region, and that start-up stalled single steps by 17-85 ms (seen as one outlier step per run).  NVML is initialised in
+    the constructor - build the sampler BEFORE the warm-up; falls back to the nvidia-smi loop when the module is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MASKS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.1):
+        self.index, self.rows, self.proc, self.period = index, [], None, period_s
+        self.nvml = self.handle = self.thread = None
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((sm, mask))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def start(self):
+        self.rows = []
+        self.stop_flag.clear()
+        if os.environ.get("LS3D_NO_CLOCKS") == "1":       # development: is the sampler itself visible in the step times?
+            self.nvml, self.proc = None, None
+            return
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -90,6 +133,14 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            sm = [r[0] for r in self.rows]
+            reasons = sorted({name for _, mask in self.rows for name, bit in self.MASKS if mask & bit})
+            return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=self.max_sm, reasons=reasons, samples=len(sm),
+                        source="NVML (nvidia_ml_py), polled every %.0f ms during the timed region" % (self.period * 1e3))
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -102,7 +153,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(sm))
+                    samples=len(sm), source="nvidia-smi -lms 200")
 
 
 def make_batches(wl, spec, n_batches, frames_per_gpu, rank, n_image_sets=2):
@@ -535,6 +586,8 @@ def main():
 
     def timed(nsteps, from_host, img_dtype, tag):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps + 1)]
+        gc.collect()
+        gc.disable()                 # no generation-2 collection in the middle of a timed step (re-enabled below)
         barrier()
         ev[0].record()
         if from_host:
@@ -553,6 +606,7 @@ def main():
                 step(dev_batches[i % NB], img_dtype)
                 ev[i + 1].record()
         barrier()
+        gc.enable()
         step_ms[tag] = [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(nsteps)]     # per-step breakdown (same events)
         return reduce_max_ms(ev[0].elapsed_time(ev[nsteps]), dev)
 
@@ -561,12 +615,12 @@ def main():
         img_dtype = TD[mode_name]
         set_mode(img_dtype)
         r = {}
-        for i in range(max(args.warmup, NB)):                 # every rotating batch (and its shapes) is seen before timing
+        sampler = ClockSampler(local_rank)                    # NVML initialised here, outside the timed region
+        for i in range(max(args.warmup, 2 * NB)):             # every rotating batch (and its shapes) is seen twice before timing
             step(dev_batches[i % NB], img_dtype)
         capi.COUNTERS.clear()
         if profile:
             gemm.PROFILE = []
-        sampler = ClockSampler(local_rank)
         sampler.start()
         prof_range = profile and os.environ.get("LS3D_PROFILE_RANGE") == "1"      # ncu --profile-from-start off: timed steps only
         if prof_range:
@@ -711,7 +765,7 @@ def main():
                 gref = dict(unavailable=repr(e)[:300])
 
     if rank == 0:
-        line = dict(base, value=value, steps=args.steps, warmup=max(args.warmup, NB), ms_per_step=ms / args.steps,
+        line = dict(base, value=value, steps=args.steps, warmup=max(args.warmup, 2 * NB), ms_per_step=ms / args.steps,
                     config=dict(workload=args.workload, description=wl["desc"], frames_per_gpu=fpg, global_frames_per_step=fpg * world,
                                 points_per_step_per_gpu=npts, image_branch_dtype=args.image_dtype if wl["cam"] else None,
                                 raw_image_hw=list(spec["img_hw"]) if wl["cam"] else None,

@@ -195,53 +195,58 @@ constexpr int CT_MAXL = 48;
 constexpr int CT_E = 96;
 
 
-// out[l][e] = bias[e] + sum_c in[l][c] * Wt[c][e] for all l < L, e < NOUT.  One thread owns an output column and
-// keeps the L accumulators in registers, so every weight is read from global exactly once per CTA (coalesced over e)
-// and the activations come from shared memory as broadcasts.
-template <int MAXL, class StoreFn>
-__device__ __forceinline__ void tokens_matvec(const float* __restrict__ Wt, const float* __restrict__ bias, int nin,
-                                               int nout, const float* in_s, int ld_in, int L, StoreFn store) {
-  // nin is a multiple of 8 and ld_in a multiple of 4 (96 / 48 / 32 here): 8 independent weight loads are in flight per
-  // step and the activations are read as two broadcast float4 per token.
-  for (int e = threadIdx.x; e < nout; e += blockDim.x) {
-    float acc[MAXL];
-    const float b = bias[e];
-#pragma unroll
-    for (int l = 0; l < MAXL; ++l) acc[l] = b;
-    // the next step's 8 weights are in flight while this step's L x 8 FMAs run (the loop is otherwise a chain of exposed
-    // L2 / DRAM latencies: one CTA per frame has nothing else to switch to)
-    float wn[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) wn[i] = __ldg(Wt + (size_t)i * nout + e);
-    for (int c0 = 0; c0 < nin; c0 += 8) {
-      float w[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = wn[i];
-      if (c0 + 8 < nin) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) wn[i] = __ldg(Wt + (size_t)(c0 + 8 + i) * nout + e);
-      }
-#pragma unroll
-      for (int l = 0; l < MAXL; ++l) {
-        if (l < L) {
-          const float4 x0 = *reinterpret_cast<const float4*>(in_s + l * ld_in + c0);
-          const float4 x1 = *reinterpret_cast<const float4*>(in_s + l * ld_in + c0 + 4);
-          float a = acc[l];
-          a = fmaf(x0.x, w[0], a); a = fmaf(x0.y, w[1], a); a = fmaf(x0.z, w[2], a); a = fmaf(x0.w, w[3], a);
-          a = fmaf(x1.x, w[4], a); a = fmaf(x1.y, w[5], a); a = fmaf(x1.z, w[6], a); a = fmaf(x1.w, w[7], a);
-          acc[l] = a;
-        }
-      }
-    }
-#pragma unroll
-    for (int l = 0; l < MAXL; ++l)
-      if (l < L) store(l, e, acc[l]);
-  }
-}
-
 // L2 prefetch of a parameter block (one 128-byte line per thread and step)
 __device__ __forceinline__ void prefetch_l2(const float* p, int nfloats) {
   for (int i = threadIdx.x * 32; i < nfloats; i += blockDim.x * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i));
+}
+
+// out[l][e0..e0+3] = bias + sum_c in[l][c] * Wt[c][e0..e0+3]: a thread owns TL tokens x 4 output columns (4 TL accumulators).
+// Per 4 input channels it reads 4 weight float4 (global, coalesced over the column groups, next block prefetched) and TL
+// activation float4 (shared-memory broadcasts) for 16 TL FMAs.  A column-per-thread mapping spends one broadcast
+// LDS.128 per 4 FMAs - on one CTA that is bound by the shared-memory pipe (~4 cycles per warp-wide LDS.128), 12x off the FMA
+// rate; with TL = 9 the ratio is 1 : 36.
+template <int TL, class StoreFn>
+__device__ __forceinline__ void tokens_gemm(const float* __restrict__ Wt, const float* __restrict__ bias, int nin, int nout,
+                                             const float* in_s, int ld_in, int L, StoreFn store) {
+  const int ncg = nout >> 2;
+  const int ntg = (L + TL - 1) / TL;
+  for (int t = threadIdx.x; t < ncg * ntg; t += blockDim.x) {
+    const int cgp = t % ncg, tg = t / ncg;
+    const int e0 = cgp * 4, l0 = tg * TL;
+    float4 acc[TL];
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + e0));
+#pragma unroll
+    for (int i = 0; i < TL; ++i) acc[i] = b4;
+    const float* xr[TL];
+#pragma unroll
+    for (int i = 0; i < TL; ++i) xr[i] = in_s + min(l0 + i, L - 1) * ld_in;
+    const float4* wp = reinterpret_cast<const float4*>(Wt + e0);
+    float4 wn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wn[i] = __ldg(wp + (size_t)i * ncg);
+    for (int c0 = 0; c0 < nin; c0 += 4) {
+      float4 w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = wn[i];
+      if (c0 + 4 < nin) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wn[i] = __ldg(wp + (size_t)(c0 + 4 + i) * ncg);
+      }
+#pragma unroll
+      for (int i = 0; i < TL; ++i) {
+        const float4 x = *reinterpret_cast<const float4*>(xr[i] + c0);
+        float4 a = acc[i];
+        a.x = fmaf(x.x, w[0].x, a.x); a.y = fmaf(x.x, w[0].y, a.y); a.z = fmaf(x.x, w[0].z, a.z); a.w = fmaf(x.x, w[0].w, a.w);
+        a.x = fmaf(x.y, w[1].x, a.x); a.y = fmaf(x.y, w[1].y, a.y); a.z = fmaf(x.y, w[1].z, a.z); a.w = fmaf(x.y, w[1].w, a.w);
+        a.x = fmaf(x.z, w[2].x, a.x); a.y = fmaf(x.z, w[2].y, a.y); a.z = fmaf(x.z, w[2].z, a.z); a.w = fmaf(x.z, w[2].w, a.w);
+        a.x = fmaf(x.w, w[3].x, a.x); a.y = fmaf(x.w, w[3].y, a.y); a.z = fmaf(x.w, w[3].z, a.z); a.w = fmaf(x.w, w[3].w, a.w);
+        acc[i] = a;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TL; ++i)
+      if (l0 + i < L) store(l0 + i, e0, acc[i]);
+  }
 }
 
 __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restrict__ emb1, int C1,
@@ -278,8 +283,8 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
   for (int o = threadIdx.x; o < ncls * C1; o += blockDim.x) e1s[o] = emb1[(size_t)b * ncls * C1 + o];
   for (int o = threadIdx.x; o < ncls * C2; o += blockDim.x) e2s[o] = emb2[(size_t)b * ncls * C2 + o];
   __syncthreads();
-  tokens_matvec<CT_MAXL / 2>(P1t, b1, C1, E, e1s, C1, ncls, [&](int l, int e, float v) { mem[l][e] = v; });
-  tokens_matvec<CT_MAXL / 2>(P2t, b2, C2, E, e2s, C2, ncls, [&](int l, int e, float v) { mem[ncls + l][e] = v; });
+  tokens_gemm<2>(P1t, b1, C1, E, e1s, C1, ncls, [&](int l, int e, float4 v) { *reinterpret_cast<float4*>(&mem[l][e]) = v; });
+  tokens_gemm<2>(P2t, b2, C2, E, e2s, C2, ncls, [&](int l, int e, float4 v) { *reinterpret_cast<float4*>(&mem[ncls + l][e]) = v; });
   __syncthreads();
   for (int ly = 0; ly < n_layer; ++ly) {
     const float* Wint = lp + (size_t)ly * layer_sz;
@@ -293,7 +298,9 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
     const float* Wvt = bk + E;
     const float* bv = Wvt + E * E;
     // in-projection
-    tokens_matvec<CT_MAXL>(Wint, bin, E, 3 * E, &mem[0][0], E, L, [&](int l, int e, float v) { qkv[l][e] = v; });
+    tokens_gemm<9>(Wint, bin, E, 3 * E, &mem[0][0], E, L, [&](int l, int e, float4 v) {      // qkv rows are 3E + 1 floats apart
+      qkv[l][e] = v.x; qkv[l][e + 1] = v.y; qkv[l][e + 2] = v.z; qkv[l][e + 3] = v.w;
+    });
     __syncthreads();
     // scores
     const float scale = rsqrtf((float)dh);
@@ -322,7 +329,10 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
     }
     __syncthreads();
     // out-projection + residual (into qkv[:, :E] as scratch)
-    tokens_matvec<CT_MAXL>(Woutt, bout, E, E, &att[0][0], E, L, [&](int l, int e, float v) { qkv[l][e] = mem[l][e] + v; });
+    tokens_gemm<3>(Woutt, bout, E, E, &att[0][0], E, L, [&](int l, int e, float4 v) {
+      qkv[l][e] = mem[l][e] + v.x; qkv[l][e + 1] = mem[l][e + 1] + v.y; qkv[l][e + 2] = mem[l][e + 2] + v.z;
+      qkv[l][e + 3] = mem[l][e + 3] + v.w;
+    });
     __syncthreads();
     // LayerNorm (norm1), one warp per token
     for (int l = threadIdx.x >> 5; l < L; l += blockDim.x >> 5) {
@@ -342,43 +352,15 @@ __global__ void __launch_bounds__(512) class_tokens_kernel(const float* __restri
     __syncthreads();
     // k / v projections for the point cross-attention of this layer
     {
-      // threads [0, E) own a K column, threads [E, 2E) a V column (one pass, weights read once)
-      for (int o = threadIdx.x; o < 2 * E; o += blockDim.x) {
-        const int which = o / E, e = o % E;
-        const float* Wt = which ? Wvt : Wkt;
-        float acc[CT_MAXL];
-        const float bb = which ? bv[e] : bk[e];
-#pragma unroll
-        for (int l = 0; l < CT_MAXL; ++l) acc[l] = bb;
-        float wn[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) wn[i] = __ldg(Wt + i * E + e);
-        for (int c0 = 0; c0 < E; c0 += 8) {
-          float w[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) w[i] = wn[i];
-          if (c0 + 8 < E) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) wn[i] = __ldg(Wt + (c0 + 8 + i) * E + e);
-          }
-#pragma unroll
-          for (int l = 0; l < CT_MAXL; ++l) {
-            if (l < L) {
-              const float4 x0 = *reinterpret_cast<const float4*>(&mem[l][c0]);
-              const float4 x1 = *reinterpret_cast<const float4*>(&mem[l][c0 + 4]);
-              float a = acc[l];
-              a = fmaf(x0.x, w[0], a); a = fmaf(x0.y, w[1], a); a = fmaf(x0.z, w[2], a); a = fmaf(x0.w, w[3], a);
-              a = fmaf(x1.x, w[4], a); a = fmaf(x1.y, w[5], a); a = fmaf(x1.z, w[6], a); a = fmaf(x1.w, w[7], a);
-              acc[l] = a;
-            }
-          }
-        }
-        const int h = e / dh, d = e % dh;
-        float* dst = which ? Vout : Kout;
-#pragma unroll
-        for (int l = 0; l < CT_MAXL; ++l)
-          if (l < L) dst[((((size_t)ly * B + b) * n_head + h) * L + l) * dh + d] = acc[l];
-      }
+      const size_t base = ((size_t)ly * B + b) * n_head;
+      auto kv_store = [&](float* dst) {
+        return [=](int l, int e, float4 v) {                       // [head][token][dh], dh = E / n_head (a multiple of 4)
+          const int h = e / dh, d = e - h * dh;
+          *reinterpret_cast<float4*>(dst + ((base + h) * L + l) * dh + d) = v;
+        };
+      };
+      tokens_gemm<3>(Wkt, bk, E, E, &mem[0][0], E, L, kv_store(Kout));
+      tokens_gemm<3>(Wvt, bv, E, E, &mem[0][0], E, L, kv_store(Vout));
     }
     if (mem_out)
       for (int o = threadIdx.x; o < L * E; o += blockDim.x)
