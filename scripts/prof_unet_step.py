@@ -24,10 +24,14 @@ batch = bench.to_device(bench.make_batches(wl, spec, 1, 3, 0, n_image_sets=1)[0]
 with torch.no_grad():
     for _ in range(2):
         model(bench.build_gpu_example(spec, batch, torch.float32, dev), return_loss=False)
-    ex = bench.build_gpu_example(spec, batch, torch.float32, dev)
+    inputs_in_range = os.environ.get("LS3D_PROFILE_INPUTS") == "1"      # also profile projection / resize / voxelization
+    if not inputs_in_range:
+        ex = bench.build_gpu_example(spec, batch, torch.float32, dev)
     gemm.PROFILE, gemm.COUNT = [], []
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
+    if inputs_in_range:
+        ex = bench.build_gpu_example(spec, batch, torch.float32, dev)
     model(ex, return_loss=False)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
