@@ -187,6 +187,11 @@ int ls3d_three_nn_grid(const float* points, int32_t ld_p, int32_t n, const void*
                        int32_t* todo_count, float* dist2, int32_t* idx, void* stream);
 int ls3d_three_interpolate(const float* feat, int32_t ld_f, int32_t C, const float* dist2, const int32_t* idx, int32_t n,
                            float* out, int32_t ld_out, int32_t round_out, void* stream);
+/* Segment table of a batch-sorted tensor: off[b] = first row whose batch column (fp32 when is_float, else int32; `stride`
+ * elements between rows) is >= b, off[n_frames] = n.  What the reference obtains with per-frame boolean masks
+ * (det3d/models/point_heads/point_utils.py:19-21, context_module.py:38-47). */
+int ls3d_frame_offsets(const void* batch_col, int32_t is_float, int64_t stride, int32_t n, int32_t n_frames, int32_t* off,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera feature sampling.

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "ls3d_rulebook_scatter": ([P, I, I, I, I, P, I, P, P, P, P, P], ctypes.c_int),
     "ls3d_three_nn_grid": ([P, I, I, P, P, I, I, I, I, P, P, P, P, P, P, P, P, P, P], ctypes.c_int),
     "ls3d_three_nn": ([I, I, I, P, P, P, P, P], ctypes.c_int),
+    "ls3d_frame_offsets": ([P, I, L, I, I, P, P], ctypes.c_int),
     "ls3d_three_interpolate": ([P, I, I, P, P, I, P, I, I, P], ctypes.c_int),
     "ls3d_sample_image_features": ([P, I, I, I, I, I, I, P, I, P, P, I, I, P], ctypes.c_int),
     "ls3d_project_points": ([P, I, I, I, P, P, I, I, I, I, I, P, P], ctypes.c_int),
@@ -168,7 +169,7 @@ COUNTERS = {}
 KERNELS_PER_CALL = {"ls3d_gather_gemm": 1, "ls3d_gemm_pack_bf16x3": 1, "ls3d_tile_plan_build": 1, "ls3d_voxelize": 8, "ls3d_vfe_descriptor": 1, "ls3d_vfe_token_attn": 1,
                     "ls3d_vfe_token_max": 1, "ls3d_grid_build": 4, "ls3d_grid_build_strided": 4, "ls3d_grid_enumerate": 1,
                     "ls3d_rulebook_gather": 1, "ls3d_rulebook_scatter": 1, "ls3d_three_nn_grid": 3, "ls3d_three_nn": 1,
-                    "ls3d_three_interpolate": 1, "ls3d_sample_image_features": 1, "ls3d_project_points": 1, "ls3d_project_points_global": 1,
+                    "ls3d_three_interpolate": 1, "ls3d_frame_offsets": 1, "ls3d_sample_image_features": 1, "ls3d_project_points": 1, "ls3d_project_points_global": 1,
                     "ls3d_resize_images_u8": 1, "ls3d_upsample_sum": 1, "ls3d_upsample_sum_f16": 1,
                     "ls3d_conv3x3_f16": 1, "ls3d_conv3x3_f16_pack": 1, "ls3d_conv_f16": 1, "ls3d_conv_f16_dual": 1, "ls3d_upsample_sum_dual": 1, "ls3d_cast_f16": 1, "ls3d_conv_f16_pack": 1, "ls3d_conv_f16_pack_split": 1, "ls3d_conv_f16_ex": 1, "ls3d_conv_f16_multi": 1, "ls3d_conv_f16_kb": 1, "ls3d_conv_f16_pack_ex": 1, "ls3d_pad3_f16": 1, "ls3d_cast_f32": 1, "ls3d_normalize_images_u8": 1, "ls3d_token_attention": 1, "ls3d_sffm_decoder": 1, "ls3d_class_embed": 4,
                     "ls3d_class_tokens": 1}

@@ -337,6 +337,38 @@ __global__ void three_nn_tiled_kernel(int n, int m, const float* __restrict__ un
   }
 }
 
+// Row offsets of the frames of a batch-sorted tensor: off[b] = first row whose batch column is >= b (off[B] = n).  The rows of
+// `points` / `voxel_coords` are concatenated frame by frame by the reference's collate (collate.py:141-150), so this is the
+// segment table every per-frame op of the heads needs (the reference masks `batch_idx == i` per frame: point_utils.py:19-21).
+template <typename T>
+__global__ void frame_offsets_kernel(const T* __restrict__ col, long long stride, int n, int B, int* __restrict__ off) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > B) return;
+  int lo = 0, hi = n;                     // lower bound of b in the non-decreasing batch column
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((float)col[(size_t)mid * stride] < (float)b) lo = mid + 1;
+    else hi = mid;
+  }
+  off[b] = lo;
+}
+
+}  // namespace ls3d
+
+extern "C" int ls3d_frame_offsets(const void* batch_col, int32_t is_float, int64_t stride, int32_t n, int32_t n_frames,
+                                  int32_t* off, void* stream) {
+  using namespace ls3d;
+  if (!off || n < 0 || n_frames < 1 || (n > 0 && !batch_col) || stride < 1) return LS3D_ERR_ARG;
+  const int threads = 32, blocks = (n_frames + 1 + threads - 1) / threads;
+  if (is_float)
+    frame_offsets_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>((const float*)batch_col, stride, n, n_frames, off);
+  else
+    frame_offsets_kernel<int><<<blocks, threads, 0, (cudaStream_t)stream>>>((const int*)batch_col, stride, n, n_frames, off);
+  LS3D_LAUNCH_CHECK();
+  return LS3D_OK;
+}
+
+namespace ls3d {
 }  // namespace ls3d
 
 // drop-in for three_nn_wrapper_fast(b, n, m, unknown, known, dist2, idx) (pointnet2_api.cpp:10-24, interpolate.cpp:17-30)

@@ -20,11 +20,10 @@ from .registry import POINT_HEADS
 
 
 def _offsets(batch_col, batch_size):
-    """Row offsets [B+1] (int32, device) of frames in a tensor sorted by its batch column."""
-    counts = torch.bincount(batch_col.long(), minlength=batch_size)[:batch_size]
-    off = torch.zeros(batch_size + 1, dtype=torch.int32, device=batch_col.device)
-    off[1:] = torch.cumsum(counts, 0).int()
-    return off
+    """Row offsets [B+1] (int32, device) of frames in a tensor sorted by its batch column (collate order)."""
+    if batch_col.dtype not in (torch.float32, torch.int32):
+        batch_col = batch_col.int()
+    return ops.frame_offsets(batch_col, batch_size)
 
 
 def make_convcls_head(fc_cfg, input_channels, output_channels, dp_ratio=0):
@@ -123,11 +122,9 @@ def _predict(out_logits, example, test_cfg):
         metas = example["metadata"] if has_meta else [None] * batch_size
         labels = torch.argmax(out_logits, dim=1)
         # frames are contiguous (collate order): per-frame masks of the reference == slices
-        counts = torch.bincount(stack_points[:, 0].long(), minlength=batch_size)[:batch_size].cpu().tolist()
-        lo = 0
+        off = _offsets(stack_points[:, 0], batch_size).cpu().tolist()
         for i in range(batch_size):
-            sl = slice(lo, lo + counts[i])
-            lo += counts[i]
+            sl = slice(off[i], off[i + 1])
             ret = {"metadata": metas[i], "pred_point_sem_labels": labels[sl]}
             if "point_sem_labels" in example:
                 ret["point_sem_labels"] = example["point_sem_labels"][sl]

@@ -190,6 +190,17 @@ def three_nn_grid(points, grid, voxel_size, range_min, point_off, voxel_off, vox
     return d2, idx
 
 
+def frame_offsets(batch_col, batch_size):
+    """Row offsets [B+1] (int32, device) of the frames of a batch-sorted tensor; ``batch_col`` = its batch column (a strided
+    1-D view, fp32 or int32)."""
+    assert batch_col.dim() == 1 and batch_col.dtype in (torch.float32, torch.int32)
+    off = _i32(batch_col.device, batch_size + 1)
+    n = batch_col.shape[0]
+    check(capi.lib().ls3d_frame_offsets(ptr(batch_col), int(batch_col.dtype == torch.float32), batch_col.stride(0) if n else 1, n,
+                                        batch_size, ptr(off), stream_ptr()), "ls3d_frame_offsets")
+    return off
+
+
 def three_nn(unknown, known):
     """Reference-signature 3-NN (three_nn_wrapper_fast): unknown [B, N, 3], known [B, M, 3] -> (dist2 [B, N, 3] squared,
     idx [B, N, 3] int32 per-batch rows)."""

@@ -655,3 +655,20 @@ def test_conv_kb_streamed_weights_vs_fp64(n, h, w, cin, cout, res, relu, stride)
         ref16 = ref16.relu()
     assert n32 is None
     assert float((o16.double() - ref16).abs().max() / ref16.abs().max()) <= 6e-4
+
+
+def test_frame_offsets_vs_bincount():
+    """ls3d_frame_offsets (segment table of a batch-sorted tensor) vs bincount + cumsum; fp32 strided column (points) and int32
+    column (voxel coordinates), an empty frame in the middle, an empty tensor."""
+    ops, _ = _ops()
+    counts = [1000, 0, 37, 4096, 1]
+    col = torch.cat([torch.full((c,), b) for b, c in enumerate(counts)])
+    ref = torch.tensor([0] + list(np.cumsum(counts)), dtype=torch.int32)
+    pts = torch.randn(col.numel(), 6)
+    pts[:, 0] = col.float()
+    pts = pts.to(DEV)
+    assert torch.equal(ops.frame_offsets(pts[:, 0], len(counts)).cpu(), ref)
+    coords = torch.zeros(col.numel(), 4, dtype=torch.int32)
+    coords[:, 0] = col.int()
+    assert torch.equal(ops.frame_offsets(coords.to(DEV)[:, 0], len(counts)).cpu(), ref)
+    assert torch.equal(ops.frame_offsets(torch.empty(0, dtype=torch.int32, device=DEV), 3).cpu(), torch.zeros(4, dtype=torch.int32))
