@@ -121,3 +121,44 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(d, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(d, f)
+
+
+def test_cabi_host_side_queries_and_argument_errors():
+    """Entry points that answer on the host (sizes, supported-shape queries) and the argument checks that run before any CUDA
+    call: usable without a GPU, same status-code contract (0 ok, -1 bad argument) as include/ls3d.h states."""
+    import ctypes
+
+    from lidarseg3d_b200 import capi
+    L = capi.lib()
+    nbytes, cp, npd = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int32()
+    # bf16x3 weight image: one n_pad * 128-byte block per (offset, 32-channel chunk)
+    assert L.ls3d_gemm_packed_bytes(27, 13, 32, ctypes.byref(nbytes), ctypes.byref(cp), ctypes.byref(npd)) == 0
+    assert (nbytes.value, cp.value, npd.value) == (27 * 1 * 32 * 128, 16, 32)
+    assert L.ls3d_gemm_packed_bytes(1, 192, 96, ctypes.byref(nbytes), ctypes.byref(cp), ctypes.byref(npd)) == 0
+    assert (nbytes.value, cp.value, npd.value) == (6 * 96 * 128, 192, 96)
+    assert L.ls3d_gemm_packed_bytes(1, 96, 300, ctypes.byref(nbytes), None, None) == -1          # cout > 256
+    assert L.ls3d_gemm_pack_bf16x3(None, 1, 96, 96, None, None) == -1
+    # fused decoder: weight image = q (3 x 12 KB) + out (3 x 12 KB) + linear1 (3 x 24 KB) + linear2 (6 x 12 KB) per layer
+    wb, vf = ctypes.c_int64(), ctypes.c_int64()
+    assert L.ls3d_sffm_decoder_weight_bytes(6, ctypes.byref(wb), ctypes.byref(vf)) == 0
+    assert wb.value == 6 * (12 * 12288 + 3 * 24576) and vf.value == 6 * 864 + 192
+    assert L.ls3d_sffm_decoder_weight_bytes(9, ctypes.byref(wb), ctypes.byref(vf)) == -1          # > 8 layers
+    fake = 1 << 20                                                                             # never dereferenced: the shape check fails first
+    assert L.ls3d_sffm_decoder(fake, 96, 10, fake, fake, fake, fake, fake, 1, 34, 6, 4, 64, 192, 1, 0.2, 1e-5, fake, 96, None) == -1
+    assert L.ls3d_sffm_decoder(fake, 96, 10, fake, fake, fake, fake, fake, 1, 34, 6, 8, 96, 192, 1, 0.2, 1e-5, fake, 96, None) == -1
+    assert L.ls3d_sffm_decoder(None, 96, 0, None, None, None, None, None, 1, 34, 6, 4, 96, 192, 1, 0.2, 1e-5, None, 96, None) == 0   # n = 0
+    # streamed-weight convolution: shapes it serves / refuses
+    ok = ctypes.c_int32()
+    assert L.ls3d_conv_f16_kb_supported(72, 72, 3, 1, 1, 1, 18 * 40 * 60, ctypes.byref(ok)) == 0 and ok.value == 1
+    assert L.ls3d_conv_f16_kb_supported(144, 72, 3, 1, 1, 1, 18 * 20 * 30, ctypes.byref(ok)) == 0 and ok.value == 1
+    assert L.ls3d_conv_f16_kb_supported(72, 72, 3, 2, 1, 1, 18 * 20 * 30, ctypes.byref(ok)) == 0 and ok.value == 1
+    assert L.ls3d_conv_f16_kb_supported(72, 144, 3, 1, 1, 1, 18 * 40 * 60, ctypes.byref(ok)) == 0 and ok.value == 0   # slice > 128 ch
+    assert L.ls3d_conv_f16_kb_supported(72, 72, 5, 1, 1, 1, 1000, ctypes.byref(ok)) == -1
+    assert L.ls3d_conv_f16_kb_supported(70, 72, 3, 1, 1, 1, 1000, ctypes.byref(ok)) == -1                              # cin % 8
+    # segment table, tile plan sizes
+    assert L.ls3d_frame_offsets(None, 1, 6, 100, 3, fake, None) == -1
+    assert L.ls3d_frame_offsets(fake, 1, 6, 100, 0, fake, None) == -1
+    hb, lb, pb = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    assert L.ls3d_tile_plan_bytes(27, 1000, ctypes.byref(hb), ctypes.byref(lb), ctypes.byref(pb)) == 0
+    assert hb.value == 8 * 32 * 4 + 16 and lb.value == 8 * 27 * 128 * 2 + 16
+    assert L.ls3d_tile_plan_bytes(28, 1000, ctypes.byref(hb), ctypes.byref(lb), ctypes.byref(pb)) == -1               # > 27 offsets
