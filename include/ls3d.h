@@ -35,10 +35,8 @@ typedef struct ls3d_gemm_args {
   const int32_t* nbr; /* [koff][m_out] input row per (offset, output row), -1 = none; NULL =   */
                       /* identity (dense Linear, requires koff == 1)                           */
   int32_t koff, m_out;
-  const float* w;     /* precise=2: ls3d_gemm_pack_bf16x3 image (below);                          */
-                      /* precise=0: [koff][n_pad][cin_pad] (K-major) tf32-rounded, zero padded;  */
-                      /* precise=1: [koff][2][n_pad][cin_pad] = {trunc_tf32(W), W - trunc_tf32(W)} */
-  int32_t cin_pad;    /* multiple of 8 (16 with precise=2), >= c0 + c1                         */
+  const float* w;     /* ls3d_gemm_pack_bf16x3 image (below)                                     */
+  int32_t cin_pad;    /* multiple of 16, >= c0 + c1                                            */
   int32_t n_pad;      /* multiple of 16 in [16, 256]                                           */
   int32_t cout;       /* valid output columns (<= n_pad)                                       */
   int32_t epi;        /* LS3D_EPI_LINEAR | LS3D_EPI_ATTN                                       */
@@ -65,12 +63,11 @@ typedef struct ls3d_gemm_args {
   int32_t ld_mask;       /*   (feature completion, point_seg_mseg3d_head.py:314-334)                */
   float* out;         /* [m_out, ld_out]                                                       */
   int32_t ld_out;
-  int32_t round_out;  /* 1: store outputs rounded to tf32 (cvt.rna); only useful with precise=0, where the  */
-                      /* operands of the next GEMM are truncated to tf32 by the tensor core               */
+  int32_t round_out;  /* must be 0 (tf32 rounding of stored outputs: retired single-pass engine)                  */
   int32_t debug_skip; /* development only, must be 0: bit0 no A gathers, bit1 no W loads, bit2 no MMA, bit3 no epilogue */
-  int32_t precise;    /* 2 (default engine): error-compensated bf16x3 - operands split on chip into bf16 hi + lo,        */
+  int32_t precise;    /* must be 2: error-compensated bf16x3 - operands split on chip into bf16 hi + lo,                  */
                       /*    x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, fp32 accumulate (~2^-17 per product, fp32-equivalent);    */
-                      /*    `w` = ls3d_gemm_pack_bf16x3 image.  1: 3xTF32, 0: single-pass TF32 (comparison engines)      */
+                      /*    `w` = ls3d_gemm_pack_bf16x3 image.  (0 / 1 named the retired TF32 / 3xTF32 engines.)         */
   /* Tile plan of the rulebook `nbr` (ls3d_tile_plan_build; NULL = gather per pair).  With a plan, sparse launches run    */
   /* on the gather-once engine (csrc/gather_gemm_once.cu): distinct input rows of a tile staged once, all offsets served  */
   /* from shared memory.  The plan is a pure function of `nbr` and is cached with it (spconv's indice_key cache).         */

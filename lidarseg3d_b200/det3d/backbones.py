@@ -2,7 +2,7 @@
 
 Same constructor kwargs, state-dict names and ``forward(batch_dict) -> batch_dict`` contract as the reference; the
 spconv modules are replaced by parameter holders, and the forward runs on the bitmap rulebook kernels
-(csrc/rulebook.cu) + the tcgen05 gather-GEMM (csrc/gather_gemm.cu) with BatchNorm / ReLU / residual / concat /
+(csrc/rulebook.cu) + the tcgen05 gather-GEMM (csrc/gather_gemm_once.cu) with BatchNorm / ReLU / residual / concat /
 channel-reduction fused into the GEMM epilogue.
 """
 import math
@@ -187,8 +187,6 @@ class UNetSCN3D(Prepared):
             levels[lv].subm_table()
         # ---- phase 2: features
         vf = pad_cols(voxel_features.float())
-        if not gemm.PRECISE:
-            vf = gemm.round_tf32(vf)          # single-pass TF32 mode: operands must be tf32-representable
         x = self._conv(vf, P["conv_input"], lv1.subm_table())
         for pk in P["conv1"]:
             x = self._block(x, pk, lv1.subm_table())

@@ -24,12 +24,9 @@ COUNT = None
 DEBUG_SKIP = 0      # development only (see ls3d_gemm_args.debug_skip)
 
 
-# Arithmetic engine of every gather-GEMM launch (csrc/gather_gemm*.cu):
-#   2 (default): "bf16x3" - operands split into bf16 hi + lo on the fly, x_hi.W_hi + x_hi.W_lo + x_lo.W_hi with fp32
-#                accumulate (~2^-17 relative error per product; activations stay exact fp32 in HBM)
-#   1 / True   : error-compensated 3xTF32 (~2^-22 per product), the slower reference engine
-#   0 / False  : single-pass TF32 with tf32-rounded activations (~2e-3 relative error after the full network: fails the
-#                1e-3 logit gate, kept for comparison only)
+# Arithmetic of every gather-GEMM launch (csrc/gather_gemm*.cu): "bf16x3" - operands split into bf16 hi + lo on the fly,
+# x_hi.W_hi + x_hi.W_lo + x_lo.W_hi with fp32 accumulate (~2^-17 relative error per product; activations stay exact fp32 in
+# HBM).  ``ls3d_gemm_args.precise`` = 2 names it on the C ABI (the round-1 TF32 / 3xTF32 engines 0 / 1 are retired).
 PRECISE = 2
 # Sparse launches (nbr given) of the bf16x3 engine run on the gather-once kernel (csrc/gather_gemm_once.cu) with the tile
 # plan of their rulebook; False = per-pair gather kernel (csrc/gather_gemm_bf16x3.cu), which also serves the dense Linears.
@@ -43,27 +40,18 @@ def trunc_tf32(x: torch.Tensor) -> torch.Tensor:
 
 
 class PackedWeight:
-    """W[koff][cin][cout] (spconv layout, reference scn_unet.py weight [kz,ky,kx,Cin,Cout]) packed as
-    [koff][n_pad][cin_pad] K-major, tf32-rounded, zero padded."""
+    """W[koff][cin][cout] (spconv layout, reference scn_unet.py weight [kz,ky,kx,Cin,Cout]) as the bf16x3 weight image of
+    include/ls3d.h (ls3d_gemm_pack_bf16x3): one swizzled [W_hi ; W_lo] block per (offset, 32-channel chunk)."""
 
     def __init__(self, w_kio: torch.Tensor):
         assert w_kio.dim() == 3
         koff, cin, cout = w_kio.shape
         self.koff, self.cin, self.cout = koff, cin, cout
-        self.precise = int(PRECISE)
-        self.cin_pad = pad_to(cin, 16 if self.precise == 2 else 8)
+        self.precise = 2
+        self.cin_pad = pad_to(cin, 16)
         self.n_pad = pad_to(cout, 16)
-        wt = w_kio.float().permute(0, 2, 1)
-        if self.precise == 2:
-            buf = self._pack_bf16x3_device(w_kio) if w_kio.is_cuda else self._pack_bf16x3(wt)
-        elif self.precise:
-            buf = torch.zeros(koff, 2, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
-            hi = trunc_tf32(wt)
-            buf[:, 0, :cout, :cin] = hi
-            buf[:, 1, :cout, :cin] = wt - hi
-        else:
-            buf = torch.zeros(koff, self.n_pad, self.cin_pad, dtype=torch.float32, device=w_kio.device)
-            buf[:, :cout, :cin] = round_tf32(wt)
+        # CPU tensors (host-side tests of the layout) go through the tensor-op restatement of the same image
+        buf = self._pack_bf16x3_device(w_kio) if w_kio.is_cuda else self._pack_bf16x3(w_kio.float().permute(0, 2, 1))
         self.data = buf.contiguous()
 
     def _pack_bf16x3_device(self, w_kio):
@@ -168,7 +156,7 @@ def run(x0, pw: PackedWeight, *, x1=None, nbr=None, m_out=None, scale=None, shif
     if out is None:
         out = torch.empty(m, pw.cout, dtype=torch.float32, device=x0.device)
     a.out, a.ld_out = capi.ptr(out), out.stride(0)
-    a.round_out = int(round_out and not pw.precise)
+    a.round_out = 0            # tf32 rounding of stored activations belonged to the retired single-pass engine
     a.precise = int(pw.precise)
     a.debug_skip = DEBUG_SKIP
     if COUNT is not None:
