@@ -588,7 +588,7 @@ def test_sffm_decoder_fused_vs_fp64(n, nl, L):
         x = d["n3"](x + d["l2"](F.relu(d["l1"](x))))
         for v in md.values():
             v.float()
-    ref = norm_tgt.double()(x)
+    ref = norm_tgt.double()(x).detach()
     err = float((out.double() - ref).abs().max())
     assert err <= 2e-4, err
 

@@ -162,3 +162,30 @@ def test_cabi_host_side_queries_and_argument_errors():
     assert L.ls3d_tile_plan_bytes(27, 1000, ctypes.byref(hb), ctypes.byref(lb), ctypes.byref(pb)) == 0
     assert hb.value == 8 * 32 * 4 + 16 and lb.value == 8 * 27 * 128 * 2 + 16
     assert L.ls3d_tile_plan_bytes(28, 1000, ctypes.byref(hb), ctypes.byref(lb), ctypes.byref(pb)) == -1               # > 27 offsets
+
+
+def test_conv_plan_routes_weight_heavy_convolutions_to_the_streamed_weight_kernel(monkeypatch):
+    """ConvPlan (det3d/img_backbones.py) at the bench's HRNet-w18 shapes: the 72- / 144-channel 3x3 convolutions and the stride-2
+    fuse convolutions into those branches go to ls3d_conv_f16_kb (whole input range per launch, <= 80-channel output slices);
+    the high-resolution small-channel convolutions and every 1x1 stay on the resident-weight kernel.  Host logic only."""
+    import torch
+
+    from lidarseg3d_b200 import ops
+    from lidarseg3d_b200.det3d.img_backbones import ConvPlan
+    monkeypatch.setattr(ops, "pack_conv_ex", lambda w, stride, split: torch.zeros(1))      # geometry only, no device
+    n = 18
+
+    def plan(co, ci, k, st, f32, h, w):
+        return ConvPlan(torch.zeros(co, ci, k, k), torch.zeros(co), k, st, exact=True, fp32out=f32, pixels=n * h * w)
+
+    for co, ci, st, f32, h, w, slices in [(72, 72, 1, True, 40, 60, 1), (72, 72, 1, False, 40, 60, 1), (144, 144, 1, True, 20, 30, 2),
+                                          (144, 144, 1, False, 20, 30, 2), (72, 40, 2, True, 80, 120, 1), (144, 72, 2, True, 40, 60, 2),
+                                          (144, 24, 2, True, 40, 60, 2)]:
+        p = plan(co, ci, 3, st, f32, h, w)
+        assert p.ok and p.kb and p.ci == ci and len(p.passes) == slices and p.cs <= 80, (co, ci, st, f32)
+        assert [pp[1] for pp in p.passes] == [0] * slices                      # every slice reads the whole input range
+    for co, ci, k, st, f32, h, w in [(24, 24, 3, 1, True, 160, 240), (40, 40, 3, 1, False, 80, 120), (40, 24, 3, 2, True, 160, 240),
+                                     (256, 64, 1, 1, True, 160, 240), (64, 256, 1, 1, False, 160, 240), (24, 256, 3, 1, True, 160, 240),
+                                     (64, 64, 3, 2, True, 320, 480)]:
+        p = plan(co, ci, k, st, f32, h, w)
+        assert p.ok and not p.kb, (co, ci, k, st)
