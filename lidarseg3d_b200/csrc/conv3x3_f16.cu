@@ -578,7 +578,8 @@ __device__ __forceinline__ void epilogue_rows_direct(const Args& p, const Direct
 // the T halos of the group stay staged in shared memory with T accumulators in tensor memory, and the slice's weight image
 // streams ONCE per item through a two-slot ring (cp.async.bulk of G consecutive MMAs' B tiles, which the packed layout
 // already stores contiguously) while the MMA warp walks block-outer / tile-inner: every MMA runs at the slice's full N and
-// a weight byte is fetched once per T tiles.  3x3 stride 1 only; epilogue = epilogue_rows (same arithmetic, same outputs).
+// a weight byte is fetched once per T tiles.  3x3 with stride 1 or 2 (phase-plane halos as in the kernel above; 1x1 works too
+// but loses to the staged TMA stores at high resolution); epilogue = epilogue_rows_direct (same arithmetic, global loads / stores).
 constexpr int KB_WSLOTS = 3;               // weight ring depth: bytes in flight from L2 while the MMAs of a block run
 struct KbArgs {
   int T;                      // tiles per group = stages = accumulators (T * nb <= 512 TMEM columns)

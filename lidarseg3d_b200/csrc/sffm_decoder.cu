@@ -19,7 +19,9 @@
 //     i.e. 24 of the 96 channels (48 of the 192 FFN channels) of each of its points: bias, the 34-token cross attention of
 //     its head on the CUDA cores (fp32), residual, exact two-pass LayerNorm (row sums exchanged through shared memory between
 //     the four warps of a point), ReLU, operand split; 1 MMA-issue warp; 1 loader warp.  (Four warps per scheduler: a single
-//     row warp per scheduler left every shared-memory / tensor-memory / FMA latency exposed - 1.3 ms per launch against 0.x.)
+//     row warp per scheduler left every shared-memory / tensor-memory / FMA latency exposed - 1.32 ms per launch against 0.83.)
+// Measured bound (ncu, profiles/r02_ncu_sffm_decoder*): the attention phase - one broadcast LDS.128 of K / V per 4 FMAs keeps
+// the shared-memory pipe, not the FMA pipe, busy; the four GEMM phases of a layer cost ~5.2 k cycles of tensor pipe per tile.
 // Arithmetic is the unfused path's: x_hi.W_hi + x_hi.W_lo + x_lo.W_hi bf16 products with fp32 accumulation (~2^-17 per
 // product), fp32 softmax / LayerNorm.
 #include "common.cuh"
