@@ -645,6 +645,7 @@ def main():
             # (both are persistent one-CTA-per-SM grids), which stretches its start-to-end events by the camera kernels' share
             if wl["cam"]:
                 model.serialize_branches = True
+                model.__dict__["_img_time_events"] = []          # camera-graph replay time, alone on the GPU in this pass
             gemm.PROFILE = []
             for i in range(NB):
                 step(dev_batches[i], img_dtype)
@@ -653,6 +654,19 @@ def main():
             gemm.PROFILE = None
             if wl["cam"]:
                 model.serialize_branches = False
+                r["camera_events"] = model.__dict__.pop("_img_time_events", None)
+                try:                                              # static description of the camera convolutions (one eager pass)
+                    from lidarseg3d_b200 import ops as _ops
+                    model.use_image_graph = False
+                    _ops.CONV_PROFILE = []
+                    step(dev_batches[0], img_dtype)
+                    torch.cuda.synchronize()
+                    r["conv_launches"] = [{k: v for k, v in c.items() if k not in ("e0", "e1")} for c in _ops.CONV_PROFILE]
+                except Exception as e:                            # never let the extra block take the bench line down
+                    r["conv_launches"] = repr(e)[:200]
+                finally:
+                    _ops.CONV_PROFILE = None
+                    model.use_image_graph = not args.eager_images
         # ---- e2e: pinned host buffers -> labels on the host
         for i in range(2):
             step(to_device(batches[i], dev), img_dtype)
@@ -737,6 +751,37 @@ def main():
                     all_gemm=dict(launches_per_step=len(al) // n_serial_steps, gbs=ab / am / 1e6, tflops=af / am / 1e9,
                                   share_of_step=(am / n_serial_steps) / (ms / args.steps)))
 
+    # ---- second roofline block: the camera-branch convolutions (the largest share of the step's kernel time)
+    roof_cam = None
+    if rank == 0 and wl["cam"] and isinstance(main_r.get("conv_launches"), list) and main_r.get("camera_events"):
+        try:
+            peaks2 = {}
+            try:
+                peaks2 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            peak2 = float(peaks2.get("hbm_gbs", 6650.0))
+            cam_ms = float(np.mean([a.elapsed_time(b) for a, b in main_r["camera_events"]]))
+            byts = 0.0
+            for c in main_r["conv_launches"]:
+                ho, wo = ((c["h"] + 1) // 2, (c["w"] + 1) // 2) if c["stride"] == 2 else (c["h"], c["w"])
+                pin, pout = c["n"] * c["h"] * c["w"], c["n"] * ho * wo
+                byts += pin * c["cin"] * 2 + pout * c["cout"] * (6 if c["out32"] else 2) + (pout * c["cout"] * (4 if c["out32"] else 2)
+                                                                                          if c["res"] else 0)
+            n_kb = sum(1 for c in main_r["conv_launches"] if c.get("kb"))
+            roof_cam = dict(bound="hbm", kernel="conv3x3_f16_kernel (%d launches) + conv3x3_kb_kernel (%d) of the HRNet-w18 / FCN camera "
+                                                "branch" % (len(main_r["conv_launches"]) - n_kb, n_kb),
+                            achieved=byts / cam_ms / 1e6, peak=peak2, unit="GB/s", frac=byts / cam_ms / 1e6 / peak2, traffic=None,
+                            algorithmic_bytes_per_step=byts, ms_per_step=cam_ms, share_of_step=cam_ms / (ms / args.steps),
+                            measured="CUDA events around the camera CUDA-graph replay, live in this run, in the serialised pass (the graph "
+                                     "alone on the GPU); bytes = per launch fp16 operand in + fp32 map and fp16 copy out (+ fp32 residual), "
+                                     "summed over the convolution launches; the graph time also contains the branch fusions and class "
+                                     "embeddings (~10 %), so `achieved` is a lower bound for the convolutions",
+                            evidence="profiles/r02_ncu_conv_all_launches_raw.csv (ncu --set full of every convolution launch), "
+                                     "profiles/r02_prof_camera_dual.txt (per-shape time vs HBM floor)")
+        except Exception as e:
+            roof_cam = dict(unavailable=repr(e)[:200])
+
     # ---- parity gate on one full-size batch (also the CPU baseline sample), spconv-style GPU baseline
     parity = cb = gref = None
     if rank == 0 and world == 1:
@@ -779,7 +824,7 @@ def main():
                     e2e=dict(value=e2e, unit="frames/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=in_bytes,
                              d2h_bytes_per_step=npts * 2 + 4 * (fpg + 4),
                              note="two-deep upload pipeline: batch i+1 copies on a side stream while batch i computes"),
-                    roofline=roof, cpu_baseline=cb, parity=parity, gpu_reference=gref)
+                    roofline=roof, roofline_camera_conv=roof_cam, cpu_baseline=cb, parity=parity, gpu_reference=gref)
         for name, sec_r in sec_rs.items():
             tag = {"fp16": "fp16cam", "fp32": "fp32lib"}.get(name, name)
             line["value_" + tag] = frames / (sec_r["ms"] / 1e3)

@@ -151,8 +151,16 @@ class SegMSeg3DNet(_SegBase):
                     outs = self._image_branch(static_in, batch_size)
                 ent = cache[key] = (g, static_in, outs, (c0, capi.snapshot()))
             g, static_in, outs, counted = ent
+            rec = self.__dict__.get("_img_time_events")                # measurement aid (bench.py): events around the replay
+            if rec is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record(side)
             static_in.copy_(images, non_blocking=True)
             g.replay()
+            if rec is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(side)
+                rec.append((e0, e1))
             capi.add_replay(*counted)                                  # launch accounting: the captured C-ABI kernels ran again
         return outs, side
 
