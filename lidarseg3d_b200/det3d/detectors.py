@@ -178,7 +178,11 @@ class SegMSeg3DNet(_SegBase):
             else:
                 feats, img_logits, cam_emb = self._image_branch(images, batch_size)
             _, c, ho, wo = feats.shape
-            if side is not None and self.serialize_branches:
+            # image_dtype None = the camera branch on LIBRARY convolutions (cuDNN / cuBLAS pick sm_100 tensor-memory kernels of
+            # their own): those are not run underneath this package's persistent tcgen05 kernels - the one abort seen in this
+            # project (CUDA "illegal instruction") happened in a library-convolution mode with the two streams
+            # concurrent, and the own-kernel modes lose nothing by this
+            if side is not None and (self.serialize_branches or self.image_dtype is None):
                 torch.cuda.current_stream().wait_stream(side)
             data = self._lidar_branch(example)
             data["points_cuv"] = example["points_cuv"]
